@@ -1,0 +1,159 @@
+/*
+ * gotranseq_b200.h -- C ABI of the B200-native translation hot path.
+ *
+ * This is the drop-in boundary for gotranseq's `transeq.Translate`
+ * (reference: transeq/transeq.go:114, `func Translate(inputSequence io.Reader, out io.Writer,
+ * options Options) error`).  The reference has no FFI of its own (pure Go, CGO_ENABLED=0,
+ * .goreleaser.yml:7); these are the entry points a cgo shim for that function binds
+ * (see INTEGRATION.md for the Go side).  Plain pointers and sizes only.
+ *
+ * Everything between "bytes of a nucleotide FASTA" and "bytes of the protein FASTA" runs on
+ * the GPU (sm_100a kernels in gotranseq_b200/csrc/).  There is no CPU fallback: if no CUDA
+ * device is usable every entry point that needs one fails with GTS_ERR_CUDA.
+ */
+#ifndef GOTRANSEQ_B200_H
+#define GOTRANSEQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GTS_VERSION "0.1.0"
+
+/* Return codes. 0 = success; the text for the last failure is gts_last_error(). */
+enum {
+    GTS_OK = 0,
+    GTS_ERR_FRAME = -1,    /* "wrong value for -f | --frame parameter: %s"  (transeq.go:107) */
+    GTS_ERR_TABLE = -2,    /* "invalid table code: %v"                       (ncbicode/code.go:378) */
+    GTS_ERR_CUDA = -3,     /* CUDA runtime / no device (no CPU fallback)                        */
+    GTS_ERR_NOMEM = -4,    /* host or device allocation failed                                  */
+    GTS_ERR_CAPACITY = -5, /* caller-provided output buffer too small; needed size reported     */
+    GTS_ERR_ARG = -6,      /* NULL / misaligned / out-of-range argument, wrong call order       */
+    GTS_ERR_WRITE = -7     /* "fail to write to output file: %v"             (writer.go:175)    */
+};
+
+/*
+ * Mirrors `type Options struct` (transeq/options.go:4-11) field for field.
+ * num_worker is accepted for source compatibility and ignored (the GPU path has no worker
+ * goroutines; output is always in input order, i.e. the reference's `-n 1` order).
+ */
+typedef struct gts_options {
+    const char *frame;    /* Options.Frame: "1","2","3","F","-1","-2","-3","R","6"           */
+    int32_t table;        /* Options.Table: NCBI genetic code id (ncbicode/code.go:341-363)   */
+    uint8_t clean;        /* Options.Clean: stop codon '*' -> 'X'                             */
+    uint8_t alternative;  /* Options.Alternative: frame -1 starts at the last codon           */
+    uint8_t trim;         /* Options.Trim: strip trailing 'X' / '*' of every frame            */
+    uint8_t reserved0;
+    int32_t num_worker;   /* Options.NumWorker: ignored                                       */
+    int32_t device;       /* CUDA device ordinal; -1 = the calling thread's current device    */
+    uint64_t chunk_bytes; /* streaming chunk size (bytes of FASTA per GPU pass); 0 = default  */
+} gts_options;
+
+typedef struct gts_ctx gts_ctx;
+
+/*
+ * Replaces the option decoding at the top of Translate: computeFrames (transeq.go:88-110) and
+ * createCodeArray (transeq.go:30-86, ncbicode.LoadTableCode code.go:367-388).  Validates
+ * frame / table with the reference's error texts, builds the fused forward / reverse-
+ * complement codon table, creates the CUDA streams and scratch buffers.
+ * On failure *out is NULL and gts_last_error(NULL) holds the message (thread-local).
+ */
+int gts_create(const gts_options *opt, gts_ctx **out);
+void gts_destroy(gts_ctx *ctx);
+
+/* Message of the last error on ctx (or of the last failed gts_create when ctx == NULL). */
+const char *gts_last_error(const gts_ctx *ctx);
+
+/*
+ * Option decoding only, no device needed (used by host-side checks and the CPU-only tests).
+ * gts_frame_mask: bit k set = frame index k (0..5 = 1,2,3,-1,-2,-3) requested
+ * (computeFrames, transeq.go:88-110); returns GTS_ERR_FRAME for an unknown name.
+ * gts_codon_table: fills aa64 with the table's 64 amino acids in T,C,A,G codon order
+ * (LoadTableCode, code.go:367-388); returns GTS_ERR_TABLE for an unknown id.
+ * gts_fused_lut: the 125-entry device table for (table, clean): entry c0 + 5*c1 + 25*c2
+ * (codes N=0,A=1,C=2,T=3,G=4) = forward amino acid | reverse-strand amino acid << 8.
+ */
+int gts_frame_mask(const char *frame, uint32_t *mask, int *reverse);
+int gts_codon_table(int32_t table, char aa64[64]);
+int gts_fused_lut(int32_t table, int clean, uint16_t lut[125]);
+
+/*
+ * Device-resident hot path: everything Translate does between in.Read and out.Write
+ * (readSequenceFromFasta transeq.go:183-216, newEncodedSequence encodedSequence.go:17-43,
+ * reverseComplement encodedSequence.go:71-97, writer.translate / translate3Frames / writeHeader
+ * / writeAA / trimAndReturn writer.go:57-169), on a FASTA buffer already in device memory.
+ *   d_in   device pointer to n bytes of FASTA (treated as one complete input: start of file
+ *          to EOF); any alignment, 16-byte aligned is fastest
+ *   d_out  device pointer, capacity cap bytes; receives the protein FASTA
+ *   out_n  receives the exact output size; if it exceeds cap nothing is written past cap and
+ *          GTS_ERR_CAPACITY is returned (out_n is still set, so the caller can retry)
+ *   stream a cudaStream_t (as void*; NULL = the legacy default stream).  All kernels are
+ *          enqueued on it; the call returns after the stream has finished them.
+ */
+int gts_translate_device(gts_ctx *ctx, const void *d_in, size_t n, void *d_out, size_t cap,
+                         size_t *out_n, void *stream);
+
+/*
+ * Same work, enqueue only (no host synchronisation): used to time the kernels with CUDA
+ * events on `stream`.  gts_device_result() synchronises and reports the outcome of the last
+ * enqueue (GTS_OK / GTS_ERR_CAPACITY / ...) and its output size.
+ */
+int gts_translate_device_async(gts_ctx *ctx, const void *d_in, size_t n, void *d_out, size_t cap,
+                               void *stream);
+int gts_device_result(gts_ctx *ctx, size_t *out_n);
+
+/* Upper bound of the output size used by the library when it sizes its own buffers. */
+size_t gts_output_bound_hint(const gts_ctx *ctx, size_t n);
+
+/*
+ * One-shot host call: host FASTA bytes in, host protein-FASTA bytes out (H2D, kernels, D2H).
+ * *out points into a pinned buffer owned by ctx, valid until the next call on ctx.
+ * The input is one complete FASTA (start of file to EOF).
+ */
+int gts_translate_buffer(gts_ctx *ctx, const uint8_t *in, size_t n, const uint8_t **out,
+                         size_t *out_n);
+
+/*
+ * Streaming host interface (what the Go shim's Translate loop drives; replaces the reader
+ * goroutine + channel + worker flushes of transeq.go:126-163 and writer.go:171-181):
+ *
+ *   for {
+ *       gts_acquire_input(ctx, &buf, &cap);        // pinned, C-owned
+ *       n = in.Read(buf[:cap]);
+ *       gts_submit(ctx, n, eof);                   // async H2D + kernels + D2H
+ *       while (gts_next_output(ctx, &p, &m) == GTS_OK && m > 0) {
+ *           out.Write(p[:m]); gts_release_output(ctx);
+ *       }
+ *       if eof { break }
+ *   }
+ *
+ * The library cuts the byte stream at record boundaries ("\n>"), carries the unfinished last
+ * record over to the next pass, keeps one pass in flight while the caller reads / writes, and
+ * hands results back strictly in input order.  After gts_submit(..., eof=1) the
+ * gts_next_output loop drains everything; n == 0 then means "done".
+ */
+int gts_acquire_input(gts_ctx *ctx, uint8_t **buf, size_t *cap);
+int gts_submit(gts_ctx *ctx, size_t nbytes, int eof);
+int gts_next_output(gts_ctx *ctx, const uint8_t **buf, size_t *n);
+int gts_release_output(gts_ctx *ctx);
+
+/* Counters of the last device pass / since creation (diagnostics and bench accounting). */
+typedef struct gts_stats {
+    uint64_t records;        /* records emitted by the last pass                          */
+    uint64_t nucleotides;    /* nucleotides translated by the last pass                   */
+    uint64_t in_bytes;       /* FASTA bytes of the last pass                              */
+    uint64_t out_bytes;      /* protein FASTA bytes of the last pass                      */
+    uint64_t kernel_launches;/* kernels launched since gts_create                         */
+    uint64_t h2d_bytes;      /* bytes copied host->device since gts_create                */
+    uint64_t d2h_bytes;      /* bytes copied device->host since gts_create                */
+    uint64_t passes;         /* device passes since gts_create                            */
+} gts_stats;
+int gts_get_stats(const gts_ctx *ctx, gts_stats *st);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOTRANSEQ_B200_H */
