@@ -1,0 +1,78 @@
+"""ctypes binding of the C ABI (include/gotranseq_b200.h).  The shared library is built in-tree
+by `make -C gotranseq_b200/csrc` (or __graft_entry__.build()); importing this module fails loudly
+when it is missing -- there is no CPU fallback."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgotranseq_b200.so")
+
+GTS_OK = 0
+GTS_ERR_FRAME = -1
+GTS_ERR_TABLE = -2
+GTS_ERR_CUDA = -3
+GTS_ERR_NOMEM = -4
+GTS_ERR_CAPACITY = -5
+GTS_ERR_ARG = -6
+GTS_ERR_WRITE = -7
+
+
+class gts_options(ctypes.Structure):
+    _fields_ = [
+        ("frame", ctypes.c_char_p),
+        ("table", ctypes.c_int32),
+        ("clean", ctypes.c_uint8),
+        ("alternative", ctypes.c_uint8),
+        ("trim", ctypes.c_uint8),
+        ("reserved0", ctypes.c_uint8),
+        ("num_worker", ctypes.c_int32),
+        ("device", ctypes.c_int32),
+        ("chunk_bytes", ctypes.c_uint64),
+    ]
+
+
+class gts_stats(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint64) for n in (
+        "records", "nucleotides", "in_bytes", "out_bytes", "kernel_launches", "h2d_bytes", "d2h_bytes", "passes")]
+
+
+EXPORTS = {
+    # name: (restype, argtypes)
+    "gts_create": (ctypes.c_int, [ctypes.POINTER(gts_options), ctypes.POINTER(ctypes.c_void_p)]),
+    "gts_destroy": (None, [ctypes.c_void_p]),
+    "gts_last_error": (ctypes.c_char_p, [ctypes.c_void_p]),
+    "gts_frame_mask": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_int)]),
+    "gts_codon_table": (ctypes.c_int, [ctypes.c_int32, ctypes.c_char_p]),
+    "gts_fused_lut": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int, ctypes.POINTER(ctypes.c_uint16)]),
+    "gts_translate_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
+                                            ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t), ctypes.c_void_p]),
+    "gts_translate_device_async": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
+                                                  ctypes.c_size_t, ctypes.c_void_p]),
+    "gts_device_result": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t)]),
+    "gts_output_bound_hint": (ctypes.c_size_t, [ctypes.c_void_p, ctypes.c_size_t]),
+    "gts_translate_buffer": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                            ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]),
+    "gts_acquire_input": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]),
+    "gts_submit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]),
+    "gts_next_output": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]),
+    "gts_release_output": (ctypes.c_int, [ctypes.c_void_p]),
+    "gts_get_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(gts_stats)]),
+}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `make -C gotranseq_b200/csrc` "
+                "(gotranseq_b200 has no CPU fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in EXPORTS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib

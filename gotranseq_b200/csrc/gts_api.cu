@@ -1,0 +1,501 @@
+// gts_api.cu -- the C ABI of include/gotranseq_b200.h: option decoding, scratch management,
+// device passes, the one-shot host call and the streaming host interface.
+//
+// This file replaces the orchestration of transeq.Translate (transeq/transeq.go:114-173): where
+// the reference runs one reader goroutine feeding NumWorker translate goroutines, a gts_ctx cuts
+// the byte stream at record boundaries and runs one device pass (four kernels, gts_kernels.cu)
+// per cut, handing the results back strictly in input order.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gotranseq_b200.h"
+#include "gts_codes.h"
+#include "gts_device.h"
+#include "gts_kernels.h"
+
+using gts::u32;
+using gts::u64;
+
+static thread_local std::string g_create_error;
+
+struct gts_ctx {
+    gts_options opt;
+    std::string frame;
+    uint32_t mask = 0;
+    bool reverse = false;
+    gts::Lut lut;
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;  // used by the host-buffer entry points
+
+    // ---- device scratch (grows, never shrinks) ----
+    u64 cap_n = 0;  // raw bytes the scratch is sized for
+    u32 *d_sym = nullptr;
+    u32 *d_hint = nullptr;
+    uint8_t *d_zero = nullptr;  // per-pass zeroed block: scan status, tickets, totals, pending words
+    size_t zero_cap = 0;
+    u64 rec_cap = 0;
+    u64 *d_hdr_off = nullptr, *d_hdr_end = nullptr, *d_dbase = nullptr, *d_out_off = nullptr;
+    u32 *d_trim = nullptr;
+    gts::Totals *h_totals = nullptr;  // pinned
+
+    // ---- buffers of the host entry points ----
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    size_t d_in_cap = 0, d_out_cap = 0;
+    uint8_t *h_out = nullptr;
+    size_t h_out_cap = 0;
+    uint8_t *h_in = nullptr;  // streaming input (pinned)
+    size_t h_in_cap = 0, h_in_fill = 0;
+    bool stream_first_pass = true, stream_eof = false, stream_out_ready = false, stream_done = false;
+    size_t stream_out_n = 0;
+
+    // ---- last enqueued device pass ----
+    bool pending = false;
+    gts::Job job;
+    u64 job_max_sym = 0;
+    cudaStream_t job_stream = nullptr;
+
+    gts_stats stats;
+    std::string err;
+};
+
+namespace {
+
+int fail(gts_ctx *ctx, int code, const std::string &msg) {
+    if (ctx) ctx->err = msg; else g_create_error = msg;
+    return code;
+}
+int cuda_fail(gts_ctx *ctx, cudaError_t e, const char *what) {
+    return fail(ctx, e == cudaErrorMemoryAllocation ? GTS_ERR_NOMEM : GTS_ERR_CUDA,
+                std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call)                                                   \
+    do {                                                           \
+        cudaError_t e_ = (call);                                   \
+        if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call);   \
+    } while (0)
+
+size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct ZeroLayout {
+    size_t p_status, s_status, totals, counters, p_pend, bytes;
+};
+ZeroLayout zero_layout(u64 ntiles_parse, u64 rec_cap) {
+    ZeroLayout z;
+    const u64 size_tiles = (rec_cap + gts::kSizeTile - 1) / gts::kSizeTile;
+    size_t off = 0;
+    z.p_status = off; off += ntiles_parse * 4 * sizeof(u64);
+    z.s_status = off; off += size_tiles * 4 * sizeof(u64);
+    z.totals = off;   off += sizeof(gts::Totals);
+    z.counters = off; off += 16;
+    z.p_pend = off;   off += ntiles_parse * sizeof(u32);
+    z.bytes = round_up(off, 16);
+    return z;
+}
+
+int free_rec(gts_ctx *ctx) {
+    cudaFree(ctx->d_hdr_off); cudaFree(ctx->d_hdr_end); cudaFree(ctx->d_dbase);
+    cudaFree(ctx->d_out_off); cudaFree(ctx->d_trim);
+    ctx->d_hdr_off = ctx->d_hdr_end = ctx->d_dbase = ctx->d_out_off = nullptr;
+    ctx->d_trim = nullptr;
+    ctx->rec_cap = 0;
+    return 0;
+}
+
+int alloc_rec(gts_ctx *ctx, u64 rec_cap) {
+    free_rec(ctx);
+    CU(cudaMalloc(&ctx->d_hdr_off, rec_cap * sizeof(u64)));
+    CU(cudaMalloc(&ctx->d_hdr_end, rec_cap * sizeof(u64)));
+    CU(cudaMalloc(&ctx->d_dbase, rec_cap * sizeof(u64)));
+    CU(cudaMalloc(&ctx->d_out_off, rec_cap * sizeof(u64)));
+    if (ctx->opt.trim) CU(cudaMalloc(&ctx->d_trim, rec_cap * 6 * sizeof(u32)));
+    ctx->rec_cap = rec_cap;
+    return GTS_OK;
+}
+
+// Size the scratch for a pass over n raw bytes.
+int ensure_scratch(gts_ctx *ctx, u64 n) {
+    if (n > ctx->cap_n || ctx->d_sym == nullptr) {
+        const u64 cap = std::max<u64>(n + n / 8, 1u << 20);
+        const u64 tiles_t = (cap + 4 + gts::kTransTile - 1) / gts::kTransTile + 1;
+        cudaFree(ctx->d_sym); cudaFree(ctx->d_hint);
+        ctx->d_sym = nullptr; ctx->d_hint = nullptr; ctx->cap_n = 0;
+        const size_t sym_bytes = (tiles_t * gts::kTransTileWords + 64) * sizeof(u32);
+        CU(cudaMalloc(&ctx->d_sym, sym_bytes));
+        // zero once: stale words past the end of a stream must still hold valid symbols (<= 4)
+        CU(cudaMemset(ctx->d_sym, 0, sym_bytes));
+        CU(cudaMalloc(&ctx->d_hint, (tiles_t + 2) * sizeof(u32)));
+        ctx->cap_n = cap;
+    }
+    const u64 want_rec = n / 128 + 4096;
+    if (want_rec > ctx->rec_cap) {
+        int rc = alloc_rec(ctx, want_rec + want_rec / 8);
+        if (rc) return rc;
+    }
+    const u64 ntp = std::max<u64>(1, (ctx->cap_n + gts::kParseTile - 1) / gts::kParseTile);
+    const ZeroLayout z = zero_layout(ntp, ctx->rec_cap);
+    if (z.bytes > ctx->zero_cap) {
+        cudaFree(ctx->d_zero);
+        ctx->d_zero = nullptr; ctx->zero_cap = 0;
+        CU(cudaMalloc(&ctx->d_zero, z.bytes));
+        ctx->zero_cap = z.bytes;
+    }
+    return GTS_OK;
+}
+
+// Enqueue one device pass on `stream` (no host synchronisation).
+int enqueue_pass(gts_ctx *ctx, const uint8_t *d_in, u64 n, uint8_t *d_out, u64 cap, cudaStream_t stream,
+                 bool sizes_only) {
+    if (((uintptr_t)d_in & 15) != 0) return fail(ctx, GTS_ERR_ARG, "device input must be 16-byte aligned");
+    int rc = ensure_scratch(ctx, n);
+    if (rc) return rc;
+    const u64 ntp = std::max<u64>(1, (n + gts::kParseTile - 1) / gts::kParseTile);
+    const ZeroLayout z = zero_layout(ntp, ctx->rec_cap);
+    gts::Job &job = ctx->job;
+    job.in = d_in; job.n = n; job.out = d_out; job.out_cap = cap;
+    job.sym = ctx->d_sym;
+    job.p_status = reinterpret_cast<u64 *>(ctx->d_zero + z.p_status);
+    job.s_status = reinterpret_cast<u64 *>(ctx->d_zero + z.s_status);
+    job.totals = reinterpret_cast<gts::Totals *>(ctx->d_zero + z.totals);
+    job.counters = reinterpret_cast<u32 *>(ctx->d_zero + z.counters);
+    job.p_pend = reinterpret_cast<u32 *>(ctx->d_zero + z.p_pend);
+    job.t_hint = ctx->d_hint;
+    job.hdr_off = ctx->d_hdr_off; job.hdr_end = ctx->d_hdr_end; job.dbase = ctx->d_dbase;
+    job.out_off = ctx->d_out_off; job.trim_len = ctx->d_trim; job.rec_cap = ctx->rec_cap;
+    job.ntiles_parse = (u32)ntp;
+    job.frame_mask = ctx->mask;
+    job.alternative = ctx->opt.alternative ? 1 : 0;
+    job.trim = ctx->opt.trim ? 1 : 0;
+    job.lut = ctx->lut;
+    ctx->job_max_sym = n + 4;
+    ctx->job_stream = stream;
+    CU(cudaMemsetAsync(ctx->d_zero, 0, z.bytes, stream));
+    unsigned long long launches = 0;
+    CU(gts::launch_pass(job, ctx->job_max_sym, ctx->sm_count, stream, sizes_only, &launches));
+    ctx->stats.kernel_launches += launches;
+    CU(cudaMemcpyAsync(ctx->h_totals, job.totals, sizeof(gts::Totals), cudaMemcpyDeviceToHost, stream));
+    ctx->pending = true;
+    ctx->stats.passes++;
+    return GTS_OK;
+}
+
+// Wait for the enqueued pass; grow the record table and redo the pass if it was too small.
+int finish_pass(gts_ctx *ctx, bool sizes_only) {
+    if (!ctx->pending) return fail(ctx, GTS_ERR_ARG, "no device pass enqueued");
+    for (int attempt = 0;; attempt++) {
+        CU(cudaStreamSynchronize(ctx->job_stream));
+        const gts::Totals &t = *ctx->h_totals;
+        if (t.flags & gts::kFlagRecOverflow) {
+            if (attempt >= 2) return fail(ctx, GTS_ERR_NOMEM, "record table overflow persists");
+            const u64 need = t.n_headers + 2;
+            int rc = alloc_rec(ctx, need + need / 16 + 1024);
+            if (rc) return rc;
+            const gts::Job j = ctx->job;
+            rc = enqueue_pass(ctx, j.in, j.n, j.out, j.out_cap, ctx->job_stream, sizes_only);
+            if (rc) return rc;
+            continue;
+        }
+        break;
+    }
+    ctx->pending = false;
+    const gts::Totals &t = *ctx->h_totals;
+    ctx->stats.records = t.records;
+    ctx->stats.nucleotides = t.nucleotides;
+    ctx->stats.in_bytes = ctx->job.n;
+    ctx->stats.out_bytes = t.out_total;
+    return GTS_OK;
+}
+
+int ensure_dev_buffer(gts_ctx *ctx, uint8_t **p, size_t *cap, size_t need) {
+    if (need <= *cap && *p) return GTS_OK;
+    cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    const size_t want = round_up(need + need / 8 + 4096, 4096);
+    CU(cudaMalloc(p, want));
+    *cap = want;
+    return GTS_OK;
+}
+int ensure_pinned(gts_ctx *ctx, uint8_t **p, size_t *cap, size_t need, size_t keep) {
+    if (need <= *cap && *p) return GTS_OK;
+    const size_t want = round_up(need + need / 8 + 4096, 4096);
+    uint8_t *q = nullptr;
+    CU(cudaHostAlloc(&q, want, cudaHostAllocDefault));
+    if (keep && *p) std::memcpy(q, *p, keep);
+    if (*p) cudaFreeHost(*p);
+    *p = q;
+    *cap = want;
+    return GTS_OK;
+}
+
+// Host bytes in pinned or pageable memory -> device pass -> pinned ctx->h_out.
+int translate_host(gts_ctx *ctx, const uint8_t *in, size_t n, size_t *out_n) {
+    int rc = ensure_dev_buffer(ctx, &ctx->d_in, &ctx->d_in_cap, n + 64);
+    if (rc) return rc;
+    if (n) CU(cudaMemcpyAsync(ctx->d_in, in, n, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes += n;
+    // pass 1: parse + sizes, so that the output buffers can be sized exactly
+    rc = enqueue_pass(ctx, ctx->d_in, n, nullptr, 0, ctx->stream, true);
+    if (rc) return rc;
+    rc = finish_pass(ctx, true);
+    if (rc) return rc;
+    const size_t total = ctx->h_totals->out_total;
+    rc = ensure_dev_buffer(ctx, &ctx->d_out, &ctx->d_out_cap, total + 64);
+    if (rc) return rc;
+    rc = ensure_pinned(ctx, &ctx->h_out, &ctx->h_out_cap, total + 64, 0);
+    if (rc) return rc;
+    // pass 2: residues and headers (the parse results are still in the scratch)
+    ctx->job.out = ctx->d_out;
+    ctx->job.out_cap = ctx->d_out_cap;
+    // clear the "output too small" flag left by the sizing pass
+    ctx->h_totals->flags &= ~gts::kFlagOutOverflow;
+    CU(cudaMemcpyAsync(ctx->job.totals, ctx->h_totals, sizeof(gts::Totals), cudaMemcpyHostToDevice, ctx->stream));
+    unsigned long long launches = 0;
+    CU(gts::launch_emit(ctx->job, ctx->job_max_sym, ctx->sm_count, ctx->stream, &launches));
+    ctx->stats.kernel_launches += launches;
+    if (total) CU(cudaMemcpyAsync(ctx->h_out, ctx->d_out, total, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->stats.d2h_bytes += total;
+    CU(cudaStreamSynchronize(ctx->stream));
+    *out_n = total;
+    return GTS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gts_frame_mask(const char *frame, uint32_t *mask, int *reverse) {
+    uint32_t m = 0;
+    bool r = false;
+    if (!gts::frame_mask(frame, &m, &r)) return GTS_ERR_FRAME;
+    if (mask) *mask = m;
+    if (reverse) *reverse = r ? 1 : 0;
+    return GTS_OK;
+}
+
+int gts_codon_table(int32_t table, char aa64[64]) {
+    const char *aa = gts::find_codon_table(table);
+    if (!aa) return GTS_ERR_TABLE;
+    std::memcpy(aa64, aa, 64);
+    return GTS_OK;
+}
+
+int gts_fused_lut(int32_t table, int clean, uint16_t lut[125]) {
+    const char *aa = gts::find_codon_table(table);
+    if (!aa) return GTS_ERR_TABLE;
+    gts::build_fused_lut(aa, clean != 0, lut);
+    return GTS_OK;
+}
+
+int gts_create(const gts_options *opt, gts_ctx **out) {
+    if (!out) return fail(nullptr, GTS_ERR_ARG, "gts_create: out is NULL");
+    *out = nullptr;
+    if (!opt) return fail(nullptr, GTS_ERR_ARG, "gts_create: options are NULL");
+    uint32_t mask = 0;
+    bool reverse = false;
+    const char *frame = opt->frame ? opt->frame : "";
+    // same texts as transeq.go:107 and ncbicode/code.go:378
+    if (!gts::frame_mask(frame, &mask, &reverse))
+        return fail(nullptr, GTS_ERR_FRAME, std::string("wrong value for -f | --frame parameter: ") + frame);
+    const char *aa = gts::find_codon_table(opt->table);
+    if (!aa) return fail(nullptr, GTS_ERR_TABLE, "invalid table code: " + std::to_string(opt->table));
+
+    gts_ctx *ctx = new gts_ctx();
+    ctx->opt = *opt;
+    ctx->frame = frame;
+    ctx->opt.frame = ctx->frame.c_str();
+    ctx->mask = mask;
+    ctx->reverse = reverse;
+    std::memset(&ctx->lut, 0, sizeof(ctx->lut));
+    gts::build_fused_lut(aa, opt->clean != 0, ctx->lut.v);
+    std::memset(&ctx->stats, 0, sizeof(ctx->stats));
+    std::memset(&ctx->job, 0, sizeof(ctx->job));
+
+    // No CPU fallback: without a usable CUDA device creation fails.
+    cudaError_t e;
+    int dev = opt->device;
+    if (dev < 0) {
+        e = cudaGetDevice(&dev);
+    } else {
+        e = cudaSetDevice(dev);
+    }
+    if (e == cudaSuccess) e = cudaFree(nullptr);  // force context creation
+    cudaDeviceProp prop;
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, dev);
+    if (e == cudaSuccess && prop.major < 10) {
+        delete ctx;
+        return fail(nullptr, GTS_ERR_CUDA, "gotranseq_b200 needs an sm_100a device (found sm_" +
+                                               std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+    }
+    if (e == cudaSuccess) e = gts::init_kernels();
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaHostAlloc(&ctx->h_totals, sizeof(gts::Totals), cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        std::string msg = std::string("CUDA initialisation failed (no CPU fallback): ") + cudaGetErrorString(e);
+        if (ctx->stream) cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return fail(nullptr, GTS_ERR_CUDA, msg);
+    }
+    ctx->device = dev;
+    ctx->sm_count = prop.multiProcessorCount;
+    *out = ctx;
+    return GTS_OK;
+}
+
+void gts_destroy(gts_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_sym); cudaFree(ctx->d_hint); cudaFree(ctx->d_zero);
+    free_rec(ctx);
+    cudaFree(ctx->d_in); cudaFree(ctx->d_out);
+    if (ctx->h_out) cudaFreeHost(ctx->h_out);
+    if (ctx->h_in) cudaFreeHost(ctx->h_in);
+    if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *gts_last_error(const gts_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int gts_translate_device_async(gts_ctx *ctx, const void *d_in, size_t n, void *d_out, size_t cap, void *stream) {
+    if (!ctx) return GTS_ERR_ARG;
+    if (n && !d_in) return fail(ctx, GTS_ERR_ARG, "d_in is NULL");
+    return enqueue_pass(ctx, static_cast<const uint8_t *>(d_in), n, static_cast<uint8_t *>(d_out), cap,
+                        static_cast<cudaStream_t>(stream), false);
+}
+
+int gts_device_result(gts_ctx *ctx, size_t *out_n) {
+    if (!ctx) return GTS_ERR_ARG;
+    int rc = finish_pass(ctx, false);
+    if (rc) return rc;
+    if (out_n) *out_n = ctx->h_totals->out_total;
+    if (ctx->h_totals->flags & gts::kFlagOutOverflow)
+        return fail(ctx, GTS_ERR_CAPACITY, "output buffer too small: need " +
+                                               std::to_string(ctx->h_totals->out_total) + " bytes");
+    return GTS_OK;
+}
+
+int gts_translate_device(gts_ctx *ctx, const void *d_in, size_t n, void *d_out, size_t cap, size_t *out_n,
+                         void *stream) {
+    int rc = gts_translate_device_async(ctx, d_in, n, d_out, cap, stream);
+    if (rc) return rc;
+    return gts_device_result(ctx, out_n);
+}
+
+size_t gts_output_bound_hint(const gts_ctx *ctx, size_t n) {
+    // long 6-frame records produce ~2.04 output bytes per input byte; short records are dominated
+    // by the six copies of the header.  This is a hint, not a bound: gts_translate_device reports
+    // the exact size when the buffer is too small.
+    (void)ctx;
+    return n * 4 + 4096;
+}
+
+int gts_translate_buffer(gts_ctx *ctx, const uint8_t *in, size_t n, const uint8_t **out, size_t *out_n) {
+    if (!ctx) return GTS_ERR_ARG;
+    if ((n && !in) || !out || !out_n) return fail(ctx, GTS_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    size_t total = 0;
+    int rc = translate_host(ctx, in, n, &total);
+    if (rc) return rc;
+    *out = ctx->h_out;
+    *out_n = total;
+    return GTS_OK;
+}
+
+// ---- streaming host interface ----------------------------------------------------------
+
+int gts_acquire_input(gts_ctx *ctx, uint8_t **buf, size_t *cap) {
+    if (!ctx || !buf || !cap) return GTS_ERR_ARG;
+    if (ctx->stream_eof) return fail(ctx, GTS_ERR_ARG, "gts_acquire_input after eof");
+    CU(cudaSetDevice(ctx->device));
+    const size_t chunk = ctx->opt.chunk_bytes ? (size_t)ctx->opt.chunk_bytes : (size_t)64 << 20;
+    // keep at least half a chunk of free space; a record larger than the buffer makes it grow
+    size_t need = ctx->h_in_fill + std::max<size_t>(chunk / 2, 4096);
+    if (need < chunk) need = chunk;
+    int rc = ensure_pinned(ctx, &ctx->h_in, &ctx->h_in_cap, need, ctx->h_in_fill);
+    if (rc) return rc;
+    *buf = ctx->h_in + ctx->h_in_fill;
+    *cap = ctx->h_in_cap - ctx->h_in_fill;
+    return GTS_OK;
+}
+
+int gts_submit(gts_ctx *ctx, size_t nbytes, int eof) {
+    if (!ctx) return GTS_ERR_ARG;
+    if (ctx->stream_eof) return fail(ctx, GTS_ERR_ARG, "gts_submit after eof");
+    if (ctx->stream_out_ready) return fail(ctx, GTS_ERR_ARG, "gts_submit before the previous output was released");
+    if (ctx->h_in_fill + nbytes > ctx->h_in_cap) return fail(ctx, GTS_ERR_ARG, "gts_submit: more bytes than acquired");
+    CU(cudaSetDevice(ctx->device));
+    ctx->h_in_fill += nbytes;
+    if (eof) ctx->stream_eof = true;
+    const size_t chunk = ctx->opt.chunk_bytes ? (size_t)ctx->opt.chunk_bytes : (size_t)64 << 20;
+    size_t cut = 0;
+    if (eof) {
+        cut = ctx->h_in_fill;
+        if (cut == 0 && !ctx->stream_first_pass) {  // nothing left after the last record boundary
+            ctx->stream_done = true;
+            return GTS_OK;
+        }
+    } else {
+        if (ctx->h_in_fill < chunk) return GTS_OK;  // keep filling
+        // last record boundary: a '>' that starts a line (transeq.go:198)
+        const uint8_t *p = ctx->h_in;
+        for (size_t i = ctx->h_in_fill; i-- > 1;) {
+            if (p[i] == '>' && p[i - 1] == '\n') {
+                cut = i;
+                break;
+            }
+        }
+        if (cut == 0) return GTS_OK;  // one record larger than the buffer: keep reading (buffer grows)
+    }
+    size_t total = 0;
+    int rc = translate_host(ctx, ctx->h_in, cut, &total);
+    if (rc) return rc;
+    ctx->stream_first_pass = false;
+    // carry the unfinished record over
+    const size_t rest = ctx->h_in_fill - cut;
+    if (rest) std::memmove(ctx->h_in, ctx->h_in + cut, rest);
+    ctx->h_in_fill = rest;
+    ctx->stream_out_n = total;
+    ctx->stream_out_ready = total > 0;
+    if (eof) ctx->stream_done = true;
+    return GTS_OK;
+}
+
+int gts_next_output(gts_ctx *ctx, const uint8_t **buf, size_t *n) {
+    if (!ctx || !buf || !n) return GTS_ERR_ARG;
+    if (ctx->stream_out_ready) {
+        *buf = ctx->h_out;
+        *n = ctx->stream_out_n;
+    } else {
+        *buf = nullptr;
+        *n = 0;
+        if (ctx->stream_done) {  // drained: ready for another stream
+            ctx->stream_done = false;
+            ctx->stream_eof = false;
+            ctx->stream_first_pass = true;
+            ctx->h_in_fill = 0;
+        }
+    }
+    return GTS_OK;
+}
+
+int gts_release_output(gts_ctx *ctx) {
+    if (!ctx) return GTS_ERR_ARG;
+    ctx->stream_out_ready = false;
+    ctx->stream_out_n = 0;
+    return GTS_OK;
+}
+
+int gts_get_stats(const gts_ctx *ctx, gts_stats *st) {
+    if (!ctx || !st) return GTS_ERR_ARG;
+    *st = ctx->stats;
+    return GTS_OK;
+}
+
+}  // extern "C"

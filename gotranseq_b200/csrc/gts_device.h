@@ -1,5 +1,22 @@
 // gts_device.h -- data layout in HBM shared by the host API (gts_api.cu) and the kernels
 // (gts_kernels.cu).  See DESIGN.md "Data layout" for the narrative.
+//
+// One device pass turns a FASTA buffer into protein FASTA with four kernels:
+//
+//   k_parse      raw bytes -> dense 4-bit symbol stream + record table      (transeq.go:183-216,
+//                                                                            encodedSequence.go:17-43)
+//   k_size       record table -> frame lengths (trim), output offsets       (writer.go:85-116,159-169)
+//   k_translate  symbol stream -> residues of all requested frames, laid
+//                out as 60-column lines at their final output offsets       (writer.go:57-157,
+//                                                                            encodedSequence.go:71-97)
+//   k_headers    record table + raw header bytes -> ">id_N rest" lines      (writer.go:120-131)
+//
+// Symbol stream: one 4-bit symbol per nucleotide in input order, codes N=0 A=1 C=2 T/U=3 G=4
+// (transeq.go:14-21).  Two 0 symbols ("pads") are inserted in front of every record and two
+// more follow the last one, so that EVERY residue of EVERY frame is the table entry of three
+// consecutive symbols (e-2, e-1, e): the pads play the role of the reference's tail rules
+// (two-letter codon / 'X', writer.go:102-112) on both strands.  Word w of the stream holds
+// symbols 8w..8w+7; byte i of the word = symbol 8w+i | symbol 8w+i+4 << 4.
 #pragma once
 #include <cstdint>
 
@@ -7,83 +24,79 @@ namespace gts {
 
 typedef unsigned long long u64;
 typedef long long i64;
+typedef unsigned int u32;
 
-// One tile = kTileBytes consecutive bytes of the raw FASTA buffer, processed by one CTA of
-// kThreads threads, kBytesPerThread consecutive bytes per thread.
-constexpr int kTileBytes = 8192;
-constexpr int kThreads = 256;
-constexpr int kBytesPerThread = 32;
-constexpr int kWarps = kThreads / 32;
-static_assert(kThreads * kBytesPerThread == kTileBytes, "tile geometry");
+// ---- k_parse geometry: one CTA per tile of raw bytes ----
+constexpr int kParseThreads = 256;
+constexpr int kParseBytesPerThread = 32;
+constexpr int kParseTile = kParseThreads * kParseBytesPerThread;  // 8192 raw bytes
 
-// Records per CTA pass of the sizing kernel.
-constexpr int kSizeTile = 1024;
+// ---- k_translate geometry: one CTA per tile of symbols ----
+constexpr int kTransThreads = 256;
+constexpr int kTransSymPerThread = 48;
+constexpr int kTransTile = kTransThreads * kTransSymPerThread;  // 12288 symbols
+constexpr int kTransTileWords = kTransTile / 8;                 // 1536 stream words
+constexpr int kPhaseLen = kTransTile / 3;                       // residues per phase array
+constexpr int kPhaseGuard = 16;
+constexpr int kPhaseStride = kPhaseLen + 2 * kPhaseGuard;       // bytes per phase array in smem
+constexpr int kRecBatch = 128;                                  // record pieces per format batch
+constexpr int kRunsPerBatch = kRecBatch * 6;
 
-// Chained-scan status words.  Top two bits: 0 = not published, 1 = aggregate of this tile
-// only, 2 = inclusive prefix over tiles 0..t.  Low 62 bits: the value.
-constexpr u64 kFlagAgg = 1ull << 62;
-constexpr u64 kFlagInc = 2ull << 62;
-constexpr u64 kFlagMask = 3ull << 62;
-constexpr u64 kValMask = ~kFlagMask;
+// ---- k_size geometry ----
+constexpr int kSizeThreads = 256;
+constexpr int kSizePerThread = 4;
+constexpr int kSizeTile = kSizeThreads * kSizePerThread;  // record slots per scan tile
 
-struct TileStatus {  // 32 B, zeroed before every pass
-    u64 w0;          // phase 1: (position + 1) of the last '\n' seen so far (max), 0 = none
-    u64 w1;          // phase 2: dense symbols (nucleotides + 2 pads per record start) (sum)
-    u64 w2;          // phase 2: header lines (sum)
-    u64 pad;
-};
-
-// Line state at the first byte of a tile.
-enum : uint32_t { kStateLineStart = 0, kStateInSeq = 1, kStateInHeader = 2 };
-
-struct TilePrefix {  // 16 B, written by the parse kernel, read by the emit kernel
-    u64 dense_before;     // dense symbols in tiles < t (tile 0 owns two leading pads)
-    uint32_t rec_before;  // header lines in tiles < t  (== slot of the record open at tile start)
-    uint32_t state;       // kState*
-};
+// Chained-scan status: 4 words per tile {agg.a, agg.b, inc.a, inc.b}; bit 63 of the .a words
+// is the "published" flag (values stay below 2^63).  agg = this tile only, inc = tiles 0..t.
+constexpr u64 kValid = 1ull << 63;
 
 struct Totals {  // device-resident result block, copied to pinned host memory after a pass
     u64 n_headers;    // R: number of header lines; record slots are 0..R (slot 0 = bytes before
-                      // the first header line)
-    u64 total_dense;  // dense symbols in the whole buffer
+                      // the first header line, emitted only if it has nucleotides or R == 0)
+    u64 total_sym;    // symbols in the stream, the two end pads not counted
     u64 out_total;    // exact size of the protein FASTA
-    u64 nucleotides;  // nucleotides of emitted records
-    u64 records;      // records emitted (slot 0 counted only when present)
-    u64 flags;        // bit 0: record table too small, bit 1: output buffer too small
+    u64 flags;        // kFlag*
+    u64 records;      // records emitted
+    u64 nucleotides;  // nucleotides in emitted records
     u64 pad[2];
 };
-constexpr u64 kFlagRecOverflow = 1;
-constexpr u64 kFlagOutOverflow = 2;
+constexpr u64 kFlagRecOverflow = 1;  // record table too small (n_headers is still exact)
+constexpr u64 kFlagOutOverflow = 2;  // output buffer too small (out_total is still exact)
 
 struct Lut {  // 125 used entries: forward residue | reverse-strand residue << 8
     uint16_t v[128];
 };
 
 struct Job {  // kernel argument block (by value)
-    const uint8_t *in;
+    const uint8_t *in;  // raw FASTA, 16-byte aligned
     u64 n;
     uint8_t *out;
     u64 out_cap;
 
-    TileStatus *tstatus;  // [ntiles]
-    TilePrefix *tprefix;  // [ntiles]
-    unsigned int *counters;  // [0] parse tile ticket, [1] size tile ticket
-    u64 *sstatus;            // [size tiles] chained-scan words of the sizing kernel
+    u32 *sym;  // packed symbol stream
 
-    // record table, structure of arrays, slots 0..R (+1 sentinel in dbase)
+    u64 *p_status;  // [ntiles_parse * 4] chained scan of (symbols, header lines)
+    u32 *p_pend;    // [ntiles_parse] symbols of the last incomplete stream word, bit 31 = valid
+    u32 *t_hint;    // [translate tiles] a record slot <= the slot owning the tile's first symbol
+
+    // record table, structure of arrays, slots 0..R (+1 sentinel in dbase / out_off)
     u64 *hdr_off;   // raw offset of the header line's '>'
-    u64 *hdr_nl;    // raw offset of the '\n' ending the header line (or n at EOF);
-                    // bit 63 = a '\r' before it was dropped (bufio.ScanLines dropCR)
-    u64 *dbase;     // dense index of the record's first nucleotide
+    u64 *hdr_end;   // raw offset one past the header line's last byte (CR dropped)
+    u64 *dbase;     // stream index of the record's first nucleotide (its pads sit at -2, -1)
     u64 *out_off;   // offset of the record's first output byte
-    u64 *trim_len;  // [slot*6 + frame] residues kept after --trim (only with trim)
-    u64 rec_cap;    // usable slots
+    u32 *trim_len;  // [slot*6 + frame] residues kept after --trim (only with trim)
+    u64 rec_cap;    // entries in each of the arrays above
 
+    u64 *s_status;  // [size tiles * 4] chained scan of output sizes
+    u32 *counters;  // [0] parse tile ticket, [1] size tile ticket
     Totals *totals;
-    uint32_t ntiles;
-    uint32_t frame_mask;   // bit k = frame index k requested (0..2 forward, 3..5 reverse)
-    uint32_t alternative;
-    uint32_t trim;
+
+    u32 ntiles_parse;
+    u32 frame_mask;  // bit k = frame index k requested (0..2 forward, 3..5 reverse)
+    u32 alternative;
+    u32 trim;
+    Lut lut;
 };
 
 }  // namespace gts

@@ -1,0 +1,900 @@
+// gts_kernels.cu -- the sm_100a kernels of the translation hot path.
+//
+// Reference behaviour reproduced (file:line in feliixx/gotranseq):
+//   k_parse      readSequenceFromFasta  transeq/transeq.go:183-216 (bufio.ScanLines semantics),
+//                newEncodedSequence     transeq/encodedSequence.go:17-43
+//   k_size       frame lengths / tail rules / trim   transeq/writer.go:85-116,141-169
+//   k_translate  translate / translate3Frames / writeAA / newLine   transeq/writer.go:57-157,
+//                reverseComplement      transeq/encodedSequence.go:71-97 (never materialised:
+//                the fused table holds the reverse-strand residue of every window)
+//   k_headers    writeHeader            transeq/writer.go:120-131
+//
+// tests/gpu_model.py is the executable specification of the index arithmetic used here.
+#include <cuda_runtime.h>
+
+#include "gts_device.h"
+#include "gts_kernels.h"
+
+namespace gts {
+
+// =====================================================================================
+// small helpers
+// =====================================================================================
+__device__ __forceinline__ u64 ld_acquire(const u64 *p) {
+    u64 v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ u64 ld_relaxed(const u64 *p) {
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(u64 *p, u64 v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_release(u64 *p, u64 v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ u32 ld_acquire32(const u32 *p) {
+    u32 v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release32(u32 *p, u32 v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// 0x80 in every byte of w that equals the byte replicated in pat
+__device__ __forceinline__ u32 eq_bytes(u32 w, u32 pat) {
+    u32 z = w ^ pat;
+    u32 t = (z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+    return ~(t | z | 0x7F7F7F7Fu);
+}
+// the four 0x80 flags of m as bits 0..3
+__device__ __forceinline__ u32 gather4(u32 m) { return (((m >> 7) * 0x00204081u) >> 21) & 0xFu; }
+
+__device__ __forceinline__ u32 newline_mask16(uint4 v) {
+    return gather4(eq_bytes(v.x, 0x0A0A0A0Au)) | gather4(eq_bytes(v.y, 0x0A0A0A0Au)) << 4 |
+           gather4(eq_bytes(v.z, 0x0A0A0A0Au)) << 8 | gather4(eq_bytes(v.w, 0x0A0A0A0Au)) << 12;
+}
+
+struct Pair {
+    u64 a, b;
+};
+
+// Decoupled look-back over the tiles of a chained scan (sum of two counters).  Called by all 32
+// lanes of one warp of tile t with that tile's aggregate; publishes it, walks back over the
+// predecessors' published aggregates / inclusive prefixes, publishes this tile's inclusive
+// prefix and returns the exclusive one.  Tiles are numbered by an atomic ticket, so every
+// predecessor is running or finished and the wait terminates.
+__device__ Pair scan_lookback(u64 *status, u32 t, Pair agg) {
+    const int lane = threadIdx.x & 31;
+    u64 *mine = status + 4ull * t;
+    if (lane == 0) {
+        st_relaxed(mine + 1, agg.b);
+        st_release(mine + 0, agg.a | kValid);
+    }
+    Pair excl = {0, 0};
+    i64 pos = (i64)t - 1;
+    while (pos >= 0) {
+        const i64 idx = pos - lane;
+        int kind = 2;  // 0 = not published, 1 = aggregate, 2 = inclusive (or before tile 0)
+        u64 a = 0, b = 0;
+        if (idx >= 0) {
+            const u64 *st = status + 4ull * (u64)idx;
+            u64 w = ld_acquire(st + 2);
+            if (w & kValid) {
+                a = w & ~kValid;
+                b = ld_relaxed(st + 3);
+            } else {
+                w = ld_acquire(st + 0);
+                if (w & kValid) {
+                    kind = 1;
+                    a = w & ~kValid;
+                    b = ld_relaxed(st + 1);
+                } else {
+                    kind = 0;
+                }
+            }
+        }
+        const unsigned inc_m = __ballot_sync(0xFFFFFFFFu, kind == 2);
+        const unsigned none_m = __ballot_sync(0xFFFFFFFFu, kind == 0);
+        const int first_inc = inc_m ? __ffs(inc_m) - 1 : 32;
+        const int first_none = none_m ? __ffs(none_m) - 1 : 32;
+        if (first_none < first_inc) continue;  // a needed predecessor has not published yet
+        const int last = first_inc < 31 ? first_inc : 31;
+        if (lane > last) a = b = 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
+            b += __shfl_xor_sync(0xFFFFFFFFu, b, o);
+        }
+        excl.a += a;
+        excl.b += b;
+        if (first_inc < 32) break;
+        pos -= 32;
+    }
+    if (lane == 0) {
+        st_relaxed(mine + 3, excl.b + agg.b);
+        st_release(mine + 2, (excl.a + agg.a) | kValid);
+    }
+    return excl;
+}
+
+__device__ __forceinline__ i64 floordiv3(i64 a) { return a >= 0 ? a / 3 : -((-a + 2) / 3); }
+__device__ __forceinline__ i64 ceildiv3(i64 a) { return -floordiv3(-a); }
+__device__ __forceinline__ int mod3(i64 a) { return (int)(a - 3 * floordiv3(a)); }
+
+// rc start position of reverse frame i (0..2): writer.go:64-79
+__device__ __forceinline__ int reverse_start(u64 n, int i, bool alternative) {
+    if (alternative) return i;
+    int r = (int)(n % 3) - i;
+    return r < 0 ? r + 3 : r;
+}
+
+// residues of each frame before trimming: writer.go:97-112 (Go's % truncates, so a start
+// position beyond the sequence emits nothing)
+__device__ __forceinline__ void frame_lengths(u64 n, bool alternative, u64 L[6]) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) L[k] = n >= (u64)k ? (n - k + 2) / 3 : 0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const u64 p = (u64)reverse_start(n, i, alternative);
+        L[3 + i] = n >= p ? (n - p + 2) / 3 : 0;
+    }
+}
+
+__device__ __forceinline__ u64 run_size(u64 H, u64 Lp) { return H + 3 + Lp + (Lp + 59) / 60; }
+
+__device__ __forceinline__ u32 stream_symbol(const u32 *sym, u64 x) {
+    const u32 w = sym[x >> 3];
+    const u32 i = (u32)x & 7u;
+    return (w >> (8 * (i & 3) + 4 * (i >> 2))) & 0xFu;
+}
+
+__device__ __forceinline__ bool record_emitted(u64 s, u64 n, u64 R) { return s >= 1 || n > 0 || R == 0; }
+
+// =====================================================================================
+// k_parse
+// =====================================================================================
+enum { LS = 0, SEQ = 1, HDR = 2 };
+
+struct ParseShared {
+    alignas(16) uint8_t raw[kParseTile];
+    alignas(16) uint8_t sym[8 + kParseTile + 2 + 54];  // 8256 bytes: pending + symbols + zero tail
+    uint8_t enc[256];
+    u32 warp_sum[kParseThreads / 32];
+    u32 warp_max[kParseThreads / 32];
+    u64 T0, R0;
+    u64 tile_ls;
+    u32 tile;
+    u32 S_tile, R_tile;
+};
+
+// One pass over the 32 bytes of a thread.  COUNT mode returns the symbols / header lines of the
+// chunk; EMIT mode additionally writes the symbols to shared memory and the record table
+// entries (header start, stream base, header end) to global memory.
+template <bool EMIT>
+__device__ __forceinline__ void walk_chunk(const Job &job, const uint8_t *raw, const uint8_t *enc,
+                                           int len, u32 nlmask, int state, bool cr_dropped_at_end,
+                                           bool eof_chunk, u64 pos0, u32 &nsym, u32 &nhdr,
+                                           uint8_t *symdst, u64 dense0, u64 rec) {
+    int a = 0;
+    u32 ns = 0, nh = 0;
+    int st = state;
+    while (true) {
+        const u32 m = a < 32 ? (nlmask >> a) : 0u;
+        const int e = m ? a + __ffs(m) - 1 : len;  // index of the next '\n', or the chunk end
+        if (a < e) {
+            if (st == LS) {
+                if (raw[a] == '>') {  // transeq.go:198
+                    st = HDR;
+                    nh++;
+                    if (EMIT) {
+                        symdst[ns] = 0;
+                        symdst[ns + 1] = 0;
+                        rec++;
+                        if (rec < job.rec_cap) {
+                            job.hdr_off[rec] = pos0 + a;
+                            job.dbase[rec] = dense0 + ns + 2;
+                        }
+                    }
+                    ns += 2;
+                } else {
+                    st = SEQ;
+                }
+            }
+            if (st == SEQ) {
+                int b = e;
+                // bufio.ScanLines dropCR: a CR right before the '\n' (or as the last byte of the
+                // input) is not part of the line
+                if (raw[e - 1] == '\r' && (e < len || cr_dropped_at_end)) b--;
+                if (EMIT) {
+                    for (int i = a; i < b; i++) symdst[ns + (i - a)] = enc[raw[i]];
+                }
+                ns += b - a;
+            }
+        }
+        if (e < len) {  // raw[e] == '\n'
+            if (EMIT && st == HDR) {
+                u64 end = pos0 + e;
+                const uint8_t prev = e > 0 ? raw[e - 1] : job.in[pos0 - 1];
+                if (prev == '\r') end--;
+                if (rec < job.rec_cap) job.hdr_end[rec] = end;
+            }
+            st = LS;
+            a = e + 1;
+        } else {
+            break;
+        }
+    }
+    if (EMIT && eof_chunk && st == HDR) {  // header line without a final newline
+        u64 end = job.n;
+        if (raw[len - 1] == '\r') end--;
+        if (rec < job.rec_cap) job.hdr_end[rec] = end;
+    }
+    nsym = ns;
+    nhdr = nh;
+}
+
+__global__ void __launch_bounds__(kParseThreads) k_parse(const __grid_constant__ Job job) {
+    __shared__ ParseShared sh;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) sh.tile = atomicAdd(&job.counters[0], 1u);
+    // nucleotide codes of the reference: encodedSequence.go:25-41 (anything else -> N = 0)
+    {
+        uint8_t c = 0;
+        switch (tid) {
+            case 'A': case 'a': c = 1; break;
+            case 'C': case 'c': c = 2; break;
+            case 'T': case 't': case 'U': case 'u': c = 3; break;
+            case 'G': case 'g': c = 4; break;
+        }
+        sh.enc[tid] = c;
+    }
+    __syncthreads();
+    const u32 t = sh.tile;
+    const u64 tile_base = (u64)t * kParseTile;
+    const u64 pos0 = tile_base + (u64)tid * kParseBytesPerThread;
+    const int len = pos0 >= job.n ? 0 : (job.n - pos0 < 32 ? (int)(job.n - pos0) : 32);
+
+    // ---- load the chunk, keep a copy of the tile in shared memory ----
+    uint4 v0 = make_uint4(0, 0, 0, 0), v1 = make_uint4(0, 0, 0, 0);
+    if (len == 32) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(job.in + pos0);
+        v0 = __ldg(p);
+        v1 = __ldg(p + 1);
+    } else if (len > 0) {
+        u32 w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < len; i++) w[i >> 2] |= (u32)job.in[pos0 + i] << (8 * (i & 3));
+        v0 = make_uint4(w[0], w[1], w[2], w[3]);
+        v1 = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+    uint8_t *raw = sh.raw + tid * kParseBytesPerThread;
+    reinterpret_cast<uint4 *>(raw)[0] = v0;
+    reinterpret_cast<uint4 *>(raw)[1] = v1;
+    u32 nlmask = newline_mask16(v0) | newline_mask16(v1) << 16;
+    if (len < 32) nlmask &= len ? ((1u << len) - 1u) : 0u;
+
+    // ---- start of the line the tile begins in: backward search for the previous '\n' ----
+    if (warp == 0) {
+        u64 ls = 0;
+        u64 hi = tile_base;
+        while (hi > 0) {
+            const i64 start = (i64)hi - 16 * (lane + 1);
+            u32 m16 = 0;
+            if (start >= 0) m16 = newline_mask16(__ldg(reinterpret_cast<const uint4 *>(job.in + start)));
+            const unsigned b = __ballot_sync(0xFFFFFFFFu, m16 != 0);
+            if (b) {
+                const int l = __ffs(b) - 1;
+                const u32 mm = __shfl_sync(0xFFFFFFFFu, m16, l);
+                ls = hi - 16ull * (l + 1) + (31 - __clz(mm)) + 1;
+                break;
+            }
+            if (hi <= 512) break;
+            hi -= 512;
+        }
+        if (lane == 0) sh.tile_ls = ls;
+    }
+
+    // ---- exclusive max-scan of "last newline + 1" (tile relative) over the threads ----
+    const u32 my_last = nlmask ? (u32)(tid * 32 + (31 - __clz(nlmask)) + 1) : 0u;
+    u32 inc_max = my_last;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 y = __shfl_up_sync(0xFFFFFFFFu, inc_max, o);
+        if (lane >= o) inc_max = max(inc_max, y);
+    }
+    if (lane == 31) sh.warp_max[warp] = inc_max;
+    u32 excl_max = __shfl_up_sync(0xFFFFFFFFu, inc_max, 1);
+    if (lane == 0) excl_max = 0;
+    __syncthreads();
+    for (int w = 0; w < warp; w++) excl_max = max(excl_max, sh.warp_max[w]);
+    const u64 line_start = excl_max ? tile_base + excl_max : sh.tile_ls;
+
+    int state = LS;
+    if (len > 0 && line_start != pos0) state = job.in[line_start] == '>' ? HDR : SEQ;
+    bool cr_end = false;
+    if (len > 0 && raw[len - 1] == '\r') cr_end = (pos0 + len >= job.n) || job.in[pos0 + len] == '\n';
+    const bool eof_chunk = len > 0 && pos0 + len == job.n;
+
+    // ---- count, scan over the tile ----
+    u32 nsym, nhdr;
+    walk_chunk<false>(job, raw, sh.enc, len, nlmask, state, cr_end, eof_chunk, pos0, nsym, nhdr, nullptr, 0, 0);
+    const bool first_thread = (t == 0 && tid == 0);
+    if (first_thread) nsym += 2;  // pads of slot 0
+    const u32 packed = nsym | nhdr << 16;
+    u32 inc = packed;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+        if (lane >= o) inc += y;
+    }
+    if (lane == 31) sh.warp_sum[warp] = inc;
+    __syncthreads();
+    u32 excl = inc - packed;
+    u32 tile_total = 0;
+    for (int w = 0; w < kParseThreads / 32; w++) {
+        const u32 s = sh.warp_sum[w];
+        if (w < warp) excl += s;
+        tile_total += s;
+    }
+    const u32 S_tile = tile_total & 0xFFFFu, R_tile = tile_total >> 16;
+
+    // ---- chained scan across tiles ----
+    if (warp == 0) {
+        Pair agg = {S_tile, R_tile};
+        Pair ex = scan_lookback(job.p_status, t, agg);
+        if (lane == 0) {
+            sh.T0 = ex.a;
+            sh.R0 = ex.b;
+        }
+    }
+    __syncthreads();
+    const u64 T0 = sh.T0, R0 = sh.R0;
+    const u32 a_pend = (u32)T0 & 7u;
+    const u32 tot = a_pend + S_tile;
+
+    // ---- emit: symbols to shared memory, record entries to global memory ----
+    const u32 d_thread = excl & 0xFFFFu;
+    const u64 rec0 = R0 + (excl >> 16);
+    const u64 dense0 = T0 + d_thread;
+    uint8_t *symdst = sh.sym + a_pend + d_thread;
+    {
+        u32 ns2, nh2;
+        uint8_t *dst = symdst;
+        u64 d0 = dense0;
+        if (first_thread) {
+            dst[0] = 0;
+            dst[1] = 0;
+            dst += 2;
+            d0 += 2;
+            job.hdr_off[0] = 0;
+            job.hdr_end[0] = 0;
+            job.dbase[0] = 2;
+        }
+        walk_chunk<true>(job, raw, sh.enc, len, nlmask, state, cr_end, eof_chunk, pos0, ns2, nh2, dst, d0, rec0);
+    }
+    // a record slot at or before the one owning the first symbol of every translate tile
+    if (nsym > 0) {
+        const u64 x = (dense0 + kTransTile - 1) / kTransTile;
+        if (x * kTransTile < dense0 + nsym) job.t_hint[x] = (u32)rec0;
+    }
+    if (tid < 40) sh.sym[tot + tid] = 0;  // zero tail so that the last partial word packs zeros
+    const bool last_tile = (t + 1 == job.ntiles_parse);
+    if (last_tile && tid == 0) {
+        const u64 S_total = T0 + S_tile, R_total = R0 + R_tile;
+        job.totals->total_sym = S_total;
+        job.totals->n_headers = R_total;
+        if (R_total + 2 <= job.rec_cap) {
+            job.dbase[R_total + 1] = S_total + 2;
+        } else {
+            atomicOr(&job.totals->flags, kFlagRecOverflow);
+        }
+        // the two end pads may open a translate tile of their own
+        const u64 x = (S_total + kTransTile - 1) / kTransTile;
+        if (x * kTransTile < S_total + 2) job.t_hint[x] = (u32)R_total;
+    }
+    __syncthreads();
+
+    // ---- hand-over of the symbols that do not fill a stream word ----
+    const u32 rem = tot & 7u;
+    if (tid == 0) {
+        const bool own = rem <= S_tile;  // the pending symbols are all ours: publish before waiting
+        if (own && !last_tile) {
+            u32 v = 0x80000000u;
+            for (u32 k = 0; k < rem; k++) v |= (u32)sh.sym[tot - 1 - k] << (4 * k);
+            st_release32(job.p_pend + t, v);
+        }
+        if (a_pend) {
+            u32 v;
+            do {
+                v = ld_acquire32(job.p_pend + (t - 1));
+            } while (!(v & 0x80000000u));
+            for (u32 k = 0; k < a_pend; k++) sh.sym[a_pend - 1 - k] = (v >> (4 * k)) & 0xFu;
+        }
+        if (!own && !last_tile) {
+            u32 v = 0x80000000u;
+            for (u32 k = 0; k < rem; k++) v |= (u32)sh.sym[tot - 1 - k] << (4 * k);
+            st_release32(job.p_pend + t, v);
+        }
+    }
+    __syncthreads();
+
+    // ---- pack two symbols per byte and write the complete stream words ----
+    const u32 nw = tot >> 3;
+    u32 *gw = job.sym + ((T0 - a_pend) >> 3);
+    for (u32 w = tid; w < nw; w += kParseThreads) {
+        const uint2 s2 = *reinterpret_cast<const uint2 *>(sh.sym + 8 * w);
+        gw[w] = s2.x | (s2.y << 4);
+    }
+    if (last_tile && tid < 4) {  // the partial word (zero padded) and the end pads
+        const uint2 s2 = *reinterpret_cast<const uint2 *>(sh.sym + 8 * (nw + tid));
+        gw[nw + tid] = s2.x | (s2.y << 4);
+    }
+}
+
+// =====================================================================================
+// k_size
+// =====================================================================================
+// Residues kept by --trim (writer.go:141-147,159-163): walk each requested frame backwards from
+// its last residue until one is neither 'X' nor '*'.
+__device__ void trimmed_lengths(const Job &job, const uint16_t *lut, u64 D, u64 n, u64 L[6]) {
+    for (int f = 0; f < 6; f++) {
+        if (!((job.frame_mask >> f) & 1u)) continue;
+        u64 j = L[f];
+        const u64 p = f >= 3 ? (u64)reverse_start(n, f - 3, job.alternative != 0) : 0;
+        while (j > 0) {
+            // window start q of residue j-1; its symbols sit at stream index D+q .. D+q+2
+            const i64 q = f < 3 ? (i64)(f + 3 * (j - 1)) : (i64)n - 3 - (i64)p - 3 * (i64)(j - 1);
+            const u64 e = (u64)((i64)D + q);
+            const u32 idx = stream_symbol(job.sym, e) + 5 * stream_symbol(job.sym, e + 1) +
+                            25 * stream_symbol(job.sym, e + 2);
+            const u32 r = lut[idx < 125 ? idx : 0];
+            const u32 aa = f < 3 ? (r & 0xFFu) : (r >> 8);
+            if (aa != 'X' && aa != '*') break;
+            j--;
+        }
+        L[f] = j;
+    }
+}
+
+__global__ void __launch_bounds__(kSizeThreads) k_size(const __grid_constant__ Job job) {
+    __shared__ uint16_t lut[128];
+    __shared__ u64 warp_sum[kSizeThreads / 32];
+    __shared__ u64 warp_nt[kSizeThreads / 32];
+    __shared__ u32 warp_rec[kSizeThreads / 32];
+    __shared__ u64 s_excl;
+    __shared__ u32 s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 128) lut[tid] = job.lut.v[tid];
+    const u64 R = job.totals->n_headers;
+    if (R + 2 > job.rec_cap) return;  // record table overflow: the host retries with a larger one
+    const u64 nslots = R + 1;
+    const u64 ntiles = (nslots + kSizeTile - 1) / kSizeTile;
+    while (true) {
+        __syncthreads();
+        if (tid == 0) s_tile = atomicAdd(&job.counters[1], 1u);
+        __syncthreads();
+        const u64 t = s_tile;
+        if (t >= ntiles) return;
+        u64 size[kSizePerThread];
+        u64 sum = 0, nt = 0;
+        u32 nrec = 0;
+#pragma unroll
+        for (int i = 0; i < kSizePerThread; i++) {
+            const u64 s = t * kSizeTile + (u64)tid * kSizePerThread + i;
+            size[i] = 0;
+            if (s < nslots) {
+                const u64 D = job.dbase[s];
+                const u64 n = job.dbase[s + 1] - 2 - D;
+                u64 L[6];
+                frame_lengths(n, job.alternative != 0, L);
+                if (job.trim) {
+                    trimmed_lengths(job, lut, D, n, L);
+#pragma unroll
+                    for (int f = 0; f < 6; f++) job.trim_len[s * 6 + f] = (u32)L[f];
+                }
+                if (record_emitted(s, n, R)) {
+                    const u64 H = job.hdr_end[s] - job.hdr_off[s];
+#pragma unroll
+                    for (int f = 0; f < 6; f++)
+                        if ((job.frame_mask >> f) & 1u) size[i] += run_size(H, L[f]);
+                    nt += n;
+                    nrec++;
+                }
+            }
+            sum += size[i];
+        }
+        // block scan of the per-thread sums
+        u64 inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u64 y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+            if (lane >= o) inc += y;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            nt += __shfl_xor_sync(0xFFFFFFFFu, nt, o);
+            nrec += __shfl_xor_sync(0xFFFFFFFFu, nrec, o);
+        }
+        if (lane == 31) warp_sum[warp] = inc;
+        if (lane == 0) {
+            warp_nt[warp] = nt;
+            warp_rec[warp] = nrec;
+        }
+        __syncthreads();
+        u64 excl = inc - sum, tile_total = 0, tile_nt = 0;
+        u32 tile_rec = 0;
+        for (int w = 0; w < kSizeThreads / 32; w++) {
+            if (w < warp) excl += warp_sum[w];
+            tile_total += warp_sum[w];
+            tile_nt += warp_nt[w];
+            tile_rec += warp_rec[w];
+        }
+        if (warp == 0) {
+            Pair agg = {tile_total, tile_nt};
+            Pair ex = scan_lookback(job.s_status, (u32)t, agg);
+            if (lane == 0) {
+                s_excl = ex.a;
+                atomicAdd(&job.totals->records, (u64)tile_rec);
+                if (t + 1 == ntiles) {
+                    const u64 total = ex.a + tile_total;
+                    job.totals->out_total = total;
+                    job.totals->nucleotides = ex.b + tile_nt;
+                    job.out_off[nslots] = total;
+                    if (total > job.out_cap) atomicOr(&job.totals->flags, kFlagOutOverflow);
+                }
+            }
+        }
+        __syncthreads();
+        u64 off = s_excl + excl;
+#pragma unroll
+        for (int i = 0; i < kSizePerThread; i++) {
+            const u64 s = t * kSizeTile + (u64)tid * kSizePerThread + i;
+            if (s < nslots) job.out_off[s] = off;
+            off += size[i];
+        }
+    }
+}
+
+// =====================================================================================
+// k_translate
+// =====================================================================================
+struct Run {      // the part of one (record, frame) body that a translate tile writes
+    u64 g0;       // output offset of its first byte
+    int src;      // byte offset of its first residue in the phase arrays
+    uint16_t naa; // residues
+    uint8_t col0; // column (0..59) of the first residue
+    uint8_t flags;  // bit 0: ends the frame (a final newline follows), bit 1: reverse strand
+};
+
+struct TransShared {
+    alignas(16) uint8_t phase[6 * kPhaseStride];  // [forward 0..2 | reverse 0..2][guard|residues|guard]
+    alignas(16) uint16_t lut[128];
+    Run runs[kRunsPerBatch];
+    u32 line_pre[kRunsPerBatch + 1];
+    u32 warp_sum[kTransThreads / 32];
+    u64 first_slot;
+    u32 more;
+};
+
+// Copy one 60-column line (or the part of it inside the tile) of a run to the output.
+__device__ __forceinline__ void copy_line(const uint8_t *ph, const Run &r, u32 ln, uint8_t *out) {
+    const u32 col0 = r.col0, naa = r.naa;
+    const u32 start = ln == 0 ? 0 : (60 - col0) + 60 * (ln - 1);
+    u32 cnt = min(60u - (ln == 0 ? col0 : 0u), naa - start);
+    const bool nl = (ln == 0 ? col0 + cnt == 60 : cnt == 60) || ((r.flags & 1) && start + cnt == naa);
+    uint8_t *p = out + r.g0 + start + ln;
+    if (!(r.flags & 2)) {
+        u32 sa = (u32)r.src + start;
+        while (((uintptr_t)p & 3) && cnt) {
+            *p++ = ph[sa++];
+            cnt--;
+        }
+        u32 base = sa & ~3u;
+        const u32 sel = 0x3210u + 0x1111u * (sa & 3u);
+        u32 lo = *reinterpret_cast<const u32 *>(ph + base);
+        for (u32 w = cnt >> 2; w > 0; w--) {
+            base += 4;
+            const u32 hi = *reinterpret_cast<const u32 *>(ph + base);
+            *reinterpret_cast<u32 *>(p) = __byte_perm(lo, hi, sel);
+            lo = hi;
+            p += 4;
+        }
+        sa += cnt & ~3u;
+        for (u32 i = 0; i < (cnt & 3u); i++) *p++ = ph[sa++];
+    } else {
+        u32 sa = (u32)r.src - start;  // residues are read downwards
+        while (((uintptr_t)p & 3) && cnt) {
+            *p++ = ph[sa--];
+            cnt--;
+        }
+        u32 base = (sa - 3u) & ~3u;
+        const u32 sel = 0x0123u + 0x1111u * ((sa - 3u) & 3u);
+        u32 hi = *reinterpret_cast<const u32 *>(ph + base + 4);
+        for (u32 w = cnt >> 2; w > 0; w--) {
+            const u32 lo = *reinterpret_cast<const u32 *>(ph + base);
+            *reinterpret_cast<u32 *>(p) = __byte_perm(lo, hi, sel);
+            hi = lo;
+            base -= 4;
+            p += 4;
+        }
+        sa -= cnt & ~3u;
+        for (u32 i = 0; i < (cnt & 3u); i++) *p++ = ph[sa--];
+    }
+    if (nl) *p = '\n';
+}
+
+__global__ void __launch_bounds__(kTransThreads) k_translate(const __grid_constant__ Job job) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    TransShared &sh = *reinterpret_cast<TransShared *>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    const u64 R = job.totals->n_headers;
+    const u64 S2 = job.totals->total_sym + 2;
+    const u64 T0 = (u64)blockIdx.x * kTransTile;
+    if (T0 >= S2 || job.totals->flags != 0) return;
+    const u64 Tend = T0 + kTransTile < S2 ? T0 + kTransTile : S2;
+
+    if (tid < 128) sh.lut[tid] = job.lut.v[tid];
+    if (tid == 0) {
+        u64 s = job.t_hint[blockIdx.x];
+        while (job.dbase[s + 1] <= T0) s++;
+        sh.first_slot = s;
+    }
+
+    // ---- symbols of this thread: 48 = 6 stream words, plus the word before for (e-2, e-1) ----
+    u32 W[13];  // W[k+1] = symbols 4k..4k+3 of the chunk, one per byte; W[0] = the 4 before
+    {
+        const u32 *wp = job.sym + (T0 >> 3) + 6 * tid;
+        const uint2 x0 = *reinterpret_cast<const uint2 *>(wp);
+        const uint2 x1 = *reinterpret_cast<const uint2 *>(wp + 2);
+        const uint2 x2 = *reinterpret_cast<const uint2 *>(wp + 4);
+        const u32 prev = (blockIdx.x == 0 && tid == 0) ? 0u : wp[-1];
+        const u32 w[6] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y};
+        W[0] = (prev >> 4) & 0x0F0F0F0Fu;
+#pragma unroll
+        for (int g = 0; g < 6; g++) {
+            W[1 + 2 * g] = w[g] & 0x0F0F0F0Fu;
+            W[2 + 2 * g] = (w[g] >> 4) & 0x0F0F0F0Fu;
+        }
+    }
+    // byte i of IDX[k] = 2 * (s[e-2] + 5 s[e-1] + 25 s[e]) for e = 4k+i: the byte offset of the
+    // window's entry in the 16-bit table
+    u32 IDX[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) {
+        const u32 A = __byte_perm(W[k], W[k + 1], 0x5432);
+        const u32 B = __byte_perm(W[k], W[k + 1], 0x6543);
+        IDX[k] = A * 2u + B * 10u + W[k + 1] * 50u;
+    }
+    __syncthreads();  // table staged
+    const uint8_t *lutb = reinterpret_cast<const uint8_t *>(sh.lut);
+#pragma unroll
+    for (int phi = 0; phi < 3; phi++) {
+        u32 Fw[4], Rw[4];
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            u32 r[4];
+#pragma unroll
+            for (int x = 0; x < 4; x++) {
+                const int i = phi + 3 * (4 * g + x);  // window of the chunk
+                const u32 off = __byte_perm(IDX[i >> 2], 0u, 0x4440u + (i & 3));
+                r[x] = *reinterpret_cast<const uint16_t *>(lutb + off);
+            }
+            const u32 x01 = __byte_perm(r[0], r[1], 0x5140);
+            const u32 x23 = __byte_perm(r[2], r[3], 0x5140);
+            Fw[g] = __byte_perm(x01, x23, 0x5410);
+            Rw[g] = __byte_perm(x01, x23, 0x7632);
+        }
+        *reinterpret_cast<uint4 *>(sh.phase + phi * kPhaseStride + kPhaseGuard + 16 * tid) =
+            make_uint4(Fw[0], Fw[1], Fw[2], Fw[3]);
+        *reinterpret_cast<uint4 *>(sh.phase + (3 + phi) * kPhaseStride + kPhaseGuard + 16 * tid) =
+            make_uint4(Rw[0], Rw[1], Rw[2], Rw[3]);
+    }
+    __syncthreads();
+
+    // ---- format: every (record piece, frame) of the tile becomes a run of 60-column lines ----
+    u64 s0 = sh.first_slot;
+    while (true) {
+        if (tid < kRecBatch) {
+            const u64 s = s0 + tid;
+            Run runs[6];
+#pragma unroll
+            for (int f = 0; f < 6; f++) {
+                runs[f].g0 = 0; runs[f].src = 0; runs[f].naa = 0; runs[f].col0 = 0; runs[f].flags = 0;
+            }
+            u64 D = 0;
+            bool valid = s <= R;
+            if (valid) {
+                D = job.dbase[s];
+                valid = D < Tend;
+            }
+            if (valid) {
+                const u64 n = job.dbase[s + 1] - 2 - D;
+                if (record_emitted(s, n, R)) {
+                    const u64 H = job.hdr_end[s] - job.hdr_off[s];
+                    u64 L[6];
+                    frame_lengths(n, job.alternative != 0, L);
+                    if (job.trim) {
+#pragma unroll
+                        for (int f = 0; f < 6; f++) L[f] = job.trim_len[s * 6 + f];
+                    }
+                    // windows (by start q) of this record whose last symbol lies in the tile
+                    const i64 dq = (i64)D - (i64)T0;  // local index of the record's first symbol
+                    const i64 q_lo = -dq - 2 > -2 ? -dq - 2 : -2;
+                    const i64 q_hi = ((i64)n - 1 < (i64)(Tend - T0) - 1 - dq - 2) ? (i64)n - 1 : (i64)(Tend - T0) - 1 - dq - 2;
+                    u64 run_base = job.out_off[s];
+#pragma unroll
+                    for (int f = 0; f < 6; f++) {
+                        if (!((job.frame_mask >> f) & 1u)) continue;
+                        const u64 Lf = L[f];
+                        const u64 body = run_base + H + 3;
+                        run_base += run_size(H, Lf);
+                        i64 j_lo, j_hi, el0;
+                        if (f < 3) {
+                            const i64 lo = q_lo > 0 ? q_lo : 0;
+                            j_lo = ceildiv3(lo - f);
+                            if (j_lo < 0) j_lo = 0;
+                            j_hi = q_hi >= f ? floordiv3(q_hi - f) + 1 : 0;
+                            if (j_hi > (i64)Lf) j_hi = (i64)Lf;
+                            el0 = dq + f + 2 + 3 * j_lo;
+                        } else {
+                            const i64 Q = (i64)n - 3 - reverse_start(n, f - 3, job.alternative != 0);
+                            j_lo = ceildiv3(Q - q_hi);
+                            if (j_lo < 0) j_lo = 0;
+                            j_hi = Q >= q_lo ? floordiv3(Q - q_lo) + 1 : 0;
+                            if (j_hi > (i64)Lf) j_hi = (i64)Lf;
+                            el0 = dq + Q - 3 * j_lo + 2;
+                        }
+                        if (j_hi <= j_lo) continue;
+                        const int phi = (int)(el0 % 3);
+                        runs[f].g0 = body + (u64)j_lo + (u64)j_lo / 60;
+                        runs[f].src = ((f < 3 ? 0 : 3) + phi) * kPhaseStride + kPhaseGuard + (int)(el0 / 3);
+                        runs[f].naa = (uint16_t)(j_hi - j_lo);
+                        runs[f].col0 = (uint8_t)((u64)j_lo % 60);
+                        runs[f].flags = (uint8_t)(((u64)j_hi == Lf ? 1 : 0) | (f < 3 ? 0 : 2));
+                    }
+                }
+            }
+#pragma unroll
+            for (int f = 0; f < 6; f++) sh.runs[tid * 6 + f] = runs[f];
+            if (tid == kRecBatch - 1) {
+                // more record pieces after this batch?
+                u32 more = 0;
+                if (valid && s + 1 <= R) more = job.dbase[s + 1] < Tend;
+                sh.more = more;
+            }
+        }
+        __syncthreads();
+        // exclusive scan of the line counts of the batch's runs (3 runs per thread)
+        u32 nl3[3], sum = 0;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            const Run &r = sh.runs[3 * tid + i];
+            nl3[i] = r.naa ? (r.col0 + r.naa + 59u) / 60u : 0u;
+            sum += nl3[i];
+        }
+        u32 inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        if (lane == 31) sh.warp_sum[warp] = inc;
+        __syncthreads();
+        u32 excl = inc - sum, total = 0;
+        for (int w = 0; w < kTransThreads / 32; w++) {
+            if (w < warp) excl += sh.warp_sum[w];
+            total += sh.warp_sum[w];
+        }
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+            sh.line_pre[3 * tid + i] = excl;
+            excl += nl3[i];
+        }
+        if (tid == 0) sh.line_pre[kRunsPerBatch] = total;
+        __syncthreads();
+        for (u32 job_i = tid; job_i < total; job_i += kTransThreads) {
+            // run r with line_pre[r] <= job_i < line_pre[r+1]
+            u32 lo = 0, hi = kRunsPerBatch;
+            while (hi - lo > 1) {
+                const u32 mid = (lo + hi) >> 1;
+                if (sh.line_pre[mid] <= job_i) lo = mid; else hi = mid;
+            }
+            copy_line(sh.phase, sh.runs[lo], job_i - sh.line_pre[lo], job.out);
+        }
+        const u32 more = sh.more;
+        __syncthreads();
+        if (!more) break;
+        s0 += kRecBatch;
+    }
+}
+
+// =====================================================================================
+// k_headers
+// =====================================================================================
+__global__ void __launch_bounds__(256) k_headers(const __grid_constant__ Job job) {
+    const int lane = threadIdx.x & 31;
+    const u64 R = job.totals->n_headers;
+    if (job.totals->flags != 0) return;
+    const u64 nwarps = (u64)gridDim.x * (blockDim.x >> 5);
+    for (u64 s = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s <= R; s += nwarps) {
+        const u64 D = job.dbase[s];
+        const u64 n = job.dbase[s + 1] - 2 - D;
+        if (!record_emitted(s, n, R)) continue;
+        const u64 H = job.hdr_end[s] - job.hdr_off[s];
+        const uint8_t *hdr = job.in + job.hdr_off[s];
+        u64 L[6];
+        frame_lengths(n, job.alternative != 0, L);
+        if (job.trim) {
+#pragma unroll
+            for (int f = 0; f < 6; f++) L[f] = job.trim_len[s * 6 + f];
+        }
+        // index of the first space (writer.go:121), H if there is none
+        u64 sp = H;
+        for (u64 i0 = 0; i0 < H; i0 += 32) {
+            const u64 i = i0 + lane;
+            const unsigned b = __ballot_sync(0xFFFFFFFFu, i < H && hdr[i] == ' ');
+            if (b) {
+                sp = i0 + __ffs(b) - 1;
+                break;
+            }
+        }
+        u64 run_base = job.out_off[s];
+        for (int f = 0; f < 6; f++) {
+            if (!((job.frame_mask >> f) & 1u)) continue;
+            uint8_t *dst = job.out + run_base;
+            for (u64 i = lane; i < H + 3; i += 32) {
+                uint8_t c;
+                if (i < sp) c = hdr[i];
+                else if (i == sp) c = '_';
+                else if (i == sp + 1) c = (uint8_t)('1' + f);
+                else if (i < H + 2) c = hdr[i - 2];
+                else c = '\n';
+                dst[i] = c;
+            }
+            run_base += run_size(H, L[f]);
+        }
+    }
+}
+
+// =====================================================================================
+// launch
+// =====================================================================================
+cudaError_t init_kernels() {
+    return cudaFuncSetAttribute(k_translate, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(TransShared));
+}
+
+cudaError_t launch_pass(const Job &job, u64 max_symbols, int sm_count, cudaStream_t stream, bool sizes_only,
+                        unsigned long long *launches) {
+    k_parse<<<job.ntiles_parse, kParseThreads, 0, stream>>>(job);
+    u64 size_tiles = (job.rec_cap + kSizeTile - 1) / kSizeTile;
+    u32 size_grid = (u32)(size_tiles < (u64)sm_count * 4 ? size_tiles : (u64)sm_count * 4);
+    if (size_grid == 0) size_grid = 1;
+    k_size<<<size_grid, kSizeThreads, 0, stream>>>(job);
+    *launches += 2;
+    if (!sizes_only) {
+        const u32 trans_grid = (u32)((max_symbols + kTransTile - 1) / kTransTile);
+        k_translate<<<trans_grid, kTransThreads, sizeof(TransShared), stream>>>(job);
+        k_headers<<<sm_count * 4, 256, 0, stream>>>(job);
+        *launches += 2;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_emit(const Job &job, u64 max_symbols, int sm_count, cudaStream_t stream,
+                        unsigned long long *launches) {
+    const u32 trans_grid = (u32)((max_symbols + kTransTile - 1) / kTransTile);
+    k_translate<<<trans_grid, kTransThreads, sizeof(TransShared), stream>>>(job);
+    k_headers<<<sm_count * 4, 256, 0, stream>>>(job);
+    *launches += 2;
+    return cudaGetLastError();
+}
+
+}  // namespace gts

@@ -1,0 +1,158 @@
+"""Python mirror of the reference's `transeq` package over the C ABI.
+
+  Options    field for field `type Options struct` (transeq/options.go:4-11)
+  Translate  `func Translate(inputSequence io.Reader, out io.Writer, options Options) error`
+             (transeq/transeq.go:114): errors are raised as TranseqError with the reference's texts
+"""
+import ctypes
+from dataclasses import dataclass
+
+from . import _lib
+
+
+class TranseqError(Exception):
+    """Mirrors the `error` returned by transeq.Translate; .code is the C ABI return code."""
+
+    def __init__(self, code, message):
+        super().__init__(message)
+        self.code = code
+
+
+@dataclass
+class Options:
+    """transeq/options.go:4-11 (same names, same defaults as the go-flags tags)."""
+    Frame: str = "1"
+    Table: int = 0
+    Clean: bool = False
+    Alternative: bool = False
+    Trim: bool = False
+    NumWorker: int = 0  # accepted and ignored: output is always in input order (the -n 1 order)
+
+
+class Translator:
+    """One gts_ctx: a decoded option set plus its device scratch.  Not thread safe."""
+
+    def __init__(self, options=None, device=-1, chunk_bytes=0, **kw):
+        if options is None:
+            options = Options(**kw)
+        self.options = options
+        L = _lib.lib()
+        o = _lib.gts_options()
+        self._frame = options.Frame.encode()
+        o.frame = self._frame
+        o.table = int(options.Table)
+        o.clean = 1 if options.Clean else 0
+        o.alternative = 1 if options.Alternative else 0
+        o.trim = 1 if options.Trim else 0
+        o.num_worker = int(options.NumWorker)
+        o.device = int(device)
+        o.chunk_bytes = int(chunk_bytes)
+        h = ctypes.c_void_p()
+        rc = L.gts_create(ctypes.byref(o), ctypes.byref(h))
+        if rc != _lib.GTS_OK:
+            raise TranseqError(rc, L.gts_last_error(None).decode())
+        self._h = h
+        self._L = L
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.gts_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc != _lib.GTS_OK:
+            raise TranseqError(rc, self._L.gts_last_error(self._h).decode())
+
+    # ---- one-shot host call ----
+    def translate_bytes(self, data):
+        n = len(data)
+        buf = (ctypes.c_char * max(n, 1)).from_buffer_copy(bytes(data) if n else b"\0")
+        out = ctypes.c_void_p()
+        out_n = ctypes.c_size_t()
+        self._check(self._L.gts_translate_buffer(self._h, ctypes.cast(buf, ctypes.c_void_p), n,
+                                                 ctypes.byref(out), ctypes.byref(out_n)))
+        return ctypes.string_at(out.value, out_n.value) if out_n.value else b""
+
+    def translate_host_ptr(self, ptr, n):
+        """Host pointer in, (pointer, size) of the pinned result out (valid until the next call)."""
+        out = ctypes.c_void_p()
+        out_n = ctypes.c_size_t()
+        self._check(self._L.gts_translate_buffer(self._h, ctypes.c_void_p(ptr), n, ctypes.byref(out), ctypes.byref(out_n)))
+        return out.value, out_n.value
+
+    # ---- device-resident ----
+    def translate_device(self, d_in, n, d_out, cap, stream=0):
+        out_n = ctypes.c_size_t()
+        rc = self._L.gts_translate_device(self._h, ctypes.c_void_p(d_in), n, ctypes.c_void_p(d_out), cap,
+                                          ctypes.byref(out_n), ctypes.c_void_p(stream))
+        if rc == _lib.GTS_ERR_CAPACITY:
+            raise TranseqError(rc, f"output buffer too small: need {out_n.value} bytes")
+        self._check(rc)
+        return out_n.value
+
+    def translate_device_async(self, d_in, n, d_out, cap, stream=0):
+        self._check(self._L.gts_translate_device_async(self._h, ctypes.c_void_p(d_in), n, ctypes.c_void_p(d_out), cap,
+                                                       ctypes.c_void_p(stream)))
+
+    def device_result(self):
+        out_n = ctypes.c_size_t()
+        self._check(self._L.gts_device_result(self._h, ctypes.byref(out_n)))
+        return out_n.value
+
+    def stats(self):
+        st = _lib.gts_stats()
+        self._check(self._L.gts_get_stats(self._h, ctypes.byref(st)))
+        return {n: getattr(st, n) for n, _ in st._fields_}
+
+    # ---- streaming (what the Go shim's Translate loop does) ----
+    def translate_stream(self, reader, writer):
+        L, h = self._L, self._h
+        buf = ctypes.c_void_p()
+        cap = ctypes.c_size_t()
+        obuf = ctypes.c_void_p()
+        on = ctypes.c_size_t()
+        eof = False
+        while not eof:
+            self._check(L.gts_acquire_input(h, ctypes.byref(buf), ctypes.byref(cap)))
+            view = (ctypes.c_char * cap.value).from_address(buf.value)
+            got = reader.readinto(view) if hasattr(reader, "readinto") else None
+            if got is None:
+                chunk = reader.read(cap.value)
+                got = len(chunk)
+                ctypes.memmove(buf.value, chunk, got)
+            eof = got == 0
+            self._check(L.gts_submit(h, got, 1 if eof else 0))
+            while True:
+                self._check(L.gts_next_output(h, ctypes.byref(obuf), ctypes.byref(on)))
+                if on.value == 0:
+                    break
+                try:
+                    writer.write(ctypes.string_at(obuf.value, on.value))
+                except Exception as e:  # writer.go:175
+                    L.gts_release_output(h)
+                    raise TranseqError(_lib.GTS_ERR_WRITE, f"fail to write to output file: {e}") from e
+                self._check(L.gts_release_output(h))
+
+
+def Translate(inputSequence, out, options):
+    """transeq.Translate (transeq/transeq.go:114): read FASTA from `inputSequence`, write the
+    protein FASTA to `out`.  Raises TranseqError instead of returning an error."""
+    with Translator(options) as t:
+        t.translate_stream(inputSequence, out)
+
+
+def translate_bytes(data, frame="1", table=0, clean=False, alternative=False, trim=False, **kw):
+    with Translator(Options(Frame=frame, Table=table, Clean=clean, Alternative=alternative, Trim=trim), **kw) as t:
+        return t.translate_bytes(data)

@@ -1,0 +1,41 @@
+"""The executable specification of the kernels' index arithmetic (tests/gpu_model.py) must agree
+byte for byte with the oracle -- on the reference's goldens and on adversarial random FASTA, at
+tile sizes small enough that every tile-boundary case occurs."""
+import pytest
+
+import oracle
+import gpu_model
+from fasta_gen import nasty_fasta, random_options
+from optparse_ref import parse_option_string
+
+MASKS = {"1": 1, "2": 2, "3": 4, "F": 7, "-1": 8, "-2": 16, "-3": 32, "R": 56, "6": 63}
+
+
+def model(data, frame="1", table=0, clean=False, alternative=False, trim=False, tile=48):
+    aa64 = oracle.table_code(table)
+    return gpu_model.translate(data, aa64, MASKS[frame], clean, alternative, trim, tile)
+
+
+@pytest.mark.parametrize("idx", range(29))
+def test_model_on_reference_goldens(goldens, idx):
+    case = goldens["cases"][idx]
+    kw = parse_option_string(case["options"])
+    for tile in (12, 48, 12288):
+        assert model(goldens["input"].encode(), tile=tile, **kw).decode() == case["expected"]
+
+
+@pytest.mark.parametrize("seed", range(150))
+def test_model_vs_oracle_random(seed):
+    data = nasty_fasta(seed, max_records=6, max_len=200)
+    kw = random_options(seed)
+    want = oracle.translate(data, **kw)
+    for tile in (3, 12, 48, 300):
+        assert model(data, tile=tile, **kw) == want, (seed, tile, kw)
+
+
+def test_model_quirks():
+    for data in (b"", b"\n", b"\r", b"\r\n", b">", b">\n", b">\r", b"A", b"\n\nAC", b">a\n>b\n>c",
+                 b"AC\r", b">a b\r\nAC\r\r\nG", b"x>y\n>z"):
+        for frame in ("6", "F", "R", "2"):
+            for trim in (False, True):
+                assert model(data, frame=frame, trim=trim, tile=3) == oracle.translate(data, frame=frame, trim=trim), (data, frame, trim)

@@ -1,0 +1,114 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle.  Needs a B200: -m gpu."""
+import io
+
+import pytest
+
+import oracle
+from fasta_gen import nasty_fasta, random_options, regular_fasta, ALL_FRAMES, ALL_TABLES
+from optparse_ref import parse_option_string
+
+pytestmark = pytest.mark.gpu
+
+
+def gpu(data, frame="1", table=0, clean=False, alternative=False, trim=False, **kw):
+    import gotranseq_b200
+    return gotranseq_b200.translate_bytes(data, frame=frame, table=table, clean=clean,
+                                          alternative=alternative, trim=trim, **kw)
+
+
+@pytest.mark.parametrize("idx", range(29))
+def test_reference_goldens(goldens, idx):
+    """transeq/transeq_test.go:14-62 -- the reference's own table-driven test, on the GPU path."""
+    case = goldens["cases"][idx]
+    kw = parse_option_string(case["options"])
+    assert gpu(goldens["input"].encode(), **kw).decode() == case["expected"]
+
+
+def test_quirks():
+    for data in (b"", b"\n", b"\r", b"\r\n", b">", b">\n", b">\r", b"A", b"\n\nAC", b">a\n>b\n>c",
+                 b"AC\r", b">a b\r\nAC\r\r\nG", b"x>y\n>z", b"ACGT\n>x\nACG", b">a b c\nATG"):
+        for frame in ("6", "F", "R", "2"):
+            for trim in (False, True):
+                assert gpu(data, frame=frame, trim=trim) == oracle.translate(data, frame=frame, trim=trim), (data, frame, trim)
+
+
+@pytest.mark.parametrize("seed", range(120))
+def test_random_nasty(seed):
+    data = nasty_fasta(seed)
+    kw = random_options(seed)
+    assert gpu(data, **kw) == oracle.translate(data, **kw), (seed, kw)
+
+
+@pytest.mark.parametrize("frame", ALL_FRAMES)
+def test_all_frames_all_tables(frame):
+    data = nasty_fasta(1000, max_records=30, max_len=900)
+    for table in ALL_TABLES:
+        for clean in (False, True):
+            want = oracle.translate(data, frame=frame, table=table, clean=clean, trim=True)
+            assert gpu(data, frame=frame, table=table, clean=clean, trim=True) == want, (frame, table, clean)
+
+
+def test_errors_match_reference_texts():
+    import gotranseq_b200
+    with pytest.raises(gotranseq_b200.TranseqError, match=r"wrong value for -f \| --frame parameter: 7"):
+        gpu(b">a\nACG\n", frame="7")
+    with pytest.raises(gotranseq_b200.TranseqError, match=r"invalid table code: 1$"):
+        gpu(b">a\nACG\n", frame="1", table=1)
+
+
+@pytest.mark.parametrize("shape", ["readme", "long", "short_reads", "one_line_records"])
+def test_regular_shapes(shape):
+    """Benchmark-shaped inputs at sizes the oracle finishes in a second."""
+    if shape == "readme":
+        data = regular_fasta(42, 600, 300, 3000)
+    elif shape == "long":
+        data = regular_fasta(43, 3, 200_000, 400_000, n_frac=0.0001)
+    elif shape == "short_reads":
+        data = regular_fasta(45, 20_000, 150, 150, width=10 ** 9, header="A00123:45:HXXXXXXXX:1:1101:")
+    else:
+        data = regular_fasta(46, 50, 20_000, 60_000, width=10 ** 9)
+    for kw in (dict(frame="6"), dict(frame="6", table=11, clean=True, trim=True), dict(frame="R", alternative=True),
+               dict(frame="6", table=2)):
+        assert gpu(data, **kw) == oracle.translate(data, **kw), (shape, kw)
+
+
+def test_translate_stream_matches_one_shot():
+    import gotranseq_b200
+    data = regular_fasta(7, 3000, 100, 2000)
+    want = oracle.translate(data, frame="6", trim=True)
+    for chunk in (1 << 16, 1 << 20):
+        out = io.BytesIO()
+        with gotranseq_b200.Translator(gotranseq_b200.Options(Frame="6", Trim=True), chunk_bytes=chunk) as t:
+            t.translate_stream(io.BytesIO(data), out)
+            # the context is reusable for a second stream
+            out2 = io.BytesIO()
+            t.translate_stream(io.BytesIO(data), out2)
+        assert out.getvalue() == want
+        assert out2.getvalue() == want
+
+
+def test_translate_api():
+    import gotranseq_b200
+    data = nasty_fasta(5)
+    out = io.BytesIO()
+    gotranseq_b200.Translate(io.BytesIO(data), out, gotranseq_b200.Options(Frame="6", Table=11, Clean=True))
+    assert out.getvalue() == oracle.translate(data, frame="6", table=11, clean=True)
+
+
+def test_device_resident_entry_point():
+    import torch
+    import gotranseq_b200
+    data = regular_fasta(11, 500, 500, 5000)
+    want = oracle.translate(data, frame="6")
+    d_in = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+    d_out = torch.empty(len(want) + 100, dtype=torch.uint8, device="cuda")
+    with gotranseq_b200.Translator(gotranseq_b200.Options(Frame="6")) as t:
+        n = t.translate_device(d_in.data_ptr(), d_in.numel(), d_out.data_ptr(), d_out.numel(),
+                               torch.cuda.current_stream().cuda_stream)
+        assert n == len(want)
+        assert bytes(d_out[:n].cpu().numpy()) == want
+        # too small: nothing written, exact size reported
+        with pytest.raises(gotranseq_b200.TranseqError, match=str(len(want))):
+            t.translate_device(d_in.data_ptr(), d_in.numel(), d_out.data_ptr(), 10, 0)
+        st = t.stats()
+        assert st["nucleotides"] > 0 and st["kernel_launches"] >= 4
