@@ -61,6 +61,11 @@ struct gts_ctx {
     u64 job_max_sym = 0;
     cudaStream_t job_stream = nullptr;
 
+    // ---- per-kernel timing ----
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;  // 5 per recorded pass
+    size_t prof_used = 0;
+
     gts_stats stats;
     std::string err;
 };
@@ -175,9 +180,20 @@ int enqueue_pass(gts_ctx *ctx, const uint8_t *d_in, u64 n, uint8_t *d_out, u64 c
     job.lut = ctx->lut;
     ctx->job_max_sym = n + 4;
     ctx->job_stream = stream;
+    cudaEvent_t *ev = nullptr;
+    if (ctx->profiling && !sizes_only) {
+        while (ctx->prof_events.size() < ctx->prof_used + 5) {
+            cudaEvent_t e;
+            CU(cudaEventCreate(&e));
+            ctx->prof_events.push_back(e);
+        }
+        ev = ctx->prof_events.data() + ctx->prof_used;
+        ctx->prof_used += 5;
+        CU(cudaEventRecord(ev[0], stream));
+    }
     CU(cudaMemsetAsync(ctx->d_zero, 0, z.bytes, stream));
     unsigned long long launches = 0;
-    CU(gts::launch_pass(job, ctx->job_max_sym, ctx->sm_count, stream, sizes_only, &launches));
+    CU(gts::launch_pass(job, ctx->job_max_sym, ctx->sm_count, stream, sizes_only, &launches, ev));
     ctx->stats.kernel_launches += launches;
     CU(cudaMemcpyAsync(ctx->h_totals, job.totals, sizeof(gts::Totals), cudaMemcpyDeviceToHost, stream));
     ctx->pending = true;
@@ -357,6 +373,7 @@ void gts_destroy(gts_ctx *ctx) {
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->h_in) cudaFreeHost(ctx->h_in);
     if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
+    for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -490,6 +507,39 @@ int gts_release_output(gts_ctx *ctx) {
     ctx->stream_out_ready = false;
     ctx->stream_out_n = 0;
     return GTS_OK;
+}
+
+int gts_set_profiling(gts_ctx *ctx, int enable) {
+    if (!ctx) return GTS_ERR_ARG;
+    ctx->profiling = enable != 0;
+    return GTS_OK;
+}
+
+int gts_kernel_times(gts_ctx *ctx, double ms[4], uint64_t *passes) {
+    if (!ctx || !ms) return GTS_ERR_ARG;
+    for (int k = 0; k < 4; k++) ms[k] = 0.0;
+    const size_t np = ctx->prof_used / 5;
+    for (size_t p = 0; p < np; p++) {
+        cudaEvent_t *ev = ctx->prof_events.data() + 5 * p;
+        CU(cudaEventSynchronize(ev[4]));
+        for (int k = 0; k < 4; k++) {
+            float t = 0.f;
+            CU(cudaEventElapsedTime(&t, ev[k], ev[k + 1]));
+            ms[k] += t;
+        }
+    }
+    if (passes) *passes = np;
+    ctx->prof_used = 0;
+    return GTS_OK;
+}
+
+void *gts_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void gts_host_free(void *p) {
+    if (p) cudaFreeHost(p);
 }
 
 int gts_get_stats(const gts_ctx *ctx, gts_stats *st) {

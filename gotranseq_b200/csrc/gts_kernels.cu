@@ -872,17 +872,21 @@ cudaError_t init_kernels() {
 }
 
 cudaError_t launch_pass(const Job &job, u64 max_symbols, int sm_count, cudaStream_t stream, bool sizes_only,
-                        unsigned long long *launches) {
+                        unsigned long long *launches, cudaEvent_t *ev) {
     k_parse<<<job.ntiles_parse, kParseThreads, 0, stream>>>(job);
+    if (ev) cudaEventRecord(ev[1], stream);
     u64 size_tiles = (job.rec_cap + kSizeTile - 1) / kSizeTile;
     u32 size_grid = (u32)(size_tiles < (u64)sm_count * 4 ? size_tiles : (u64)sm_count * 4);
     if (size_grid == 0) size_grid = 1;
     k_size<<<size_grid, kSizeThreads, 0, stream>>>(job);
+    if (ev) cudaEventRecord(ev[2], stream);
     *launches += 2;
     if (!sizes_only) {
         const u32 trans_grid = (u32)((max_symbols + kTransTile - 1) / kTransTile);
         k_translate<<<trans_grid, kTransThreads, sizeof(TransShared), stream>>>(job);
+        if (ev) cudaEventRecord(ev[3], stream);
         k_headers<<<sm_count * 4, 256, 0, stream>>>(job);
+        if (ev) cudaEventRecord(ev[4], stream);
         *launches += 2;
     }
     return cudaGetLastError();

@@ -11,8 +11,9 @@ cudaError_t init_kernels();
 
 // k_parse + k_size, and unless sizes_only also k_translate + k_headers, on `stream`.
 // max_symbols bounds the symbol stream (job.n + 4); *launches is advanced by the kernels started.
+// ev, when not null, points to 5 events recorded before the first and after each kernel.
 cudaError_t launch_pass(const Job &job, u64 max_symbols, int sm_count, cudaStream_t stream,
-                        bool sizes_only, unsigned long long *launches);
+                        bool sizes_only, unsigned long long *launches, cudaEvent_t *ev = nullptr);
 
 // k_translate + k_headers only (after a sizes_only pass, once the output buffer is known).
 cudaError_t launch_emit(const Job &job, u64 max_symbols, int sm_count, cudaStream_t stream,

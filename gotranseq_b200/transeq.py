@@ -116,6 +116,16 @@ class Translator:
         self._check(self._L.gts_get_stats(self._h, ctypes.byref(st)))
         return {n: getattr(st, n) for n, _ in st._fields_}
 
+    def set_profiling(self, enable):
+        self._check(self._L.gts_set_profiling(self._h, 1 if enable else 0))
+
+    def kernel_times(self):
+        """(ms[4] summed over the passes recorded since the last call, number of passes)."""
+        ms = (ctypes.c_double * 4)()
+        n = ctypes.c_uint64()
+        self._check(self._L.gts_kernel_times(self._h, ms, ctypes.byref(n)))
+        return list(ms), n.value
+
     # ---- streaming (what the Go shim's Translate loop does, INTEGRATION.md) ----
     def translate_stream(self, reader, writer):
         L, h = self._L, self._h

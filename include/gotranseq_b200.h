@@ -86,7 +86,7 @@ int gts_fused_lut(int32_t table, int clean, uint16_t lut[125]);
  * reverseComplement encodedSequence.go:71-97, writer.translate / translate3Frames / writeHeader
  * / writeAA / trimAndReturn writer.go:57-169), on a FASTA buffer already in device memory.
  *   d_in   device pointer to n bytes of FASTA (treated as one complete input: start of file
- *          to EOF); any alignment, 16-byte aligned is fastest
+ *          to EOF); must be 16-byte aligned (cudaMalloc / torch allocations are)
  *   d_out  device pointer, capacity cap bytes; receives the protein FASTA
  *   out_n  receives the exact output size; if it exceeds cap nothing is written past cap and
  *          GTS_ERR_CAPACITY is returned (out_n is still set, so the caller can retry)
@@ -152,6 +152,19 @@ typedef struct gts_stats {
     uint64_t passes;         /* device passes since gts_create                            */
 } gts_stats;
 int gts_get_stats(const gts_ctx *ctx, gts_stats *st);
+
+/*
+ * Per-kernel timing (bench.py's roofline numbers).  While enabled, CUDA events are recorded on
+ * the pass's stream around each kernel.  gts_kernel_times waits for the recorded passes, adds
+ * their durations up in ms -- [0] scratch reset + k_parse, [1] k_size, [2] k_translate,
+ * [3] k_headers -- reports how many passes that covers and starts a new accumulation.
+ */
+int gts_set_profiling(gts_ctx *ctx, int enable);
+int gts_kernel_times(gts_ctx *ctx, double ms[4], uint64_t *passes);
+
+/* Pinned host memory for callers of gts_translate_buffer that want full-speed PCIe copies. */
+void *gts_host_alloc(size_t bytes);
+void gts_host_free(void *p);
 
 #ifdef __cplusplus
 }
