@@ -41,7 +41,8 @@ struct gts_ctx {
     uint8_t *d_zero = nullptr;  // per-pass zeroed block: scan status, tickets, totals, pending words
     size_t zero_cap = 0;
     u64 rec_cap = 0;
-    u64 *d_hdr_off = nullptr, *d_hdr_end = nullptr, *d_dbase = nullptr, *d_out_off = nullptr;
+    u64 *d_hdr_off = nullptr, *d_hdr_end = nullptr, *d_dbase = nullptr;
+    gts::RecInfo *d_rec = nullptr;
     u32 *d_trim = nullptr;
     gts::Totals *h_totals = nullptr;  // pinned
 
@@ -106,8 +107,9 @@ ZeroLayout zero_layout(u64 ntiles_parse, u64 rec_cap) {
 
 int free_rec(gts_ctx *ctx) {
     cudaFree(ctx->d_hdr_off); cudaFree(ctx->d_hdr_end); cudaFree(ctx->d_dbase);
-    cudaFree(ctx->d_out_off); cudaFree(ctx->d_trim);
-    ctx->d_hdr_off = ctx->d_hdr_end = ctx->d_dbase = ctx->d_out_off = nullptr;
+    cudaFree(ctx->d_rec); cudaFree(ctx->d_trim);
+    ctx->d_hdr_off = ctx->d_hdr_end = ctx->d_dbase = nullptr;
+    ctx->d_rec = nullptr;
     ctx->d_trim = nullptr;
     ctx->rec_cap = 0;
     return 0;
@@ -118,7 +120,7 @@ int alloc_rec(gts_ctx *ctx, u64 rec_cap) {
     CU(cudaMalloc(&ctx->d_hdr_off, rec_cap * sizeof(u64)));
     CU(cudaMalloc(&ctx->d_hdr_end, rec_cap * sizeof(u64)));
     CU(cudaMalloc(&ctx->d_dbase, rec_cap * sizeof(u64)));
-    CU(cudaMalloc(&ctx->d_out_off, rec_cap * sizeof(u64)));
+    CU(cudaMalloc(&ctx->d_rec, rec_cap * sizeof(gts::RecInfo)));
     if (ctx->opt.trim) CU(cudaMalloc(&ctx->d_trim, rec_cap * 6 * sizeof(u32)));
     ctx->rec_cap = rec_cap;
     return GTS_OK;
@@ -172,7 +174,7 @@ int enqueue_pass(gts_ctx *ctx, const uint8_t *d_in, u64 n, uint8_t *d_out, u64 c
     job.p_pend = reinterpret_cast<u32 *>(ctx->d_zero + z.p_pend);
     job.t_hint = ctx->d_hint;
     job.hdr_off = ctx->d_hdr_off; job.hdr_end = ctx->d_hdr_end; job.dbase = ctx->d_dbase;
-    job.out_off = ctx->d_out_off; job.trim_len = ctx->d_trim; job.rec_cap = ctx->rec_cap;
+    job.rec = ctx->d_rec; job.trim_len = ctx->d_trim; job.rec_cap = ctx->rec_cap;
     job.ntiles_parse = (u32)ntp;
     job.frame_mask = ctx->mask;
     job.alternative = ctx->opt.alternative ? 1 : 0;

@@ -39,8 +39,13 @@ constexpr int kTransTileWords = kTransTile / 8;                 // 1536 stream w
 constexpr int kPhaseLen = kTransTile / 3;                       // residues per phase array
 constexpr int kPhaseGuard = 16;
 constexpr int kPhaseStride = kPhaseLen + 2 * kPhaseGuard;       // bytes per phase array in smem
-constexpr int kRecBatch = 128;                                  // record pieces per format batch
+constexpr int kRecBatch = 16;                                   // record pieces per format batch
 constexpr int kRunsPerBatch = kRecBatch * 6;
+// Output image of one batch in shared memory: the residue lines a tile writes (at most
+// 2 * kTransTile * 61 / 60 bytes + a few per run) plus up to 30 bytes of 16-byte alignment
+// padding per run.
+constexpr int kImageBytes = 2 * kTransTile * 61 / 60 + kRunsPerBatch * 32 + 256;
+constexpr int kImageSlots = (kImageBytes + 15) / 16;
 
 // ---- k_size geometry ----
 constexpr int kSizeThreads = 256;
@@ -64,6 +69,14 @@ struct Totals {  // device-resident result block, copied to pinned host memory a
 constexpr u64 kFlagRecOverflow = 1;  // record table too small (n_headers is still exact)
 constexpr u64 kFlagOutOverflow = 2;  // output buffer too small (out_total is still exact)
 
+struct RecInfo {  // 32 bytes per record slot, written by k_size, read by k_translate / k_headers
+    u64 out_off;  // offset of the record's first output byte
+    u64 dbase;    // stream index of the record's first nucleotide
+    u64 n;        // nucleotides
+    u32 H;        // header line bytes (CR dropped)
+    u32 emitted;  // 0: the record produces no output (empty slot 0)
+};
+
 struct Lut {  // 125 used entries: forward residue | reverse-strand residue << 8
     uint16_t v[128];
 };
@@ -84,7 +97,7 @@ struct Job {  // kernel argument block (by value)
     u64 *hdr_off;   // raw offset of the header line's '>'
     u64 *hdr_end;   // raw offset one past the header line's last byte (CR dropped)
     u64 *dbase;     // stream index of the record's first nucleotide (its pads sit at -2, -1)
-    u64 *out_off;   // offset of the record's first output byte
+    RecInfo *rec;   // per record summary (+1 sentinel: dbase = end of stream, out_off = total)
     u32 *trim_len;  // [slot*6 + frame] residues kept after --trim (only with trim)
     u64 rec_cap;    // entries in each of the arrays above
 

@@ -122,14 +122,17 @@ __device__ Pair scan_lookback(u64 *status, u32 t, Pair agg) {
     return excl;
 }
 
-__device__ __forceinline__ i64 floordiv3(i64 a) { return a >= 0 ? a / 3 : -((-a + 2) / 3); }
+// exact unsigned division by constants without the 64-bit division routine
+__device__ __forceinline__ u64 udiv3(u64 a) { return __umul64hi(a, 0xAAAAAAAAAAAAAAABull) >> 1; }
+__device__ __forceinline__ u64 udiv60(u64 a) { return __umul64hi(a >> 2, 0x8888888888888889ull) >> 3; }
+__device__ __forceinline__ i64 floordiv3(i64 a) { return a >= 0 ? (i64)udiv3((u64)a) : -(i64)udiv3((u64)(-a) + 2); }
 __device__ __forceinline__ i64 ceildiv3(i64 a) { return -floordiv3(-a); }
 __device__ __forceinline__ int mod3(i64 a) { return (int)(a - 3 * floordiv3(a)); }
 
 // rc start position of reverse frame i (0..2): writer.go:64-79
 __device__ __forceinline__ int reverse_start(u64 n, int i, bool alternative) {
     if (alternative) return i;
-    int r = (int)(n % 3) - i;
+    int r = (int)(n - 3 * udiv3(n)) - i;
     return r < 0 ? r + 3 : r;
 }
 
@@ -137,15 +140,15 @@ __device__ __forceinline__ int reverse_start(u64 n, int i, bool alternative) {
 // position beyond the sequence emits nothing)
 __device__ __forceinline__ void frame_lengths(u64 n, bool alternative, u64 L[6]) {
 #pragma unroll
-    for (int k = 0; k < 3; k++) L[k] = n >= (u64)k ? (n - k + 2) / 3 : 0;
+    for (int k = 0; k < 3; k++) L[k] = n >= (u64)k ? udiv3(n - k + 2) : 0;
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         const u64 p = (u64)reverse_start(n, i, alternative);
-        L[3 + i] = n >= p ? (n - p + 2) / 3 : 0;
+        L[3 + i] = n >= p ? udiv3(n - p + 2) : 0;
     }
 }
 
-__device__ __forceinline__ u64 run_size(u64 H, u64 Lp) { return H + 3 + Lp + (Lp + 59) / 60; }
+__device__ __forceinline__ u64 run_size(u64 H, u64 Lp) { return H + 3 + Lp + udiv60(Lp + 59); }
 
 __device__ __forceinline__ u32 stream_symbol(const u32 *sym, u64 x) {
     const u32 w = sym[x >> 3];
@@ -482,6 +485,7 @@ __global__ void __launch_bounds__(kSizeThreads) k_size(const __grid_constant__ J
         const u64 t = s_tile;
         if (t >= ntiles) return;
         u64 size[kSizePerThread];
+        RecInfo ri[kSizePerThread];
         u64 sum = 0, nt = 0;
         u32 nrec = 0;
 #pragma unroll
@@ -498,14 +502,19 @@ __global__ void __launch_bounds__(kSizeThreads) k_size(const __grid_constant__ J
 #pragma unroll
                     for (int f = 0; f < 6; f++) job.trim_len[s * 6 + f] = (u32)L[f];
                 }
-                if (record_emitted(s, n, R)) {
-                    const u64 H = job.hdr_end[s] - job.hdr_off[s];
+                const u64 H = job.hdr_end[s] - job.hdr_off[s];
+                const bool em = record_emitted(s, n, R);
+                if (em) {
 #pragma unroll
                     for (int f = 0; f < 6; f++)
                         if ((job.frame_mask >> f) & 1u) size[i] += run_size(H, L[f]);
                     nt += n;
                     nrec++;
                 }
+                ri[i].dbase = D;
+                ri[i].n = n;
+                ri[i].H = (u32)H;
+                ri[i].emitted = em ? 1u : 0u;
             }
             sum += size[i];
         }
@@ -545,7 +554,11 @@ __global__ void __launch_bounds__(kSizeThreads) k_size(const __grid_constant__ J
                     const u64 total = ex.a + tile_total;
                     job.totals->out_total = total;
                     job.totals->nucleotides = ex.b + tile_nt;
-                    job.out_off[nslots] = total;
+                    RecInfo end;  // sentinel
+                    end.out_off = total;
+                    end.dbase = job.dbase[nslots];
+                    end.n = 0; end.H = 0; end.emitted = 0;
+                    job.rec[nslots] = end;
                     if (total > job.out_cap) atomicOr(&job.totals->flags, kFlagOutOverflow);
                 }
             }
@@ -555,7 +568,10 @@ __global__ void __launch_bounds__(kSizeThreads) k_size(const __grid_constant__ J
 #pragma unroll
         for (int i = 0; i < kSizePerThread; i++) {
             const u64 s = t * kSizeTile + (u64)tid * kSizePerThread + i;
-            if (s < nslots) job.out_off[s] = off;
+            if (s < nslots) {
+                ri[i].out_off = off;
+                job.rec[s] = ri[i];
+            }
             off += size[i];
         }
     }
@@ -564,34 +580,47 @@ __global__ void __launch_bounds__(kSizeThreads) k_size(const __grid_constant__ J
 // =====================================================================================
 // k_translate
 // =====================================================================================
-struct Run {      // the part of one (record, frame) body that a translate tile writes
-    u64 g0;       // output offset of its first byte
-    int src;      // byte offset of its first residue in the phase arrays
-    uint16_t naa; // residues
-    uint8_t col0; // column (0..59) of the first residue
+struct Run {        // the part of one (record, frame) body that a translate tile writes
+    u64 g0;         // output offset of its first byte
+    int src;        // byte offset of its first residue in the phase arrays
+    u32 img;        // byte offset of its first byte in the output image
+    uint16_t naa;   // residues
+    uint16_t nbytes;  // residues + newlines
+    uint8_t col0;   // column (0..59) of the first residue
     uint8_t flags;  // bit 0: ends the frame (a final newline follows), bit 1: reverse strand
+    uint16_t pad;
 };
 
 struct TransShared {
     alignas(16) uint8_t phase[6 * kPhaseStride];  // [forward 0..2 | reverse 0..2][guard|residues|guard]
+    alignas(16) uint8_t image[kImageSlots * 16];  // the batch's output bytes, 16-byte congruent to global
     alignas(16) uint16_t lut[128];
-    Run runs[kRunsPerBatch];
+    alignas(16) Run runs[kRunsPerBatch];
     u32 line_pre[kRunsPerBatch + 1];
-    u32 warp_sum[kTransThreads / 32];
+    uint8_t slot_run[kImageSlots];
     u64 first_slot;
+    u32 nruns;       // runs in use in this batch (a multiple of 6)
+    u32 image_bytes; // image bytes in use
     u32 more;
 };
 
-// Copy one 60-column line (or the part of it inside the tile) of a run to the output.
-__device__ __forceinline__ void copy_line(const uint8_t *ph, const Run &r, u32 ln, uint8_t *out) {
+// Copy one 60-column line (or the part of it inside the tile) of a run into the output image and
+// mark the image slots it touches as belonging to the run.
+__device__ __forceinline__ void copy_line(TransShared &sh, const Run &r, u32 run_idx, u32 ln) {
+    const uint8_t *ph = sh.phase;
     const u32 col0 = r.col0, naa = r.naa;
     const u32 start = ln == 0 ? 0 : (60 - col0) + 60 * (ln - 1);
     u32 cnt = min(60u - (ln == 0 ? col0 : 0u), naa - start);
     const bool nl = (ln == 0 ? col0 + cnt == 60 : cnt == 60) || ((r.flags & 1) && start + cnt == naa);
-    uint8_t *p = out + r.g0 + start + ln;
+    const u32 d0 = r.img + start + ln;  // image offset of the line's first byte
+    {
+        const u32 s_lo = d0 >> 4, s_hi = (d0 + cnt + (nl ? 1u : 0u) - 1u) >> 4;
+        for (u32 s = s_lo; s <= s_hi; s++) sh.slot_run[s] = (uint8_t)run_idx;
+    }
+    uint8_t *p = sh.image + d0;
     if (!(r.flags & 2)) {
         u32 sa = (u32)r.src + start;
-        while (((uintptr_t)p & 3) && cnt) {
+        while (((u32)(p - sh.image) & 3u) && cnt) {
             *p++ = ph[sa++];
             cnt--;
         }
@@ -609,7 +638,7 @@ __device__ __forceinline__ void copy_line(const uint8_t *ph, const Run &r, u32 l
         for (u32 i = 0; i < (cnt & 3u); i++) *p++ = ph[sa++];
     } else {
         u32 sa = (u32)r.src - start;  // residues are read downwards
-        while (((uintptr_t)p & 3) && cnt) {
+        while (((u32)(p - sh.image) & 3u) && cnt) {
             *p++ = ph[sa--];
             cnt--;
         }
@@ -640,21 +669,30 @@ __global__ void __launch_bounds__(kTransThreads) k_translate(const __grid_consta
     if (T0 >= S2 || job.totals->flags != 0) return;
     const u64 Tend = T0 + kTransTile < S2 ? T0 + kTransTile : S2;
 
-    if (tid < 128) sh.lut[tid] = job.lut.v[tid];
-    if (tid == 0) {
-        u64 s = job.t_hint[blockIdx.x];
-        while (job.dbase[s + 1] <= T0) s++;
-        sh.first_slot = s;
-    }
-
     // ---- symbols of this thread: 48 = 6 stream words, plus the word before for (e-2, e-1) ----
+    const u32 *wp = job.sym + (T0 >> 3) + 6 * tid;
+    const uint2 x0 = *reinterpret_cast<const uint2 *>(wp);
+    const uint2 x1 = *reinterpret_cast<const uint2 *>(wp + 2);
+    const uint2 x2 = *reinterpret_cast<const uint2 *>(wp + 4);
+    const u32 prev = (blockIdx.x == 0 && tid == 0) ? 0u : wp[-1];
+
+    if (tid < 128) sh.lut[tid] = job.lut.v[tid];
+    if (warp == kTransThreads / 32 - 1) {
+        // first record slot with windows in the tile: the last one whose stream base is <= T0
+        u64 s = job.t_hint[blockIdx.x];
+        while (true) {
+            const u64 c = s + 1 + lane;
+            const bool le = c <= R && job.rec[c].dbase <= T0;
+            const unsigned b = __ballot_sync(0xFFFFFFFFu, le);
+            s += __popc(b);
+            if (b != 0xFFFFFFFFu) break;
+        }
+        if (lane == 0) sh.first_slot = s;
+    }
+    __syncthreads();  // table staged, first slot known
+
     u32 W[13];  // W[k+1] = symbols 4k..4k+3 of the chunk, one per byte; W[0] = the 4 before
     {
-        const u32 *wp = job.sym + (T0 >> 3) + 6 * tid;
-        const uint2 x0 = *reinterpret_cast<const uint2 *>(wp);
-        const uint2 x1 = *reinterpret_cast<const uint2 *>(wp + 2);
-        const uint2 x2 = *reinterpret_cast<const uint2 *>(wp + 4);
-        const u32 prev = (blockIdx.x == 0 && tid == 0) ? 0u : wp[-1];
         const u32 w[6] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y};
         W[0] = (prev >> 4) & 0x0F0F0F0Fu;
 #pragma unroll
@@ -672,7 +710,6 @@ __global__ void __launch_bounds__(kTransThreads) k_translate(const __grid_consta
         const u32 B = __byte_perm(W[k], W[k + 1], 0x6543);
         IDX[k] = A * 2u + B * 10u + W[k + 1] * 50u;
     }
-    __syncthreads();  // table staged
     const uint8_t *lutb = reinterpret_cast<const uint8_t *>(sh.lut);
 #pragma unroll
     for (int phi = 0; phi < 3; phi++) {
@@ -696,109 +733,122 @@ __global__ void __launch_bounds__(kTransThreads) k_translate(const __grid_consta
         *reinterpret_cast<uint4 *>(sh.phase + (3 + phi) * kPhaseStride + kPhaseGuard + 16 * tid) =
             make_uint4(Rw[0], Rw[1], Rw[2], Rw[3]);
     }
-    __syncthreads();
 
     // ---- format: every (record piece, frame) of the tile becomes a run of 60-column lines ----
+    const uintptr_t out_mis = (uintptr_t)job.out & 15u;
     u64 s0 = sh.first_slot;
     while (true) {
-        if (tid < kRecBatch) {
-            const u64 s = s0 + tid;
+        if (warp == 0) {
+            // lanes 0..15: one record piece each; lane 16 looks one record past the batch
+            const u64 s = s0 + lane;
             Run runs[6];
 #pragma unroll
             for (int f = 0; f < 6; f++) {
-                runs[f].g0 = 0; runs[f].src = 0; runs[f].naa = 0; runs[f].col0 = 0; runs[f].flags = 0;
+                runs[f].g0 = 0; runs[f].src = 0; runs[f].img = 0; runs[f].naa = 0; runs[f].nbytes = 0;
+                runs[f].col0 = 0; runs[f].flags = 0; runs[f].pad = 0;
             }
-            u64 D = 0;
-            bool valid = s <= R;
-            if (valid) {
-                D = job.dbase[s];
-                valid = D < Tend;
+            RecInfo ri;
+            ri.dbase = ~0ull; ri.n = 0; ri.H = 0; ri.emitted = 0; ri.out_off = 0;
+            if (lane <= kRecBatch && s <= R) {
+                const uint4 *rp = reinterpret_cast<const uint4 *>(job.rec + s);
+                const uint4 a = rp[0], b = rp[1];
+                ri.out_off = (u64)a.x | (u64)a.y << 32;
+                ri.dbase = (u64)a.z | (u64)a.w << 32;
+                ri.n = (u64)b.x | (u64)b.y << 32;
+                ri.H = b.z;
+                ri.emitted = b.w;
             }
-            if (valid) {
-                const u64 n = job.dbase[s + 1] - 2 - D;
-                if (record_emitted(s, n, R)) {
-                    const u64 H = job.hdr_end[s] - job.hdr_off[s];
-                    u64 L[6];
-                    frame_lengths(n, job.alternative != 0, L);
-                    if (job.trim) {
+            const bool valid = ri.dbase < Tend;  // slots past R keep dbase = ~0
+            u32 nlines = 0, img_need = 0;
+            if (lane < kRecBatch && valid && ri.emitted) {
+                const u64 D = ri.dbase, n = ri.n, H = ri.H;
+                u64 L[6];
+                frame_lengths(n, job.alternative != 0, L);
+                if (job.trim) {
 #pragma unroll
-                        for (int f = 0; f < 6; f++) L[f] = job.trim_len[s * 6 + f];
-                    }
-                    // windows (by start q) of this record whose last symbol lies in the tile
-                    const i64 dq = (i64)D - (i64)T0;  // local index of the record's first symbol
-                    const i64 q_lo = -dq - 2 > -2 ? -dq - 2 : -2;
-                    const i64 q_hi = ((i64)n - 1 < (i64)(Tend - T0) - 1 - dq - 2) ? (i64)n - 1 : (i64)(Tend - T0) - 1 - dq - 2;
-                    u64 run_base = job.out_off[s];
+                    for (int f = 0; f < 6; f++) L[f] = job.trim_len[s * 6 + f];
+                }
+                // windows (by start q) of this record whose last symbol lies in the tile
+                const i64 dq = (i64)D - (i64)T0;  // local index of the record's first symbol
+                const i64 q_lo = -dq - 2 > -2 ? -dq - 2 : -2;
+                const i64 q_hi = ((i64)n - 1 < (i64)(Tend - T0) - 1 - dq - 2) ? (i64)n - 1 : (i64)(Tend - T0) - 1 - dq - 2;
+                u64 run_base = ri.out_off;
 #pragma unroll
-                    for (int f = 0; f < 6; f++) {
-                        if (!((job.frame_mask >> f) & 1u)) continue;
-                        const u64 Lf = L[f];
-                        const u64 body = run_base + H + 3;
-                        run_base += run_size(H, Lf);
-                        i64 j_lo, j_hi, el0;
-                        if (f < 3) {
-                            const i64 lo = q_lo > 0 ? q_lo : 0;
-                            j_lo = ceildiv3(lo - f);
-                            if (j_lo < 0) j_lo = 0;
-                            j_hi = q_hi >= f ? floordiv3(q_hi - f) + 1 : 0;
-                            if (j_hi > (i64)Lf) j_hi = (i64)Lf;
-                            el0 = dq + f + 2 + 3 * j_lo;
-                        } else {
-                            const i64 Q = (i64)n - 3 - reverse_start(n, f - 3, job.alternative != 0);
-                            j_lo = ceildiv3(Q - q_hi);
-                            if (j_lo < 0) j_lo = 0;
-                            j_hi = Q >= q_lo ? floordiv3(Q - q_lo) + 1 : 0;
-                            if (j_hi > (i64)Lf) j_hi = (i64)Lf;
-                            el0 = dq + Q - 3 * j_lo + 2;
-                        }
-                        if (j_hi <= j_lo) continue;
-                        const int phi = (int)(el0 % 3);
-                        runs[f].g0 = body + (u64)j_lo + (u64)j_lo / 60;
-                        runs[f].src = ((f < 3 ? 0 : 3) + phi) * kPhaseStride + kPhaseGuard + (int)(el0 / 3);
-                        runs[f].naa = (uint16_t)(j_hi - j_lo);
-                        runs[f].col0 = (uint8_t)((u64)j_lo % 60);
-                        runs[f].flags = (uint8_t)(((u64)j_hi == Lf ? 1 : 0) | (f < 3 ? 0 : 2));
+                for (int f = 0; f < 6; f++) {
+                    if (!((job.frame_mask >> f) & 1u)) continue;
+                    const u64 Lf = L[f];
+                    const u64 body = run_base + H + 3;
+                    run_base += run_size(H, Lf);
+                    i64 j_lo, j_hi, el0;
+                    if (f < 3) {
+                        const i64 lo = q_lo > 0 ? q_lo : 0;
+                        j_lo = ceildiv3(lo - f);
+                        if (j_lo < 0) j_lo = 0;
+                        j_hi = q_hi >= f ? floordiv3(q_hi - f) + 1 : 0;
+                        if (j_hi > (i64)Lf) j_hi = (i64)Lf;
+                        el0 = dq + f + 2 + 3 * j_lo;
+                    } else {
+                        const i64 Q = (i64)n - 3 - reverse_start(n, f - 3, job.alternative != 0);
+                        j_lo = ceildiv3(Q - q_hi);
+                        if (j_lo < 0) j_lo = 0;
+                        j_hi = Q >= q_lo ? floordiv3(Q - q_lo) + 1 : 0;
+                        if (j_hi > (i64)Lf) j_hi = (i64)Lf;
+                        el0 = dq + Q - 3 * j_lo + 2;
                     }
+                    if (j_hi <= j_lo) continue;
+                    const u32 el = (u32)el0;            // 0 <= el0 < kTransTile
+                    const u32 m0 = el / 3u, phi = el - 3u * m0;
+                    const u64 line0 = udiv60((u64)j_lo);
+                    const u32 col0 = (u32)((u64)j_lo - 60 * line0);
+                    const u32 naa = (u32)(j_hi - j_lo);
+                    const bool fin = (u64)j_hi == Lf;
+                    const u32 q60 = (col0 + naa) / 60u;
+                    const u32 nb = naa + q60 + ((fin && (col0 + naa) != 60u * q60) ? 1u : 0u);
+                    runs[f].g0 = body + (u64)j_lo + line0;
+                    runs[f].src = (int)(((f < 3 ? 0u : 3u) + phi) * kPhaseStride + kPhaseGuard + m0);
+                    runs[f].naa = (uint16_t)naa;
+                    runs[f].nbytes = (uint16_t)nb;
+                    runs[f].col0 = (uint8_t)col0;
+                    runs[f].flags = (uint8_t)((fin ? 1 : 0) | (f < 3 ? 0 : 2));
+                    nlines += (col0 + naa + 59u) / 60u;
+                    img_need += ((nb + 15u) & ~15u) + 16u;  // its own 16-byte slots, congruent to global
                 }
             }
+            // exclusive scans over the batch's records: line jobs and image space
+            u32 lp = nlines, ip = img_need;
 #pragma unroll
-            for (int f = 0; f < 6; f++) sh.runs[tid * 6 + f] = runs[f];
-            if (tid == kRecBatch - 1) {
-                // more record pieces after this batch?
-                u32 more = 0;
-                if (valid && s + 1 <= R) more = job.dbase[s + 1] < Tend;
-                sh.more = more;
+            for (int o = 1; o < 32; o <<= 1) {
+                const u32 y = __shfl_up_sync(0xFFFFFFFFu, lp, o);
+                const u32 z = __shfl_up_sync(0xFFFFFFFFu, ip, o);
+                if (lane >= o) { lp += y; ip += z; }
             }
-        }
-        __syncthreads();
-        // exclusive scan of the line counts of the batch's runs (3 runs per thread)
-        u32 nl3[3], sum = 0;
+            const u32 total_lines = __shfl_sync(0xFFFFFFFFu, lp, 31);
+            const u32 total_img = __shfl_sync(0xFFFFFFFFu, ip, 31);
+            lp -= nlines;
+            ip -= img_need;
+            if (lane < kRecBatch) {
 #pragma unroll
-        for (int i = 0; i < 3; i++) {
-            const Run &r = sh.runs[3 * tid + i];
-            nl3[i] = r.naa ? (r.col0 + r.naa + 59u) / 60u : 0u;
-            sum += nl3[i];
+                for (int f = 0; f < 6; f++) {
+                    sh.line_pre[lane * 6 + f] = lp;
+                    if (runs[f].naa) {
+                        const u32 mis = (u32)((out_mis + runs[f].g0) & 15u);
+                        runs[f].img = ip + mis;
+                        ip += ((runs[f].nbytes + 15u) & ~15u) + 16u;
+                        lp += (runs[f].col0 + runs[f].naa + 59u) / 60u;
+                    }
+                    sh.runs[lane * 6 + f] = runs[f];
+                }
+            }
+            if (lane == 0) {
+                sh.line_pre[kRunsPerBatch] = total_lines;
+                sh.image_bytes = total_img;
+            }
+            // more record pieces after this batch?
+            const unsigned mm = __ballot_sync(0xFFFFFFFFu, lane == kRecBatch && valid);
+            if (lane == 0) sh.more = mm != 0;
         }
-        u32 inc = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const u32 y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-            if (lane >= o) inc += y;
-        }
-        if (lane == 31) sh.warp_sum[warp] = inc;
-        __syncthreads();
-        u32 excl = inc - sum, total = 0;
-        for (int w = 0; w < kTransThreads / 32; w++) {
-            if (w < warp) excl += sh.warp_sum[w];
-            total += sh.warp_sum[w];
-        }
-#pragma unroll
-        for (int i = 0; i < 3; i++) {
-            sh.line_pre[3 * tid + i] = excl;
-            excl += nl3[i];
-        }
-        if (tid == 0) sh.line_pre[kRunsPerBatch] = total;
-        __syncthreads();
+        __syncthreads();  // runs published (and, in the first round, the phase arrays complete)
+        const u32 total = sh.line_pre[kRunsPerBatch];
         for (u32 job_i = tid; job_i < total; job_i += kTransThreads) {
             // run r with line_pre[r] <= job_i < line_pre[r+1]
             u32 lo = 0, hi = kRunsPerBatch;
@@ -806,7 +856,26 @@ __global__ void __launch_bounds__(kTransThreads) k_translate(const __grid_consta
                 const u32 mid = (lo + hi) >> 1;
                 if (sh.line_pre[mid] <= job_i) lo = mid; else hi = mid;
             }
-            copy_line(sh.phase, sh.runs[lo], job_i - sh.line_pre[lo], job.out);
+            copy_line(sh, sh.runs[lo], lo, job_i - sh.line_pre[lo]);
+        }
+        __syncthreads();  // image complete
+        const u32 nslot = (sh.image_bytes + 15u) >> 4;
+        for (u32 sl = tid; sl < nslot; sl += kTransThreads) {
+            const u32 ridx = sh.slot_run[sl];
+            if (ridx >= kRunsPerBatch) continue;  // never marked
+            const Run &r = sh.runs[ridx];
+            const u32 b0 = sl << 4;
+            if (b0 + 16u <= r.img || b0 >= r.img + r.nbytes) continue;  // padding slot
+            // global address of image byte x of the run: out + g0 + (x - img)
+            uint8_t *g = job.out + r.g0 + b0 - r.img;
+            const uint4 v = *reinterpret_cast<const uint4 *>(sh.image + b0);
+            if (b0 >= r.img && b0 + 16u <= r.img + r.nbytes) {
+                *reinterpret_cast<uint4 *>(g) = v;
+            } else {
+                const u32 lo_b = b0 >= r.img ? 0u : r.img - b0;
+                const u32 hi_b = b0 + 16u <= r.img + r.nbytes ? 16u : r.img + r.nbytes - b0;
+                for (u32 i = lo_b; i < hi_b; i++) g[i] = sh.image[b0 + i];
+            }
         }
         const u32 more = sh.more;
         __syncthreads();
@@ -824,10 +893,10 @@ __global__ void __launch_bounds__(256) k_headers(const __grid_constant__ Job job
     if (job.totals->flags != 0) return;
     const u64 nwarps = (u64)gridDim.x * (blockDim.x >> 5);
     for (u64 s = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s <= R; s += nwarps) {
-        const u64 D = job.dbase[s];
-        const u64 n = job.dbase[s + 1] - 2 - D;
-        if (!record_emitted(s, n, R)) continue;
-        const u64 H = job.hdr_end[s] - job.hdr_off[s];
+        const RecInfo ri = job.rec[s];
+        if (!ri.emitted) continue;
+        const u64 n = ri.n;
+        const u64 H = ri.H;
         const uint8_t *hdr = job.in + job.hdr_off[s];
         u64 L[6];
         frame_lengths(n, job.alternative != 0, L);
@@ -845,7 +914,7 @@ __global__ void __launch_bounds__(256) k_headers(const __grid_constant__ Job job
                 break;
             }
         }
-        u64 run_base = job.out_off[s];
+        u64 run_base = ri.out_off;
         for (int f = 0; f < 6; f++) {
             if (!((job.frame_mask >> f) & 1u)) continue;
             uint8_t *dst = job.out + run_base;
