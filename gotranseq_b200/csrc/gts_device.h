@@ -42,9 +42,9 @@ constexpr int kPhaseStride = kPhaseLen + 2 * kPhaseGuard;       // bytes per pha
 constexpr int kRecBatch = 16;                                   // record pieces per format batch
 constexpr int kRunsPerBatch = kRecBatch * 6;
 // Output image of one batch in shared memory: the residue lines a tile writes (at most
-// 2 * kTransTile * 61 / 60 bytes + a few per run) plus up to 30 bytes of 16-byte alignment
-// padding per run.
-constexpr int kImageBytes = 2 * kTransTile * 61 / 60 + kRunsPerBatch * 32 + 256;
+// 2 * kTransTile * 61 / 60 bytes + a few per run) plus up to 47 bytes of 16-byte alignment
+// padding and slack per run.
+constexpr int kImageBytes = 2 * kTransTile * 61 / 60 + kRunsPerBatch * 48 + 256;
 constexpr int kImageSlots = (kImageBytes + 15) / 16;
 
 // ---- k_size geometry ----

@@ -597,87 +597,261 @@ struct TransShared {
     alignas(16) uint16_t lut[128];
     alignas(16) Run runs[kRunsPerBatch];
     u32 line_pre[kRunsPerBatch + 1];
-    uint8_t slot_run[kImageSlots];
     u64 first_slot;
-    u32 nruns;       // runs in use in this batch (a multiple of 6)
-    u32 image_bytes; // image bytes in use
     u32 more;
 };
 
-// Copy one 60-column line (or the part of it inside the tile) of a run into the output image and
-// mark the image slots it touches as belonging to the run.
-__device__ __forceinline__ void copy_line(TransShared &sh, const Run &r, u32 run_idx, u32 ln) {
+__device__ __forceinline__ u32 lds32(const uint8_t *base, u32 off) {
+    return *reinterpret_cast<const u32 *>(base + off);
+}
+
+// Copy one 60-column line of a run (or the part of it inside the tile) from the phase arrays into
+// the output image, newline included.  Whole aligned image words are written: a lane owns the
+// words whose first byte lies in its line (for a run's first line also the word holding the
+// line's first byte), so words that straddle two lines carry the start of the next line, and the
+// bytes written outside the run are image padding that is never copied out.
+__device__ __forceinline__ void copy_line(TransShared &sh, const Run &r, u32 ln) {
     const uint8_t *ph = sh.phase;
     const u32 col0 = r.col0, naa = r.naa;
     const u32 start = ln == 0 ? 0 : (60 - col0) + 60 * (ln - 1);
-    u32 cnt = min(60u - (ln == 0 ? col0 : 0u), naa - start);
-    const bool nl = (ln == 0 ? col0 + cnt == 60 : cnt == 60) || ((r.flags & 1) && start + cnt == naa);
-    const u32 d0 = r.img + start + ln;  // image offset of the line's first byte
-    {
-        const u32 s_lo = d0 >> 4, s_hi = (d0 + cnt + (nl ? 1u : 0u) - 1u) >> 4;
-        for (u32 s = s_lo; s <= s_hi; s++) sh.slot_run[s] = (uint8_t)run_idx;
-    }
-    uint8_t *p = sh.image + d0;
-    if (!(r.flags & 2)) {
-        u32 sa = (u32)r.src + start;
-        while (((u32)(p - sh.image) & 3u) && cnt) {
-            *p++ = ph[sa++];
-            cnt--;
-        }
-        u32 base = sa & ~3u;
-        const u32 sel = 0x3210u + 0x1111u * (sa & 3u);
-        u32 lo = *reinterpret_cast<const u32 *>(ph + base);
-        for (u32 w = cnt >> 2; w > 0; w--) {
-            base += 4;
-            const u32 hi = *reinterpret_cast<const u32 *>(ph + base);
-            *reinterpret_cast<u32 *>(p) = __byte_perm(lo, hi, sel);
+    const u32 cnt = min(60u - (ln == 0 ? col0 : 0u), naa - start);
+    // the newline after column 60; a frame's final newline elsewhere is patched in by the run's
+    // copy-out thread (it may fall into a word owned by the previous line)
+    const bool nl = ln == 0 ? col0 + cnt == 60 : cnt == 60;
+    const u32 d0 = r.img + start + ln;           // image offset of the line's first byte
+    const u32 dend = d0 + cnt + (nl ? 1u : 0u);  // one past its last byte
+    const u32 w_lo = ln == 0 ? (d0 & ~3u) : ((d0 + 3u) & ~3u);
+    const u32 w_hi = ((dend - 1u) & ~3u) + 4u;
+    const int nw = (int)(w_hi - w_lo) >> 2;      // <= 16 (w_hi > w_lo is not guaranteed for ln > 0)
+    const int rel = (int)w_lo - (int)d0;         // line-relative offset of the first owned byte (-3..3)
+    u32 *dst = reinterpret_cast<u32 *>(sh.image + w_lo);
+    const bool rev = (r.flags & 2) != 0;
+    if (!rev) {
+        const u32 A = (u32)(r.src + (int)start + rel);  // source byte of the first owned byte
+        const u32 base = A & ~3u;
+        const u32 sel = 0x3210u + 0x1111u * (A & 3u);
+        u32 lo = lds32(ph, base);
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const u32 hi = lds32(ph, base + 4u * (k + 1));
+            if (k < nw) dst[k] = __byte_perm(lo, hi, sel);
             lo = hi;
-            p += 4;
         }
-        sa += cnt & ~3u;
-        for (u32 i = 0; i < (cnt & 3u); i++) *p++ = ph[sa++];
     } else {
-        u32 sa = (u32)r.src - start;  // residues are read downwards
-        while (((u32)(p - sh.image) & 3u) && cnt) {
-            *p++ = ph[sa--];
-            cnt--;
-        }
-        u32 base = (sa - 3u) & ~3u;
-        const u32 sel = 0x0123u + 0x1111u * ((sa - 3u) & 3u);
-        u32 hi = *reinterpret_cast<const u32 *>(ph + base + 4);
-        for (u32 w = cnt >> 2; w > 0; w--) {
-            const u32 lo = *reinterpret_cast<const u32 *>(ph + base);
-            *reinterpret_cast<u32 *>(p) = __byte_perm(lo, hi, sel);
+        const u32 A = (u32)(r.src - (int)start - rel);  // residues are read downwards
+        const u32 base = (A - 3u) & ~3u;
+        const u32 sel = 0x0123u + 0x1111u * ((A - 3u) & 3u);
+        u32 hi = lds32(ph, base + 4u);
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const u32 lo = lds32(ph, base - 4u * k);
+            if (k < nw) dst[k] = __byte_perm(lo, hi, sel);
             hi = lo;
-            base -= 4;
-            p += 4;
         }
-        sa -= cnt & ~3u;
-        for (u32 i = 0; i < (cnt & 3u); i++) *p++ = ph[sa--];
     }
-    if (nl) *p = '\n';
+    if (nl) {
+        // the word holding line offset cnt: residues, '\n' at byte t, then the next line's start
+        const int kn = ((int)cnt - rel) >> 2;
+        const int o = rel + 4 * kn;
+        const u32 t = (u32)((int)cnt - o);
+        u32 X;
+        if (!rev) {
+            const u32 A2 = (u32)(r.src + (int)start + o);
+            X = __byte_perm(lds32(ph, A2 & ~3u), lds32(ph, (A2 & ~3u) + 4u), 0x3210u + 0x1111u * (A2 & 3u));
+        } else {
+            const u32 A2 = (u32)(r.src - (int)start - o) - 3u;
+            X = __byte_perm(lds32(ph, A2 & ~3u), lds32(ph, (A2 & ~3u) + 4u), 0x0123u + 0x1111u * (A2 & 3u));
+        }
+        // insert the newline at byte t, shifting the later bytes up (selector nibble 4 = '\n')
+        const u32 selnl = (u32)(0x4210241021402104ull >> (16u * t));
+        dst[kn] = __byte_perm(X, 0x0Au, selnl);
+    }
 }
 
-__global__ void __launch_bounds__(kTransThreads) k_translate(const __grid_constant__ Job job) {
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, u32 bytes) {
+    const u32 saddr = (u32)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr), "r"(bytes)
+                 : "memory");
+}
+
+// Threads 0..kTransThreads-1 translate (48 symbols each); the extra warp builds the run table of the
+// tile's first record batch meanwhile.  Everybody then formats lines.
+constexpr int kTransBlock = kTransThreads + 32;
+
+__global__ void __launch_bounds__(kTransBlock) k_translate(const __grid_constant__ Job job) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     TransShared &sh = *reinterpret_cast<TransShared *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool builder = warp == kTransThreads / 32;
 
     const u64 R = job.totals->n_headers;
     const u64 S2 = job.totals->total_sym + 2;
     const u64 T0 = (u64)blockIdx.x * kTransTile;
     if (T0 >= S2 || job.totals->flags != 0) return;
     const u64 Tend = T0 + kTransTile < S2 ? T0 + kTransTile : S2;
+    const uintptr_t out_mis = (uintptr_t)job.out & 15u;
 
-    // ---- symbols of this thread: 48 = 6 stream words, plus the word before for (e-2, e-1) ----
-    const u32 *wp = job.sym + (T0 >> 3) + 6 * tid;
-    const uint2 x0 = *reinterpret_cast<const uint2 *>(wp);
-    const uint2 x1 = *reinterpret_cast<const uint2 *>(wp + 2);
-    const uint2 x2 = *reinterpret_cast<const uint2 *>(wp + 4);
-    const u32 prev = (blockIdx.x == 0 && tid == 0) ? 0u : wp[-1];
+    // Build the run table of the batch of record slots s0 .. s0+kRecBatch-1 (one warp).
+    auto build_runs = [&](u64 s0) {
+        // lanes 0..15: one record piece each; lane 16 looks one record past the batch
+        const u64 s = s0 + lane;
+        Run runs[6];
+#pragma unroll
+        for (int f = 0; f < 6; f++) {
+            runs[f].g0 = 0; runs[f].src = 0; runs[f].img = 0; runs[f].naa = 0; runs[f].nbytes = 0;
+            runs[f].col0 = 0; runs[f].flags = 0; runs[f].pad = 0;
+        }
+        RecInfo ri;
+        ri.dbase = ~0ull; ri.n = 0; ri.H = 0; ri.emitted = 0; ri.out_off = 0;
+        if (lane <= kRecBatch && s <= R) {
+            const uint4 *rp = reinterpret_cast<const uint4 *>(job.rec + s);
+            const uint4 a = rp[0], b = rp[1];
+            ri.out_off = (u64)a.x | (u64)a.y << 32;
+            ri.dbase = (u64)a.z | (u64)a.w << 32;
+            ri.n = (u64)b.x | (u64)b.y << 32;
+            ri.H = b.z;
+            ri.emitted = b.w;
+        }
+        const bool valid = ri.dbase < Tend;  // slots past R keep dbase = ~0
+        u32 nlines = 0, img_need = 0;
+        if (lane < kRecBatch && valid && ri.emitted) {
+            const u64 D = ri.dbase, n = ri.n, H = ri.H;
+            u64 L[6];
+            frame_lengths(n, job.alternative != 0, L);
+            if (job.trim) {
+#pragma unroll
+                for (int f = 0; f < 6; f++) L[f] = job.trim_len[s * 6 + f];
+            }
+            // windows (by start q) of this record whose last symbol lies in the tile
+            const i64 dq = (i64)D - (i64)T0;  // local index of the record's first symbol
+            const i64 q_lo = -dq - 2 > -2 ? -dq - 2 : -2;
+            const i64 q_hi = ((i64)n - 1 < (i64)(Tend - T0) - 1 - dq - 2) ? (i64)n - 1 : (i64)(Tend - T0) - 1 - dq - 2;
+            u64 run_base = ri.out_off;
+#pragma unroll
+            for (int f = 0; f < 6; f++) {
+                if (!((job.frame_mask >> f) & 1u)) continue;
+                const u64 Lf = L[f];
+                const u64 body = run_base + H + 3;
+                run_base += run_size(H, Lf);
+                i64 j_lo, j_hi, el0;
+                if (f < 3) {
+                    const i64 lo = q_lo > 0 ? q_lo : 0;
+                    j_lo = ceildiv3(lo - f);
+                    if (j_lo < 0) j_lo = 0;
+                    j_hi = q_hi >= f ? floordiv3(q_hi - f) + 1 : 0;
+                    if (j_hi > (i64)Lf) j_hi = (i64)Lf;
+                    el0 = dq + f + 2 + 3 * j_lo;
+                } else {
+                    const i64 Q = (i64)n - 3 - reverse_start(n, f - 3, job.alternative != 0);
+                    j_lo = ceildiv3(Q - q_hi);
+                    if (j_lo < 0) j_lo = 0;
+                    j_hi = Q >= q_lo ? floordiv3(Q - q_lo) + 1 : 0;
+                    if (j_hi > (i64)Lf) j_hi = (i64)Lf;
+                    el0 = dq + Q - 3 * j_lo + 2;
+                }
+                if (j_hi <= j_lo) continue;
+                const u32 el = (u32)el0;  // 0 <= el0 < kTransTile
+                const u32 m0 = el / 3u, phi = el - 3u * m0;
+                const u64 line0 = udiv60((u64)j_lo);
+                const u32 col0 = (u32)((u64)j_lo - 60 * line0);
+                const u32 naa = (u32)(j_hi - j_lo);
+                const bool fin = (u64)j_hi == Lf;
+                const u32 q60 = (col0 + naa) / 60u;
+                const u32 nb = naa + q60 + ((fin && (col0 + naa) != 60u * q60) ? 1u : 0u);
+                runs[f].g0 = body + (u64)j_lo + line0;
+                runs[f].src = (int)(((f < 3 ? 0u : 3u) + phi) * kPhaseStride + kPhaseGuard + m0);
+                runs[f].naa = (uint16_t)naa;
+                runs[f].nbytes = (uint16_t)nb;
+                runs[f].col0 = (uint8_t)col0;
+                runs[f].flags = (uint8_t)((fin ? 1 : 0) | (f < 3 ? 0 : 2));
+                nlines += (col0 + naa + 59u) / 60u;
+                img_need += ((nb + 15u) & ~15u) + 32u;  // its own 16-byte slots, congruent to global
+            }
+        }
+        // exclusive scans over the batch's records: line jobs and image space
+        u32 lp = nlines, ip = img_need;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 y = __shfl_up_sync(0xFFFFFFFFu, lp, o);
+            const u32 z = __shfl_up_sync(0xFFFFFFFFu, ip, o);
+            if (lane >= o) { lp += y; ip += z; }
+        }
+        const u32 total_lines = __shfl_sync(0xFFFFFFFFu, lp, 31);
+        lp -= nlines;
+        ip -= img_need;
+        if (lane < kRecBatch) {
+#pragma unroll
+            for (int f = 0; f < 6; f++) {
+                sh.line_pre[lane * 6 + f] = lp;
+                if (runs[f].naa) {
+                    const u32 mis = (u32)((out_mis + runs[f].g0) & 15u);
+                    runs[f].img = ip + 16u + mis;  // one slot of slack in front: line 0 writes its whole first word
+                    ip += ((runs[f].nbytes + 15u) & ~15u) + 32u;
+                    lp += (runs[f].col0 + runs[f].naa + 59u) / 60u;
+                }
+                sh.runs[lane * 6 + f] = runs[f];
+            }
+        }
+        if (lane == 0) sh.line_pre[kRunsPerBatch] = total_lines;
+        // more record pieces after this batch?
+        const unsigned mm = __ballot_sync(0xFFFFFFFFu, lane == kRecBatch && valid);
+        if (lane == 0) sh.more = mm != 0;
+    };
 
-    if (tid < 128) sh.lut[tid] = job.lut.v[tid];
-    if (warp == kTransThreads / 32 - 1) {
+    u64 s0 = 0;
+    if (!builder) {
+        // ---- symbols of this thread: 48 = 6 stream words, plus the word before for (e-2, e-1) ----
+        const u32 *wp = job.sym + (T0 >> 3) + 6 * tid;
+        const uint2 x0 = *reinterpret_cast<const uint2 *>(wp);
+        const uint2 x1 = *reinterpret_cast<const uint2 *>(wp + 2);
+        const uint2 x2 = *reinterpret_cast<const uint2 *>(wp + 4);
+        const u32 prev = (blockIdx.x == 0 && tid == 0) ? 0u : wp[-1];
+        if (tid < 128) sh.lut[tid] = job.lut.v[tid];
+        asm volatile("bar.sync 1, %0;" ::"r"(kTransThreads) : "memory");  // table staged (translating warps only)
+
+        u32 W[13];  // W[k+1] = symbols 4k..4k+3 of the chunk, one per byte; W[0] = the 4 before
+        {
+            const u32 w[6] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y};
+            W[0] = (prev >> 4) & 0x0F0F0F0Fu;
+#pragma unroll
+            for (int g = 0; g < 6; g++) {
+                W[1 + 2 * g] = w[g] & 0x0F0F0F0Fu;
+                W[2 + 2 * g] = (w[g] >> 4) & 0x0F0F0F0Fu;
+            }
+        }
+        // byte i of IDX[k] = 2 * (s[e-2] + 5 s[e-1] + 25 s[e]) for e = 4k+i: the byte offset of the
+        // window's entry in the 16-bit table
+        u32 IDX[12];
+#pragma unroll
+        for (int k = 0; k < 12; k++) {
+            const u32 A = __byte_perm(W[k], W[k + 1], 0x5432);
+            const u32 B = __byte_perm(W[k], W[k + 1], 0x6543);
+            IDX[k] = A * 2u + B * 10u + W[k + 1] * 50u;
+        }
+        const uint8_t *lutb = reinterpret_cast<const uint8_t *>(sh.lut);
+#pragma unroll
+        for (int phi = 0; phi < 3; phi++) {
+            u32 Fw[4], Rw[4];
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                u32 r[4];
+#pragma unroll
+                for (int x = 0; x < 4; x++) {
+                    const int i = phi + 3 * (4 * g + x);  // window of the chunk
+                    const u32 off = __byte_perm(IDX[i >> 2], 0u, 0x4440u + (i & 3));
+                    r[x] = *reinterpret_cast<const uint16_t *>(lutb + off);
+                }
+                const u32 x01 = __byte_perm(r[0], r[1], 0x5140);
+                const u32 x23 = __byte_perm(r[2], r[3], 0x5140);
+                Fw[g] = __byte_perm(x01, x23, 0x5410);
+                Rw[g] = __byte_perm(x01, x23, 0x7632);
+            }
+            *reinterpret_cast<uint4 *>(sh.phase + phi * kPhaseStride + kPhaseGuard + 16 * tid) =
+                make_uint4(Fw[0], Fw[1], Fw[2], Fw[3]);
+            *reinterpret_cast<uint4 *>(sh.phase + (3 + phi) * kPhaseStride + kPhaseGuard + 16 * tid) =
+                make_uint4(Rw[0], Rw[1], Rw[2], Rw[3]);
+        }
+    } else {
         // first record slot with windows in the tile: the last one whose stream base is <= T0
         u64 s = job.t_hint[blockIdx.x];
         while (true) {
@@ -688,199 +862,51 @@ __global__ void __launch_bounds__(kTransThreads) k_translate(const __grid_consta
             if (b != 0xFFFFFFFFu) break;
         }
         if (lane == 0) sh.first_slot = s;
+        build_runs(s);
     }
-    __syncthreads();  // table staged, first slot known
-
-    u32 W[13];  // W[k+1] = symbols 4k..4k+3 of the chunk, one per byte; W[0] = the 4 before
-    {
-        const u32 w[6] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y};
-        W[0] = (prev >> 4) & 0x0F0F0F0Fu;
-#pragma unroll
-        for (int g = 0; g < 6; g++) {
-            W[1 + 2 * g] = w[g] & 0x0F0F0F0Fu;
-            W[2 + 2 * g] = (w[g] >> 4) & 0x0F0F0F0Fu;
-        }
-    }
-    // byte i of IDX[k] = 2 * (s[e-2] + 5 s[e-1] + 25 s[e]) for e = 4k+i: the byte offset of the
-    // window's entry in the 16-bit table
-    u32 IDX[12];
-#pragma unroll
-    for (int k = 0; k < 12; k++) {
-        const u32 A = __byte_perm(W[k], W[k + 1], 0x5432);
-        const u32 B = __byte_perm(W[k], W[k + 1], 0x6543);
-        IDX[k] = A * 2u + B * 10u + W[k + 1] * 50u;
-    }
-    const uint8_t *lutb = reinterpret_cast<const uint8_t *>(sh.lut);
-#pragma unroll
-    for (int phi = 0; phi < 3; phi++) {
-        u32 Fw[4], Rw[4];
-#pragma unroll
-        for (int g = 0; g < 4; g++) {
-            u32 r[4];
-#pragma unroll
-            for (int x = 0; x < 4; x++) {
-                const int i = phi + 3 * (4 * g + x);  // window of the chunk
-                const u32 off = __byte_perm(IDX[i >> 2], 0u, 0x4440u + (i & 3));
-                r[x] = *reinterpret_cast<const uint16_t *>(lutb + off);
-            }
-            const u32 x01 = __byte_perm(r[0], r[1], 0x5140);
-            const u32 x23 = __byte_perm(r[2], r[3], 0x5140);
-            Fw[g] = __byte_perm(x01, x23, 0x5410);
-            Rw[g] = __byte_perm(x01, x23, 0x7632);
-        }
-        *reinterpret_cast<uint4 *>(sh.phase + phi * kPhaseStride + kPhaseGuard + 16 * tid) =
-            make_uint4(Fw[0], Fw[1], Fw[2], Fw[3]);
-        *reinterpret_cast<uint4 *>(sh.phase + (3 + phi) * kPhaseStride + kPhaseGuard + 16 * tid) =
-            make_uint4(Rw[0], Rw[1], Rw[2], Rw[3]);
-    }
+    __syncthreads();  // phase arrays and the first run table complete
+    s0 = sh.first_slot;
 
     // ---- format: every (record piece, frame) of the tile becomes a run of 60-column lines ----
-    const uintptr_t out_mis = (uintptr_t)job.out & 15u;
-    u64 s0 = sh.first_slot;
     while (true) {
-        if (warp == 0) {
-            // lanes 0..15: one record piece each; lane 16 looks one record past the batch
-            const u64 s = s0 + lane;
-            Run runs[6];
-#pragma unroll
-            for (int f = 0; f < 6; f++) {
-                runs[f].g0 = 0; runs[f].src = 0; runs[f].img = 0; runs[f].naa = 0; runs[f].nbytes = 0;
-                runs[f].col0 = 0; runs[f].flags = 0; runs[f].pad = 0;
-            }
-            RecInfo ri;
-            ri.dbase = ~0ull; ri.n = 0; ri.H = 0; ri.emitted = 0; ri.out_off = 0;
-            if (lane <= kRecBatch && s <= R) {
-                const uint4 *rp = reinterpret_cast<const uint4 *>(job.rec + s);
-                const uint4 a = rp[0], b = rp[1];
-                ri.out_off = (u64)a.x | (u64)a.y << 32;
-                ri.dbase = (u64)a.z | (u64)a.w << 32;
-                ri.n = (u64)b.x | (u64)b.y << 32;
-                ri.H = b.z;
-                ri.emitted = b.w;
-            }
-            const bool valid = ri.dbase < Tend;  // slots past R keep dbase = ~0
-            u32 nlines = 0, img_need = 0;
-            if (lane < kRecBatch && valid && ri.emitted) {
-                const u64 D = ri.dbase, n = ri.n, H = ri.H;
-                u64 L[6];
-                frame_lengths(n, job.alternative != 0, L);
-                if (job.trim) {
-#pragma unroll
-                    for (int f = 0; f < 6; f++) L[f] = job.trim_len[s * 6 + f];
-                }
-                // windows (by start q) of this record whose last symbol lies in the tile
-                const i64 dq = (i64)D - (i64)T0;  // local index of the record's first symbol
-                const i64 q_lo = -dq - 2 > -2 ? -dq - 2 : -2;
-                const i64 q_hi = ((i64)n - 1 < (i64)(Tend - T0) - 1 - dq - 2) ? (i64)n - 1 : (i64)(Tend - T0) - 1 - dq - 2;
-                u64 run_base = ri.out_off;
-#pragma unroll
-                for (int f = 0; f < 6; f++) {
-                    if (!((job.frame_mask >> f) & 1u)) continue;
-                    const u64 Lf = L[f];
-                    const u64 body = run_base + H + 3;
-                    run_base += run_size(H, Lf);
-                    i64 j_lo, j_hi, el0;
-                    if (f < 3) {
-                        const i64 lo = q_lo > 0 ? q_lo : 0;
-                        j_lo = ceildiv3(lo - f);
-                        if (j_lo < 0) j_lo = 0;
-                        j_hi = q_hi >= f ? floordiv3(q_hi - f) + 1 : 0;
-                        if (j_hi > (i64)Lf) j_hi = (i64)Lf;
-                        el0 = dq + f + 2 + 3 * j_lo;
-                    } else {
-                        const i64 Q = (i64)n - 3 - reverse_start(n, f - 3, job.alternative != 0);
-                        j_lo = ceildiv3(Q - q_hi);
-                        if (j_lo < 0) j_lo = 0;
-                        j_hi = Q >= q_lo ? floordiv3(Q - q_lo) + 1 : 0;
-                        if (j_hi > (i64)Lf) j_hi = (i64)Lf;
-                        el0 = dq + Q - 3 * j_lo + 2;
-                    }
-                    if (j_hi <= j_lo) continue;
-                    const u32 el = (u32)el0;            // 0 <= el0 < kTransTile
-                    const u32 m0 = el / 3u, phi = el - 3u * m0;
-                    const u64 line0 = udiv60((u64)j_lo);
-                    const u32 col0 = (u32)((u64)j_lo - 60 * line0);
-                    const u32 naa = (u32)(j_hi - j_lo);
-                    const bool fin = (u64)j_hi == Lf;
-                    const u32 q60 = (col0 + naa) / 60u;
-                    const u32 nb = naa + q60 + ((fin && (col0 + naa) != 60u * q60) ? 1u : 0u);
-                    runs[f].g0 = body + (u64)j_lo + line0;
-                    runs[f].src = (int)(((f < 3 ? 0u : 3u) + phi) * kPhaseStride + kPhaseGuard + m0);
-                    runs[f].naa = (uint16_t)naa;
-                    runs[f].nbytes = (uint16_t)nb;
-                    runs[f].col0 = (uint8_t)col0;
-                    runs[f].flags = (uint8_t)((fin ? 1 : 0) | (f < 3 ? 0 : 2));
-                    nlines += (col0 + naa + 59u) / 60u;
-                    img_need += ((nb + 15u) & ~15u) + 16u;  // its own 16-byte slots, congruent to global
-                }
-            }
-            // exclusive scans over the batch's records: line jobs and image space
-            u32 lp = nlines, ip = img_need;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const u32 y = __shfl_up_sync(0xFFFFFFFFu, lp, o);
-                const u32 z = __shfl_up_sync(0xFFFFFFFFu, ip, o);
-                if (lane >= o) { lp += y; ip += z; }
-            }
-            const u32 total_lines = __shfl_sync(0xFFFFFFFFu, lp, 31);
-            const u32 total_img = __shfl_sync(0xFFFFFFFFu, ip, 31);
-            lp -= nlines;
-            ip -= img_need;
-            if (lane < kRecBatch) {
-#pragma unroll
-                for (int f = 0; f < 6; f++) {
-                    sh.line_pre[lane * 6 + f] = lp;
-                    if (runs[f].naa) {
-                        const u32 mis = (u32)((out_mis + runs[f].g0) & 15u);
-                        runs[f].img = ip + mis;
-                        ip += ((runs[f].nbytes + 15u) & ~15u) + 16u;
-                        lp += (runs[f].col0 + runs[f].naa + 59u) / 60u;
-                    }
-                    sh.runs[lane * 6 + f] = runs[f];
-                }
-            }
-            if (lane == 0) {
-                sh.line_pre[kRunsPerBatch] = total_lines;
-                sh.image_bytes = total_img;
-            }
-            // more record pieces after this batch?
-            const unsigned mm = __ballot_sync(0xFFFFFFFFu, lane == kRecBatch && valid);
-            if (lane == 0) sh.more = mm != 0;
-        }
-        __syncthreads();  // runs published (and, in the first round, the phase arrays complete)
         const u32 total = sh.line_pre[kRunsPerBatch];
-        for (u32 job_i = tid; job_i < total; job_i += kTransThreads) {
+        for (u32 job_i = tid; job_i < total; job_i += kTransBlock) {
             // run r with line_pre[r] <= job_i < line_pre[r+1]
             u32 lo = 0, hi = kRunsPerBatch;
             while (hi - lo > 1) {
                 const u32 mid = (lo + hi) >> 1;
                 if (sh.line_pre[mid] <= job_i) lo = mid; else hi = mid;
             }
-            copy_line(sh, sh.runs[lo], lo, job_i - sh.line_pre[lo]);
+            copy_line(sh, sh.runs[lo], job_i - sh.line_pre[lo]);
         }
-        __syncthreads();  // image complete
-        const u32 nslot = (sh.image_bytes + 15u) >> 4;
-        for (u32 sl = tid; sl < nslot; sl += kTransThreads) {
-            const u32 ridx = sh.slot_run[sl];
-            if (ridx >= kRunsPerBatch) continue;  // never marked
-            const Run &r = sh.runs[ridx];
-            const u32 b0 = sl << 4;
-            if (b0 + 16u <= r.img || b0 >= r.img + r.nbytes) continue;  // padding slot
-            // global address of image byte x of the run: out + g0 + (x - img)
-            uint8_t *g = job.out + r.g0 + b0 - r.img;
-            const uint4 v = *reinterpret_cast<const uint4 *>(sh.image + b0);
-            if (b0 >= r.img && b0 + 16u <= r.img + r.nbytes) {
-                *reinterpret_cast<uint4 *>(g) = v;
-            } else {
-                const u32 lo_b = b0 >= r.img ? 0u : r.img - b0;
-                const u32 hi_b = b0 + 16u <= r.img + r.nbytes ? 16u : r.img + r.nbytes - b0;
-                for (u32 i = lo_b; i < hi_b; i++) g[i] = sh.image[b0 + i];
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // image writes -> visible to the bulk copy engine
+        __syncthreads();                                               // image complete
+        if (tid < kRunsPerBatch) {
+            const Run r = sh.runs[tid];
+            if (r.naa) {
+                const u32 lo16 = (r.img + 15u) & ~15u, end = r.img + r.nbytes, hi16 = end & ~15u;
+                uint8_t *g = job.out + r.g0;  // global address of image byte r.img
+                if (r.flags & 1) {            // the frame's final newline (writer.go:164-166)
+                    sh.image[end - 1u] = '\n';
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                }
+                if (hi16 > lo16) {
+                    bulk_store(g + (lo16 - r.img), sh.image + lo16, hi16 - lo16);
+                    for (u32 x = r.img; x < lo16; x++) g[x - r.img] = sh.image[x];
+                    for (u32 x = hi16; x < end; x++) g[x - r.img] = sh.image[x];
+                } else {
+                    for (u32 x = r.img; x < end; x++) g[x - r.img] = sh.image[x];
+                }
             }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // image may be reused / CTA may exit
         }
         const u32 more = sh.more;
         __syncthreads();
         if (!more) break;
         s0 += kRecBatch;
+        if (builder) build_runs(s0);
+        __syncthreads();
     }
 }
 
@@ -952,7 +978,7 @@ cudaError_t launch_pass(const Job &job, u64 max_symbols, int sm_count, cudaStrea
     *launches += 2;
     if (!sizes_only) {
         const u32 trans_grid = (u32)((max_symbols + kTransTile - 1) / kTransTile);
-        k_translate<<<trans_grid, kTransThreads, sizeof(TransShared), stream>>>(job);
+        k_translate<<<trans_grid, kTransBlock, sizeof(TransShared), stream>>>(job);
         if (ev) cudaEventRecord(ev[3], stream);
         k_headers<<<sm_count * 4, 256, 0, stream>>>(job);
         if (ev) cudaEventRecord(ev[4], stream);
@@ -964,7 +990,7 @@ cudaError_t launch_pass(const Job &job, u64 max_symbols, int sm_count, cudaStrea
 cudaError_t launch_emit(const Job &job, u64 max_symbols, int sm_count, cudaStream_t stream,
                         unsigned long long *launches) {
     const u32 trans_grid = (u32)((max_symbols + kTransTile - 1) / kTransTile);
-    k_translate<<<trans_grid, kTransThreads, sizeof(TransShared), stream>>>(job);
+    k_translate<<<trans_grid, kTransBlock, sizeof(TransShared), stream>>>(job);
     k_headers<<<sm_count * 4, 256, 0, stream>>>(job);
     *launches += 2;
     return cudaGetLastError();
