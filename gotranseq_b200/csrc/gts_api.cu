@@ -137,7 +137,7 @@ int ensure_scratch(gts_ctx *ctx, u64 n) {
         CU(cudaMalloc(&ctx->d_sym, sym_bytes));
         // zero once: stale words past the end of a stream must still hold valid symbols (<= 4)
         CU(cudaMemset(ctx->d_sym, 0, sym_bytes));
-        CU(cudaMalloc(&ctx->d_hint, (tiles_t + 2) * sizeof(u32)));
+        CU(cudaMalloc(&ctx->d_hint, (tiles_t * gts::kTransWarps + 8) * sizeof(u32)));
         ctx->cap_n = cap;
     }
     const u64 want_rec = n / 128 + 4096;

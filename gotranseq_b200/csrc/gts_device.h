@@ -31,21 +31,23 @@ constexpr int kParseThreads = 256;
 constexpr int kParseBytesPerThread = 32;
 constexpr int kParseTile = kParseThreads * kParseBytesPerThread;  // 8192 raw bytes
 
-// ---- k_translate geometry: one CTA per tile of symbols ----
-constexpr int kTransThreads = 256;
+// ---- k_translate geometry: one warp per sub-tile of symbols, kTransWarps sub-tiles per CTA ----
 constexpr int kTransSymPerThread = 48;
-constexpr int kTransTile = kTransThreads * kTransSymPerThread;  // 12288 symbols
-constexpr int kTransTileWords = kTransTile / 8;                 // 1536 stream words
-constexpr int kPhaseLen = kTransTile / 3;                       // residues per phase array
+constexpr int kTransSub = 32 * kTransSymPerThread;        // 1536 symbols per warp
+constexpr int kTransSubWords = kTransSub / 8;             // 192 stream words
+constexpr int kTransWarps = 8;                            // translating warps per CTA (+ 1 builder warp)
+constexpr int kTransTile = kTransWarps * kTransSub;       // 12288 symbols per CTA
+constexpr int kTransTileWords = kTransTile / 8;
+constexpr int kTransBlock = (kTransWarps + 1) * 32;
+constexpr int kPhaseLen = kTransSub / 3;                  // residues per phase array (per warp)
 constexpr int kPhaseGuard = 16;
-constexpr int kPhaseStride = kPhaseLen + 2 * kPhaseGuard;       // bytes per phase array in smem
-constexpr int kRecBatch = 16;                                   // record pieces per format batch
+constexpr int kPhaseStride = kPhaseLen + 2 * kPhaseGuard; // bytes per phase array in smem
+constexpr int kRecBatch = 4;                              // record pieces per sub-tile and format batch
 constexpr int kRunsPerBatch = kRecBatch * 6;
-// Output image of one batch in shared memory: the residue lines a tile writes (at most
-// 2 * kTransTile * 61 / 60 bytes + a few per run) plus up to 47 bytes of 16-byte alignment
-// padding and slack per run.
-constexpr int kImageBytes = 2 * kTransTile * 61 / 60 + kRunsPerBatch * 48 + 256;
-constexpr int kImageSlots = (kImageBytes + 15) / 16;
+// Output image of one sub-tile batch in shared memory: the residue lines a sub-tile writes (at most
+// 2 * kTransSub * 61 / 60 bytes + one final newline per run) plus up to 34 bytes of 16-byte
+// alignment padding per run.
+constexpr int kImageBytes = (2 * kTransSub * 61 / 60 + kRunsPerBatch * 35 + 128 + 15) / 16 * 16;
 
 // ---- k_size geometry ----
 constexpr int kSizeThreads = 256;
@@ -91,7 +93,7 @@ struct Job {  // kernel argument block (by value)
 
     u64 *p_status;  // [ntiles_parse * 4] chained scan of (symbols, header lines)
     u32 *p_pend;    // [ntiles_parse] symbols of the last incomplete stream word, bit 31 = valid
-    u32 *t_hint;    // [translate tiles] a record slot <= the slot owning the tile's first symbol
+    u32 *t_hint;    // [translate sub-tiles] the record slot owning the sub-tile's first symbol
 
     // record table, structure of arrays, slots 0..R (+1 sentinel in dbase / out_off)
     u64 *hdr_off;   // raw offset of the header line's '>'

@@ -182,9 +182,10 @@ template <bool EMIT>
 __device__ __forceinline__ void walk_chunk(const Job &job, const uint8_t *raw, const uint8_t *enc,
                                            int len, u32 nlmask, int state, bool cr_dropped_at_end,
                                            bool eof_chunk, u64 pos0, u32 &nsym, u32 &nhdr,
-                                           uint8_t *symdst, u64 dense0, u64 rec) {
+                                           uint8_t *symdst, u64 dense0, u64 rec, int xb = -1,
+                                           u32 *hdr_before_xb = nullptr) {
     int a = 0;
-    u32 ns = 0, nh = 0;
+    u32 ns = 0, nh = 0, nb = 0;
     int st = state;
     while (true) {
         const u32 m = a < 32 ? (nlmask >> a) : 0u;
@@ -198,6 +199,7 @@ __device__ __forceinline__ void walk_chunk(const Job &job, const uint8_t *raw, c
                         symdst[ns] = 0;
                         symdst[ns + 1] = 0;
                         rec++;
+                        if ((int)ns + 2 <= xb) nb++;
                         if (rec < job.rec_cap) {
                             job.hdr_off[rec] = pos0 + a;
                             job.dbase[rec] = dense0 + ns + 2;
@@ -239,6 +241,7 @@ __device__ __forceinline__ void walk_chunk(const Job &job, const uint8_t *raw, c
     }
     nsym = ns;
     nhdr = nh;
+    if (EMIT && hdr_before_xb) *hdr_before_xb = nb;
 }
 
 __global__ void __launch_bounds__(kParseThreads) k_parse(const __grid_constant__ Job job) {
@@ -379,12 +382,16 @@ __global__ void __launch_bounds__(kParseThreads) k_parse(const __grid_constant__
             job.hdr_end[0] = 0;
             job.dbase[0] = 2;
         }
-        walk_chunk<true>(job, raw, sh.enc, len, nlmask, state, cr_end, eof_chunk, pos0, ns2, nh2, dst, d0, rec0);
-    }
-    // a record slot at or before the one owning the first symbol of every translate tile
-    if (nsym > 0) {
-        const u64 x = (dense0 + kTransTile - 1) / kTransTile;
-        if (x * kTransTile < dense0 + nsym) job.t_hint[x] = (u32)rec0;
+        // does a translate sub-tile start inside this chunk's symbols?  (at most one: nsym < kTransSub)
+        const u64 x = (dense0 + kTransSub - 1) / kTransSub;
+        const bool has_x = nsym > 0 && x * kTransSub < dense0 + nsym;
+        const int xb = has_x ? (int)(x * kTransSub - d0) : -1;  // relative to the walk's first symbol
+        u32 nb = 0;
+        walk_chunk<true>(job, raw, sh.enc, len, nlmask, state, cr_end, eof_chunk, pos0, ns2, nh2, dst, d0, rec0,
+                         xb, &nb);
+        // the record slot owning the tile's first symbol: the last one whose first nucleotide is at or
+        // before it (tile 0 starts with slot 0's pads)
+        if (has_x) job.t_hint[x] = (u32)(rec0 + nb);
     }
     if (tid < 40) sh.sym[tot + tid] = 0;  // zero tail so that the last partial word packs zeros
     const bool last_tile = (t + 1 == job.ntiles_parse);
@@ -398,8 +405,8 @@ __global__ void __launch_bounds__(kParseThreads) k_parse(const __grid_constant__
             atomicOr(&job.totals->flags, kFlagRecOverflow);
         }
         // the two end pads may open a translate tile of their own
-        const u64 x = (S_total + kTransTile - 1) / kTransTile;
-        if (x * kTransTile < S_total + 2) job.t_hint[x] = (u32)R_total;
+        const u64 x = (S_total + kTransSub - 1) / kTransSub;
+        if (x * kTransSub < S_total + 2) job.t_hint[x] = (u32)R_total;
     }
     __syncthreads();
 
@@ -580,10 +587,10 @@ __global__ void __launch_bounds__(kSizeThreads) k_size(const __grid_constant__ J
 // =====================================================================================
 // k_translate
 // =====================================================================================
-struct Run {        // the part of one (record, frame) body that a translate tile writes
+struct Run {        // the part of one (record, frame) body that a sub-tile writes
     u64 g0;         // output offset of its first byte
-    int src;        // byte offset of its first residue in the phase arrays
-    u32 img;        // byte offset of its first byte in the output image
+    int src;        // byte offset of its first residue in the warp's phase arrays
+    u32 img;        // byte offset of its first byte in the warp's output image
     uint16_t naa;   // residues
     uint16_t nbytes;  // residues + newlines
     uint8_t col0;   // column (0..59) of the first residue
@@ -591,40 +598,48 @@ struct Run {        // the part of one (record, frame) body that a translate til
     uint16_t pad;
 };
 
-struct TransShared {
-    alignas(16) uint8_t phase[6 * kPhaseStride];  // [forward 0..2 | reverse 0..2][guard|residues|guard]
-    alignas(16) uint8_t image[kImageSlots * 16];  // the batch's output bytes, 16-byte congruent to global
-    alignas(16) uint16_t lut[128];
+struct RunTable {    // the run table of one batch of record pieces of one sub-tile
     alignas(16) Run runs[kRunsPerBatch];
     u32 line_pre[kRunsPerBatch + 1];
-    u64 first_slot;
-    u32 more;
+    u32 more;        // record pieces of the sub-tile left after this batch
+    u32 next_slot;   // first record slot of the next batch
+};
+
+struct WarpShared {  // private to one translating warp
+    alignas(16) uint8_t phase[6 * kPhaseStride];  // [forward 0..2 | reverse 0..2][guard|residues|guard]
+    alignas(16) uint8_t image[kImageBytes];       // the batch's output bytes, 16-byte congruent to global
+    RunTable rt[2];  // the builder warp fills one for the next tile while the other is in use
+};
+
+struct TransShared {
+    WarpShared w[kTransWarps];
+    alignas(16) uint16_t lut[128];
 };
 
 __device__ __forceinline__ u32 lds32(const uint8_t *base, u32 off) {
     return *reinterpret_cast<const u32 *>(base + off);
 }
 
-// Copy one 60-column line of a run (or the part of it inside the tile) from the phase arrays into
-// the output image, newline included.  Whole aligned image words are written: a lane owns the
-// words whose first byte lies in its line (for a run's first line also the word holding the
+// Copy one 60-column line of a run (or the part of it inside the sub-tile) from the phase arrays
+// into the output image, newline included.  Whole aligned image words are written: a lane owns
+// the words whose first byte lies in its line (for a run's first line also the word holding the
 // line's first byte), so words that straddle two lines carry the start of the next line, and the
 // bytes written outside the run are image padding that is never copied out.
-__device__ __forceinline__ void copy_line(TransShared &sh, const Run &r, u32 ln) {
-    const uint8_t *ph = sh.phase;
+__device__ __forceinline__ void copy_line(WarpShared &ws, const Run &r, u32 ln) {
+    const uint8_t *ph = ws.phase;
     const u32 col0 = r.col0, naa = r.naa;
     const u32 start = ln == 0 ? 0 : (60 - col0) + 60 * (ln - 1);
     const u32 cnt = min(60u - (ln == 0 ? col0 : 0u), naa - start);
     // the newline after column 60; a frame's final newline elsewhere is patched in by the run's
-    // copy-out thread (it may fall into a word owned by the previous line)
+    // copy-out lane (it may fall into a word owned by the previous line)
     const bool nl = ln == 0 ? col0 + cnt == 60 : cnt == 60;
     const u32 d0 = r.img + start + ln;           // image offset of the line's first byte
     const u32 dend = d0 + cnt + (nl ? 1u : 0u);  // one past its last byte
     const u32 w_lo = ln == 0 ? (d0 & ~3u) : ((d0 + 3u) & ~3u);
     const u32 w_hi = ((dend - 1u) & ~3u) + 4u;
-    const int nw = (int)(w_hi - w_lo) >> 2;      // <= 16 (w_hi > w_lo is not guaranteed for ln > 0)
+    const int nw = (int)(w_hi - w_lo) >> 2;      // <= 16, may be <= 0 for a short last line
     const int rel = (int)w_lo - (int)d0;         // line-relative offset of the first owned byte (-3..3)
-    u32 *dst = reinterpret_cast<u32 *>(sh.image + w_lo);
+    u32 *dst = reinterpret_cast<u32 *>(ws.image + w_lo);
     const bool rev = (r.flags & 2) != 0;
     if (!rev) {
         const u32 A = (u32)(r.src + (int)start + rel);  // source byte of the first owned byte
@@ -674,239 +689,281 @@ __device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, u32 byt
                  : "memory");
 }
 
-// Threads 0..kTransThreads-1 translate (48 symbols each); the extra warp builds the run table of the
-// tile's first record batch meanwhile.  Everybody then formats lines.
-constexpr int kTransBlock = kTransThreads + 32;
+// Run table of one batch of record pieces of one sub-tile.  Called by a group of `width` (4 or 32)
+// consecutive lanes, lane `gl` of the group handling record slot s0 + gl (gl < kRecBatch); lane
+// kRecBatch of the group, when present, only looks whether the sub-tile has more record pieces.
+__device__ __forceinline__ void build_runs(const Job &job, RunTable &ws, u64 R, u64 T0, u64 Tend, bool sub_valid,
+                                           u64 s0, int gl, int width, uintptr_t out_mis) {
+    const u64 s = s0 + gl;
+    Run runs[6];
+#pragma unroll
+    for (int f = 0; f < 6; f++) {
+        runs[f].g0 = 0; runs[f].src = 0; runs[f].img = 0; runs[f].naa = 0; runs[f].nbytes = 0;
+        runs[f].col0 = 0; runs[f].flags = 0; runs[f].pad = 0;
+    }
+    RecInfo ri;
+    ri.dbase = ~0ull; ri.n = 0; ri.H = 0; ri.emitted = 0; ri.out_off = 0;
+    u64 next_dbase = ~0ull;  // stream base of the record after this lane's
+    if (sub_valid && gl < kRecBatch && s <= R) {
+        const uint4 *rp = reinterpret_cast<const uint4 *>(job.rec + s);
+        const uint4 a = rp[0], b = rp[1];
+        ri.out_off = (u64)a.x | (u64)a.y << 32;
+        ri.dbase = (u64)a.z | (u64)a.w << 32;
+        ri.n = (u64)b.x | (u64)b.y << 32;
+        ri.H = b.z;
+        ri.emitted = b.w;
+        if (gl == kRecBatch - 1 && s + 1 <= R) next_dbase = job.rec[s + 1].dbase;
+    }
+    const bool valid = ri.dbase < Tend;  // slots past R keep dbase = ~0
+    u32 nlines = 0, img_need = 0;
+    if (valid && ri.emitted) {
+        const u64 D = ri.dbase, n = ri.n, H = ri.H;
+        u64 L[6];
+        frame_lengths(n, job.alternative != 0, L);
+        if (job.trim) {
+#pragma unroll
+            for (int f = 0; f < 6; f++) L[f] = job.trim_len[s * 6 + f];
+        }
+        // windows (by start q) of this record whose last symbol lies in the sub-tile
+        const i64 dq = (i64)D - (i64)T0;  // local index of the record's first symbol
+        const i64 q_lo = -dq - 2 > -2 ? -dq - 2 : -2;
+        const i64 q_hi = ((i64)n - 1 < (i64)(Tend - T0) - 1 - dq - 2) ? (i64)n - 1 : (i64)(Tend - T0) - 1 - dq - 2;
+        u64 run_base = ri.out_off;
+#pragma unroll
+        for (int f = 0; f < 6; f++) {
+            if (!((job.frame_mask >> f) & 1u)) continue;
+            const u64 Lf = L[f];
+            const u64 body = run_base + H + 3;
+            run_base += run_size(H, Lf);
+            i64 j_lo, j_hi, el0;
+            if (f < 3) {
+                const i64 lo = q_lo > 0 ? q_lo : 0;
+                j_lo = ceildiv3(lo - f);
+                if (j_lo < 0) j_lo = 0;
+                j_hi = q_hi >= f ? floordiv3(q_hi - f) + 1 : 0;
+                if (j_hi > (i64)Lf) j_hi = (i64)Lf;
+                el0 = dq + f + 2 + 3 * j_lo;
+            } else {
+                const i64 Q = (i64)n - 3 - reverse_start(n, f - 3, job.alternative != 0);
+                j_lo = ceildiv3(Q - q_hi);
+                if (j_lo < 0) j_lo = 0;
+                j_hi = Q >= q_lo ? floordiv3(Q - q_lo) + 1 : 0;
+                if (j_hi > (i64)Lf) j_hi = (i64)Lf;
+                el0 = dq + Q - 3 * j_lo + 2;
+            }
+            if (j_hi <= j_lo) continue;
+            const u32 el = (u32)el0;  // 0 <= el0 < kTransSub
+            const u32 m0 = el / 3u, phi = el - 3u * m0;
+            const u64 line0 = udiv60((u64)j_lo);
+            const u32 col0 = (u32)((u64)j_lo - 60 * line0);
+            const u32 naa = (u32)(j_hi - j_lo);
+            const bool fin = (u64)j_hi == Lf;
+            const u32 q60 = (col0 + naa) / 60u;
+            const u32 nb = naa + q60 + ((fin && (col0 + naa) != 60u * q60) ? 1u : 0u);
+            runs[f].g0 = body + (u64)j_lo + line0;
+            runs[f].src = (int)(((f < 3 ? 0u : 3u) + phi) * kPhaseStride + kPhaseGuard + m0);
+            runs[f].naa = (uint16_t)naa;
+            runs[f].nbytes = (uint16_t)nb;
+            runs[f].col0 = (uint8_t)col0;
+            runs[f].flags = (uint8_t)((fin ? 1 : 0) | (f < 3 ? 0 : 2));
+            nlines += (col0 + naa + 59u) / 60u;
+            // image space: 16-byte congruent start, then room for the last word's overhang
+            const u32 mis = (u32)((out_mis + runs[f].g0) & 15u);
+            img_need += (mis + nb + 3u + 15u) & ~15u;
+        }
+    }
+    // exclusive scans over the group's records: line jobs and image space
+    u32 lp = nlines, ip = img_need;
+#pragma unroll
+    for (int o = 1; o < kRecBatch; o <<= 1) {
+        const u32 y = __shfl_up_sync(0xFFFFFFFFu, lp, o, width);
+        const u32 z = __shfl_up_sync(0xFFFFFFFFu, ip, o, width);
+        if (gl >= o) { lp += y; ip += z; }
+    }
+    const u32 total_lines = __shfl_sync(0xFFFFFFFFu, lp, kRecBatch - 1, width);
+    lp -= nlines;
+    ip -= img_need;
+    if (gl < kRecBatch) {
+#pragma unroll
+        for (int f = 0; f < 6; f++) {
+            ws.line_pre[gl * 6 + f] = lp;
+            if (runs[f].naa) {
+                const u32 mis = (u32)((out_mis + runs[f].g0) & 15u);
+                runs[f].img = ip + mis;
+                ip += (mis + runs[f].nbytes + 3u + 15u) & ~15u;
+                lp += (runs[f].col0 + runs[f].naa + 59u) / 60u;
+            }
+            ws.runs[gl * 6 + f] = runs[f];
+        }
+        if (gl == 0) ws.line_pre[kRunsPerBatch] = total_lines;
+        if (gl == kRecBatch - 1) {
+            ws.more = (valid && next_dbase < Tend) ? 1u : 0u;
+            ws.next_slot = (u32)(s + 1);
+        }
+    }
+}
 
-__global__ void __launch_bounds__(kTransBlock) k_translate(const __grid_constant__ Job job) {
+// Copy the bytes [lo, hi) of the image (hi - lo < 16, both inside one aligned 16-byte slot) to
+// global memory with at most four naturally aligned stores; g is the global address of image byte 0.
+__device__ __forceinline__ void store_edge(const uint8_t *image, uint8_t *g, u32 lo, u32 hi) {
+    u32 x = lo;
+    if ((x & 1u) && x + 1u <= hi) { g[x] = image[x]; x += 1u; }
+    if ((x & 2u) && x + 2u <= hi) { *reinterpret_cast<uint16_t *>(g + x) = *reinterpret_cast<const uint16_t *>(image + x); x += 2u; }
+    if ((x & 4u) && x + 4u <= hi) { *reinterpret_cast<u32 *>(g + x) = *reinterpret_cast<const u32 *>(image + x); x += 4u; }
+    if (x + 8u <= hi) { *reinterpret_cast<uint2 *>(g + x) = *reinterpret_cast<const uint2 *>(image + x); x += 8u; }
+    if (x + 4u <= hi) { *reinterpret_cast<u32 *>(g + x) = *reinterpret_cast<const u32 *>(image + x); x += 4u; }
+    if (x + 2u <= hi) { *reinterpret_cast<uint16_t *>(g + x) = *reinterpret_cast<const uint16_t *>(image + x); x += 2u; }
+    if (x + 1u <= hi) { g[x] = image[x]; }
+}
+
+// Persistent CTAs.  Warps 0..kTransWarps-1 translate one sub-tile each per CTA tile (48 symbols per
+// lane); the extra warp builds, one tile ahead, the run table of every sub-tile's first record
+// batch.  One CTA barrier per tile hands the tables over; every warp then formats and stores its
+// own sub-tile.
+__global__ void __launch_bounds__(kTransBlock, 3) k_translate(const __grid_constant__ Job job) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     TransShared &sh = *reinterpret_cast<TransShared *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool builder = warp == kTransThreads / 32;
+    const bool builder = warp == kTransWarps;
 
     const u64 R = job.totals->n_headers;
     const u64 S2 = job.totals->total_sym + 2;
-    const u64 T0 = (u64)blockIdx.x * kTransTile;
-    if (T0 >= S2 || job.totals->flags != 0) return;
-    const u64 Tend = T0 + kTransTile < S2 ? T0 + kTransTile : S2;
+    if (job.totals->flags != 0) return;
+    const u64 ntiles = (S2 + kTransTile - 1) / kTransTile;
     const uintptr_t out_mis = (uintptr_t)job.out & 15u;
 
-    // Build the run table of the batch of record slots s0 .. s0+kRecBatch-1 (one warp).
-    auto build_runs = [&](u64 s0) {
-        // lanes 0..15: one record piece each; lane 16 looks one record past the batch
-        const u64 s = s0 + lane;
-        Run runs[6];
-#pragma unroll
-        for (int f = 0; f < 6; f++) {
-            runs[f].g0 = 0; runs[f].src = 0; runs[f].img = 0; runs[f].naa = 0; runs[f].nbytes = 0;
-            runs[f].col0 = 0; runs[f].flags = 0; runs[f].pad = 0;
+    if (builder) {
+        // 4 lanes per sub-tile: the first kRecBatch record pieces of each
+        const int w = lane >> 2, gl = lane & 3;
+        u32 it = 0;
+        for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+            const u64 sub = tile * kTransWarps + w;
+            const u64 T0 = sub * kTransSub;
+            const bool sub_valid = T0 < S2;
+            const u64 Tend = T0 + kTransSub < S2 ? T0 + kTransSub : S2;
+            const u64 s0 = sub_valid ? job.t_hint[sub] : 0;
+            build_runs(job, sh.w[w].rt[it & 1], R, T0, Tend, sub_valid, s0, gl, 4, out_mis);
+            __syncthreads();  // hands tile `it` over
         }
-        RecInfo ri;
-        ri.dbase = ~0ull; ri.n = 0; ri.H = 0; ri.emitted = 0; ri.out_off = 0;
-        if (lane <= kRecBatch && s <= R) {
-            const uint4 *rp = reinterpret_cast<const uint4 *>(job.rec + s);
-            const uint4 a = rp[0], b = rp[1];
-            ri.out_off = (u64)a.x | (u64)a.y << 32;
-            ri.dbase = (u64)a.z | (u64)a.w << 32;
-            ri.n = (u64)b.x | (u64)b.y << 32;
-            ri.H = b.z;
-            ri.emitted = b.w;
+        return;
+    }
+
+    if (tid < 128) sh.lut[tid] = job.lut.v[tid];
+    asm volatile("bar.sync 1, %0;" ::"r"(kTransWarps * 32) : "memory");  // table staged (translating warps only)
+    const uint8_t *lutb = reinterpret_cast<const uint8_t *>(sh.lut);
+    WarpShared &ws = sh.w[warp];
+
+    // symbols of this lane in the CTA's first tile: 48 = 6 stream words, plus the word before for
+    // (e-2, e-1)
+    u32 w6[6] = {0, 0, 0, 0, 0, 0}, prev = 0;
+    auto load_symbols = [&](u64 tile) {
+        const u64 sub = tile * kTransWarps + warp;
+        const u64 T0 = sub * kTransSub;
+        if (tile < ntiles && T0 < S2) {
+            const u32 *wp = job.sym + (T0 >> 3) + 6 * lane;
+            const uint2 x0 = *reinterpret_cast<const uint2 *>(wp);
+            const uint2 x1 = *reinterpret_cast<const uint2 *>(wp + 2);
+            const uint2 x2 = *reinterpret_cast<const uint2 *>(wp + 4);
+            prev = (sub == 0 && lane == 0) ? 0u : wp[-1];
+            w6[0] = x0.x; w6[1] = x0.y; w6[2] = x1.x; w6[3] = x1.y; w6[4] = x2.x; w6[5] = x2.y;
         }
-        const bool valid = ri.dbase < Tend;  // slots past R keep dbase = ~0
-        u32 nlines = 0, img_need = 0;
-        if (lane < kRecBatch && valid && ri.emitted) {
-            const u64 D = ri.dbase, n = ri.n, H = ri.H;
-            u64 L[6];
-            frame_lengths(n, job.alternative != 0, L);
-            if (job.trim) {
-#pragma unroll
-                for (int f = 0; f < 6; f++) L[f] = job.trim_len[s * 6 + f];
-            }
-            // windows (by start q) of this record whose last symbol lies in the tile
-            const i64 dq = (i64)D - (i64)T0;  // local index of the record's first symbol
-            const i64 q_lo = -dq - 2 > -2 ? -dq - 2 : -2;
-            const i64 q_hi = ((i64)n - 1 < (i64)(Tend - T0) - 1 - dq - 2) ? (i64)n - 1 : (i64)(Tend - T0) - 1 - dq - 2;
-            u64 run_base = ri.out_off;
-#pragma unroll
-            for (int f = 0; f < 6; f++) {
-                if (!((job.frame_mask >> f) & 1u)) continue;
-                const u64 Lf = L[f];
-                const u64 body = run_base + H + 3;
-                run_base += run_size(H, Lf);
-                i64 j_lo, j_hi, el0;
-                if (f < 3) {
-                    const i64 lo = q_lo > 0 ? q_lo : 0;
-                    j_lo = ceildiv3(lo - f);
-                    if (j_lo < 0) j_lo = 0;
-                    j_hi = q_hi >= f ? floordiv3(q_hi - f) + 1 : 0;
-                    if (j_hi > (i64)Lf) j_hi = (i64)Lf;
-                    el0 = dq + f + 2 + 3 * j_lo;
-                } else {
-                    const i64 Q = (i64)n - 3 - reverse_start(n, f - 3, job.alternative != 0);
-                    j_lo = ceildiv3(Q - q_hi);
-                    if (j_lo < 0) j_lo = 0;
-                    j_hi = Q >= q_lo ? floordiv3(Q - q_lo) + 1 : 0;
-                    if (j_hi > (i64)Lf) j_hi = (i64)Lf;
-                    el0 = dq + Q - 3 * j_lo + 2;
-                }
-                if (j_hi <= j_lo) continue;
-                const u32 el = (u32)el0;  // 0 <= el0 < kTransTile
-                const u32 m0 = el / 3u, phi = el - 3u * m0;
-                const u64 line0 = udiv60((u64)j_lo);
-                const u32 col0 = (u32)((u64)j_lo - 60 * line0);
-                const u32 naa = (u32)(j_hi - j_lo);
-                const bool fin = (u64)j_hi == Lf;
-                const u32 q60 = (col0 + naa) / 60u;
-                const u32 nb = naa + q60 + ((fin && (col0 + naa) != 60u * q60) ? 1u : 0u);
-                runs[f].g0 = body + (u64)j_lo + line0;
-                runs[f].src = (int)(((f < 3 ? 0u : 3u) + phi) * kPhaseStride + kPhaseGuard + m0);
-                runs[f].naa = (uint16_t)naa;
-                runs[f].nbytes = (uint16_t)nb;
-                runs[f].col0 = (uint8_t)col0;
-                runs[f].flags = (uint8_t)((fin ? 1 : 0) | (f < 3 ? 0 : 2));
-                nlines += (col0 + naa + 59u) / 60u;
-                img_need += ((nb + 15u) & ~15u) + 32u;  // its own 16-byte slots, congruent to global
-            }
-        }
-        // exclusive scans over the batch's records: line jobs and image space
-        u32 lp = nlines, ip = img_need;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const u32 y = __shfl_up_sync(0xFFFFFFFFu, lp, o);
-            const u32 z = __shfl_up_sync(0xFFFFFFFFu, ip, o);
-            if (lane >= o) { lp += y; ip += z; }
-        }
-        const u32 total_lines = __shfl_sync(0xFFFFFFFFu, lp, 31);
-        lp -= nlines;
-        ip -= img_need;
-        if (lane < kRecBatch) {
-#pragma unroll
-            for (int f = 0; f < 6; f++) {
-                sh.line_pre[lane * 6 + f] = lp;
-                if (runs[f].naa) {
-                    const u32 mis = (u32)((out_mis + runs[f].g0) & 15u);
-                    runs[f].img = ip + 16u + mis;  // one slot of slack in front: line 0 writes its whole first word
-                    ip += ((runs[f].nbytes + 15u) & ~15u) + 32u;
-                    lp += (runs[f].col0 + runs[f].naa + 59u) / 60u;
-                }
-                sh.runs[lane * 6 + f] = runs[f];
-            }
-        }
-        if (lane == 0) sh.line_pre[kRunsPerBatch] = total_lines;
-        // more record pieces after this batch?
-        const unsigned mm = __ballot_sync(0xFFFFFFFFu, lane == kRecBatch && valid);
-        if (lane == 0) sh.more = mm != 0;
     };
+    load_symbols(blockIdx.x);
 
-    u64 s0 = 0;
-    if (!builder) {
-        // ---- symbols of this thread: 48 = 6 stream words, plus the word before for (e-2, e-1) ----
-        const u32 *wp = job.sym + (T0 >> 3) + 6 * tid;
-        const uint2 x0 = *reinterpret_cast<const uint2 *>(wp);
-        const uint2 x1 = *reinterpret_cast<const uint2 *>(wp + 2);
-        const uint2 x2 = *reinterpret_cast<const uint2 *>(wp + 4);
-        const u32 prev = (blockIdx.x == 0 && tid == 0) ? 0u : wp[-1];
-        if (tid < 128) sh.lut[tid] = job.lut.v[tid];
-        asm volatile("bar.sync 1, %0;" ::"r"(kTransThreads) : "memory");  // table staged (translating warps only)
-
-        u32 W[13];  // W[k+1] = symbols 4k..4k+3 of the chunk, one per byte; W[0] = the 4 before
+    u32 it = 0;
+    for (u64 tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
         {
-            const u32 w[6] = {x0.x, x0.y, x1.x, x1.y, x2.x, x2.y};
+            u32 W[13];  // W[k+1] = symbols 4k..4k+3 of the chunk, one per byte; W[0] = the 4 before
             W[0] = (prev >> 4) & 0x0F0F0F0Fu;
 #pragma unroll
             for (int g = 0; g < 6; g++) {
-                W[1 + 2 * g] = w[g] & 0x0F0F0F0Fu;
-                W[2 + 2 * g] = (w[g] >> 4) & 0x0F0F0F0Fu;
+                W[1 + 2 * g] = w6[g] & 0x0F0F0F0Fu;
+                W[2 + 2 * g] = (w6[g] >> 4) & 0x0F0F0F0Fu;
             }
-        }
-        // byte i of IDX[k] = 2 * (s[e-2] + 5 s[e-1] + 25 s[e]) for e = 4k+i: the byte offset of the
-        // window's entry in the 16-bit table
-        u32 IDX[12];
+            // byte i of IDX[k] = 2 * (s[e-2] + 5 s[e-1] + 25 s[e]) for e = 4k+i: the byte offset of
+            // the window's entry in the 16-bit table
+            u32 IDX[12];
 #pragma unroll
-        for (int k = 0; k < 12; k++) {
-            const u32 A = __byte_perm(W[k], W[k + 1], 0x5432);
-            const u32 B = __byte_perm(W[k], W[k + 1], 0x6543);
-            IDX[k] = A * 2u + B * 10u + W[k + 1] * 50u;
-        }
-        const uint8_t *lutb = reinterpret_cast<const uint8_t *>(sh.lut);
+            for (int k = 0; k < 12; k++) {
+                const u32 A = __byte_perm(W[k], W[k + 1], 0x5432);
+                const u32 B = __byte_perm(W[k], W[k + 1], 0x6543);
+                IDX[k] = A * 2u + B * 10u + W[k + 1] * 50u;
+            }
+            load_symbols(tile + gridDim.x);  // prefetch the next tile's symbols
 #pragma unroll
-        for (int phi = 0; phi < 3; phi++) {
-            u32 Fw[4], Rw[4];
+            for (int phi = 0; phi < 3; phi++) {
+                u32 Fw[4], Rw[4];
 #pragma unroll
-            for (int g = 0; g < 4; g++) {
-                u32 r[4];
+                for (int g = 0; g < 4; g++) {
+                    u32 r[4];
 #pragma unroll
-                for (int x = 0; x < 4; x++) {
-                    const int i = phi + 3 * (4 * g + x);  // window of the chunk
-                    const u32 off = __byte_perm(IDX[i >> 2], 0u, 0x4440u + (i & 3));
-                    r[x] = *reinterpret_cast<const uint16_t *>(lutb + off);
+                    for (int x = 0; x < 4; x++) {
+                        const int i = phi + 3 * (4 * g + x);  // window of the chunk
+                        const u32 off = __byte_perm(IDX[i >> 2], 0u, 0x4440u + (i & 3));
+                        r[x] = *reinterpret_cast<const uint16_t *>(lutb + off);
+                    }
+                    const u32 x01 = __byte_perm(r[0], r[1], 0x5140);
+                    const u32 x23 = __byte_perm(r[2], r[3], 0x5140);
+                    Fw[g] = __byte_perm(x01, x23, 0x5410);
+                    Rw[g] = __byte_perm(x01, x23, 0x7632);
                 }
-                const u32 x01 = __byte_perm(r[0], r[1], 0x5140);
-                const u32 x23 = __byte_perm(r[2], r[3], 0x5140);
-                Fw[g] = __byte_perm(x01, x23, 0x5410);
-                Rw[g] = __byte_perm(x01, x23, 0x7632);
+                *reinterpret_cast<uint4 *>(ws.phase + phi * kPhaseStride + kPhaseGuard + 16 * lane) =
+                    make_uint4(Fw[0], Fw[1], Fw[2], Fw[3]);
+                *reinterpret_cast<uint4 *>(ws.phase + (3 + phi) * kPhaseStride + kPhaseGuard + 16 * lane) =
+                    make_uint4(Rw[0], Rw[1], Rw[2], Rw[3]);
             }
-            *reinterpret_cast<uint4 *>(sh.phase + phi * kPhaseStride + kPhaseGuard + 16 * tid) =
-                make_uint4(Fw[0], Fw[1], Fw[2], Fw[3]);
-            *reinterpret_cast<uint4 *>(sh.phase + (3 + phi) * kPhaseStride + kPhaseGuard + 16 * tid) =
-                make_uint4(Rw[0], Rw[1], Rw[2], Rw[3]);
         }
-    } else {
-        // first record slot with windows in the tile: the last one whose stream base is <= T0
-        u64 s = job.t_hint[blockIdx.x];
-        while (true) {
-            const u64 c = s + 1 + lane;
-            const bool le = c <= R && job.rec[c].dbase <= T0;
-            const unsigned b = __ballot_sync(0xFFFFFFFFu, le);
-            s += __popc(b);
-            if (b != 0xFFFFFFFFu) break;
-        }
-        if (lane == 0) sh.first_slot = s;
-        build_runs(s);
-    }
-    __syncthreads();  // phase arrays and the first run table complete
-    s0 = sh.first_slot;
+        __syncthreads();  // this tile's run tables are complete (and the warp's phase arrays)
 
-    // ---- format: every (record piece, frame) of the tile becomes a run of 60-column lines ----
-    while (true) {
-        const u32 total = sh.line_pre[kRunsPerBatch];
-        for (u32 job_i = tid; job_i < total; job_i += kTransBlock) {
-            // run r with line_pre[r] <= job_i < line_pre[r+1]
-            u32 lo = 0, hi = kRunsPerBatch;
-            while (hi - lo > 1) {
-                const u32 mid = (lo + hi) >> 1;
-                if (sh.line_pre[mid] <= job_i) lo = mid; else hi = mid;
+        // ---- format: every (record piece, frame) of the sub-tile becomes a run of 60-column lines ----
+        const u64 sub = tile * kTransWarps + warp;
+        const u64 T0 = sub * kTransSub;
+        if (T0 >= S2) continue;
+        const u64 Tend = T0 + kTransSub < S2 ? T0 + kTransSub : S2;
+        RunTable &rt = ws.rt[it & 1];
+        while (true) {
+            const u32 total = rt.line_pre[kRunsPerBatch];
+            const u32 more = rt.more;
+            const u64 next_slot = rt.next_slot;
+            for (u32 job_i = lane; job_i < total; job_i += 32) {
+                // run r with line_pre[r] <= job_i < line_pre[r+1] (kRunsPerBatch = 24 entries)
+                u32 lo = rt.line_pre[16] <= job_i ? 16u : 0u;
+                if (lo + 8u < kRunsPerBatch && rt.line_pre[lo + 8u] <= job_i) lo += 8u;
+                if (rt.line_pre[lo + 4u] <= job_i) lo += 4u;
+                if (rt.line_pre[lo + 2u] <= job_i) lo += 2u;
+                if (rt.line_pre[lo + 1u] <= job_i) lo += 1u;
+                copy_line(ws, rt.runs[lo], job_i - rt.line_pre[lo]);
             }
-            copy_line(sh, sh.runs[lo], job_i - sh.line_pre[lo]);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // image writes -> visible to the bulk copy engine
-        __syncthreads();                                               // image complete
-        if (tid < kRunsPerBatch) {
-            const Run r = sh.runs[tid];
-            if (r.naa) {
-                const u32 lo16 = (r.img + 15u) & ~15u, end = r.img + r.nbytes, hi16 = end & ~15u;
-                uint8_t *g = job.out + r.g0;  // global address of image byte r.img
-                if (r.flags & 1) {            // the frame's final newline (writer.go:164-166)
-                    sh.image[end - 1u] = '\n';
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // image writes -> visible to the bulk copy engine
+            __syncwarp();                                                  // image complete
+            if (lane < kRunsPerBatch) {
+                const Run r = rt.runs[lane];
+                if (r.naa) {
+                    const u32 lo16 = (r.img + 15u) & ~15u, end = r.img + r.nbytes, hi16 = end & ~15u;
+                    uint8_t *g = job.out + r.g0 - r.img;  // global address of image byte 0 (16-byte congruent)
+                    if (r.flags & 1) {                    // the frame's final newline (writer.go:164-166)
+                        ws.image[end - 1u] = '\n';
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    }
+                    if (hi16 > lo16) {
+                        bulk_store(g + lo16, ws.image + lo16, hi16 - lo16);
+                        store_edge(ws.image, g, r.img, lo16);
+                        store_edge(ws.image, g, hi16, end);
+                    } else if (end <= lo16) {
+                        store_edge(ws.image, g, r.img, end);
+                    } else {  // straddles one slot boundary without filling a slot
+                        store_edge(ws.image, g, r.img, lo16);
+                        store_edge(ws.image, g, lo16, end);
+                    }
                 }
-                if (hi16 > lo16) {
-                    bulk_store(g + (lo16 - r.img), sh.image + lo16, hi16 - lo16);
-                    for (u32 x = r.img; x < lo16; x++) g[x - r.img] = sh.image[x];
-                    for (u32 x = hi16; x < end; x++) g[x - r.img] = sh.image[x];
-                } else {
-                    for (u32 x = r.img; x < end; x++) g[x - r.img] = sh.image[x];
-                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // image may be reused / warp may exit
             }
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // image may be reused / CTA may exit
+            if (!more) break;
+            __syncwarp();
+            build_runs(job, rt, R, T0, Tend, true, next_slot, lane, 32, out_mis);
+            __syncwarp();
         }
-        const u32 more = sh.more;
-        __syncthreads();
-        if (!more) break;
-        s0 += kRecBatch;
-        if (builder) build_runs(s0);
-        __syncthreads();
     }
 }
 
@@ -977,7 +1034,8 @@ cudaError_t launch_pass(const Job &job, u64 max_symbols, int sm_count, cudaStrea
     if (ev) cudaEventRecord(ev[2], stream);
     *launches += 2;
     if (!sizes_only) {
-        const u32 trans_grid = (u32)((max_symbols + kTransTile - 1) / kTransTile);
+        const u64 trans_tiles = (max_symbols + kTransTile - 1) / kTransTile;
+        const u32 trans_grid = (u32)(trans_tiles < (u64)sm_count * 3 ? trans_tiles : (u64)sm_count * 3);
         k_translate<<<trans_grid, kTransBlock, sizeof(TransShared), stream>>>(job);
         if (ev) cudaEventRecord(ev[3], stream);
         k_headers<<<sm_count * 4, 256, 0, stream>>>(job);
@@ -989,7 +1047,8 @@ cudaError_t launch_pass(const Job &job, u64 max_symbols, int sm_count, cudaStrea
 
 cudaError_t launch_emit(const Job &job, u64 max_symbols, int sm_count, cudaStream_t stream,
                         unsigned long long *launches) {
-    const u32 trans_grid = (u32)((max_symbols + kTransTile - 1) / kTransTile);
+    const u64 trans_tiles = (max_symbols + kTransTile - 1) / kTransTile;
+    const u32 trans_grid = (u32)(trans_tiles < (u64)sm_count * 3 ? trans_tiles : (u64)sm_count * 3);
     k_translate<<<trans_grid, kTransBlock, sizeof(TransShared), stream>>>(job);
     k_headers<<<sm_count * 4, 256, 0, stream>>>(job);
     *launches += 2;
