@@ -51,13 +51,17 @@ __device__ __forceinline__ u32 eq_bytes(u32 w, u32 pat) {
     u32 t = (z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
     return ~(t | z | 0x7F7F7F7Fu);
 }
+// PTX prmt in its default mode: selector nibble bit 3 replicates the chosen byte's sign bit
+// (__byte_perm masks that bit away, and costs an extra AND for run-time selectors)
+__device__ __forceinline__ u32 prmt(u32 a, u32 b, u32 sel) {
+    u32 r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+
 // the four 0x80 flags of m as bits 0..3
 __device__ __forceinline__ u32 gather4(u32 m) { return (((m >> 7) * 0x00204081u) >> 21) & 0xFu; }
 
-__device__ __forceinline__ u32 newline_mask16(uint4 v) {
-    return gather4(eq_bytes(v.x, 0x0A0A0A0Au)) | gather4(eq_bytes(v.y, 0x0A0A0A0Au)) << 4 |
-           gather4(eq_bytes(v.z, 0x0A0A0A0Au)) << 8 | gather4(eq_bytes(v.w, 0x0A0A0A0Au)) << 12;
-}
 
 struct Pair {
     u64 a, b;
@@ -165,27 +169,19 @@ enum { LS = 0, SEQ = 1, HDR = 2 };
 
 struct ParseShared {
     alignas(16) uint8_t raw[kParseTile];
-    alignas(16) uint8_t sym[8 + kParseTile + 2 + 54];  // 8256 bytes: pending + symbols + zero tail
+    alignas(16) uint8_t sym[kParseTile + 96];  // the tile's symbols, one per byte, tile relative (+ zero tail)
     uint8_t enc[256];
     u32 warp_sum[kParseThreads / 32];
-    u32 warp_max[kParseThreads / 32];
     u64 T0, R0;
-    u64 tile_ls;
     u32 tile;
-    u32 S_tile, R_tile;
 };
 
-// One pass over the 32 bytes of a thread.  COUNT mode returns the symbols / header lines of the
-// chunk; EMIT mode additionally writes the symbols to shared memory and the record table
-// entries (header start, stream base, header end) to global memory.
-template <bool EMIT>
-__device__ __forceinline__ void walk_chunk(const Job &job, const uint8_t *raw, const uint8_t *enc,
-                                           int len, u32 nlmask, int state, bool cr_dropped_at_end,
-                                           bool eof_chunk, u64 pos0, u32 &nsym, u32 &nhdr,
-                                           uint8_t *symdst, u64 dense0, u64 rec, int xb = -1,
-                                           u32 *hdr_before_xb = nullptr) {
+// Symbols and header lines of one 32-byte chunk (scalar walk over its lines; used for the chunks
+// the fast path does not take).  Same line rules as tests/gpu_model.py parse().
+__device__ __forceinline__ void count_chunk(const uint8_t *raw, int len, u32 nlmask, int state,
+                                            bool cr_dropped_at_end, u32 &nsym, u32 &nhdr) {
     int a = 0;
-    u32 ns = 0, nh = 0, nb = 0;
+    u32 ns = 0, nh = 0;
     int st = state;
     while (true) {
         const u32 m = a < 32 ? (nlmask >> a) : 0u;
@@ -195,16 +191,6 @@ __device__ __forceinline__ void walk_chunk(const Job &job, const uint8_t *raw, c
                 if (raw[a] == '>') {  // transeq.go:198
                     st = HDR;
                     nh++;
-                    if (EMIT) {
-                        symdst[ns] = 0;
-                        symdst[ns + 1] = 0;
-                        rec++;
-                        if ((int)ns + 2 <= xb) nb++;
-                        if (rec < job.rec_cap) {
-                            job.hdr_off[rec] = pos0 + a;
-                            job.dbase[rec] = dense0 + ns + 2;
-                        }
-                    }
                     ns += 2;
                 } else {
                     st = SEQ;
@@ -215,33 +201,53 @@ __device__ __forceinline__ void walk_chunk(const Job &job, const uint8_t *raw, c
                 // bufio.ScanLines dropCR: a CR right before the '\n' (or as the last byte of the
                 // input) is not part of the line
                 if (raw[e - 1] == '\r' && (e < len || cr_dropped_at_end)) b--;
-                if (EMIT) {
-                    for (int i = a; i < b; i++) symdst[ns + (i - a)] = enc[raw[i]];
-                }
                 ns += b - a;
             }
         }
-        if (e < len) {  // raw[e] == '\n'
-            if (EMIT && st == HDR) {
-                u64 end = pos0 + e;
-                const uint8_t prev = e > 0 ? raw[e - 1] : job.in[pos0 - 1];
-                if (prev == '\r') end--;
-                if (rec < job.rec_cap) job.hdr_end[rec] = end;
-            }
+        if (e < len) {
             st = LS;
             a = e + 1;
         } else {
             break;
         }
     }
-    if (EMIT && eof_chunk && st == HDR) {  // header line without a final newline
-        u64 end = job.n;
-        if (raw[len - 1] == '\r') end--;
-        if (rec < job.rec_cap) job.hdr_end[rec] = end;
-    }
     nsym = ns;
     nhdr = nh;
-    if (EMIT && hdr_before_xb) *hdr_before_xb = nb;
+}
+
+// 0x80 in every byte of x that is '\n'
+__device__ __forceinline__ u32 newline_flags(u32 x) {
+    return __vabsdiffu4(__vabsdiffu4(x, 0x0A0A0A0Au), 0x80808080u) & 0x80808080u;
+}
+__device__ __forceinline__ u32 newline_mask16(uint4 v) {
+    return gather4(newline_flags(v.x)) | gather4(newline_flags(v.y)) << 4 | gather4(newline_flags(v.z)) << 8 |
+           gather4(newline_flags(v.w)) << 12;
+}
+
+// Nucleotide codes of four bytes at once (encodedSequence.go:25-41): A/a 1, C/c 2, T/t/U/u 3,
+// G/g 4, anything else 0.  The low three bits of (byte ^ 'A') tell the five letters apart; two
+// byte-permute table lookups give the letter that index stands for and its code, and the code is
+// kept only where the byte (case folded) equals that letter.
+__device__ __forceinline__ u32 encode4(u32 x) {
+    const u32 w = x ^ 0x41414141u;
+    const u32 idx = w & 0x07070707u;
+    const u32 sel = prmt(idx | (idx >> 4), 0u, 0x4420);
+    const u32 canon = prmt(0xFF02FF00u, 0xFF061514u, sel);  // A0 C2 U4 T5 G6
+    const u32 code = prmt(0x00020001u, 0x00040303u, sel);
+    const u32 diff = (w & 0xDFDFDFDFu) ^ canon;
+    const u32 ok = prmt(__vabsdiffu4(diff, 0x80808080u), 0u, 0xBA98);  // 0xFF where diff == 0
+    return code & ok;
+}
+
+// remove byte p (0..31) from the 32 bytes in C[0..7]; C[8] supplies the byte shifted in
+__device__ __forceinline__ void remove_byte(u32 (&C)[9], int p) {
+    const int pw = p >> 2;
+    const u32 mid = 0x3210u + ((0x1111u << (4 * (p & 3))) & 0xFFFFu);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const u32 sel = i < pw ? 0x3210u : (i == pw ? mid : 0x4321u);
+        C[i] = prmt(C[i], C[i + 1], sel);
+    }
 }
 
 __global__ void __launch_bounds__(kParseThreads) k_parse(const __grid_constant__ Job job) {
@@ -250,7 +256,6 @@ __global__ void __launch_bounds__(kParseThreads) k_parse(const __grid_constant__
     const int lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) sh.tile = atomicAdd(&job.counters[0], 1u);
-    // nucleotide codes of the reference: encodedSequence.go:25-41 (anything else -> N = 0)
     {
         uint8_t c = 0;
         switch (tid) {
@@ -264,7 +269,8 @@ __global__ void __launch_bounds__(kParseThreads) k_parse(const __grid_constant__
     __syncthreads();
     const u32 t = sh.tile;
     const u64 tile_base = (u64)t * kParseTile;
-    const u64 pos0 = tile_base + (u64)tid * kParseBytesPerThread;
+    const u64 warp_base = tile_base + (u64)warp * 1024u;
+    const u64 pos0 = warp_base + (u64)lane * kParseBytesPerThread;
     const int len = pos0 >= job.n ? 0 : (job.n - pos0 < 32 ? (int)(job.n - pos0) : 32);
 
     // ---- load the chunk, keep a copy of the tile in shared memory ----
@@ -285,10 +291,12 @@ __global__ void __launch_bounds__(kParseThreads) k_parse(const __grid_constant__
     u32 nlmask = newline_mask16(v0) | newline_mask16(v1) << 16;
     if (len < 32) nlmask &= len ? ((1u << len) - 1u) : 0u;
 
-    // ---- start of the line the tile begins in: backward search for the previous '\n' ----
-    if (warp == 0) {
-        u64 ls = 0;
-        u64 hi = tile_base;
+    // ---- start of the line each chunk begins in ----
+    // inside the warp: max-scan of "position after the last newline"; before the warp's first
+    // byte: backward search for the previous '\n'
+    u64 warp_ls = 0;
+    {
+        u64 hi = warp_base < job.n ? warp_base : 0;  // warps past the end do not search
         while (hi > 0) {
             const i64 start = (i64)hi - 16 * (lane + 1);
             u32 m16 = 0;
@@ -297,41 +305,67 @@ __global__ void __launch_bounds__(kParseThreads) k_parse(const __grid_constant__
             if (b) {
                 const int l = __ffs(b) - 1;
                 const u32 mm = __shfl_sync(0xFFFFFFFFu, m16, l);
-                ls = hi - 16ull * (l + 1) + (31 - __clz(mm)) + 1;
+                warp_ls = hi - 16ull * (l + 1) + (31 - __clz(mm)) + 1;
                 break;
             }
             if (hi <= 512) break;
             hi -= 512;
         }
-        if (lane == 0) sh.tile_ls = ls;
     }
-
-    // ---- exclusive max-scan of "last newline + 1" (tile relative) over the threads ----
-    const u32 my_last = nlmask ? (u32)(tid * 32 + (31 - __clz(nlmask)) + 1) : 0u;
+    const u32 my_last = nlmask ? (u32)(lane * 32 + (31 - __clz(nlmask)) + 1) : 0u;
     u32 inc_max = my_last;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const u32 y = __shfl_up_sync(0xFFFFFFFFu, inc_max, o);
         if (lane >= o) inc_max = max(inc_max, y);
     }
-    if (lane == 31) sh.warp_max[warp] = inc_max;
     u32 excl_max = __shfl_up_sync(0xFFFFFFFFu, inc_max, 1);
     if (lane == 0) excl_max = 0;
-    __syncthreads();
-    for (int w = 0; w < warp; w++) excl_max = max(excl_max, sh.warp_max[w]);
-    const u64 line_start = excl_max ? tile_base + excl_max : sh.tile_ls;
+    const u64 line_start = excl_max ? warp_base + excl_max : warp_ls;
 
     int state = LS;
     if (len > 0 && line_start != pos0) state = job.in[line_start] == '>' ? HDR : SEQ;
-    bool cr_end = false;
-    if (len > 0 && raw[len - 1] == '\r') cr_end = (pos0 + len >= job.n) || job.in[pos0 + len] == '\n';
+    const bool last_cr = len > 0 && raw[len - 1] == '\r';
+    const bool cr_end = last_cr && ((pos0 + len >= job.n) || job.in[pos0 + len] == '\n');
     const bool eof_chunk = len > 0 && pos0 + len == job.n;
-
-    // ---- count, scan over the tile ----
-    u32 nsym, nhdr;
-    walk_chunk<false>(job, raw, sh.enc, len, nlmask, state, cr_end, eof_chunk, pos0, nsym, nhdr, nullptr, 0, 0);
     const bool first_thread = (t == 0 && tid == 0);
-    if (first_thread) nsym += 2;  // pads of slot 0
+
+    // ---- classify the chunk ----
+    //   fast:  32 bytes of sequence lines only, at most two bytes to drop (newline, CR)
+    //   slow:  anything with a header line start / end in it, or short (end of input), ...
+    //   none:  no symbols (inside a header line, or past the end of the input)
+    u32 removed = 0;
+    bool slow = false, fast = false;
+    if (len > 0) {
+        if (state == HDR) {
+            slow = nlmask != 0 || eof_chunk;  // the header line ends here
+        } else {
+            slow = (state == LS && raw[0] == '>') || len < 32 || first_thread;
+            u32 m = nlmask;
+            u32 crd = cr_end ? (1u << (len - 1)) : 0u;
+            while (m) {
+                const int e = __ffs(m) - 1;
+                m &= m - 1;
+                if (e + 1 < len && raw[e + 1] == '>') slow = true;
+                if (e > 0 && raw[e - 1] == '\r') crd |= 1u << (e - 1);
+            }
+            removed = nlmask | crd;
+            if (__popc(removed) > 2) slow = true;
+            fast = !slow;
+        }
+    }
+    u32 nsym = 0, nhdr = 0;
+    if (fast) {
+        nsym = 32u - (u32)__popc(removed);
+    } else if (slow) {
+        count_chunk(raw, len, nlmask, state, cr_end, nsym, nhdr);
+        if (first_thread) nsym += 2;  // pads of slot 0
+    } else if (first_thread) {
+        nsym = 2;  // empty input
+        slow = true;
+    }
+
+    // ---- scan over the tile ----
     const u32 packed = nsym | nhdr << 16;
     u32 inc = packed;
 #pragma unroll
@@ -343,14 +377,16 @@ __global__ void __launch_bounds__(kParseThreads) k_parse(const __grid_constant__
     __syncthreads();
     u32 excl = inc - packed;
     u32 tile_total = 0;
+#pragma unroll
     for (int w = 0; w < kParseThreads / 32; w++) {
         const u32 s = sh.warp_sum[w];
         if (w < warp) excl += s;
         tile_total += s;
     }
     const u32 S_tile = tile_total & 0xFFFFu, R_tile = tile_total >> 16;
+    const u32 d = excl & 0xFFFFu;  // tile-relative index of the chunk's first symbol
 
-    // ---- chained scan across tiles ----
+    // ---- chained scan across tiles (warp 0), overlapped with the fast chunks of the others ----
     if (warp == 0) {
         Pair agg = {S_tile, R_tile};
         Pair ex = scan_lookback(job.p_status, t, agg);
@@ -359,41 +395,156 @@ __global__ void __launch_bounds__(kParseThreads) k_parse(const __grid_constant__
             sh.R0 = ex.b;
         }
     }
-    __syncthreads();
-    const u64 T0 = sh.T0, R0 = sh.R0;
-    const u32 a_pend = (u32)T0 & 7u;
-    const u32 tot = a_pend + S_tile;
 
-    // ---- emit: symbols to shared memory, record entries to global memory ----
-    const u32 d_thread = excl & 0xFFFFu;
-    const u64 rec0 = R0 + (excl >> 16);
-    const u64 dense0 = T0 + d_thread;
-    uint8_t *symdst = sh.sym + a_pend + d_thread;
+    // ---- fast chunks: encode, drop the newline / CR bytes, store whole words ----
     {
-        u32 ns2, nh2;
-        uint8_t *dst = symdst;
-        u64 d0 = dense0;
-        if (first_thread) {
-            dst[0] = 0;
-            dst[1] = 0;
-            dst += 2;
-            d0 += 2;
-            job.hdr_off[0] = 0;
-            job.hdr_end[0] = 0;
-            job.dbase[0] = 2;
+        // "big" chunks (fast, hence >= 30 symbols) link up: a chunk's last, partial word is
+        // completed with the first symbols of the next lane's chunk and stored whole
+        const unsigned bigm = __ballot_sync(0xFFFFFFFFu, fast);
+        u32 C[9];
+        C[8] = 0;
+        if (fast) {
+            C[0] = encode4(v0.x); C[1] = encode4(v0.y); C[2] = encode4(v0.z); C[3] = encode4(v0.w);
+            C[4] = encode4(v1.x); C[5] = encode4(v1.y); C[6] = encode4(v1.z); C[7] = encode4(v1.w);
+            u32 rm = removed;
+            while (rm) {
+                const int p = 31 - __clz(rm);
+                rm &= ~(1u << p);
+                remove_byte(C, p);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) C[i] = 0;
         }
-        // does a translate sub-tile start inside this chunk's symbols?  (at most one: nsym < kTransSub)
-        const u64 x = (dense0 + kTransSub - 1) / kTransSub;
-        const bool has_x = nsym > 0 && x * kTransSub < dense0 + nsym;
-        const int xb = has_x ? (int)(x * kTransSub - d0) : -1;  // relative to the walk's first symbol
-        u32 nb = 0;
-        walk_chunk<true>(job, raw, sh.enc, len, nlmask, state, cr_end, eof_chunk, pos0, ns2, nh2, dst, d0, rec0,
-                         xb, &nb);
-        // the record slot owning the tile's first symbol: the last one whose first nucleotide is at or
-        // before it (tile 0 starts with slot 0's pads)
-        if (has_x) job.t_hint[x] = (u32)(rec0 + nb);
+        const u32 next3 = __shfl_down_sync(0xFFFFFFFFu, C[0], 1);
+        if (fast) {
+            const bool link_next = lane < 31 && ((bigm >> (lane + 1)) & 1u);
+            const bool link_prev = lane > 0 && ((bigm >> (lane - 1)) & 1u);
+            const u32 k = nsym;  // 30..32
+            if (link_next) {      // append the next chunk's first three symbols after symbol k-1
+                const u32 shb = 8u * (k & 3u);
+                if (k == 32u) {
+                    C[8] = next3;
+                } else {
+                    C[7] |= next3 << shb;
+                    C[8] = next3 >> (32u - shb);  // shb is 16 or 24 here
+                }
+            }
+            const u32 a = d & 3u;
+            const u32 selA = 0x3210u + 0x1111u * (4u - a);
+            u32 D[9];
+            D[0] = prmt(0u, C[0], selA);
+#pragma unroll
+            for (int j = 1; j < 9; j++) D[j] = prmt(C[j - 1], C[j], selA);
+            u32 *dstw = reinterpret_cast<u32 *>(sh.sym + (d - a));
+            uint8_t *dstb = sh.sym + (d - a);
+            // word 0: whole if aligned; otherwise its bytes a..3 are ours unless the previous lane stores them
+            if (a == 0) {
+                dstw[0] = D[0];
+            } else if (!link_prev) {
+                if (a <= 1) dstb[1] = (uint8_t)(D[0] >> 8);
+                if (a <= 2) dstb[2] = (uint8_t)(D[0] >> 16);
+                dstb[3] = (uint8_t)(D[0] >> 24);
+            }
+#pragma unroll
+            for (int j = 1; j < 7; j++) dstw[j] = D[j];  // always whole (k >= 28)
+            const u32 jt = (a + k) >> 2, nb = (a + k) & 3u;  // last, partial word and its bytes
+            if (jt > 7) dstw[7] = D[7];
+            if (nb) {
+                const u32 Dt = jt == 7 ? D[7] : D[8];
+                if (link_next) {
+                    dstw[jt] = Dt;
+                } else {
+                    dstb[4 * jt] = (uint8_t)Dt;
+                    if (nb >= 2) dstb[4 * jt + 1] = (uint8_t)(Dt >> 8);
+                    if (nb >= 3) dstb[4 * jt + 2] = (uint8_t)(Dt >> 16);
+                }
+            }
+        }
     }
-    if (tid < 40) sh.sym[tot + tid] = 0;  // zero tail so that the last partial word packs zeros
+    __syncthreads();  // T0 / R0 known
+    const u64 T0 = sh.T0, R0 = sh.R0;
+
+    // ---- slow chunks: the 32 lanes of the warp take one byte each ----
+    {
+        unsigned slowm = __ballot_sync(0xFFFFFFFFu, slow);
+        while (slowm) {
+            const int c = __ffs(slowm) - 1;
+            slowm &= slowm - 1;
+            const int c_len = __shfl_sync(0xFFFFFFFFu, len, c);
+            const int c_state = __shfl_sync(0xFFFFFFFFu, state, c);
+            const u32 c_d = __shfl_sync(0xFFFFFFFFu, d, c);
+            const u32 c_rec = __shfl_sync(0xFFFFFFFFu, excl >> 16, c);
+            const bool c_cr_end = __shfl_sync(0xFFFFFFFFu, (int)cr_end, c) != 0;
+            const bool c_eof = __shfl_sync(0xFFFFFFFFu, (int)eof_chunk, c) != 0;
+            const bool c_first = (t == 0 && warp == 0 && c == 0);
+            const u64 c_pos0 = warp_base + (u64)c * 32u;
+            const bool valid = lane < c_len;
+            const uint8_t b = valid ? sh.raw[(warp * 32 + c) * 32 + lane] : 0;
+            const unsigned lt = (1u << lane) - 1u;
+            const unsigned nl = __ballot_sync(0xFFFFFFFFu, valid && b == '\n');
+            const unsigned before = nl & lt;
+            const int ls = before ? 32 - __clz(before) : -1;  // start of this byte's line, -1: before the chunk
+            const int first_idx = ls >= 0 ? ls : 0;
+            const uint8_t first = (uint8_t)__shfl_sync(0xFFFFFFFFu, (int)b, first_idx);
+            const bool fresh = ls >= 0 || c_state == LS;  // the line starts inside the chunk
+            const bool is_hdr = fresh ? first == '>' : c_state == HDR;
+            const bool is_nl = valid && b == '\n';
+            const bool hstart = valid && !is_nl && fresh && lane == first_idx && b == '>';
+            const unsigned hs = __ballot_sync(0xFFFFFFFFu, hstart);
+            const uint8_t nextb = (uint8_t)__shfl_down_sync(0xFFFFFFFFu, (int)b, 1);
+            const bool next_nl = lane + 1 < c_len ? nextb == '\n' : c_cr_end;
+            const bool keep = valid && !is_nl && !is_hdr && !(b == '\r' && next_nl);
+            const unsigned keepm = __ballot_sync(0xFFFFFFFFu, keep);
+            const u32 lead = c_first ? 2u : 0u;
+            const u32 off = lead + (u32)__popc(keepm & lt) + 2u * (u32)__popc(hs & lt);
+            if (c_first && lane == 0) {  // slot 0: the bytes before the first header line
+                sh.sym[0] = 0;
+                sh.sym[1] = 0;
+                job.hdr_off[0] = 0;
+                job.hdr_end[0] = 0;
+                job.dbase[0] = 2;
+            }
+            if (keep) sh.sym[c_d + off] = sh.enc[b];
+            const u64 rec_before = R0 + c_rec + (u64)__popc(hs & lt);  // header lines before this byte
+            if (hstart) {
+                sh.sym[c_d + off] = 0;
+                sh.sym[c_d + off + 1] = 0;
+                const u64 rec = rec_before + 1;
+                if (rec < job.rec_cap) {
+                    job.hdr_off[rec] = c_pos0 + lane;
+                    job.dbase[rec] = T0 + c_d + off + 2;
+                }
+            }
+            const uint8_t prevb = (uint8_t)__shfl_up_sync(0xFFFFFFFFu, (int)b, 1);
+            if (is_nl && is_hdr) {  // the header line ends here
+                const uint8_t pb = lane > 0 ? prevb : job.in[c_pos0 - 1];
+                const u64 end = c_pos0 + lane - (pb == '\r' ? 1 : 0);
+                if (rec_before < job.rec_cap) job.hdr_end[rec_before] = end;
+            }
+            if (c_eof && lane == c_len - 1 && !is_nl && is_hdr) {  // header line without a final newline
+                const u64 rec = rec_before + (hstart ? 1 : 0);
+                const u64 end = job.n - (b == '\r' ? 1 : 0);
+                if (rec < job.rec_cap) job.hdr_end[rec] = end;
+            }
+            // the record slot owning the first symbol of a translate sub-tile that starts in this chunk
+            const u32 c_nsym = __shfl_sync(0xFFFFFFFFu, nsym, c);
+            const u64 g0 = T0 + c_d;
+            const u64 x = (g0 + kTransSub - 1) / kTransSub;
+            if (c_nsym > 0 && x * kTransSub < g0 + c_nsym) {
+                const u64 xs = x * kTransSub;  // stream index of the sub-tile's first symbol
+                const unsigned le = __ballot_sync(0xFFFFFFFFu, hstart && T0 + c_d + off + 2 <= xs);
+                if (lane == 0) job.t_hint[x] = (u32)(R0 + c_rec + (u64)__popc(le));
+            }
+        }
+    }
+    // sub-tile starts inside fast chunks (no header line there: the slot is the one open at the chunk)
+    if (fast) {
+        const u64 g0 = T0 + d;
+        const u64 x = (g0 + kTransSub - 1) / kTransSub;
+        if (x * kTransSub < g0 + nsym) job.t_hint[x] = (u32)(R0 + (excl >> 16));
+    }
+    if (tid < 64) sh.sym[S_tile + tid] = 0;  // zero tail so that the last partial word packs zeros
     const bool last_tile = (t + 1 == job.ntiles_parse);
     if (last_tile && tid == 0) {
         const u64 S_total = T0 + S_tile, R_total = R0 + R_tile;
@@ -404,46 +555,74 @@ __global__ void __launch_bounds__(kParseThreads) k_parse(const __grid_constant__
         } else {
             atomicOr(&job.totals->flags, kFlagRecOverflow);
         }
-        // the two end pads may open a translate tile of their own
+        // the two end pads may open a translate sub-tile of their own
         const u64 x = (S_total + kTransSub - 1) / kTransSub;
         if (x * kTransSub < S_total + 2) job.t_hint[x] = (u32)R_total;
     }
-    __syncthreads();
+    __syncthreads();  // all symbols staged
 
-    // ---- hand-over of the symbols that do not fill a stream word ----
-    const u32 rem = tot & 7u;
+    // ---- pack two symbols per byte and write the stream words ----
+    // stream word w of the tile holds the tile's symbols 8w-a .. 8w-a+7 (a = symbols of the stream's
+    // last incomplete word that the previous tiles left pending)
+    const u32 a_pend = (u32)T0 & 7u;
+    const u32 tot = a_pend + S_tile;
+    const u32 nw = tot >> 3, rem = tot & 7u;
+    u32 *gw = job.sym + ((T0 - a_pend) >> 3);
+    {
+        const u32 sh4 = (8u - a_pend) & 3u;                // byte misalignment of word w's first symbol
+        const u32 sel = 0x3210u + 0x1111u * sh4;
+        for (u32 w = tid + (a_pend ? 1u : 0u); w < nw; w += kParseThreads) {
+            const u32 s0 = 8u * w - a_pend;                // tile-relative index of the word's first symbol
+            const u32 base = s0 & ~3u;
+            const u32 x0 = *reinterpret_cast<const u32 *>(sh.sym + base);
+            const u32 x1 = *reinterpret_cast<const u32 *>(sh.sym + base + 4);
+            const u32 x2 = *reinterpret_cast<const u32 *>(sh.sym + base + 8);
+            const u32 lo = prmt(x0, x1, sel), hi = prmt(x1, x2, sel);
+            gw[w] = lo | (hi << 4);
+        }
+    }
     if (tid == 0) {
+        // hand-over of the symbols that do not fill a stream word
         const bool own = rem <= S_tile;  // the pending symbols are all ours: publish before waiting
+        u32 pv = 0;
         if (own && !last_tile) {
             u32 v = 0x80000000u;
-            for (u32 k = 0; k < rem; k++) v |= (u32)sh.sym[tot - 1 - k] << (4 * k);
+            for (u32 k = 0; k < rem; k++) v |= (u32)sh.sym[S_tile - 1 - k] << (4 * k);
             st_release32(job.p_pend + t, v);
         }
         if (a_pend) {
-            u32 v;
             do {
-                v = ld_acquire32(job.p_pend + (t - 1));
-            } while (!(v & 0x80000000u));
-            for (u32 k = 0; k < a_pend; k++) sh.sym[a_pend - 1 - k] = (v >> (4 * k)) & 0xFu;
+                pv = ld_acquire32(job.p_pend + (t - 1));
+            } while (!(pv & 0x80000000u));
         }
-        if (!own && !last_tile) {
+        // symbol i (0..7) of the tile's first stream word: pending ones first, then ours
+        auto first_word_sym = [&](u32 i) -> u32 {
+            if (i < a_pend) return (pv >> (4 * (a_pend - 1 - i))) & 0xFu;
+            const u32 j = i - a_pend;
+            return j < S_tile ? sh.sym[j] : 0u;
+        };
+        if (a_pend && (nw >= 1 || last_tile)) {
+            u32 word = 0;
+            for (u32 i = 0; i < 8; i++) word |= first_word_sym(i) << (8 * (i & 3) + 4 * (i >> 2));
+            gw[0] = word;
+        }
+        if (!own && !last_tile) {  // fewer than 8 symbols in all: pass the predecessors' on as well
             u32 v = 0x80000000u;
-            for (u32 k = 0; k < rem; k++) v |= (u32)sh.sym[tot - 1 - k] << (4 * k);
+            for (u32 k = 0; k < rem; k++) v |= first_word_sym(rem - 1 - k) << (4 * k);
             st_release32(job.p_pend + t, v);
         }
-    }
-    __syncthreads();
-
-    // ---- pack two symbols per byte and write the complete stream words ----
-    const u32 nw = tot >> 3;
-    u32 *gw = job.sym + ((T0 - a_pend) >> 3);
-    for (u32 w = tid; w < nw; w += kParseThreads) {
-        const uint2 s2 = *reinterpret_cast<const uint2 *>(sh.sym + 8 * w);
-        gw[w] = s2.x | (s2.y << 4);
-    }
-    if (last_tile && tid < 4) {  // the partial word (zero padded) and the end pads
-        const uint2 s2 = *reinterpret_cast<const uint2 *>(sh.sym + 8 * (nw + tid));
-        gw[nw + tid] = s2.x | (s2.y << 4);
+        if (last_tile) {
+            // the last partial word (zero padded) and the end pads
+            for (u32 w = (nw == 0 && a_pend) ? 1u : nw; w < nw + 4; w++) {
+                u32 word = 0;
+                for (u32 i = 0; i < 8; i++) {
+                    const i64 j = (i64)(8u * w + i) - (i64)a_pend;
+                    const u32 s = (j >= 0 && j < (i64)S_tile) ? sh.sym[j] : 0u;
+                    word |= s << (8 * (i & 3) + 4 * (i >> 2));
+                }
+                gw[w] = word;
+            }
+        }
     }
 }
 
@@ -649,7 +828,7 @@ __device__ __forceinline__ void copy_line(WarpShared &ws, const Run &r, u32 ln) 
 #pragma unroll
         for (int k = 0; k < 16; k++) {
             const u32 hi = lds32(ph, base + 4u * (k + 1));
-            if (k < nw) dst[k] = __byte_perm(lo, hi, sel);
+            if (k < nw) dst[k] = prmt(lo, hi, sel);
             lo = hi;
         }
     } else {
@@ -660,7 +839,7 @@ __device__ __forceinline__ void copy_line(WarpShared &ws, const Run &r, u32 ln) 
 #pragma unroll
         for (int k = 0; k < 16; k++) {
             const u32 lo = lds32(ph, base - 4u * k);
-            if (k < nw) dst[k] = __byte_perm(lo, hi, sel);
+            if (k < nw) dst[k] = prmt(lo, hi, sel);
             hi = lo;
         }
     }
@@ -672,14 +851,14 @@ __device__ __forceinline__ void copy_line(WarpShared &ws, const Run &r, u32 ln) 
         u32 X;
         if (!rev) {
             const u32 A2 = (u32)(r.src + (int)start + o);
-            X = __byte_perm(lds32(ph, A2 & ~3u), lds32(ph, (A2 & ~3u) + 4u), 0x3210u + 0x1111u * (A2 & 3u));
+            X = prmt(lds32(ph, A2 & ~3u), lds32(ph, (A2 & ~3u) + 4u), 0x3210u + 0x1111u * (A2 & 3u));
         } else {
             const u32 A2 = (u32)(r.src - (int)start - o) - 3u;
-            X = __byte_perm(lds32(ph, A2 & ~3u), lds32(ph, (A2 & ~3u) + 4u), 0x0123u + 0x1111u * (A2 & 3u));
+            X = prmt(lds32(ph, A2 & ~3u), lds32(ph, (A2 & ~3u) + 4u), 0x0123u + 0x1111u * (A2 & 3u));
         }
         // insert the newline at byte t, shifting the later bytes up (selector nibble 4 = '\n')
         const u32 selnl = (u32)(0x4210241021402104ull >> (16u * t));
-        dst[kn] = __byte_perm(X, 0x0Au, selnl);
+        dst[kn] = prmt(X, 0x0Au, selnl);
     }
 }
 
@@ -885,8 +1064,8 @@ __global__ void __launch_bounds__(kTransBlock, 3) k_translate(const __grid_const
             u32 IDX[12];
 #pragma unroll
             for (int k = 0; k < 12; k++) {
-                const u32 A = __byte_perm(W[k], W[k + 1], 0x5432);
-                const u32 B = __byte_perm(W[k], W[k + 1], 0x6543);
+                const u32 A = prmt(W[k], W[k + 1], 0x5432);
+                const u32 B = prmt(W[k], W[k + 1], 0x6543);
                 IDX[k] = A * 2u + B * 10u + W[k + 1] * 50u;
             }
             load_symbols(tile + gridDim.x);  // prefetch the next tile's symbols
@@ -899,13 +1078,13 @@ __global__ void __launch_bounds__(kTransBlock, 3) k_translate(const __grid_const
 #pragma unroll
                     for (int x = 0; x < 4; x++) {
                         const int i = phi + 3 * (4 * g + x);  // window of the chunk
-                        const u32 off = __byte_perm(IDX[i >> 2], 0u, 0x4440u + (i & 3));
+                        const u32 off = prmt(IDX[i >> 2], 0u, 0x4440u + (i & 3));
                         r[x] = *reinterpret_cast<const uint16_t *>(lutb + off);
                     }
-                    const u32 x01 = __byte_perm(r[0], r[1], 0x5140);
-                    const u32 x23 = __byte_perm(r[2], r[3], 0x5140);
-                    Fw[g] = __byte_perm(x01, x23, 0x5410);
-                    Rw[g] = __byte_perm(x01, x23, 0x7632);
+                    const u32 x01 = prmt(r[0], r[1], 0x5140);
+                    const u32 x23 = prmt(r[2], r[3], 0x5140);
+                    Fw[g] = prmt(x01, x23, 0x5410);
+                    Rw[g] = prmt(x01, x23, 0x7632);
                 }
                 *reinterpret_cast<uint4 *>(ws.phase + phi * kPhaseStride + kPhaseGuard + 16 * lane) =
                     make_uint4(Fw[0], Fw[1], Fw[2], Fw[3]);
