@@ -45,6 +45,7 @@ struct gts_ctx {
     gts::RecInfo *d_rec = nullptr;
     u32 *d_trim = nullptr;
     gts::Totals *h_totals = nullptr;  // pinned
+    u64 *d_dbg = nullptr;             // phase timing sums (GTS_PHASE_TIMING builds with GTS_PHASE_TIMING=1 set)
 
     // ---- buffers of the host entry points ----
     uint8_t *d_in = nullptr, *d_out = nullptr;
@@ -90,13 +91,17 @@ int cuda_fail(gts_ctx *ctx, cudaError_t e, const char *what) {
 size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct ZeroLayout {
-    size_t p_status, s_status, totals, counters, p_pend, bytes;
+    size_t p_agg, p_gagg, p_ginc, s_status, totals, counters, p_pend, bytes;
 };
 ZeroLayout zero_layout(u64 ntiles_parse, u64 rec_cap) {
     ZeroLayout z;
     const u64 size_tiles = (rec_cap + gts::kSizeTile - 1) / gts::kSizeTile;
     size_t off = 0;
-    z.p_status = off; off += ntiles_parse * 4 * sizeof(u64);
+    const u64 groups = (ntiles_parse + 31) / 32;
+    z.p_ginc = off;   off += groups * 2 * sizeof(u64);  // 16-byte entries first (aligned)
+    z.p_gagg = off;   off += groups * sizeof(u64);
+    z.p_agg = off;    off += ntiles_parse * sizeof(u32);
+    off = round_up(off, 16);
     z.s_status = off; off += size_tiles * 4 * sizeof(u64);
     z.totals = off;   off += sizeof(gts::Totals);
     z.counters = off; off += 16;
@@ -167,7 +172,9 @@ int enqueue_pass(gts_ctx *ctx, const uint8_t *d_in, u64 n, uint8_t *d_out, u64 c
     gts::Job &job = ctx->job;
     job.in = d_in; job.n = n; job.out = d_out; job.out_cap = cap;
     job.sym = ctx->d_sym;
-    job.p_status = reinterpret_cast<u64 *>(ctx->d_zero + z.p_status);
+    job.p_agg = reinterpret_cast<u32 *>(ctx->d_zero + z.p_agg);
+    job.p_gagg = reinterpret_cast<u64 *>(ctx->d_zero + z.p_gagg);
+    job.p_ginc = reinterpret_cast<u64 *>(ctx->d_zero + z.p_ginc);
     job.s_status = reinterpret_cast<u64 *>(ctx->d_zero + z.s_status);
     job.totals = reinterpret_cast<gts::Totals *>(ctx->d_zero + z.totals);
     job.counters = reinterpret_cast<u32 *>(ctx->d_zero + z.counters);
@@ -180,6 +187,7 @@ int enqueue_pass(gts_ctx *ctx, const uint8_t *d_in, u64 n, uint8_t *d_out, u64 c
     job.alternative = ctx->opt.alternative ? 1 : 0;
     job.trim = ctx->opt.trim ? 1 : 0;
     job.lut = ctx->lut;
+    job.dbg = ctx->d_dbg;
     ctx->job_max_sym = n + 4;
     ctx->job_stream = stream;
     cudaEvent_t *ev = nullptr;
@@ -361,6 +369,12 @@ int gts_create(const gts_options *opt, gts_ctx **out) {
     }
     ctx->device = dev;
     ctx->sm_count = prop.multiProcessorCount;
+#ifdef GTS_PHASE_TIMING
+    if (std::getenv("GTS_PHASE_TIMING")) {
+        cudaMalloc(&ctx->d_dbg, 64 * sizeof(u64));
+        cudaMemset(ctx->d_dbg, 0, 64 * sizeof(u64));
+    }
+#endif
     *out = ctx;
     return GTS_OK;
 }
@@ -369,6 +383,15 @@ void gts_destroy(gts_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->d_dbg) {
+        u64 h[64];
+        cudaDeviceSynchronize();
+        cudaMemcpy(h, ctx->d_dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        std::fprintf(stderr, "[gts phase timing, ns summed over tiles, %llu passes]", (unsigned long long)ctx->stats.passes);
+        for (int i = 0; i < 16; i++) std::fprintf(stderr, " p%d=%llu", i, (unsigned long long)h[i]);
+        std::fprintf(stderr, "\n");
+        cudaFree(ctx->d_dbg);
+    }
     cudaFree(ctx->d_sym); cudaFree(ctx->d_hint); cudaFree(ctx->d_zero);
     free_rec(ctx);
     cudaFree(ctx->d_in); cudaFree(ctx->d_out);

@@ -91,7 +91,10 @@ struct Job {  // kernel argument block (by value)
 
     u32 *sym;  // packed symbol stream
 
-    u64 *p_status;  // [ntiles_parse * 4] chained scan of (symbols, header lines)
+    // two-level chained scan of (symbols, header lines) over the parse tiles, groups of 32 tiles
+    u32 *p_agg;     // [ntiles_parse] bit 31 valid | header lines << 14 | symbols      (one tile)
+    u64 *p_gagg;    // [groups] bit 63 valid | header lines << 32 | symbols            (one group)
+    u64 *p_ginc;    // [groups * 2] {bit 63 valid | symbols, header lines} of groups 0..g
     u32 *p_pend;    // [ntiles_parse] symbols of the last incomplete stream word, bit 31 = valid
     u32 *t_hint;    // [translate sub-tiles] the record slot owning the sub-tile's first symbol
 
@@ -106,6 +109,7 @@ struct Job {  // kernel argument block (by value)
     u64 *s_status;  // [size tiles * 4] chained scan of output sizes
     u32 *counters;  // [0] parse tile ticket, [1] size tile ticket
     Totals *totals;
+    u64 *dbg;       // optional phase timing sums (GTS_PHASE_TIMING builds), else nullptr
 
     u32 ntiles_parse;
     u32 frame_mask;  // bit k = frame index k requested (0..2 forward, 3..5 reverse)

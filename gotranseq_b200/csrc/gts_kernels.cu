@@ -59,6 +59,24 @@ __device__ __forceinline__ u32 prmt(u32 a, u32 b, u32 sel) {
     return r;
 }
 
+#ifdef GTS_PHASE_TIMING
+__device__ __forceinline__ u64 gtime() {
+    u64 t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define PHASE_MARK(job, idx, t_prev)                                                     \
+    do {                                                                                 \
+        if ((job).dbg && threadIdx.x == 0) {                                             \
+            const u64 now_ = gtime();                                                    \
+            atomicAdd((job).dbg + (idx), now_ - (t_prev));                               \
+            (t_prev) = now_;                                                             \
+        }                                                                                \
+    } while (0)
+#else
+#define PHASE_MARK(job, idx, t_prev) do { } while (0)
+#endif
+
 // the four 0x80 flags of m as bits 0..3
 __device__ __forceinline__ u32 gather4(u32 m) { return (((m >> 7) * 0x00204081u) >> 21) & 0xFu; }
 
@@ -129,6 +147,115 @@ __device__ Pair scan_lookback(u64 *status, u32 t, Pair agg) {
 // exact unsigned division by constants without the 64-bit division routine
 __device__ __forceinline__ u64 udiv3(u64 a) { return __umul64hi(a, 0xAAAAAAAAAAAAAAABull) >> 1; }
 __device__ __forceinline__ u64 udiv60(u64 a) { return __umul64hi(a >> 2, 0x8888888888888889ull) >> 3; }
+__device__ __forceinline__ u32 ld_relaxed32(const u32 *p) {
+    u32 v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Two-level variant for the parse tiles.  A one-level look-back advances by one 32-tile window per
+// global-memory round trip, which caps the kernel at 32 tiles per microsecond; here a tile waits
+// only for the aggregates of the tiles of its own group of 32 (published without any dependency),
+// and the chained look-back runs over whole groups, i.e. 1024 tiles per round trip.  Every status
+// entry carries its flag in the same (at most 16-byte, naturally aligned) word as its payload, so
+// plain volatile accesses are enough -- no fences on the critical path.
+// Called by the 32 lanes of one warp; S < 2^14, R < 2^13 per tile.
+__device__ __forceinline__ void st_volatile_v2(u64 *p, u64 a, u64 b) {
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void ld_volatile_v2(const u64 *p, u64 &a, u64 &b) {
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ u64 ld_volatile64(const u64 *p) {
+    u64 v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ u32 ld_volatile32(const u32 *p) {
+    u32 v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile32(u32 *p, u32 v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_volatile64(u64 *p, u64 v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ Pair scan_lookback2(const Job &job, u32 t, u32 S, u32 R) {
+    const int lane = threadIdx.x & 31;
+    const u32 g = t >> 5, r = t & 31u;
+    if (lane == 0) st_volatile32(job.p_agg + t, 0x80000000u | (R << 14) | S);
+    // issue the first round of both levels at once: the aggregates of the tiles before this one in
+    // its group, and the status of the 32 groups before this group
+    const bool in_group = (u32)lane < r;
+    const i64 gidx0 = (i64)g - 1 - lane;
+    u32 v = in_group ? ld_volatile32(job.p_agg + (g << 5) + lane) : 0x80000000u;
+    u64 ia = 0, ib = 0, ga = 0;
+    if (gidx0 >= 0) {
+        ld_volatile_v2(job.p_ginc + 2 * gidx0, ia, ib);
+        ga = ld_volatile64(job.p_gagg + gidx0);
+    }
+    // step 1: sum of the aggregates of the tiles before this one in its group
+    while (!(v & 0x80000000u)) v = ld_volatile32(job.p_agg + (g << 5) + lane);
+    u32 ps = in_group ? (v & 0x3FFFu) : 0u, pr = in_group ? ((v >> 14) & 0x1FFFu) : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ps += __shfl_xor_sync(0xFFFFFFFFu, ps, o);
+        pr += __shfl_xor_sync(0xFFFFFFFFu, pr, o);
+    }
+    const bool anchor = r == 31u;  // the group's last tile publishes the group's aggregate / prefix
+    const u64 gs = (u64)ps + S, gr = (u64)pr + R;
+    if (anchor && lane == 0) st_volatile64(job.p_gagg + g, kValid | (gr << 32) | gs);
+    // step 2: chained look-back over the groups before this one
+    Pair excl = {0, 0};
+    i64 pos = (i64)g - 1;
+    bool first_round = true;
+    while (pos >= 0) {
+        const i64 idx = pos - lane;
+        int kind = 2;  // 0 = not published, 1 = aggregate, 2 = inclusive (or before group 0)
+        u64 a = 0, b = 0;
+        if (idx >= 0) {
+            if (!first_round) {
+                ld_volatile_v2(job.p_ginc + 2 * idx, ia, ib);
+                ga = ld_volatile64(job.p_gagg + idx);
+            }
+            if (ia & kValid) {
+                a = ia & ~kValid;
+                b = ib;
+            } else if (ga & kValid) {
+                kind = 1;
+                a = ga & 0xFFFFFFFFull;
+                b = (ga & ~kValid) >> 32;
+            } else {
+                kind = 0;
+            }
+        }
+        first_round = false;
+        const unsigned inc_m = __ballot_sync(0xFFFFFFFFu, kind == 2);
+        const unsigned none_m = __ballot_sync(0xFFFFFFFFu, kind == 0);
+        const int first_inc = inc_m ? __ffs(inc_m) - 1 : 32;
+        const int first_none = none_m ? __ffs(none_m) - 1 : 32;
+        if (first_none < first_inc) continue;  // a needed group has not published yet
+        const int last = first_inc < 31 ? first_inc : 31;
+        if (lane > last) a = b = 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
+            b += __shfl_xor_sync(0xFFFFFFFFu, b, o);
+        }
+        excl.a += a;
+        excl.b += b;
+        if (first_inc < 32) break;
+        pos -= 32;
+    }
+    if (anchor && lane == 0) st_volatile_v2(job.p_ginc + 2 * (u64)g, (excl.a + gs) | kValid, excl.b + gr);
+    excl.a += ps;
+    excl.b += pr;
+    return excl;
+}
+
 __device__ __forceinline__ i64 floordiv3(i64 a) { return a >= 0 ? (i64)udiv3((u64)a) : -(i64)udiv3((u64)(-a) + 2); }
 __device__ __forceinline__ i64 ceildiv3(i64 a) { return -floordiv3(-a); }
 __device__ __forceinline__ int mod3(i64 a) { return (int)(a - 3 * floordiv3(a)); }
@@ -255,6 +382,9 @@ __global__ void __launch_bounds__(kParseThreads) k_parse(const __grid_constant__
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
 
+#ifdef GTS_PHASE_TIMING
+    u64 tprev = gtime();
+#endif
     if (tid == 0) sh.tile = atomicAdd(&job.counters[0], 1u);
     {
         uint8_t c = 0;
@@ -267,6 +397,7 @@ __global__ void __launch_bounds__(kParseThreads) k_parse(const __grid_constant__
         sh.enc[tid] = c;
     }
     __syncthreads();
+    PHASE_MARK(job, 0, tprev);  // ticket
     const u32 t = sh.tile;
     const u64 tile_base = (u64)t * kParseTile;
     const u64 warp_base = tile_base + (u64)warp * 1024u;
@@ -365,6 +496,7 @@ __global__ void __launch_bounds__(kParseThreads) k_parse(const __grid_constant__
         slow = true;
     }
 
+    PHASE_MARK(job, 1, tprev);  // load, masks, line start, classify, count
     // ---- scan over the tile ----
     const u32 packed = nsym | nhdr << 16;
     u32 inc = packed;
@@ -387,9 +519,10 @@ __global__ void __launch_bounds__(kParseThreads) k_parse(const __grid_constant__
     const u32 d = excl & 0xFFFFu;  // tile-relative index of the chunk's first symbol
 
     // ---- chained scan across tiles (warp 0), overlapped with the fast chunks of the others ----
+    PHASE_MARK(job, 2, tprev);  // barrier + tile scan
     if (warp == 0) {
-        Pair agg = {S_tile, R_tile};
-        Pair ex = scan_lookback(job.p_status, t, agg);
+        Pair ex = scan_lookback2(job, t, S_tile, R_tile);
+        PHASE_MARK(job, 3, tprev);  // look-back
         if (lane == 0) {
             sh.T0 = ex.a;
             sh.R0 = ex.b;
@@ -462,7 +595,9 @@ __global__ void __launch_bounds__(kParseThreads) k_parse(const __grid_constant__
             }
         }
     }
+    PHASE_MARK(job, 4, tprev);  // warp 0's fast chunks
     __syncthreads();  // T0 / R0 known
+    PHASE_MARK(job, 5, tprev);  // barrier
     const u64 T0 = sh.T0, R0 = sh.R0;
 
     // ---- slow chunks: the 32 lanes of the warp take one byte each ----
@@ -559,7 +694,9 @@ __global__ void __launch_bounds__(kParseThreads) k_parse(const __grid_constant__
         const u64 x = (S_total + kTransSub - 1) / kTransSub;
         if (x * kTransSub < S_total + 2) job.t_hint[x] = (u32)R_total;
     }
+    PHASE_MARK(job, 6, tprev);  // slow chunks, hints
     __syncthreads();  // all symbols staged
+    PHASE_MARK(job, 7, tprev);  // barrier
 
     // ---- pack two symbols per byte and write the stream words ----
     // stream word w of the tile holds the tile's symbols 8w-a .. 8w-a+7 (a = symbols of the stream's
@@ -581,6 +718,7 @@ __global__ void __launch_bounds__(kParseThreads) k_parse(const __grid_constant__
             gw[w] = lo | (hi << 4);
         }
     }
+    PHASE_MARK(job, 8, tprev);  // pack
     if (tid == 0) {
         // hand-over of the symbols that do not fill a stream word
         const bool own = rem <= S_tile;  // the pending symbols are all ours: publish before waiting
@@ -588,11 +726,11 @@ __global__ void __launch_bounds__(kParseThreads) k_parse(const __grid_constant__
         if (own && !last_tile) {
             u32 v = 0x80000000u;
             for (u32 k = 0; k < rem; k++) v |= (u32)sh.sym[S_tile - 1 - k] << (4 * k);
-            st_release32(job.p_pend + t, v);
+            st_volatile32(job.p_pend + t, v);
         }
         if (a_pend) {
             do {
-                pv = ld_acquire32(job.p_pend + (t - 1));
+                pv = ld_volatile32(job.p_pend + (t - 1));
             } while (!(pv & 0x80000000u));
         }
         // symbol i (0..7) of the tile's first stream word: pending ones first, then ours
@@ -609,7 +747,7 @@ __global__ void __launch_bounds__(kParseThreads) k_parse(const __grid_constant__
         if (!own && !last_tile) {  // fewer than 8 symbols in all: pass the predecessors' on as well
             u32 v = 0x80000000u;
             for (u32 k = 0; k < rem; k++) v |= first_word_sym(rem - 1 - k) << (4 * k);
-            st_release32(job.p_pend + t, v);
+            st_volatile32(job.p_pend + t, v);
         }
         if (last_tile) {
             // the last partial word (zero padded) and the end pads
@@ -624,6 +762,7 @@ __global__ void __launch_bounds__(kParseThreads) k_parse(const __grid_constant__
             }
         }
     }
+    PHASE_MARK(job, 9, tprev);  // pending hand-over
 }
 
 // =====================================================================================
