@@ -35,13 +35,16 @@ struct gts_ctx {
     cudaStream_t stream = nullptr;  // used by the host-buffer entry points
 
     // ---- device scratch (grows, never shrinks) ----
-    u64 cap_n = 0;  // raw bytes the scratch is sized for
+    u64 cap_n = 0;  // raw bytes the per-tile scratch is sized for
     u32 *d_sym = nullptr;
-    u32 *d_hint = nullptr;
-    uint8_t *d_zero = nullptr;  // per-pass zeroed block: scan status, tickets, totals, pending words
+    gts::TileInfo *d_tile_info = nullptr;
+    gts::TilePrefix *d_tile_pre = nullptr;
+    uint16_t *d_chunk_hint = nullptr;
+    uint8_t *d_zero = nullptr;  // per-pass zeroed block: scan status, tickets, totals
     size_t zero_cap = 0;
     u64 rec_cap = 0;
-    u64 *d_hdr_off = nullptr, *d_hdr_end = nullptr, *d_dbase = nullptr;
+    gts::HeaderEvent *d_events = nullptr;
+    u64 *d_hdr_off = nullptr, *d_dbase = nullptr, *d_loc = nullptr;
     gts::RecInfo *d_rec = nullptr;
     u32 *d_trim = nullptr;
     gts::Totals *h_totals = nullptr;  // pinned
@@ -60,7 +63,6 @@ struct gts_ctx {
     // ---- last enqueued device pass ----
     bool pending = false;
     gts::Job job;
-    u64 job_max_sym = 0;
     cudaStream_t job_stream = nullptr;
 
     // ---- per-kernel timing ----
@@ -91,29 +93,26 @@ int cuda_fail(gts_ctx *ctx, cudaError_t e, const char *what) {
 size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 struct ZeroLayout {
-    size_t p_agg, p_gagg, p_ginc, s_status, totals, counters, p_pend, bytes;
+    size_t t_status, s_status, totals, counters, bytes;
 };
-ZeroLayout zero_layout(u64 ntiles_parse, u64 rec_cap) {
+ZeroLayout zero_layout(u64 ntiles, u64 rec_cap) {
     ZeroLayout z;
+    const u64 scan_tiles = (ntiles + gts::kScanTile - 1) / gts::kScanTile;
     const u64 size_tiles = (rec_cap + gts::kSizeTile - 1) / gts::kSizeTile;
     size_t off = 0;
-    const u64 groups = (ntiles_parse + 31) / 32;
-    z.p_ginc = off;   off += groups * 2 * sizeof(u64);  // 16-byte entries first (aligned)
-    z.p_gagg = off;   off += groups * sizeof(u64);
-    z.p_agg = off;    off += ntiles_parse * sizeof(u32);
-    off = round_up(off, 16);
+    z.t_status = off; off += scan_tiles * 4 * sizeof(u64);
     z.s_status = off; off += size_tiles * 4 * sizeof(u64);
     z.totals = off;   off += sizeof(gts::Totals);
     z.counters = off; off += 16;
-    z.p_pend = off;   off += ntiles_parse * sizeof(u32);
     z.bytes = round_up(off, 16);
     return z;
 }
 
 int free_rec(gts_ctx *ctx) {
-    cudaFree(ctx->d_hdr_off); cudaFree(ctx->d_hdr_end); cudaFree(ctx->d_dbase);
+    cudaFree(ctx->d_events); cudaFree(ctx->d_hdr_off); cudaFree(ctx->d_dbase); cudaFree(ctx->d_loc);
     cudaFree(ctx->d_rec); cudaFree(ctx->d_trim);
-    ctx->d_hdr_off = ctx->d_hdr_end = ctx->d_dbase = nullptr;
+    ctx->d_events = nullptr;
+    ctx->d_hdr_off = ctx->d_dbase = ctx->d_loc = nullptr;
     ctx->d_rec = nullptr;
     ctx->d_trim = nullptr;
     ctx->rec_cap = 0;
@@ -122,27 +121,33 @@ int free_rec(gts_ctx *ctx) {
 
 int alloc_rec(gts_ctx *ctx, u64 rec_cap) {
     free_rec(ctx);
+    CU(cudaMalloc(&ctx->d_events, rec_cap * sizeof(gts::HeaderEvent)));
     CU(cudaMalloc(&ctx->d_hdr_off, rec_cap * sizeof(u64)));
-    CU(cudaMalloc(&ctx->d_hdr_end, rec_cap * sizeof(u64)));
     CU(cudaMalloc(&ctx->d_dbase, rec_cap * sizeof(u64)));
+    CU(cudaMalloc(&ctx->d_loc, rec_cap * sizeof(u64)));
     CU(cudaMalloc(&ctx->d_rec, rec_cap * sizeof(gts::RecInfo)));
     if (ctx->opt.trim) CU(cudaMalloc(&ctx->d_trim, rec_cap * 6 * sizeof(u32)));
     ctx->rec_cap = rec_cap;
     return GTS_OK;
 }
 
+u64 parse_tiles(u64 n) { return std::max<u64>(1, (n + gts::kParseTile - 1) / gts::kParseTile); }
+
 // Size the scratch for a pass over n raw bytes.
 int ensure_scratch(gts_ctx *ctx, u64 n) {
     if (n > ctx->cap_n || ctx->d_sym == nullptr) {
         const u64 cap = std::max<u64>(n + n / 8, 1u << 20);
-        const u64 tiles_t = (cap + 4 + gts::kTransTile - 1) / gts::kTransTile + 1;
-        cudaFree(ctx->d_sym); cudaFree(ctx->d_hint);
-        ctx->d_sym = nullptr; ctx->d_hint = nullptr; ctx->cap_n = 0;
-        const size_t sym_bytes = (tiles_t * gts::kTransTileWords + 64) * sizeof(u32);
+        const u64 tiles = parse_tiles(cap);
+        cudaFree(ctx->d_sym); cudaFree(ctx->d_tile_info); cudaFree(ctx->d_tile_pre); cudaFree(ctx->d_chunk_hint);
+        ctx->d_sym = nullptr; ctx->d_tile_info = nullptr; ctx->d_tile_pre = nullptr; ctx->d_chunk_hint = nullptr;
+        ctx->cap_n = 0;
+        const size_t sym_bytes = (tiles + 2) * gts::kSlotWords * sizeof(u32);
         CU(cudaMalloc(&ctx->d_sym, sym_bytes));
-        // zero once: stale words past the end of a stream must still hold valid symbols (<= 4)
+        // zero once: stale words past the end of a slot must still hold valid symbols (<= 4)
         CU(cudaMemset(ctx->d_sym, 0, sym_bytes));
-        CU(cudaMalloc(&ctx->d_hint, (tiles_t * gts::kTransWarps + 8) * sizeof(u32)));
+        CU(cudaMalloc(&ctx->d_tile_info, tiles * sizeof(gts::TileInfo)));
+        CU(cudaMalloc(&ctx->d_tile_pre, tiles * sizeof(gts::TilePrefix)));
+        CU(cudaMalloc(&ctx->d_chunk_hint, tiles * gts::kTransWarps * sizeof(uint16_t)));
         ctx->cap_n = cap;
     }
     const u64 want_rec = n / 128 + 4096;
@@ -150,8 +155,7 @@ int ensure_scratch(gts_ctx *ctx, u64 n) {
         int rc = alloc_rec(ctx, want_rec + want_rec / 8);
         if (rc) return rc;
     }
-    const u64 ntp = std::max<u64>(1, (ctx->cap_n + gts::kParseTile - 1) / gts::kParseTile);
-    const ZeroLayout z = zero_layout(ntp, ctx->rec_cap);
+    const ZeroLayout z = zero_layout(parse_tiles(ctx->cap_n), ctx->rec_cap);
     if (z.bytes > ctx->zero_cap) {
         cudaFree(ctx->d_zero);
         ctx->d_zero = nullptr; ctx->zero_cap = 0;
@@ -167,28 +171,27 @@ int enqueue_pass(gts_ctx *ctx, const uint8_t *d_in, u64 n, uint8_t *d_out, u64 c
     if (((uintptr_t)d_in & 15) != 0) return fail(ctx, GTS_ERR_ARG, "device input must be 16-byte aligned");
     int rc = ensure_scratch(ctx, n);
     if (rc) return rc;
-    const u64 ntp = std::max<u64>(1, (n + gts::kParseTile - 1) / gts::kParseTile);
-    const ZeroLayout z = zero_layout(ntp, ctx->rec_cap);
+    const u64 ntiles = parse_tiles(n);
+    const ZeroLayout z = zero_layout(ntiles, ctx->rec_cap);
     gts::Job &job = ctx->job;
     job.in = d_in; job.n = n; job.out = d_out; job.out_cap = cap;
     job.sym = ctx->d_sym;
-    job.p_agg = reinterpret_cast<u32 *>(ctx->d_zero + z.p_agg);
-    job.p_gagg = reinterpret_cast<u64 *>(ctx->d_zero + z.p_gagg);
-    job.p_ginc = reinterpret_cast<u64 *>(ctx->d_zero + z.p_ginc);
+    job.tile_info = ctx->d_tile_info;
+    job.tile_pre = ctx->d_tile_pre;
+    job.chunk_hint = ctx->d_chunk_hint;
+    job.events = ctx->d_events;
+    job.hdr_off = ctx->d_hdr_off; job.dbase = ctx->d_dbase; job.loc = ctx->d_loc;
+    job.rec = ctx->d_rec; job.trim_len = ctx->d_trim; job.rec_cap = ctx->rec_cap;
+    job.t_status = reinterpret_cast<u64 *>(ctx->d_zero + z.t_status);
     job.s_status = reinterpret_cast<u64 *>(ctx->d_zero + z.s_status);
     job.totals = reinterpret_cast<gts::Totals *>(ctx->d_zero + z.totals);
     job.counters = reinterpret_cast<u32 *>(ctx->d_zero + z.counters);
-    job.p_pend = reinterpret_cast<u32 *>(ctx->d_zero + z.p_pend);
-    job.t_hint = ctx->d_hint;
-    job.hdr_off = ctx->d_hdr_off; job.hdr_end = ctx->d_hdr_end; job.dbase = ctx->d_dbase;
-    job.rec = ctx->d_rec; job.trim_len = ctx->d_trim; job.rec_cap = ctx->rec_cap;
-    job.ntiles_parse = (u32)ntp;
+    job.dbg = ctx->d_dbg;
+    job.ntiles = (u32)ntiles;
     job.frame_mask = ctx->mask;
     job.alternative = ctx->opt.alternative ? 1 : 0;
     job.trim = ctx->opt.trim ? 1 : 0;
     job.lut = ctx->lut;
-    job.dbg = ctx->d_dbg;
-    ctx->job_max_sym = n + 4;
     ctx->job_stream = stream;
     cudaEvent_t *ev = nullptr;
     if (ctx->profiling && !sizes_only) {
@@ -202,9 +205,16 @@ int enqueue_pass(gts_ctx *ctx, const uint8_t *d_in, u64 n, uint8_t *d_out, u64 c
         CU(cudaEventRecord(ev[0], stream));
     }
     CU(cudaMemsetAsync(ctx->d_zero, 0, z.bytes, stream));
-    unsigned long long launches = 0;
-    CU(gts::launch_pass(job, ctx->job_max_sym, ctx->sm_count, stream, sizes_only, &launches, ev));
-    ctx->stats.kernel_launches += launches;
+    CU(gts::launch_parse(job, stream));
+    if (ev) CU(cudaEventRecord(ev[1], stream));
+    CU(gts::launch_sizes(job, ctx->sm_count, stream));
+    if (ev) CU(cudaEventRecord(ev[2], stream));
+    ctx->stats.kernel_launches += 4;
+    if (!sizes_only) {
+        CU(gts::launch_emit(job, ctx->sm_count, stream, ev ? ev[3] : nullptr));
+        if (ev) CU(cudaEventRecord(ev[4], stream));
+        ctx->stats.kernel_launches += 2;
+    }
     CU(cudaMemcpyAsync(ctx->h_totals, job.totals, sizeof(gts::Totals), cudaMemcpyDeviceToHost, stream));
     ctx->pending = true;
     ctx->stats.passes++;
@@ -281,9 +291,8 @@ int translate_host(gts_ctx *ctx, const uint8_t *in, size_t n, size_t *out_n) {
     // clear the "output too small" flag left by the sizing pass
     ctx->h_totals->flags &= ~gts::kFlagOutOverflow;
     CU(cudaMemcpyAsync(ctx->job.totals, ctx->h_totals, sizeof(gts::Totals), cudaMemcpyHostToDevice, ctx->stream));
-    unsigned long long launches = 0;
-    CU(gts::launch_emit(ctx->job, ctx->job_max_sym, ctx->sm_count, ctx->stream, &launches));
-    ctx->stats.kernel_launches += launches;
+    CU(gts::launch_emit(ctx->job, ctx->sm_count, ctx->stream, nullptr));
+    ctx->stats.kernel_launches += 2;
     if (total) CU(cudaMemcpyAsync(ctx->h_out, ctx->d_out, total, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->stats.d2h_bytes += total;
     CU(cudaStreamSynchronize(ctx->stream));
@@ -392,7 +401,8 @@ void gts_destroy(gts_ctx *ctx) {
         std::fprintf(stderr, "\n");
         cudaFree(ctx->d_dbg);
     }
-    cudaFree(ctx->d_sym); cudaFree(ctx->d_hint); cudaFree(ctx->d_zero);
+    cudaFree(ctx->d_sym); cudaFree(ctx->d_tile_info); cudaFree(ctx->d_tile_pre); cudaFree(ctx->d_chunk_hint);
+    cudaFree(ctx->d_zero);
     free_rec(ctx);
     cudaFree(ctx->d_in); cudaFree(ctx->d_out);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);

@@ -1,0 +1,165 @@
+// gts_common.cuh -- device helpers shared by the kernels (memory-model loads/stores, byte SIMD,
+// chained scan, frame arithmetic).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "gts_device.h"
+
+namespace gts {
+
+// ---- flagged status words of the chained scans ----
+__device__ __forceinline__ u64 ld_acquire(const u64 *p) {
+    u64 v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ u64 ld_relaxed(const u64 *p) {
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(u64 *p, u64 v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_release(u64 *p, u64 v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// PTX prmt in its default mode: selector nibble bit 3 replicates the chosen byte's sign bit
+// (__byte_perm masks that bit away, and costs an extra AND for run-time selectors)
+__device__ __forceinline__ u32 prmt(u32 a, u32 b, u32 sel) {
+    u32 r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+
+#ifdef GTS_PHASE_TIMING
+__device__ __forceinline__ u64 gtime() {
+    u64 t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define PHASE_MARK(job, idx, t_prev)                                                     \
+    do {                                                                                 \
+        if ((job).dbg && threadIdx.x == 0) {                                             \
+            const u64 now_ = gtime();                                                    \
+            atomicAdd((job).dbg + (idx), now_ - (t_prev));                               \
+            (t_prev) = now_;                                                             \
+        }                                                                                \
+    } while (0)
+#else
+#define PHASE_MARK(job, idx, t_prev) do { } while (0)
+#endif
+
+// the four 0x80 flags of m as bits 0..3
+__device__ __forceinline__ u32 gather4(u32 m) { return (((m >> 7) * 0x00204081u) >> 21) & 0xFu; }
+
+// 0x80 in every byte of x that is '\n'
+__device__ __forceinline__ u32 newline_flags(u32 x) {
+    return __vabsdiffu4(__vabsdiffu4(x, 0x0A0A0A0Au), 0x80808080u) & 0x80808080u;
+}
+__device__ __forceinline__ u32 newline_mask16(uint4 v) {
+    return gather4(newline_flags(v.x)) | gather4(newline_flags(v.y)) << 4 | gather4(newline_flags(v.z)) << 8 |
+           gather4(newline_flags(v.w)) << 12;
+}
+
+struct Pair {
+    u64 a, b;
+};
+
+// Decoupled look-back over the tiles of a chained scan (sum of two counters).  Called by all 32
+// lanes of one warp of tile t with that tile's aggregate; publishes it, walks back over the
+// predecessors' published aggregates / inclusive prefixes, publishes this tile's inclusive
+// prefix and returns the exclusive one.  Tiles are numbered by an atomic ticket, so every
+// predecessor is running or finished and the wait terminates.
+__device__ __forceinline__ Pair scan_lookback(u64 *status, u32 t, Pair agg) {
+    const int lane = threadIdx.x & 31;
+    u64 *mine = status + 4ull * t;
+    if (lane == 0) {
+        st_relaxed(mine + 1, agg.b);
+        st_release(mine + 0, agg.a | kValid);
+    }
+    Pair excl = {0, 0};
+    i64 pos = (i64)t - 1;
+    while (pos >= 0) {
+        const i64 idx = pos - lane;
+        int kind = 2;  // 0 = not published, 1 = aggregate, 2 = inclusive (or before tile 0)
+        u64 a = 0, b = 0;
+        if (idx >= 0) {
+            const u64 *st = status + 4ull * (u64)idx;
+            u64 w = ld_acquire(st + 2);
+            if (w & kValid) {
+                a = w & ~kValid;
+                b = ld_relaxed(st + 3);
+            } else {
+                w = ld_acquire(st + 0);
+                if (w & kValid) {
+                    kind = 1;
+                    a = w & ~kValid;
+                    b = ld_relaxed(st + 1);
+                } else {
+                    kind = 0;
+                }
+            }
+        }
+        const unsigned inc_m = __ballot_sync(0xFFFFFFFFu, kind == 2);
+        const unsigned none_m = __ballot_sync(0xFFFFFFFFu, kind == 0);
+        const int first_inc = inc_m ? __ffs(inc_m) - 1 : 32;
+        const int first_none = none_m ? __ffs(none_m) - 1 : 32;
+        if (first_none < first_inc) continue;  // a needed predecessor has not published yet
+        const int last = first_inc < 31 ? first_inc : 31;
+        if (lane > last) a = b = 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(0xFFFFFFFFu, a, o);
+            b += __shfl_xor_sync(0xFFFFFFFFu, b, o);
+        }
+        excl.a += a;
+        excl.b += b;
+        if (first_inc < 32) break;
+        pos -= 32;
+    }
+    if (lane == 0) {
+        st_relaxed(mine + 3, excl.b + agg.b);
+        st_release(mine + 2, (excl.a + agg.a) | kValid);
+    }
+    return excl;
+}
+
+// exact unsigned division by constants without the 64-bit division routine
+__device__ __forceinline__ u64 udiv3(u64 a) { return __umul64hi(a, 0xAAAAAAAAAAAAAAABull) >> 1; }
+__device__ __forceinline__ u64 udiv60(u64 a) { return __umul64hi(a >> 2, 0x8888888888888889ull) >> 3; }
+__device__ __forceinline__ i64 floordiv3(i64 a) { return a >= 0 ? (i64)udiv3((u64)a) : -(i64)udiv3((u64)(-a) + 2); }
+__device__ __forceinline__ i64 ceildiv3(i64 a) { return -floordiv3(-a); }
+
+// rc start position of reverse frame i (0..2): writer.go:64-79
+__device__ __forceinline__ int reverse_start(u64 n, int i, bool alternative) {
+    if (alternative) return i;
+    int r = (int)(n - 3 * udiv3(n)) - i;
+    return r < 0 ? r + 3 : r;
+}
+
+// residues of each frame before trimming: writer.go:97-112 (Go's % truncates, so a start
+// position beyond the sequence emits nothing)
+__device__ __forceinline__ void frame_lengths(u64 n, bool alternative, u64 L[6]) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) L[k] = n >= (u64)k ? udiv3(n - k + 2) : 0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const u64 p = (u64)reverse_start(n, i, alternative);
+        L[3 + i] = n >= p ? udiv3(n - p + 2) : 0;
+    }
+}
+
+__device__ __forceinline__ u64 run_size(u64 H, u64 Lp) { return H + 3 + Lp + udiv60(Lp + 59); }
+
+__device__ __forceinline__ bool record_emitted(u64 s, u64 n, u64 R) { return s >= 1 || n > 0 || R == 0; }
+
+// symbol i of a tile's slot
+__device__ __forceinline__ u32 slot_symbol(const u32 *sym, u32 tile, u32 i) {
+    const u32 w = sym[(u64)tile * kSlotWords + (i >> 3)];
+    const u32 b = i & 7u;
+    return (w >> (8 * (b & 3) + 4 * (b >> 2))) & 0xFu;
+}
+
+}  // namespace gts

@@ -1,13 +1,15 @@
-// gts_device.h -- data layout in HBM shared by the host API (gts_api.cu) and the kernels
-// (gts_kernels.cu).  See DESIGN.md "Data layout" for the narrative.
+// gts_device.h -- data layout in HBM shared by the host API (gts_api.cu) and the kernels.
+// See DESIGN.md "Data layout" for the narrative.
 //
-// One device pass turns a FASTA buffer into protein FASTA with four kernels:
+// One device pass turns a FASTA buffer into protein FASTA with six kernels:
 //
-//   k_parse      raw bytes -> dense 4-bit symbol stream + record table      (transeq.go:183-216,
+//   k_parse      raw bytes -> per-tile 4-bit symbol slots + header events   (transeq.go:183-216,
 //                                                                            encodedSequence.go:17-43)
+//   k_tile_scan  per-tile symbol / header counts -> stream offsets of the tiles
+//   k_records    header events + tile offsets -> record table (header offset, stream base)
 //   k_size       record table -> frame lengths (trim), output offsets       (writer.go:85-116,159-169)
-//   k_translate  symbol stream -> residues of all requested frames, laid
-//                out as 60-column lines at their final output offsets       (writer.go:57-157,
+//   k_translate  symbols -> residues of all requested frames, laid out as
+//                60-column lines at their final output offsets              (writer.go:57-157,
 //                                                                            encodedSequence.go:71-97)
 //   k_headers    record table + raw header bytes -> ">id_N rest" lines      (writer.go:120-131)
 //
@@ -15,8 +17,13 @@
 // (transeq.go:14-21).  Two 0 symbols ("pads") are inserted in front of every record and two
 // more follow the last one, so that EVERY residue of EVERY frame is the table entry of three
 // consecutive symbols (e-2, e-1, e): the pads play the role of the reference's tail rules
-// (two-letter codon / 'X', writer.go:102-112) on both strands.  Word w of the stream holds
-// symbols 8w..8w+7; byte i of the word = symbol 8w+i | symbol 8w+i+4 << 4.
+// (two-letter codon / 'X', writer.go:102-112) on both strands.
+//
+// The stream is stored as one fixed-size slot per parse tile (kParseTile raw bytes): tile t's
+// symbols are compacted inside its slot only, so k_parse has no dependency between tiles; the
+// stream index of a symbol is T0[t] + its index in the slot, with T0 the exclusive scan of the
+// tiles' symbol counts (k_tile_scan).  Word w of a slot holds its symbols 8w..8w+7; byte i of the
+// word = symbol 8w+i | symbol 8w+i+4 << 4.
 #pragma once
 #include <cstdint>
 
@@ -30,26 +37,29 @@ typedef unsigned int u32;
 constexpr int kParseThreads = 256;
 constexpr int kParseBytesPerThread = 32;
 constexpr int kParseTile = kParseThreads * kParseBytesPerThread;  // 8192 raw bytes
+constexpr int kSlotSyms = kParseTile + 64;  // symbols a slot can hold: the tile's bytes + 2 leading + 2 end pads
+constexpr int kSlotWords = kSlotSyms / 8;   // 1032 stream words per slot
 
-// ---- k_translate geometry: one warp per sub-tile of symbols, kTransWarps sub-tiles per CTA ----
+// ---- k_translate geometry: one CTA per parse tile, one warp per chunk of its symbols ----
 constexpr int kTransSymPerThread = 48;
-constexpr int kTransSub = 32 * kTransSymPerThread;        // 1536 symbols per warp
+constexpr int kTransSub = 32 * kTransSymPerThread;        // 1536 symbols per warp ("chunk")
 constexpr int kTransSubWords = kTransSub / 8;             // 192 stream words
-constexpr int kTransWarps = 8;                            // translating warps per CTA (+ 1 builder warp)
-constexpr int kTransTile = kTransWarps * kTransSub;       // 12288 symbols per CTA
-constexpr int kTransTileWords = kTransTile / 8;
-constexpr int kTransBlock = (kTransWarps + 1) * 32;
+constexpr int kTransWarps = (kSlotSyms + kTransSub - 1) / kTransSub;  // 6 chunks cover a slot
+constexpr int kTransBlock = (kTransWarps + 1) * 32;       // + 1 builder warp
 constexpr int kPhaseLen = kTransSub / 3;                  // residues per phase array (per warp)
 constexpr int kPhaseGuard = 16;
 constexpr int kPhaseStride = kPhaseLen + 2 * kPhaseGuard; // bytes per phase array in smem
-constexpr int kRecBatch = 4;                              // record pieces per sub-tile and format batch
+constexpr int kRecBatch = 4;                              // record pieces per chunk and format batch
 constexpr int kRunsPerBatch = kRecBatch * 6;
-// Output image of one sub-tile batch in shared memory: the residue lines a sub-tile writes (at most
+// Output image of one chunk batch in shared memory: the residue lines a chunk writes (at most
 // 2 * kTransSub * 61 / 60 bytes + one final newline per run) plus up to 34 bytes of 16-byte
 // alignment padding per run.
 constexpr int kImageBytes = (2 * kTransSub * 61 / 60 + kRunsPerBatch * 35 + 128 + 15) / 16 * 16;
 
-// ---- k_size geometry ----
+// ---- k_tile_scan / k_size geometry ----
+constexpr int kScanThreads = 256;
+constexpr int kScanPerThread = 8;
+constexpr int kScanTile = kScanThreads * kScanPerThread;  // parse tiles per scan tile
 constexpr int kSizeThreads = 256;
 constexpr int kSizePerThread = 4;
 constexpr int kSizeTile = kSizeThreads * kSizePerThread;  // record slots per scan tile
@@ -71,6 +81,26 @@ struct Totals {  // device-resident result block, copied to pinned host memory a
 constexpr u64 kFlagRecOverflow = 1;  // record table too small (n_headers is still exact)
 constexpr u64 kFlagOutOverflow = 2;  // output buffer too small (out_total is still exact)
 
+struct TileInfo {  // 8 bytes per parse tile, written by k_parse
+    uint16_t nsym;  // symbols in the tile's slot (pads included)
+    uint16_t nhdr;  // header lines starting in the tile
+    uint8_t tail;   // its last two symbols: last | second-to-last << 4
+    uint8_t pad[3];
+};
+
+struct TilePrefix {  // 16 bytes per parse tile, written by k_tile_scan
+    u64 T0;     // stream index of the slot's first symbol
+    u32 R0;     // header lines before the tile == record slot open at its first byte
+    u32 carry;  // the two symbols before the tile: last | second-to-last << 4
+};
+
+struct HeaderEvent {  // 16 bytes per header line, appended by k_parse in no particular order
+    u64 hdr_off;   // raw offset of the '>'
+    u32 tile;
+    uint16_t k;    // index of the header line among those starting in its tile
+    uint16_t pos;  // slot index of the record's first nucleotide (its pads sit at pos-2, pos-1)
+};
+
 struct RecInfo {  // 32 bytes per record slot, written by k_size, read by k_translate / k_headers
     u64 out_off;  // offset of the record's first output byte
     u64 dbase;    // stream index of the record's first nucleotide
@@ -89,29 +119,28 @@ struct Job {  // kernel argument block (by value)
     uint8_t *out;
     u64 out_cap;
 
-    u32 *sym;  // packed symbol stream
+    u32 *sym;              // [ntiles * kSlotWords] symbol slots
+    TileInfo *tile_info;   // [ntiles]
+    TilePrefix *tile_pre;  // [ntiles]
+    uint16_t *chunk_hint;  // [ntiles * kTransWarps] header lines of the tile whose record starts at
+                           // or before the chunk's first symbol
+    HeaderEvent *events;   // [rec_cap]
 
-    // two-level chained scan of (symbols, header lines) over the parse tiles, groups of 32 tiles
-    u32 *p_agg;     // [ntiles_parse] bit 31 valid | header lines << 14 | symbols      (one tile)
-    u64 *p_gagg;    // [groups] bit 63 valid | header lines << 32 | symbols            (one group)
-    u64 *p_ginc;    // [groups * 2] {bit 63 valid | symbols, header lines} of groups 0..g
-    u32 *p_pend;    // [ntiles_parse] symbols of the last incomplete stream word, bit 31 = valid
-    u32 *t_hint;    // [translate sub-tiles] the record slot owning the sub-tile's first symbol
-
-    // record table, structure of arrays, slots 0..R (+1 sentinel in dbase / out_off)
+    // record table, slots 0..R (+1 sentinel)
     u64 *hdr_off;   // raw offset of the header line's '>'
-    u64 *hdr_end;   // raw offset one past the header line's last byte (CR dropped)
     u64 *dbase;     // stream index of the record's first nucleotide (its pads sit at -2, -1)
+    u64 *loc;       // tile << 16 | slot index of the record's first nucleotide
     RecInfo *rec;   // per record summary (+1 sentinel: dbase = end of stream, out_off = total)
     u32 *trim_len;  // [slot*6 + frame] residues kept after --trim (only with trim)
     u64 rec_cap;    // entries in each of the arrays above
 
+    u64 *t_status;  // [tile-scan tiles * 4] chained scan of the parse tiles' counts
     u64 *s_status;  // [size tiles * 4] chained scan of output sizes
-    u32 *counters;  // [0] parse tile ticket, [1] size tile ticket
+    u32 *counters;  // [0] tile-scan ticket, [1] size ticket, [2] header events appended
     Totals *totals;
     u64 *dbg;       // optional phase timing sums (GTS_PHASE_TIMING builds), else nullptr
 
-    u32 ntiles_parse;
+    u32 ntiles;      // parse tiles
     u32 frame_mask;  // bit k = frame index k requested (0..2 forward, 3..5 reverse)
     u32 alternative;
     u32 trim;

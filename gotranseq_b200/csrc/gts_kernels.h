@@ -1,4 +1,5 @@
-// gts_kernels.h -- host-callable launchers of the kernels in gts_kernels.cu.
+// gts_kernels.h -- host-callable launchers of the kernels (gts_parse.cu, gts_size.cu,
+// gts_translate.cu).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -9,14 +10,9 @@ namespace gts {
 // Per-device one-time kernel attribute setup (dynamic shared memory of k_translate).
 cudaError_t init_kernels();
 
-// k_parse + k_size, and unless sizes_only also k_translate + k_headers, on `stream`.
-// max_symbols bounds the symbol stream (job.n + 4); *launches is advanced by the kernels started.
-// ev, when not null, points to 5 events recorded before the first and after each kernel.
-cudaError_t launch_pass(const Job &job, u64 max_symbols, int sm_count, cudaStream_t stream,
-                        bool sizes_only, unsigned long long *launches, cudaEvent_t *ev = nullptr);
-
-// k_translate + k_headers only (after a sizes_only pass, once the output buffer is known).
-cudaError_t launch_emit(const Job &job, u64 max_symbols, int sm_count, cudaStream_t stream,
-                        unsigned long long *launches);
+cudaError_t launch_parse(const Job &job, cudaStream_t stream);                // k_parse
+cudaError_t launch_sizes(const Job &job, int sm_count, cudaStream_t stream);  // k_tile_scan, k_records, k_size
+// k_translate, k_headers; ev_mid (optional) is recorded between the two
+cudaError_t launch_emit(const Job &job, int sm_count, cudaStream_t stream, cudaEvent_t ev_mid);
 
 }  // namespace gts

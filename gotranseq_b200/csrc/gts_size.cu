@@ -1,0 +1,337 @@
+// gts_size.cu -- k_tile_scan, k_records, k_size: from the per-tile results of k_parse to the record
+// table with output offsets.
+//
+// Reference behaviour reproduced (feliixx/gotranseq):
+//   frame lengths / tail rules   transeq/writer.go:85-116 (Go's % truncates)
+//   trim                         transeq/writer.go:141-147,159-169
+//   header line = bytes up to the line's '\n', one trailing '\r' dropped (bufio.ScanLines)
+#include "gts_common.cuh"
+#include "gts_kernels.h"
+
+namespace gts {
+
+// =====================================================================================
+// k_tile_scan: exclusive scan of the parse tiles' symbol / header counts
+// =====================================================================================
+__global__ void __launch_bounds__(kScanThreads) k_tile_scan(const __grid_constant__ Job job) {
+    __shared__ u64 warp_s[kScanThreads / 32];
+    __shared__ u64 warp_r[kScanThreads / 32];
+    __shared__ u64 s_excl_s, s_excl_r;
+    __shared__ u32 s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 ntiles = job.ntiles;
+    const u32 nscan = (ntiles + kScanTile - 1) / kScanTile;
+    while (true) {
+        __syncthreads();
+        if (tid == 0) s_tile = atomicAdd(&job.counters[0], 1u);
+        __syncthreads();
+        const u32 st = s_tile;
+        if (st >= nscan) return;
+        const u32 t0 = st * kScanTile + tid * kScanPerThread;
+        u32 ns[kScanPerThread], nh[kScanPerThread];
+        u64 sum_s = 0, sum_r = 0;
+#pragma unroll
+        for (int i = 0; i < kScanPerThread; i++) {
+            ns[i] = nh[i] = 0;
+            if (t0 + i < ntiles) {
+                const TileInfo ti = job.tile_info[t0 + i];
+                ns[i] = ti.nsym;
+                nh[i] = ti.nhdr;
+            }
+            sum_s += ns[i];
+            sum_r += nh[i];
+        }
+        u64 inc_s = sum_s, inc_r = sum_r;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u64 ys = __shfl_up_sync(0xFFFFFFFFu, inc_s, o);
+            const u64 yr = __shfl_up_sync(0xFFFFFFFFu, inc_r, o);
+            if (lane >= o) { inc_s += ys; inc_r += yr; }
+        }
+        if (lane == 31) { warp_s[warp] = inc_s; warp_r[warp] = inc_r; }
+        __syncthreads();
+        u64 ex_s = inc_s - sum_s, ex_r = inc_r - sum_r, tot_s = 0, tot_r = 0;
+        for (int w = 0; w < kScanThreads / 32; w++) {
+            if (w < warp) { ex_s += warp_s[w]; ex_r += warp_r[w]; }
+            tot_s += warp_s[w];
+            tot_r += warp_r[w];
+        }
+        if (warp == 0) {
+            Pair agg = {tot_s, tot_r};
+            Pair ex = scan_lookback(job.t_status, st, agg);
+            if (lane == 0) {
+                s_excl_s = ex.a;
+                s_excl_r = ex.b;
+                if (st + 1 == nscan) {
+                    // totals; the last tile's two end pads are not counted as stream symbols
+                    const u64 S2 = ex.a + tot_s, R = ex.b + tot_r;
+                    job.totals->total_sym = S2 - 2;
+                    job.totals->n_headers = R;
+                    if (R + 2 <= job.rec_cap) {
+                        // slot 0 (bytes before the first header line) and the sentinel after the last record
+                        job.hdr_off[0] = 0;
+                        job.dbase[0] = 2;
+                        job.loc[0] = 2;
+                        job.dbase[R + 1] = S2;
+                        job.loc[R + 1] = (u64)(ntiles - 1) << 16 | job.tile_info[ntiles - 1].nsym;
+                    } else {
+                        atomicOr(&job.totals->flags, kFlagRecOverflow);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        u64 T = s_excl_s + ex_s, Rr = s_excl_r + ex_r;
+#pragma unroll
+        for (int i = 0; i < kScanPerThread; i++) {
+            const u32 t = t0 + i;
+            if (t < ntiles) {
+                // the two symbols before the tile (windows reach back two symbols)
+                u32 got = 0, carry = 0;
+                for (i64 u = (i64)t - 1; got < 2 && u >= 0; u--) {
+                    const TileInfo ti = job.tile_info[u];
+                    if (ti.nsym >= 1) {
+                        carry |= (u32)(ti.tail & 0xFu) << (4 * got);
+                        got++;
+                        if (got < 2 && ti.nsym >= 2) {
+                            carry |= (u32)(ti.tail >> 4) << (4 * got);
+                            got++;
+                        }
+                    }
+                }
+                TilePrefix tp;
+                tp.T0 = T;
+                tp.R0 = (u32)Rr;
+                tp.carry = carry;
+                job.tile_pre[t] = tp;
+            }
+            T += ns[i];
+            Rr += nh[i];
+        }
+    }
+}
+
+// =====================================================================================
+// k_records: header events -> record table
+// =====================================================================================
+__global__ void __launch_bounds__(256) k_records(const __grid_constant__ Job job) {
+    const u64 R = job.totals->n_headers;
+    if (R + 2 > job.rec_cap) return;  // overflow: the host retries with a larger table
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < R; e += stride) {
+        const HeaderEvent ev = job.events[e];
+        const TilePrefix tp = job.tile_pre[ev.tile];
+        const u64 slot = (u64)tp.R0 + ev.k + 1;
+        job.hdr_off[slot] = ev.hdr_off;
+        job.dbase[slot] = tp.T0 + ev.pos;
+        job.loc[slot] = (u64)ev.tile << 16 | ev.pos;
+    }
+}
+
+// =====================================================================================
+// k_size
+// =====================================================================================
+struct Cursor {  // a position in the symbol stream: (tile, index in its slot)
+    u32 tile;
+    int pos;
+};
+__device__ __forceinline__ void cursor_move(const Job &job, Cursor &c, int delta) {
+    c.pos += delta;
+    while (c.pos < 0) {
+        c.tile--;
+        c.pos += job.tile_info[c.tile].nsym;
+    }
+    while (true) {
+        const int n = job.tile_info[c.tile].nsym;
+        if (c.pos < n) break;
+        c.pos -= n;
+        c.tile++;
+    }
+}
+// table index of the window starting at the cursor; the cursor ends on the window's last symbol
+__device__ __forceinline__ u32 cursor_window(const Job &job, Cursor &c) {
+    const u32 s0 = slot_symbol(job.sym, c.tile, (u32)c.pos);
+    cursor_move(job, c, 1);
+    const u32 s1 = slot_symbol(job.sym, c.tile, (u32)c.pos);
+    cursor_move(job, c, 1);
+    const u32 s2 = slot_symbol(job.sym, c.tile, (u32)c.pos);
+    return s0 + 5 * s1 + 25 * s2;
+}
+
+// Residues kept by --trim (writer.go:141-147,159-163): walk each requested frame backwards from
+// its last residue until one is neither 'X' nor '*'.
+__device__ void trimmed_lengths(const Job &job, const uint16_t *lut, u64 s, u64 n, u64 L[6]) {
+    for (int f = 0; f < 6; f++) {
+        if (!((job.frame_mask >> f) & 1u)) continue;
+        u64 j = L[f];
+        if (j == 0) continue;
+        Cursor c;
+        if (f < 3) {
+            // forward: residue j-1 is the window starting at nucleotide f + 3(j-1); start from the
+            // record's end (two symbols before the next record's first nucleotide)
+            const u64 l = job.loc[s + 1];
+            c.tile = (u32)(l >> 16);
+            c.pos = (int)(l & 0xFFFFu);
+            const i64 q = (i64)f + 3 * (i64)(j - 1);
+            cursor_move(job, c, (int)(q - (i64)n - 2));
+            while (true) {
+                const u32 idx = cursor_window(job, c);
+                const u32 aa = lut[idx < 125 ? idx : 0] & 0xFFu;
+                if (aa != 'X' && aa != '*') break;
+                if (--j == 0) break;
+                cursor_move(job, c, -5);
+            }
+        } else {
+            // reverse: residue j-1 is the window starting at nucleotide n-3-p-3(j-1), i.e. near the
+            // record's start for the last residues; walk forwards from there
+            const u64 l = job.loc[s];
+            c.tile = (u32)(l >> 16);
+            c.pos = (int)(l & 0xFFFFu);
+            const i64 p = reverse_start(n, f - 3, job.alternative != 0);
+            const i64 q = (i64)n - 3 - p - 3 * (i64)(j - 1);
+            cursor_move(job, c, (int)q);
+            while (true) {
+                const u32 idx = cursor_window(job, c);
+                const u32 aa = lut[idx < 125 ? idx : 0] >> 8;
+                if (aa != 'X' && aa != '*') break;
+                if (--j == 0) break;
+                cursor_move(job, c, 1);
+            }
+        }
+        L[f] = j;
+    }
+}
+
+__global__ void __launch_bounds__(kSizeThreads) k_size(const __grid_constant__ Job job) {
+    __shared__ uint16_t lut[128];
+    __shared__ u64 warp_sum[kSizeThreads / 32];
+    __shared__ u64 warp_nt[kSizeThreads / 32];
+    __shared__ u32 warp_rec[kSizeThreads / 32];
+    __shared__ u64 s_excl;
+    __shared__ u32 s_tile;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 128) lut[tid] = job.lut.v[tid];
+    const u64 R = job.totals->n_headers;
+    if (R + 2 > job.rec_cap) return;  // record table overflow: the host retries with a larger one
+    const u64 nslots = R + 1;
+    const u64 ntiles = (nslots + kSizeTile - 1) / kSizeTile;
+    while (true) {
+        __syncthreads();
+        if (tid == 0) s_tile = atomicAdd(&job.counters[1], 1u);
+        __syncthreads();
+        const u64 t = s_tile;
+        if (t >= ntiles) return;
+        u64 size[kSizePerThread];
+        RecInfo ri[kSizePerThread];
+        u64 sum = 0, nt = 0;
+        u32 nrec = 0;
+#pragma unroll
+        for (int i = 0; i < kSizePerThread; i++) {
+            const u64 s = t * kSizeTile + (u64)tid * kSizePerThread + i;
+            size[i] = 0;
+            if (s < nslots) {
+                const u64 D = job.dbase[s];
+                const u64 n = job.dbase[s + 1] - 2 - D;
+                u64 L[6];
+                frame_lengths(n, job.alternative != 0, L);
+                if (job.trim) {
+                    trimmed_lengths(job, lut, s, n, L);
+#pragma unroll
+                    for (int f = 0; f < 6; f++) job.trim_len[s * 6 + f] = (u32)L[f];
+                }
+                // header line: up to its '\n' (or the end of the input), one trailing CR dropped
+                u64 H = 0;
+                if (s >= 1) {
+                    const u64 off = job.hdr_off[s];
+                    u64 p = off;
+                    while (p < job.n && job.in[p] != '\n') p++;
+                    H = p - off;
+                    if (job.in[p - 1] == '\r') H--;  // p > off: the line holds at least the '>'
+                }
+                const bool em = record_emitted(s, n, R);
+                if (em) {
+#pragma unroll
+                    for (int f = 0; f < 6; f++)
+                        if ((job.frame_mask >> f) & 1u) size[i] += run_size(H, L[f]);
+                    nt += n;
+                    nrec++;
+                }
+                ri[i].dbase = D;
+                ri[i].n = n;
+                ri[i].H = (u32)H;
+                ri[i].emitted = em ? 1u : 0u;
+            }
+            sum += size[i];
+        }
+        // block scan of the per-thread sums
+        u64 inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u64 y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+            if (lane >= o) inc += y;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            nt += __shfl_xor_sync(0xFFFFFFFFu, nt, o);
+            nrec += __shfl_xor_sync(0xFFFFFFFFu, nrec, o);
+        }
+        if (lane == 31) warp_sum[warp] = inc;
+        if (lane == 0) {
+            warp_nt[warp] = nt;
+            warp_rec[warp] = nrec;
+        }
+        __syncthreads();
+        u64 excl = inc - sum, tile_total = 0, tile_nt = 0;
+        u32 tile_rec = 0;
+        for (int w = 0; w < kSizeThreads / 32; w++) {
+            if (w < warp) excl += warp_sum[w];
+            tile_total += warp_sum[w];
+            tile_nt += warp_nt[w];
+            tile_rec += warp_rec[w];
+        }
+        if (warp == 0) {
+            Pair agg = {tile_total, tile_nt};
+            Pair ex = scan_lookback(job.s_status, (u32)t, agg);
+            if (lane == 0) {
+                s_excl = ex.a;
+                atomicAdd(&job.totals->records, (u64)tile_rec);
+                if (t + 1 == ntiles) {
+                    const u64 total = ex.a + tile_total;
+                    job.totals->out_total = total;
+                    job.totals->nucleotides = ex.b + tile_nt;
+                    RecInfo end;  // sentinel
+                    end.out_off = total;
+                    end.dbase = job.dbase[nslots];
+                    end.n = 0; end.H = 0; end.emitted = 0;
+                    job.rec[nslots] = end;
+                    if (total > job.out_cap) atomicOr(&job.totals->flags, kFlagOutOverflow);
+                }
+            }
+        }
+        __syncthreads();
+        u64 off = s_excl + excl;
+#pragma unroll
+        for (int i = 0; i < kSizePerThread; i++) {
+            const u64 s = t * kSizeTile + (u64)tid * kSizePerThread + i;
+            if (s < nslots) {
+                ri[i].out_off = off;
+                job.rec[s] = ri[i];
+            }
+            off += size[i];
+        }
+    }
+}
+
+cudaError_t launch_sizes(const Job &job, int sm_count, cudaStream_t stream) {
+    const u32 nscan = (job.ntiles + kScanTile - 1) / kScanTile;
+    k_tile_scan<<<nscan < (u32)sm_count ? nscan : (u32)sm_count, kScanThreads, 0, stream>>>(job);
+    const u64 rec_blocks = (job.rec_cap + 255) / 256;
+    k_records<<<(u32)(rec_blocks < (u64)sm_count * 8 ? rec_blocks : (u64)sm_count * 8), 256, 0, stream>>>(job);
+    const u64 size_tiles = (job.rec_cap + kSizeTile - 1) / kSizeTile;
+    u32 size_grid = (u32)(size_tiles < (u64)sm_count * 4 ? size_tiles : (u64)sm_count * 4);
+    if (size_grid == 0) size_grid = 1;
+    k_size<<<size_grid, kSizeThreads, 0, stream>>>(job);
+    return cudaGetLastError();
+}
+
+}  // namespace gts
