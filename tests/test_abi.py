@@ -1,0 +1,95 @@
+"""The C-ABI shared library loads without a GPU and exports every symbol include/gotranseq_b200.h
+declares; option decoding (no device needed) matches the reference's tables."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    with open(os.path.join(ROOT, "include", "gotranseq_b200.h")) as f:
+        src = f.read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(gts_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_the_whole_header():
+    from gotranseq_b200 import _lib
+    L = _lib.lib()
+    names = declared_symbols()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in gotranseq_b200.h but not exported"
+    assert set(names) == set(_lib.EXPORTS), "ctypes binding and header disagree"
+
+
+def test_frame_masks_match_compute_frames():
+    # transeq.go:88-110
+    from gotranseq_b200 import _lib
+    L = _lib.lib()
+    want = {"1": 1, "2": 2, "3": 4, "F": 7, "-1": 8, "-2": 16, "-3": 32, "R": 56, "6": 63}
+    for name, m in want.items():
+        mask = ctypes.c_uint32()
+        rev = ctypes.c_int()
+        assert L.gts_frame_mask(name.encode(), ctypes.byref(mask), ctypes.byref(rev)) == 0
+        assert mask.value == m and rev.value == int(m >= 8)
+    for bad in ("", "7", "f", "-4", "66"):
+        assert L.gts_frame_mask(bad.encode(), None, None) == _lib.GTS_ERR_FRAME
+
+
+def test_codon_tables_match_the_oracle():
+    # ncbicode/code.go:367-388 (oracle: independent transcription as standard + diffs)
+    from gotranseq_b200 import _lib
+    L = _lib.lib()
+    from fasta_gen import ALL_TABLES
+    for t in ALL_TABLES:
+        buf = ctypes.create_string_buffer(64)
+        assert L.gts_codon_table(t, buf) == 0
+        assert buf.raw.decode() == oracle.table_code(t), t
+    assert L.gts_codon_table(1, ctypes.create_string_buffer(64)) == _lib.GTS_ERR_TABLE
+    assert L.gts_codon_table(31, ctypes.create_string_buffer(64)) == _lib.GTS_ERR_TABLE
+
+
+def test_fused_lut_matches_the_reference_code_array():
+    # transeq.go:30-86: codes[n1 | n2<<8 | n3<<16]; reverse strand = complement, reversed (encodedSequence.go:71-97)
+    from gotranseq_b200 import _lib
+    L = _lib.lib()
+    comp = lambda c: 0 if c == 0 else ((c - 1) ^ 2) + 1
+    for t in (0, 2, 11, 23, 30):
+        for clean in (0, 1):
+            ca = oracle.code_array(t, bool(clean))
+            lut = (ctypes.c_uint16 * 125)()
+            assert L.gts_fused_lut(t, clean, lut) == 0
+            for c0 in range(5):
+                for c1 in range(5):
+                    for c2 in range(5):
+                        v = lut[c0 + 5 * c1 + 25 * c2]
+                        assert (v & 0xFF) == ca[c0 | c1 << 8 | c2 << 16]
+                        assert (v >> 8) == ca[comp(c2) | comp(c1) << 8 | comp(c0) << 16]
+
+
+def test_reference_tables_if_checkout_present():
+    """Re-derive the effective codon maps from the reference's own source when it is mounted."""
+    path = "/root/reference/ncbicode/code.go"
+    if not os.path.exists(path):
+        pytest.skip("reference checkout not present")
+    src = open(path).read()
+    std = dict(re.findall(r'"([ACGT]{3})":\s*\'(.)\'', src[src.index("standard = map"):src.index("}", src.index("standard = map"))]))
+    assert len(std) == 64
+    order = "TCAG"
+    aa = "".join(std[a + b + c] for a in order for b in order for c in order)
+    assert aa == oracle.table_code(0)
+
+
+def test_no_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import gotranseq_b200
+    with pytest.raises(gotranseq_b200.TranseqError, match="no CPU fallback"):
+        gotranseq_b200.translate_bytes(b">a\nACG\n")
