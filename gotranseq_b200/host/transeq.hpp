@@ -1,0 +1,30 @@
+// transeq.hpp -- C++ host-side mirror of the reference's `transeq` package over the C ABI
+// (include/gotranseq_b200.h).  The Go toolchain is absent in this image, so this is the compiled
+// host layer a drop-in user links against; INTEGRATION.md shows the equivalent cgo shim.
+//
+//   transeq::Options    field for field `type Options struct` (transeq/options.go:4-11)
+//   transeq::Translate  `func Translate(inputSequence io.Reader, out io.Writer, options Options) error`
+//                       (transeq/transeq.go:114): returns an empty string on success, otherwise the
+//                       error text (same texts as the reference: transeq.go:107, ncbicode/code.go:378,
+//                       writer.go:175)
+#pragma once
+#include <istream>
+#include <ostream>
+#include <string>
+
+namespace transeq {
+
+struct Options {
+    std::string Frame = "1";   // -f | --frame
+    int Table = 0;             // -t | --table
+    bool Clean = false;        // -c | --clean
+    bool Alternative = false;  // -a | --alternative
+    bool Trim = false;         // -T | --trim
+    int NumWorker = 0;         // -n | --numcpu: accepted and ignored (output is in input order)
+    int Device = -1;           // CUDA device ordinal, -1 = current
+    unsigned long long ChunkBytes = 0;  // streaming chunk size, 0 = library default
+};
+
+std::string Translate(std::istream &inputSequence, std::ostream &out, const Options &options);
+
+}  // namespace transeq

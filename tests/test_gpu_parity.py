@@ -112,3 +112,49 @@ def test_device_resident_entry_point():
             t.translate_device(d_in.data_ptr(), d_in.numel(), d_out.data_ptr(), 10, 0)
         st = t.stats()
         assert st["nucleotides"] > 0 and st["kernel_launches"] >= 4
+
+
+def test_cli_reference_goldens(goldens, tmp_path):
+    """The `gotranseq` CLI (gotranseq_b200/host/main.cpp) with the reference's flags (main.go:21-37)."""
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gotranseq_b200", "bin", "gotranseq")
+    src = tmp_path / "test.fna"
+    src.write_bytes(goldens["input"].encode())
+    for case in goldens["cases"][::3]:
+        flags = ["-" + t if t.startswith("-") else t for t in case["options"].split()]  # -frame=6 -> --frame=6
+        dst = tmp_path / "out.faa"
+        r = subprocess.run([exe, "-s", str(src), "-o", str(dst)] + flags, capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0 and r.stdout == "", r.stdout
+        assert dst.read_bytes().decode() == case["expected"], case["options"]
+    # errors are printed, exit code stays 0 (main.go:87-90)
+    r = subprocess.run([exe, "-s", str(src), "-o", str(tmp_path / "o"), "-f", "9"], capture_output=True, text=True)
+    assert r.returncode == 0 and "wrong value for -f | --frame parameter: 9" in r.stdout
+
+
+@pytest.mark.parametrize("name", ["readme189", "contigs", "chromosome", "short_reads"])
+def test_benchmark_shapes_full_size(name):
+    """BASELINE.json configs at (or near) their full sizes, byte-compared with the oracle, plus
+    size-independent properties: sharding invariance and frame decomposition."""
+    import numpy as np
+    import gotranseq_b200
+    import workloads
+    from gotranseq_b200 import shard
+    gen, opts = workloads.WORKLOADS[name]
+    if name == "contigs":
+        data = gen(n_records=12)            # 60 MB of the 25 GB config
+    elif name == "short_reads":
+        data = gen(n_reads=1_000_000)       # 204 MB of the 20 GB config
+    else:
+        data = gen()
+    want = oracle.translate(np.frombuffer(data, dtype=np.uint8), num_worker=1, **opts)
+    O = gotranseq_b200.Options(Frame=opts["frame"], Table=opts.get("table", 0), Clean=opts.get("clean", False),
+                               Alternative=opts.get("alternative", False), Trim=opts.get("trim", False))
+    with gotranseq_b200.Translator(O) as t:
+        got = t.translate_bytes(data)
+        assert len(got) == len(want)
+        assert got == want
+        # record sharding (what each GPU of a multi-GPU run computes) leaves the bytes unchanged
+        if name != "chromosome":
+            parts = [t.translate_bytes(data[a:b]) for a, b in shard.shard_ranges(data, 3) if b > a]
+            assert b"".join(parts) == want
