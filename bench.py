@@ -270,8 +270,6 @@ def main():
         # algorithmic bytes of one k_translate launch: the packed symbol stream it reads (4 bits per
         # symbol: nucleotides + 2 pads per record) + the residue lines it writes (output - headers)
         st = tr.stats()
-        hdr_out = 0
-        import re
         nrec = st["records"]
         # header bytes written by k_headers: 6 x (H + 3) per record
         hdr_in = nbytes - nt - data.count(b"\n")  # header bytes incl '>'
@@ -297,7 +295,8 @@ def main():
                          "algorithmic_bytes_per_launch": trans_bytes, "ms_per_launch": trans_ms},
             "path": {"bytes_per_step_per_gpu": path_bytes, "achieved_GBps_per_gpu": path_gbs, "frac_of_peak": path_gbs / peak,
                      "note": "(FASTA in + protein FASTA out) / device time of the whole path"},
-            "kernels_ms_per_step": {"reset+k_parse": kms[0] / max(kpasses, 1), "k_size": kms[1] / max(kpasses, 1),
+            "kernels_ms_per_step": {"reset+k_parse": kms[0] / max(kpasses, 1),
+                                    "k_tile_scan+k_records+k_size": kms[1] / max(kpasses, 1),
                                     "k_translate": kms[2] / max(kpasses, 1), "k_headers": kms[3] / max(kpasses, 1)},
             "bytes": {"in": nbytes, "out": out_n, "nucleotides": nt, "records": nrec},
         }
