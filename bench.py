@@ -173,6 +173,7 @@ def main():
     ap.add_argument("--ref-sample-bytes", type=int, default=48_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end loop (default: min(steps, 10))")
+    ap.add_argument("--chunk-mb", type=float, default=0, help="pipeline chunk of the host entry point (0 = library default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank, local_rank, world = env_rank()
@@ -206,7 +207,7 @@ def main():
 
     O = gotranseq_b200.Options(Frame=opts.get("frame", "1"), Table=opts.get("table", 0), Clean=opts.get("clean", False),
                                Alternative=opts.get("alternative", False), Trim=opts.get("trim", False))
-    tr = gotranseq_b200.Translator(O, device=local_rank)
+    tr = gotranseq_b200.Translator(O, device=local_rank, chunk_bytes=int(args.chunk_mb * (1 << 20)))
     stream = torch.cuda.current_stream().cuda_stream
 
     # ---- device-resident: input already in HBM, output stays in HBM ----

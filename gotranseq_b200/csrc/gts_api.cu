@@ -60,6 +60,13 @@ struct gts_ctx {
     bool stream_first_pass = true, stream_eof = false, stream_out_ready = false, stream_done = false;
     size_t stream_out_n = 0;
 
+    // ---- chunk pipeline of the host entry points: H2D / kernels / D2H overlap ----
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;  // `stream` above runs the kernels
+    uint8_t *p_in[2] = {nullptr, nullptr}, *p_out[2] = {nullptr, nullptr};
+    size_t p_in_cap[2] = {0, 0}, p_out_cap[2] = {0, 0};
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
+    gts::Totals *h_totals2 = nullptr;  // pinned, one per pipeline slot
+
     // ---- last enqueued device pass ----
     bool pending = false;
     gts::Job job;
@@ -167,7 +174,7 @@ int ensure_scratch(gts_ctx *ctx, u64 n) {
 
 // Enqueue one device pass on `stream` (no host synchronisation).
 int enqueue_pass(gts_ctx *ctx, const uint8_t *d_in, u64 n, uint8_t *d_out, u64 cap, cudaStream_t stream,
-                 bool sizes_only) {
+                 bool sizes_only, gts::Totals *h_dst = nullptr, bool more_follows = false) {
     if (((uintptr_t)d_in & 15) != 0) return fail(ctx, GTS_ERR_ARG, "device input must be 16-byte aligned");
     int rc = ensure_scratch(ctx, n);
     if (rc) return rc;
@@ -191,6 +198,7 @@ int enqueue_pass(gts_ctx *ctx, const uint8_t *d_in, u64 n, uint8_t *d_out, u64 c
     job.frame_mask = ctx->mask;
     job.alternative = ctx->opt.alternative ? 1 : 0;
     job.trim = ctx->opt.trim ? 1 : 0;
+    job.more_follows = more_follows ? 1 : 0;
     job.lut = ctx->lut;
     ctx->job_stream = stream;
     cudaEvent_t *ev = nullptr;
@@ -215,7 +223,7 @@ int enqueue_pass(gts_ctx *ctx, const uint8_t *d_in, u64 n, uint8_t *d_out, u64 c
         if (ev) CU(cudaEventRecord(ev[4], stream));
         ctx->stats.kernel_launches += 2;
     }
-    CU(cudaMemcpyAsync(ctx->h_totals, job.totals, sizeof(gts::Totals), cudaMemcpyDeviceToHost, stream));
+    CU(cudaMemcpyAsync(h_dst ? h_dst : ctx->h_totals, job.totals, sizeof(gts::Totals), cudaMemcpyDeviceToHost, stream));
     ctx->pending = true;
     ctx->stats.passes++;
     return GTS_OK;
@@ -270,7 +278,7 @@ int ensure_pinned(gts_ctx *ctx, uint8_t **p, size_t *cap, size_t need, size_t ke
 }
 
 // Host bytes in pinned or pageable memory -> device pass -> pinned ctx->h_out.
-int translate_host(gts_ctx *ctx, const uint8_t *in, size_t n, size_t *out_n) {
+int translate_host_simple(gts_ctx *ctx, const uint8_t *in, size_t n, size_t *out_n) {
     int rc = ensure_dev_buffer(ctx, &ctx->d_in, &ctx->d_in_cap, n + 64);
     if (rc) return rc;
     if (n) CU(cudaMemcpyAsync(ctx->d_in, in, n, cudaMemcpyHostToDevice, ctx->stream));
@@ -297,6 +305,114 @@ int translate_host(gts_ctx *ctx, const uint8_t *in, size_t n, size_t *out_n) {
     ctx->stats.d2h_bytes += total;
     CU(cudaStreamSynchronize(ctx->stream));
     *out_n = total;
+    return GTS_OK;
+}
+
+
+// Record boundary (a '>' that starts a line) closest below `pos`, searched back to `lo`; 0 = none.
+size_t boundary_below(const uint8_t *p, size_t lo, size_t pos) {
+    for (size_t i = pos; i > lo + 1; i--)
+        if (p[i - 1] == '>' && p[i - 2] == '\n') return i - 1;
+    return 0;
+}
+
+// Host bytes -> pinned ctx->h_out through a two-slot pipeline of record-aligned chunks: the copy
+// in of chunk i+1 and the copy out of chunk i-1 run while chunk i is in the kernels.  Falls back
+// to the simple two-pass path when the input is small, has a record larger than a chunk, or a
+// chunk overflows one of the (generously) estimated buffers.
+int translate_host(gts_ctx *ctx, const uint8_t *in, size_t n, size_t *out_n) {
+    const size_t chunk = ctx->opt.chunk_bytes ? (size_t)ctx->opt.chunk_bytes : (size_t)16 << 20;
+    if (n < 2 * chunk) return translate_host_simple(ctx, in, n, out_n);
+    // ---- cut points ----
+    std::vector<size_t> cuts;
+    cuts.push_back(0);
+    while (n - cuts.back() > chunk + chunk / 2) {
+        const size_t b = boundary_below(in, cuts.back(), cuts.back() + chunk);
+        if (b == 0) return translate_host_simple(ctx, in, n, out_n);  // a record larger than a chunk
+        cuts.push_back(b);
+    }
+    cuts.push_back(n);
+    const size_t nchunks = cuts.size() - 1;
+    // ---- resources ----
+    if (!ctx->s_h2d) {
+        CU(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; b++) {
+            CU(cudaEventCreateWithFlags(&ctx->ev_h2d[b], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&ctx->ev_comp[b], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&ctx->ev_d2h[b], cudaEventDisableTiming));
+        }
+        CU(cudaHostAlloc(&ctx->h_totals2, 2 * sizeof(gts::Totals), cudaHostAllocDefault));
+    }
+    const size_t in_need = chunk + chunk / 2 + 64, out_need = 4 * in_need;
+    for (int b = 0; b < 2; b++) {
+        int rc = ensure_dev_buffer(ctx, &ctx->p_in[b], &ctx->p_in_cap[b], in_need);
+        if (rc) return rc;
+        rc = ensure_dev_buffer(ctx, &ctx->p_out[b], &ctx->p_out_cap[b], out_need);
+        if (rc) return rc;
+    }
+    int rc = ensure_pinned(ctx, &ctx->h_out, &ctx->h_out_cap, n * 2 + n / 4 + (1 << 20), 0);
+    if (rc) return rc;
+    rc = ensure_scratch(ctx, in_need);  // no reallocation while chunks are in flight
+    if (rc) return rc;
+
+    size_t out_off = 0;
+    bool fallback = false;
+    // retire chunk j: wait for its kernels, read its exact size, copy it out behind the others
+    auto retire = [&](size_t j) -> int {
+        const int b = (int)(j & 1);
+        CU(cudaEventSynchronize(ctx->ev_comp[b]));
+        const gts::Totals &t = ctx->h_totals2[b];
+        if (t.flags != 0) {  // record table or output estimate too small: redo everything the simple way
+            fallback = true;
+            return GTS_OK;
+        }
+        if (out_off + t.out_total > ctx->h_out_cap) {
+            CU(cudaStreamSynchronize(ctx->s_d2h));
+            int r2 = ensure_pinned(ctx, &ctx->h_out, &ctx->h_out_cap, (out_off + t.out_total) * 3 / 2, out_off);
+            if (r2) return r2;
+        }
+        CU(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_comp[b], 0));
+        if (t.out_total)
+            CU(cudaMemcpyAsync(ctx->h_out + out_off, ctx->p_out[b], t.out_total, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        CU(cudaEventRecord(ctx->ev_d2h[b], ctx->s_d2h));
+        out_off += t.out_total;
+        ctx->stats.d2h_bytes += t.out_total;
+        ctx->stats.records += t.records;
+        ctx->stats.nucleotides += t.nucleotides;
+        return GTS_OK;
+    };
+    ctx->stats.records = 0;
+    ctx->stats.nucleotides = 0;
+    for (size_t i = 0; i < nchunks && !fallback; i++) {
+        const int b = (int)(i & 1);
+        const size_t lo = cuts[i], len = cuts[i + 1] - cuts[i];
+        if (i >= 2) CU(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_comp[b], 0));  // chunk i-2 has left p_in[b]
+        CU(cudaMemcpyAsync(ctx->p_in[b], in + lo, len, cudaMemcpyHostToDevice, ctx->s_h2d));
+        CU(cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
+        ctx->stats.h2d_bytes += len;
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
+        if (i >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));  // chunk i-2 has left p_out[b]
+        rc = enqueue_pass(ctx, ctx->p_in[b], len, ctx->p_out[b], ctx->p_out_cap[b], ctx->stream, false,
+                          &ctx->h_totals2[b], i + 1 < nchunks);
+        if (rc) return rc;
+        CU(cudaEventRecord(ctx->ev_comp[b], ctx->stream));
+        if (i >= 1) {
+            rc = retire(i - 1);
+            if (rc) return rc;
+        }
+    }
+    if (!fallback) {
+        rc = retire(nchunks - 1);
+        if (rc) return rc;
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(ctx->s_d2h));
+    ctx->pending = false;
+    if (fallback) return translate_host_simple(ctx, in, n, out_n);
+    ctx->stats.in_bytes = n;
+    ctx->stats.out_bytes = out_off;
+    *out_n = out_off;
     return GTS_OK;
 }
 
@@ -405,6 +521,15 @@ void gts_destroy(gts_ctx *ctx) {
     cudaFree(ctx->d_zero);
     free_rec(ctx);
     cudaFree(ctx->d_in); cudaFree(ctx->d_out);
+    for (int b = 0; b < 2; b++) {
+        cudaFree(ctx->p_in[b]); cudaFree(ctx->p_out[b]);
+        if (ctx->ev_h2d[b]) cudaEventDestroy(ctx->ev_h2d[b]);
+        if (ctx->ev_comp[b]) cudaEventDestroy(ctx->ev_comp[b]);
+        if (ctx->ev_d2h[b]) cudaEventDestroy(ctx->ev_d2h[b]);
+    }
+    if (ctx->h_totals2) cudaFreeHost(ctx->h_totals2);
+    if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->h_in) cudaFreeHost(ctx->h_in);
     if (ctx->h_totals) cudaFreeHost(ctx->h_totals);

@@ -153,7 +153,11 @@ __device__ __forceinline__ void frame_lengths(u64 n, bool alternative, u64 L[6])
 
 __device__ __forceinline__ u64 run_size(u64 H, u64 Lp) { return H + 3 + Lp + udiv60(Lp + 59); }
 
-__device__ __forceinline__ bool record_emitted(u64 s, u64 n, u64 R) { return s >= 1 || n > 0 || R == 0; }
+// transeq.go:198-213: a record is sent when a header line follows it (if it has any bytes) and,
+// always, at the end of the stream
+__device__ __forceinline__ bool record_emitted(u64 s, u64 n, u64 R, bool more_follows) {
+    return s >= 1 || n > 0 || (R == 0 && !more_follows);
+}
 
 // symbol i of a tile's slot
 __device__ __forceinline__ u32 slot_symbol(const u32 *sym, u32 tile, u32 i) {

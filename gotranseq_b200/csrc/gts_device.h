@@ -144,6 +144,7 @@ struct Job {  // kernel argument block (by value)
     u32 frame_mask;  // bit k = frame index k requested (0..2 forward, 3..5 reverse)
     u32 alternative;
     u32 trim;
+    u32 more_follows;  // this buffer is not the end of the stream: an empty slot 0 is never emitted
     Lut lut;
 };
 

@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(kSizeThreads) k_size(const __grid_constant__ J
                     H = p - off;
                     if (job.in[p - 1] == '\r') H--;  // p > off: the line holds at least the '>'
                 }
-                const bool em = record_emitted(s, n, R);
+                const bool em = record_emitted(s, n, R, job.more_follows != 0);
                 if (em) {
 #pragma unroll
                     for (int f = 0; f < 6; f++)
