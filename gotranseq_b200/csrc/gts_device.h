@@ -130,6 +130,7 @@ struct Job {  // kernel argument block (by value)
     u64 *hdr_off;   // raw offset of the header line's '>'
     u64 *dbase;     // stream index of the record's first nucleotide (its pads sit at -2, -1)
     u64 *loc;       // tile << 16 | slot index of the record's first nucleotide
+    u64 *hinfo;     // header line bytes (CR dropped) | index of its first space << 32
     RecInfo *rec;   // per record summary (+1 sentinel: dbase = end of stream, out_off = total)
     u32 *trim_len;  // [slot*6 + frame] residues kept after --trim (only with trim)
     u64 rec_cap;    // entries in each of the arrays above

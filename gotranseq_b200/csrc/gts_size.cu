@@ -125,6 +125,20 @@ __global__ void __launch_bounds__(256) k_records(const __grid_constant__ Job job
         job.hdr_off[slot] = ev.hdr_off;
         job.dbase[slot] = tp.T0 + ev.pos;
         job.loc[slot] = (u64)ev.tile << 16 | ev.pos;
+        // header line: up to its '\n' (or the end of the input), one trailing CR dropped
+        // (bufio.ScanLines); sp = index of its first space (writer.go:121), H if there is none
+        const u64 off = ev.hdr_off;
+        u64 p = off, sp = ~0ull;
+        while (p < job.n) {
+            const uint8_t c = job.in[p];
+            if (c == '\n') break;
+            if (c == ' ' && sp == ~0ull) sp = p - off;
+            p++;
+        }
+        u64 H = p - off;
+        if (job.in[p - 1] == '\r') H--;  // p > off: the line holds at least the '>'
+        if (sp > H) sp = H;
+        job.hinfo[slot] = H | sp << 32;
     }
 }
 
@@ -239,15 +253,7 @@ __global__ void __launch_bounds__(kSizeThreads) k_size(const __grid_constant__ J
 #pragma unroll
                     for (int f = 0; f < 6; f++) job.trim_len[s * 6 + f] = (u32)L[f];
                 }
-                // header line: up to its '\n' (or the end of the input), one trailing CR dropped
-                u64 H = 0;
-                if (s >= 1) {
-                    const u64 off = job.hdr_off[s];
-                    u64 p = off;
-                    while (p < job.n && job.in[p] != '\n') p++;
-                    H = p - off;
-                    if (job.in[p - 1] == '\r') H--;  // p > off: the line holds at least the '>'
-                }
+                const u64 H = s >= 1 ? (job.hinfo[s] & 0xFFFFFFFFull) : 0;
                 const bool em = record_emitted(s, n, R, job.more_follows != 0);
                 if (em) {
 #pragma unroll
