@@ -406,6 +406,10 @@ __global__ void __launch_bounds__(kTransBlock, 4) k_translate(const __grid_const
 // =====================================================================================
 // k_headers
 // =====================================================================================
+// Header line of one frame (writer.go:120-131): the header's bytes with '_' and the frame digit
+// inserted before its first space (or appended), then '\n'.  One warp per record, lane i holding
+// output bytes i, i+32, ...: the line is assembled once (only the digit differs between frames)
+// and stored once per requested frame.
 __global__ void __launch_bounds__(256) k_headers(const __grid_constant__ Job job) {
     const int lane = threadIdx.x & 31;
     const u64 R = job.totals->n_headers;
@@ -414,39 +418,31 @@ __global__ void __launch_bounds__(256) k_headers(const __grid_constant__ Job job
     for (u64 s = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s <= R; s += nwarps) {
         const RecInfo ri = job.rec[s];
         if (!ri.emitted) continue;
-        const u64 n = ri.n;
-        const u64 H = ri.H;
+        const u32 H = ri.H;
+        const u32 sp = s >= 1 ? (u32)(job.hinfo[s] >> 32) : 0u;
         const uint8_t *hdr = job.in + job.hdr_off[s];
+        // run sizes of the six frames
         u64 L[6];
-        frame_lengths(n, job.alternative != 0, L);
+        frame_lengths(ri.n, job.alternative != 0, L);
         if (job.trim) {
 #pragma unroll
             for (int f = 0; f < 6; f++) L[f] = job.trim_len[s * 6 + f];
         }
-        // index of the first space (writer.go:121), H if there is none
-        u64 sp = H;
-        for (u64 i0 = 0; i0 < H; i0 += 32) {
-            const u64 i = i0 + lane;
-            const unsigned b = __ballot_sync(0xFFFFFFFFu, i < H && hdr[i] == ' ');
-            if (b) {
-                sp = i0 + __ffs(b) - 1;
-                break;
+        for (u32 i0 = 0; i0 < H + 3; i0 += 32) {
+            const u32 i = i0 + lane;
+            // byte i of the line; the digit at sp+1 is patched per frame
+            uint8_t c = '\n';
+            if (i < sp) c = hdr[i];
+            else if (i == sp) c = '_';
+            else if (i > sp + 1 && i < H + 2) c = hdr[i - 2];
+            const bool digit = i == sp + 1;
+            u64 run_base = ri.out_off;
+#pragma unroll
+            for (int f = 0; f < 6; f++) {
+                if (!((job.frame_mask >> f) & 1u)) continue;
+                if (i < H + 3) job.out[run_base + i] = digit ? (uint8_t)('1' + f) : c;
+                run_base += run_size(H, L[f]);
             }
-        }
-        u64 run_base = ri.out_off;
-        for (int f = 0; f < 6; f++) {
-            if (!((job.frame_mask >> f) & 1u)) continue;
-            uint8_t *dst = job.out + run_base;
-            for (u64 i = lane; i < H + 3; i += 32) {
-                uint8_t c;
-                if (i < sp) c = hdr[i];
-                else if (i == sp) c = '_';
-                else if (i == sp + 1) c = (uint8_t)('1' + f);
-                else if (i < H + 2) c = hdr[i - 2];
-                else c = '\n';
-                dst[i] = c;
-            }
-            run_base += run_size(H, L[f]);
         }
     }
 }
