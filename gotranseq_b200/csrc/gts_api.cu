@@ -77,6 +77,8 @@ struct gts_ctx {
     std::vector<cudaEvent_t> prof_events;  // 5 per recorded pass
     size_t prof_used = 0;
 
+    bool poison = false;  // GTS_POISON_OUTPUT=1: fill the output with 0xEE first (tests: no byte left unwritten)
+
     gts_stats stats;
     std::string err;
 };
@@ -153,6 +155,9 @@ int ensure_scratch(gts_ctx *ctx, u64 n) {
         CU(cudaMalloc(&ctx->d_sym, sym_bytes));
         // zero once: stale words past the end of a slot must still hold valid symbols (<= 4)
         CU(cudaMemset(ctx->d_sym, 0, sym_bytes));
+        // the memset runs on the legacy stream, the passes on non-blocking streams: without this
+        // it can land after the first k_parse has written its slots
+        CU(cudaDeviceSynchronize());
         CU(cudaMalloc(&ctx->d_tile_info, tiles * sizeof(gts::TileInfo)));
         CU(cudaMalloc(&ctx->d_tile_pre, tiles * sizeof(gts::TilePrefix)));
         CU(cudaMalloc(&ctx->d_chunk_hint, tiles * gts::kTransWarps * sizeof(uint16_t)));
@@ -295,6 +300,7 @@ int translate_host_simple(gts_ctx *ctx, const uint8_t *in, size_t n, size_t *out
     rc = ensure_pinned(ctx, &ctx->h_out, &ctx->h_out_cap, total + 64, 0);
     if (rc) return rc;
     // pass 2: residues and headers (the parse results are still in the scratch)
+    if (ctx->poison && total) CU(cudaMemsetAsync(ctx->d_out, 0xEE, total, ctx->stream));
     ctx->job.out = ctx->d_out;
     ctx->job.out_cap = ctx->d_out_cap;
     // clear the "output too small" flag left by the sizing pass
@@ -394,6 +400,7 @@ int translate_host(gts_ctx *ctx, const uint8_t *in, size_t n, size_t *out_n) {
         ctx->stats.h2d_bytes += len;
         CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
         if (i >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));  // chunk i-2 has left p_out[b]
+        if (ctx->poison) CU(cudaMemsetAsync(ctx->p_out[b], 0xEE, ctx->p_out_cap[b], ctx->stream));
         rc = enqueue_pass(ctx, ctx->p_in[b], len, ctx->p_out[b], ctx->p_out_cap[b], ctx->stream, false,
                           &ctx->h_totals2[b], i + 1 < nchunks);
         if (rc) return rc;
@@ -495,6 +502,7 @@ int gts_create(const gts_options *opt, gts_ctx **out) {
     }
     ctx->device = dev;
     ctx->sm_count = prop.multiProcessorCount;
+    ctx->poison = std::getenv("GTS_POISON_OUTPUT") != nullptr;
 #ifdef GTS_PHASE_TIMING
     if (std::getenv("GTS_PHASE_TIMING")) {
         cudaMalloc(&ctx->d_dbg, 64 * sizeof(u64));

@@ -232,7 +232,7 @@ __device__ __forceinline__ void build_runs(const Job &job, RunTable &ws, u64 R, 
 }
 
 // Copy the bytes [lo, hi) of the image (hi - lo < 16, both inside one aligned 16-byte slot) to
-// global memory with at most four naturally aligned stores; g is the global address of image byte 0.
+// global memory with naturally aligned stores; g is the global address of image byte 0.
 __device__ __forceinline__ void store_edge(const uint8_t *image, uint8_t *g, u32 lo, u32 hi) {
     u32 x = lo;
     if ((x & 1u) && x + 1u <= hi) { g[x] = image[x]; x += 1u; }
@@ -242,6 +242,24 @@ __device__ __forceinline__ void store_edge(const uint8_t *image, uint8_t *g, u32
     if (x + 4u <= hi) { *reinterpret_cast<u32 *>(g + x) = *reinterpret_cast<const u32 *>(image + x); x += 4u; }
     if (x + 2u <= hi) { *reinterpret_cast<uint16_t *>(g + x) = *reinterpret_cast<const uint16_t *>(image + x); x += 2u; }
     if (x + 1u <= hi) { g[x] = image[x]; }
+}
+// The 1..15 bytes in front of the 16-byte aligned image offset `end`: one store per set bit of the length.
+__device__ __forceinline__ void store_head(const uint8_t *image, uint8_t *g, u32 lo, u32 end) {
+    const u32 h = end - lo;
+    u32 x = end;
+    if (h & 8u) { x -= 8u; *reinterpret_cast<uint2 *>(g + x) = *reinterpret_cast<const uint2 *>(image + x); }
+    if (h & 4u) { x -= 4u; *reinterpret_cast<u32 *>(g + x) = *reinterpret_cast<const u32 *>(image + x); }
+    if (h & 2u) { x -= 2u; *reinterpret_cast<uint16_t *>(g + x) = *reinterpret_cast<const uint16_t *>(image + x); }
+    if (h & 1u) { x -= 1u; g[x] = image[x]; }
+}
+// The 1..15 bytes behind the 16-byte aligned image offset `lo`.
+__device__ __forceinline__ void store_tail(const uint8_t *image, uint8_t *g, u32 lo, u32 end) {
+    const u32 t = end - lo;
+    u32 x = lo;
+    if (t & 8u) { *reinterpret_cast<uint2 *>(g + x) = *reinterpret_cast<const uint2 *>(image + x); x += 8u; }
+    if (t & 4u) { *reinterpret_cast<u32 *>(g + x) = *reinterpret_cast<const u32 *>(image + x); x += 4u; }
+    if (t & 2u) { *reinterpret_cast<uint16_t *>(g + x) = *reinterpret_cast<const uint16_t *>(image + x); x += 2u; }
+    if (t & 1u) { g[x] = image[x]; }
 }
 
 // Persistent CTAs, one parse tile (slot) per iteration.  Warps 0..kTransWarps-1 translate one
@@ -383,8 +401,8 @@ __global__ void __launch_bounds__(kTransBlock, 4) k_translate(const __grid_const
                     }
                     if (hi16 > lo16) {
                         bulk_store(g + lo16, ws.image + lo16, hi16 - lo16);
-                        store_edge(ws.image, g, r.img, lo16);
-                        store_edge(ws.image, g, hi16, end);
+                        store_head(ws.image, g, r.img, lo16);
+                        store_tail(ws.image, g, hi16, end);
                     } else if (end <= lo16) {
                         store_edge(ws.image, g, r.img, end);
                     } else {  // straddles one slot boundary without filling a slot
