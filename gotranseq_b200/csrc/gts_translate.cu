@@ -425,15 +425,15 @@ __global__ void __launch_bounds__(kTransBlock, 4) k_translate(const __grid_const
 // k_headers
 // =====================================================================================
 // Header line of one frame (writer.go:120-131): the header's bytes with '_' and the frame digit
-// inserted before its first space (or appended), then '\n'.  One warp per record, lane i holding
-// output bytes i, i+32, ...: the line is assembled once (only the digit differs between frames)
+// inserted before its first space (or appended), then '\n'.  Half a warp per record, lane i holding
+// output bytes i, i+16, ...: the line is assembled once (only the digit differs between frames)
 // and stored once per requested frame.
 __global__ void __launch_bounds__(256) k_headers(const __grid_constant__ Job job) {
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, sub = lane & 15, half = lane >> 4;
     const u64 R = job.totals->n_headers;
     if (job.totals->flags != 0) return;
-    const u64 nwarps = (u64)gridDim.x * (blockDim.x >> 5);
-    for (u64 s = (u64)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); s <= R; s += nwarps) {
+    const u64 nhalf = (u64)gridDim.x * (blockDim.x >> 4);
+    for (u64 s = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 4; s <= R; s += nhalf) {
         const RecInfo ri = job.rec[s];
         if (!ri.emitted) continue;
         const u32 H = ri.H;
@@ -446,8 +446,7 @@ __global__ void __launch_bounds__(256) k_headers(const __grid_constant__ Job job
 #pragma unroll
             for (int f = 0; f < 6; f++) L[f] = job.trim_len[s * 6 + f];
         }
-        for (u32 i0 = 0; i0 < H + 3; i0 += 32) {
-            const u32 i = i0 + lane;
+        for (u32 i = sub; i < H + 3; i += 16) {
             // byte i of the line; the digit at sp+1 is patched per frame
             uint8_t c = '\n';
             if (i < sp) c = hdr[i];
@@ -458,11 +457,12 @@ __global__ void __launch_bounds__(256) k_headers(const __grid_constant__ Job job
 #pragma unroll
             for (int f = 0; f < 6; f++) {
                 if (!((job.frame_mask >> f) & 1u)) continue;
-                if (i < H + 3) job.out[run_base + i] = digit ? (uint8_t)('1' + f) : c;
+                job.out[run_base + i] = digit ? (uint8_t)('1' + f) : c;
                 run_base += run_size(H, L[f]);
             }
         }
     }
+    (void)half;
 }
 
 // =====================================================================================
