@@ -59,6 +59,7 @@ EXPORTS = {
     "gts_get_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(gts_stats)]),
     "gts_set_profiling": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "gts_kernel_times": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]),
+    "gts_set_max_line_length": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t]),
     "gts_host_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
     "gts_host_free": (None, [ctypes.c_void_p]),
 }

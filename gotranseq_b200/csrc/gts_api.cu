@@ -77,6 +77,11 @@ struct gts_ctx {
     std::vector<cudaEvent_t> prof_events;  // 5 per recorded pass
     size_t prof_used = 0;
 
+    u64 max_line = 100ull << 20;  // bufio.Scanner token limit of the reference (transeq.go:27)
+    gts::NlPart *d_scan_nl = nullptr;
+    size_t scan_nl_cap = 0;
+    bool last_truncated = false;  // the last host translation stopped at an over-long line
+    bool stream_truncated = false;
     bool poison = false;  // GTS_POISON_OUTPUT=1: fill the output with 0xEE first (tests: no byte left unwritten)
 
     gts_stats stats;
@@ -168,6 +173,13 @@ int ensure_scratch(gts_ctx *ctx, u64 n) {
         int rc = alloc_rec(ctx, want_rec + want_rec / 8);
         if (rc) return rc;
     }
+    const size_t nscan = (parse_tiles(ctx->cap_n) + gts::kScanTile - 1) / gts::kScanTile;
+    if (nscan > ctx->scan_nl_cap) {
+        cudaFree(ctx->d_scan_nl);
+        ctx->d_scan_nl = nullptr; ctx->scan_nl_cap = 0;
+        CU(cudaMalloc(&ctx->d_scan_nl, nscan * sizeof(gts::NlPart)));
+        ctx->scan_nl_cap = nscan;
+    }
     const ZeroLayout z = zero_layout(parse_tiles(ctx->cap_n), ctx->rec_cap);
     if (z.bytes > ctx->zero_cap) {
         cudaFree(ctx->d_zero);
@@ -200,6 +212,8 @@ int enqueue_pass(gts_ctx *ctx, const uint8_t *d_in, u64 n, uint8_t *d_out, u64 c
     job.totals = reinterpret_cast<gts::Totals *>(ctx->d_zero + z.totals);
     job.counters = reinterpret_cast<u32 *>(ctx->d_zero + z.counters);
     job.dbg = ctx->d_dbg;
+    job.scan_nl = ctx->d_scan_nl;
+    job.max_line = ctx->max_line;
     job.ntiles = (u32)ntiles;
     job.frame_mask = ctx->mask;
     job.alternative = ctx->opt.alternative ? 1 : 0;
@@ -241,8 +255,18 @@ int finish_pass(gts_ctx *ctx, bool sizes_only) {
     for (int attempt = 0;; attempt++) {
         CU(cudaStreamSynchronize(ctx->job_stream));
         const gts::Totals &t = *ctx->h_totals;
+        if (t.flags & gts::kFlagLongLine) {
+            // the reference stops reading at a line of >= 100 MiB (transeq.go:186): redo the pass on
+            // the bytes in front of that line
+            if (attempt >= 3) return fail(ctx, GTS_ERR_ARG, "over-long line handling did not converge");
+            const gts::Job j = ctx->job;
+            ctx->last_truncated = true;
+            int rc = enqueue_pass(ctx, j.in, t.cut, j.out, j.out_cap, ctx->job_stream, sizes_only);
+            if (rc) return rc;
+            continue;
+        }
         if (t.flags & gts::kFlagRecOverflow) {
-            if (attempt >= 2) return fail(ctx, GTS_ERR_NOMEM, "record table overflow persists");
+            if (attempt >= 3) return fail(ctx, GTS_ERR_NOMEM, "record table overflow persists");
             const u64 need = t.n_headers + 2;
             int rc = alloc_rec(ctx, need + need / 16 + 1024);
             if (rc) return rc;
@@ -285,6 +309,7 @@ int ensure_pinned(gts_ctx *ctx, uint8_t **p, size_t *cap, size_t need, size_t ke
 
 // Host bytes in pinned or pageable memory -> device pass -> pinned ctx->h_out.
 int translate_host_simple(gts_ctx *ctx, const uint8_t *in, size_t n, size_t *out_n) {
+    ctx->last_truncated = false;
     int rc = ensure_dev_buffer(ctx, &ctx->d_in, &ctx->d_in_cap, n + 64);
     if (rc) return rc;
     if (n) CU(cudaMemcpyAsync(ctx->d_in, in, n, cudaMemcpyHostToDevice, ctx->stream));
@@ -329,7 +354,9 @@ size_t boundary_below(const uint8_t *p, size_t lo, size_t pos) {
 // chunk overflows one of the (generously) estimated buffers.
 int translate_host(gts_ctx *ctx, const uint8_t *in, size_t n, size_t *out_n) {
     const size_t chunk = ctx->opt.chunk_bytes ? (size_t)ctx->opt.chunk_bytes : (size_t)16 << 20;
-    if (n < 2 * chunk) return translate_host_simple(ctx, in, n, out_n);
+    ctx->last_truncated = false;
+    // (a chunk shorter than the line limit cannot hold an over-long line; otherwise use the simple path)
+    if (n < 2 * chunk || chunk + chunk / 2 >= ctx->max_line) return translate_host_simple(ctx, in, n, out_n);
     // ---- cut points ----
     std::vector<size_t> cuts;
     cuts.push_back(0);
@@ -527,7 +554,7 @@ void gts_destroy(gts_ctx *ctx) {
         cudaFree(ctx->d_dbg);
     }
     cudaFree(ctx->d_sym); cudaFree(ctx->d_tile_info); cudaFree(ctx->d_tile_pre); cudaFree(ctx->d_chunk_hint);
-    cudaFree(ctx->d_zero);
+    cudaFree(ctx->d_zero); cudaFree(ctx->d_scan_nl);
     free_rec(ctx);
     cudaFree(ctx->d_in); cudaFree(ctx->d_out);
     for (int b = 0; b < 2; b++) {
@@ -619,6 +646,11 @@ int gts_submit(gts_ctx *ctx, size_t nbytes, int eof) {
     CU(cudaSetDevice(ctx->device));
     ctx->h_in_fill += nbytes;
     if (eof) ctx->stream_eof = true;
+    if (ctx->stream_truncated) {  // the reference has stopped reading: the rest of the stream is ignored
+        ctx->h_in_fill = 0;
+        if (eof) ctx->stream_done = true;
+        return GTS_OK;
+    }
     const size_t chunk = ctx->opt.chunk_bytes ? (size_t)ctx->opt.chunk_bytes : (size_t)64 << 20;
     size_t cut = 0;
     if (eof) {
@@ -643,6 +675,10 @@ int gts_submit(gts_ctx *ctx, size_t nbytes, int eof) {
     int rc = translate_host(ctx, ctx->h_in, cut, &total);
     if (rc) return rc;
     ctx->stream_first_pass = false;
+    if (ctx->last_truncated) {
+        ctx->stream_truncated = true;
+        ctx->h_in_fill = cut;  // nothing is carried over
+    }
     // carry the unfinished record over
     const size_t rest = ctx->h_in_fill - cut;
     if (rest) std::memmove(ctx->h_in, ctx->h_in + cut, rest);
@@ -662,6 +698,7 @@ int gts_next_output(gts_ctx *ctx, const uint8_t **buf, size_t *n) {
         *buf = nullptr;
         *n = 0;
         if (ctx->stream_done) {  // drained: ready for another stream
+            ctx->stream_truncated = false;
             ctx->stream_done = false;
             ctx->stream_eof = false;
             ctx->stream_first_pass = true;
@@ -675,6 +712,13 @@ int gts_release_output(gts_ctx *ctx) {
     if (!ctx) return GTS_ERR_ARG;
     ctx->stream_out_ready = false;
     ctx->stream_out_n = 0;
+    return GTS_OK;
+}
+
+int gts_set_max_line_length(gts_ctx *ctx, size_t n) {
+    if (!ctx) return GTS_ERR_ARG;
+    if (n < 2 * (size_t)gts::kParseTile) return fail(ctx, GTS_ERR_ARG, "line limit must be at least 16384 bytes");
+    ctx->max_line = n;
     return GTS_OK;
 }
 

@@ -76,16 +76,28 @@ struct Totals {  // device-resident result block, copied to pinned host memory a
     u64 flags;        // kFlag*
     u64 records;      // records emitted
     u64 nucleotides;  // nucleotides in emitted records
-    u64 pad[2];
+    u64 cut;          // with kFlagLongLine: the reference stops reading at this offset
+    u64 pad[1];
 };
 constexpr u64 kFlagRecOverflow = 1;  // record table too small (n_headers is still exact)
 constexpr u64 kFlagOutOverflow = 2;  // output buffer too small (out_total is still exact)
+constexpr u64 kFlagLongLine = 4;     // a line of >= max_line bytes: the pass must be redone on [0, cut)
 
-struct TileInfo {  // 8 bytes per parse tile, written by k_parse
-    uint16_t nsym;  // symbols in the tile's slot (pads included)
-    uint16_t nhdr;  // header lines starting in the tile
-    uint8_t tail;   // its last two symbols: last | second-to-last << 4
-    uint8_t pad[3];
+struct TileInfo {  // 16 bytes per parse tile, written by k_parse
+    uint16_t nsym;      // symbols in the tile's slot (pads included)
+    uint16_t nhdr;      // header lines starting in the tile
+    uint8_t tail;       // its last two symbols: last | second-to-last << 4
+    uint8_t has_nl;     // the tile holds a '\n' (filled in only when the input can hold an over-long line)
+    uint16_t first_nl;  // offset of its first / last '\n' in the tile
+    uint16_t last_nl;
+    uint16_t pad[3];
+};
+
+struct NlPart {  // newline summary of a run of tiles, for the over-long line rule (transeq.go:27,186)
+    i64 first;   // position of its first '\n', -1 = none
+    i64 last;    // position of its last '\n', -1 = none
+    i64 cut;     // start of the first line of >= max_line bytes lying between two of its newlines, -1 = none
+    i64 pad;
 };
 
 struct TilePrefix {  // 16 bytes per parse tile, written by k_tile_scan
@@ -136,6 +148,8 @@ struct Job {  // kernel argument block (by value)
     u64 rec_cap;    // entries in each of the arrays above
 
     u64 *t_status;  // [tile-scan tiles * 4] chained scan of the parse tiles' counts
+    NlPart *scan_nl;// [tile-scan tiles] newline summaries (only used when n >= max_line)
+    u64 max_line;   // bufio.Scanner token limit of the reference: 100 MiB (transeq.go:27)
     u64 *s_status;  // [size tiles * 4] chained scan of output sizes
     u32 *counters;  // [0] tile-scan ticket, [1] size ticket, [2] header events appended
     Totals *totals;

@@ -22,6 +22,7 @@ struct ParseShared {
     alignas(16) uint8_t sym[kSlotSyms + 32];  // the tile's symbols, one per byte (+ zero tail)
     uint8_t enc[256];
     u32 warp_sum[kParseThreads / 32];
+    u32 warp_nl[kParseThreads / 32];  // first newline << 16 | last newline + 1 of each warp (tile relative)
     volatile u32 ev_base;  // first slot of the tile's header events, ~0u until allocated
 };
 
@@ -248,6 +249,17 @@ __global__ void __launch_bounds__(kParseThreads) k_parse(const __grid_constant__
         if (lane >= o) inc += y;
     }
     if (lane == 31) sh.warp_sum[warp] = inc;
+    const bool track_nl = job.n >= job.max_line;  // only then can a line reach the reference's limit
+    if (track_nl) {
+        u32 fn = nlmask ? (u32)(tid * 32 + __ffs(nlmask) - 1) : 0xFFFFu;
+        u32 ln = nlmask ? (u32)(tid * 32 + (31 - __clz(nlmask)) + 1) : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            fn = min(fn, __shfl_xor_sync(0xFFFFFFFFu, fn, o));
+            ln = max(ln, __shfl_xor_sync(0xFFFFFFFFu, ln, o));
+        }
+        if (lane == 0) sh.warp_nl[warp] = fn << 16 | ln;
+    }
     __syncthreads();
     u32 excl = inc - packed;
     u32 tile_total = 0;
@@ -432,6 +444,19 @@ __global__ void __launch_bounds__(kParseThreads) k_parse(const __grid_constant__
         const u32 l1 = S_tile >= 1 ? sh.sym[S_tile - 1] : 0u, l2 = S_tile >= 2 ? sh.sym[S_tile - 2] : 0u;
         ti.tail = (uint8_t)(l1 | l2 << 4);
         ti.pad[0] = ti.pad[1] = ti.pad[2] = 0;
+        ti.has_nl = 0; ti.first_nl = 0; ti.last_nl = 0;
+        if (track_nl) {
+            u32 fn = 0xFFFFu, ln = 0;
+            for (int w = 0; w < kParseThreads / 32; w++) {
+                fn = min(fn, sh.warp_nl[w] >> 16);
+                ln = max(ln, sh.warp_nl[w] & 0xFFFFu);
+            }
+            if (ln) {
+                ti.has_nl = 1;
+                ti.first_nl = (uint16_t)fn;
+                ti.last_nl = (uint16_t)(ln - 1);
+            }
+        }
         job.tile_info[t] = ti;
     }
     PHASE_MARK(job, 6, tprev);  // pack

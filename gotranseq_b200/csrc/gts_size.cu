@@ -10,6 +10,18 @@
 
 namespace gts {
 
+// Over-long line rule (transeq.go:27,186: bufio.Scanner gives up at a line of >= 100 MiB and the
+// reference silently stops reading there).  Newline summaries are folded left to right; a line
+// starts after the previous newline (or at 0) and its length excludes its own newline.
+__device__ __forceinline__ void nl_fold(NlPart &acc, const NlPart &p, u64 max_line) {
+    if (acc.cut < 0) {
+        if (acc.last >= 0 && p.first >= 0 && (u64)(p.first - acc.last - 1) >= max_line) acc.cut = acc.last + 1;
+        else if (p.cut >= 0) acc.cut = p.cut;
+    }
+    if (acc.first < 0) acc.first = p.first;
+    if (p.last >= 0) acc.last = p.last;
+}
+
 // =====================================================================================
 // k_tile_scan: exclusive scan of the parse tiles' symbol / header counts
 // =====================================================================================
@@ -18,6 +30,7 @@ __global__ void __launch_bounds__(kScanThreads) k_tile_scan(const __grid_constan
     __shared__ u64 warp_r[kScanThreads / 32];
     __shared__ u64 s_excl_s, s_excl_r;
     __shared__ u32 s_tile;
+    __shared__ NlPart s_nl[kScanThreads];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 ntiles = job.ntiles;
     const u32 nscan = (ntiles + kScanTile - 1) / kScanTile;
@@ -30,6 +43,10 @@ __global__ void __launch_bounds__(kScanThreads) k_tile_scan(const __grid_constan
         const u32 t0 = st * kScanTile + tid * kScanPerThread;
         u32 ns[kScanPerThread], nh[kScanPerThread];
         u64 sum_s = 0, sum_r = 0;
+        const bool track_nl = job.n >= job.max_line;
+        NlPart mine;
+        mine.first = mine.last = mine.cut = -1;
+        mine.pad = 0;
 #pragma unroll
         for (int i = 0; i < kScanPerThread; i++) {
             ns[i] = nh[i] = 0;
@@ -37,9 +54,29 @@ __global__ void __launch_bounds__(kScanThreads) k_tile_scan(const __grid_constan
                 const TileInfo ti = job.tile_info[t0 + i];
                 ns[i] = ti.nsym;
                 nh[i] = ti.nhdr;
+                if (track_nl && ti.has_nl) {
+                    // inside one tile no line can reach the limit (it is at least two tiles long)
+                    NlPart p;
+                    p.first = (i64)(t0 + i) * kParseTile + ti.first_nl;
+                    p.last = (i64)(t0 + i) * kParseTile + ti.last_nl;
+                    p.cut = -1;
+                    p.pad = 0;
+                    nl_fold(mine, p, job.max_line);
+                }
             }
             sum_s += ns[i];
             sum_r += nh[i];
+        }
+        if (track_nl) {
+            // fold the lanes' summaries in lane order (5 shuffle rounds are not enough for a
+            // non-commutative fold of 3 fields, so lane 0 walks its warp: 32 short steps)
+            s_nl[tid] = mine;
+            __syncwarp();
+            if (lane == 0) {
+                NlPart acc = mine;
+                for (int i = 1; i < 32; i++) nl_fold(acc, s_nl[tid + i], job.max_line);
+                s_nl[tid] = acc;
+            }
         }
         u64 inc_s = sum_s, inc_r = sum_r;
 #pragma unroll
@@ -55,6 +92,13 @@ __global__ void __launch_bounds__(kScanThreads) k_tile_scan(const __grid_constan
             if (w < warp) { ex_s += warp_s[w]; ex_r += warp_r[w]; }
             tot_s += warp_s[w];
             tot_r += warp_r[w];
+        }
+        if (track_nl && tid == kScanThreads - 1) {  // (after the barrier above) fold the threads' summaries
+            NlPart acc;
+            acc.first = acc.last = acc.cut = -1;
+            acc.pad = 0;
+            for (int w = 0; w < kScanThreads / 32; w++) nl_fold(acc, s_nl[32 * w], job.max_line);
+            job.scan_nl[st] = acc;
         }
         if (warp == 0) {
             Pair agg = {tot_s, tot_r};
@@ -115,6 +159,26 @@ __global__ void __launch_bounds__(kScanThreads) k_tile_scan(const __grid_constan
 // k_records: header events -> record table
 // =====================================================================================
 __global__ void __launch_bounds__(256) k_records(const __grid_constant__ Job job) {
+    if (job.n >= job.max_line && blockIdx.x == 0 && threadIdx.x == 0) {
+        // over-long line rule: fold the scan tiles' newline summaries, then the unterminated last line
+        const u32 nscan = (job.ntiles + kScanTile - 1) / kScanTile;
+        NlPart acc;
+        acc.first = acc.last = acc.cut = -1;
+        acc.pad = 0;
+        i64 cut = -1;
+        for (u32 i = 0; i < nscan && cut < 0; i++) {
+            const NlPart p = job.scan_nl[i];
+            // the first line of the input starts at 0 without a newline in front of it
+            if (acc.last < 0 && p.first >= 0 && (u64)p.first >= job.max_line) cut = 0;
+            nl_fold(acc, p, job.max_line);
+            if (cut < 0) cut = acc.cut;
+        }
+        if (cut < 0 && job.n - (u64)(acc.last + 1) >= job.max_line) cut = acc.last + 1;
+        if (cut >= 0) {
+            job.totals->cut = (u64)cut;
+            atomicOr(&job.totals->flags, kFlagLongLine);
+        }
+    }
     const u64 R = job.totals->n_headers;
     if (R + 2 > job.rec_cap) return;  // overflow: the host retries with a larger table
     const u64 stride = (u64)gridDim.x * blockDim.x;

@@ -116,6 +116,10 @@ class Translator:
         self._check(self._L.gts_get_stats(self._h, ctypes.byref(st)))
         return {n: getattr(st, n) for n, _ in st._fields_}
 
+    def set_max_line_length(self, n):
+        """Test hook: the reference's bufio.Scanner token limit (transeq.go:27), default 100 MiB."""
+        self._check(self._L.gts_set_max_line_length(self._h, n))
+
     def set_profiling(self, enable):
         self._check(self._L.gts_set_profiling(self._h, 1 if enable else 0))
 

@@ -162,6 +162,14 @@ int gts_get_stats(const gts_ctx *ctx, gts_stats *st);
 int gts_set_profiling(gts_ctx *ctx, int enable);
 int gts_kernel_times(gts_ctx *ctx, double ms[4], uint64_t *passes);
 
+/*
+ * The reference reads lines through a bufio.Scanner limited to 100 MiB (transeq.go:27,186): at a
+ * line of that length or more it silently stops reading and translates what it has seen so far.
+ * The library reproduces this; this hook lowers the limit (>= 16384) so that tests can reach it,
+ * like the oracle's to_set_max_line_length.
+ */
+int gts_set_max_line_length(gts_ctx *ctx, size_t n);
+
 /* Pinned host memory for callers of gts_translate_buffer that want full-speed PCIe copies. */
 void *gts_host_alloc(size_t bytes);
 void gts_host_free(void *p);

@@ -158,3 +158,41 @@ def test_benchmark_shapes_full_size(name):
         if name != "chromosome":
             parts = [t.translate_bytes(data[a:b]) for a, b in shard.shard_ranges(data, 3) if b > a]
             assert b"".join(parts) == want
+
+
+def test_over_long_lines():
+    """transeq.go:27,186: the reference's scanner gives up at a line of >= 100 MiB and the rest of
+    the input is silently ignored.  Checked with the limit lowered on both sides."""
+    import random
+    import gotranseq_b200
+    cap = 20000
+    rng = random.Random(5)
+    seq = lambda n: "".join(rng.choice("ACGT") for _ in range(n))
+    rec = lambda i, n, w=60: ">r%d\n" % i + "\n".join(seq(n)[j:j + w] for j in range(0, n, w)) + "\n"
+    cases = {
+        "long sequence line in the middle": rec(0, 500) + ">long\n" + seq(30000) + "\n" + rec(1, 300),
+        "long header line": rec(0, 500) + ">" + "h" * 25000 + "\nACGT\n" + rec(1, 300),
+        "first line too long": seq(cap + 5) + "\n" + rec(0, 100),
+        "unterminated last line too long": rec(0, 700) + rec(1, 50) + ">x\n" + seq(cap),
+        "exactly at the limit": rec(0, 90) + ">y\n" + seq(cap) + "\n" + rec(1, 90),
+        "one below the limit": rec(0, 90) + ">y\n" + seq(cap - 1) + "\n" + rec(1, 90),
+        "CR counts": rec(0, 90) + ">y\n" + seq(cap - 1) + "\r\n" + rec(1, 90),
+        "many lines, none too long": rec(0, 90) + ">z\n" + "\n".join(seq(cap - 1) for _ in range(4)) + "\n" + rec(2, 10),
+        "second of two long lines": rec(0, 10) + ">a\n" + seq(cap - 1) + "\n" + seq(cap + 1) + "\n" + seq(3 * cap) + "\n" + rec(1, 10),
+        "far into a large input": "".join(rec(i, 3000) for i in range(60)) + ">q\n" + seq(2 * cap) + "\n" + rec(99, 30),
+    }
+    oracle.set_max_line_length(cap)
+    try:
+        for name, text in cases.items():
+            data = text.encode()
+            for kw in (dict(frame="6"), dict(frame="F", trim=True)):
+                want = oracle.translate(data, **kw)
+                O = gotranseq_b200.Options(Frame=kw["frame"], Trim=kw.get("trim", False))
+                with gotranseq_b200.Translator(O, chunk_bytes=1 << 16) as t:
+                    t.set_max_line_length(cap)
+                    assert t.translate_bytes(data) == want, name
+                    out = io.BytesIO()
+                    t.translate_stream(io.BytesIO(data), out)
+                    assert out.getvalue() == want, name + " (stream)"
+    finally:
+        oracle.set_max_line_length(100 << 20)
