@@ -474,7 +474,13 @@ cudaError_t init_kernels() {
 }
 
 cudaError_t launch_emit(const Job &job, int sm_count, cudaStream_t stream, cudaEvent_t ev_mid) {
-    const u32 grid = job.ntiles < (u32)sm_count * 4 ? job.ntiles : (u32)sm_count * 4;
+    static int per_sm = 0;  // resident CTAs per SM: the persistent grid is exactly one wave
+    if (!per_sm) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_translate, kTransBlock, sizeof(TransShared)) !=
+                cudaSuccess || per_sm < 1)
+            per_sm = 3;
+    }
+    const u32 grid = job.ntiles < (u32)(sm_count * per_sm) ? job.ntiles : (u32)(sm_count * per_sm);
     k_translate<<<grid, kTransBlock, sizeof(TransShared), stream>>>(job);
     if (ev_mid) cudaEventRecord(ev_mid, stream);
     k_headers<<<sm_count * 4, 256, 0, stream>>>(job);
