@@ -33,6 +33,8 @@ struct gts_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;  // used by the host-buffer entry points
+    cudaStream_t s_side = nullptr;  // k_headers runs here, next to k_translate
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
     // ---- device scratch (grows, never shrinks) ----
     u64 cap_n = 0;  // raw bytes the per-tile scratch is sized for
@@ -239,7 +241,7 @@ int enqueue_pass(gts_ctx *ctx, const uint8_t *d_in, u64 n, uint8_t *d_out, u64 c
     if (ev) CU(cudaEventRecord(ev[2], stream));
     ctx->stats.kernel_launches += 4;
     if (!sizes_only) {
-        CU(gts::launch_emit(job, ctx->sm_count, stream, ev ? ev[3] : nullptr));
+        CU(gts::launch_emit(job, ctx->sm_count, stream, ev ? ev[3] : nullptr, ctx->s_side, ctx->ev_fork, ctx->ev_join));
         if (ev) CU(cudaEventRecord(ev[4], stream));
         ctx->stats.kernel_launches += 2;
     }
@@ -331,7 +333,7 @@ int translate_host_simple(gts_ctx *ctx, const uint8_t *in, size_t n, size_t *out
     // clear the "output too small" flag left by the sizing pass
     ctx->h_totals->flags &= ~gts::kFlagOutOverflow;
     CU(cudaMemcpyAsync(ctx->job.totals, ctx->h_totals, sizeof(gts::Totals), cudaMemcpyHostToDevice, ctx->stream));
-    CU(gts::launch_emit(ctx->job, ctx->sm_count, ctx->stream, nullptr));
+    CU(gts::launch_emit(ctx->job, ctx->sm_count, ctx->stream, nullptr, ctx->s_side, ctx->ev_fork, ctx->ev_join));
     ctx->stats.kernel_launches += 2;
     if (total) CU(cudaMemcpyAsync(ctx->h_out, ctx->d_out, total, cudaMemcpyDeviceToHost, ctx->stream));
     ctx->stats.d2h_bytes += total;
@@ -520,6 +522,9 @@ int gts_create(const gts_options *opt, gts_ctx **out) {
     }
     if (e == cudaSuccess) e = gts::init_kernels();
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaHostAlloc(&ctx->h_totals, sizeof(gts::Totals), cudaHostAllocDefault);
     if (e != cudaSuccess) {
         std::string msg = std::string("CUDA initialisation failed (no CPU fallback): ") + cudaGetErrorString(e);
@@ -571,6 +576,9 @@ void gts_destroy(gts_ctx *ctx) {
     if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->s_side) cudaStreamDestroy(ctx->s_side);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     delete ctx;
 }
 

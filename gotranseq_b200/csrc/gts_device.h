@@ -48,7 +48,8 @@ constexpr int kTransWarps = (kSlotSyms + kTransSub - 1) / kTransSub;  // 6 chunk
 constexpr int kTransBlock = (kTransWarps + 1) * 32;       // + 1 builder warp
 constexpr int kPhaseLen = kTransSub / 3;                  // residues per phase array (per warp)
 constexpr int kPhaseGuard = 16;
-constexpr int kPhaseStride = kPhaseLen + 2 * kPhaseGuard; // bytes per phase array in smem
+constexpr int kPhasePad = 0;                              // extra bytes that rotate the arrays over the banks
+constexpr int kPhaseStride = kPhaseLen + 2 * kPhaseGuard + kPhasePad; // bytes per phase array in smem
 constexpr int kRecBatch = 4;                              // record pieces per chunk and format batch
 constexpr int kRunsPerBatch = kRecBatch * 6;
 // Output image of one chunk batch in shared memory: the residue lines a chunk writes (at most

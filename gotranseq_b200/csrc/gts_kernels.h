@@ -12,7 +12,9 @@ cudaError_t init_kernels();
 
 cudaError_t launch_parse(const Job &job, cudaStream_t stream);                // k_parse
 cudaError_t launch_sizes(const Job &job, int sm_count, cudaStream_t stream);  // k_tile_scan, k_records, k_size
-// k_translate, k_headers; ev_mid (optional) is recorded between the two
-cudaError_t launch_emit(const Job &job, int sm_count, cudaStream_t stream, cudaEvent_t ev_mid);
+// k_translate and k_headers; with a side stream (and two events to fork / join) the two run
+// concurrently; ev_mid (optional) is recorded on `stream` after k_translate
+cudaError_t launch_emit(const Job &job, int sm_count, cudaStream_t stream, cudaEvent_t ev_mid,
+                        cudaStream_t side = nullptr, cudaEvent_t ev_fork = nullptr, cudaEvent_t ev_join = nullptr);
 
 }  // namespace gts

@@ -473,7 +473,10 @@ cudaError_t init_kernels() {
                                 (int)sizeof(TransShared));
 }
 
-cudaError_t launch_emit(const Job &job, int sm_count, cudaStream_t stream, cudaEvent_t ev_mid) {
+// k_headers only needs the record table, so it runs on `side` (when given) next to k_translate: the
+// persistent k_translate grid leaves room for its small CTAs on every SM.
+cudaError_t launch_emit(const Job &job, int sm_count, cudaStream_t stream, cudaEvent_t ev_mid, cudaStream_t side,
+                        cudaEvent_t ev_fork, cudaEvent_t ev_join) {
     static int per_sm = 0;  // resident CTAs per SM: the persistent grid is exactly one wave
     if (!per_sm) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_translate, kTransBlock, sizeof(TransShared)) !=
@@ -481,9 +484,19 @@ cudaError_t launch_emit(const Job &job, int sm_count, cudaStream_t stream, cudaE
             per_sm = 3;
     }
     const u32 grid = job.ntiles < (u32)(sm_count * per_sm) ? job.ntiles : (u32)(sm_count * per_sm);
-    k_translate<<<grid, kTransBlock, sizeof(TransShared), stream>>>(job);
-    if (ev_mid) cudaEventRecord(ev_mid, stream);
-    k_headers<<<sm_count * 4, 256, 0, stream>>>(job);
+    if (side) {
+        cudaEventRecord(ev_fork, stream);
+        cudaStreamWaitEvent(side, ev_fork, 0);
+        k_headers<<<sm_count * 4, 256, 0, side>>>(job);
+        cudaEventRecord(ev_join, side);
+        k_translate<<<grid, kTransBlock, sizeof(TransShared), stream>>>(job);
+        if (ev_mid) cudaEventRecord(ev_mid, stream);
+        cudaStreamWaitEvent(stream, ev_join, 0);
+    } else {
+        k_translate<<<grid, kTransBlock, sizeof(TransShared), stream>>>(job);
+        if (ev_mid) cudaEventRecord(ev_mid, stream);
+        k_headers<<<sm_count * 4, 256, 0, stream>>>(job);
+    }
     return cudaGetLastError();
 }
 
