@@ -24,6 +24,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "6-frame Gbp/s device-resident"
+# DRAM bytes of one k_translate launch on the default workload, from the committed ncu capture
+# (profiles/r1c_ncu_full_summary.txt: 134.43 MB read + 339.85 MB written); null for other workloads
+NCU_TRAFFIC = {"readme189": 134429696 + 339853312}
 UNIT = "Gbp/s"
 
 
@@ -292,7 +295,9 @@ def main():
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_translate", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": NCU_TRAFFIC.get(args.workload), "peak_source": peak_src,
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one k_translate launch, "
+                                           "ncu --set full capture profiles/r1c_ncu_full_summary.txt",
                          "algorithmic_bytes_per_launch": trans_bytes, "ms_per_launch": trans_ms},
             "path": {"bytes_per_step_per_gpu": path_bytes, "achieved_GBps_per_gpu": path_gbs, "frac_of_peak": path_gbs / peak,
                      "note": "(FASTA in + protein FASTA out) / device time of the whole path"},

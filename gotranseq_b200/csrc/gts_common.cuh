@@ -51,16 +51,19 @@ __device__ __forceinline__ u64 gtime() {
 #define PHASE_MARK(job, idx, t_prev) do { } while (0)
 #endif
 
-// the four 0x80 flags of m as bits 0..3
-__device__ __forceinline__ u32 gather4(u32 m) { return (((m >> 7) * 0x00204081u) >> 21) & 0xFu; }
-
 // 0x80 in every byte of x that is '\n'
 __device__ __forceinline__ u32 newline_flags(u32 x) {
     return __vabsdiffu4(__vabsdiffu4(x, 0x0A0A0A0Au), 0x80808080u) & 0x80808080u;
 }
+// Bit i of the result = byte i of the 16 bytes is '\n'.  The per-byte flags (0x80) of a word are
+// gathered with one integer dot product: flags . (1,2,4,8) = 128 * nibble, accumulated over the
+// four words with the weights shifted by the nibble position.
 __device__ __forceinline__ u32 newline_mask16(uint4 v) {
-    return gather4(newline_flags(v.x)) | gather4(newline_flags(v.y)) << 4 | gather4(newline_flags(v.z)) << 8 |
-           gather4(newline_flags(v.w)) << 12;
+    u32 acc = __dp4a(newline_flags(v.x), 0x08040201u, 0u);                // bits 7..10
+    acc = __dp4a(newline_flags(v.y), 0x80402010u, acc);                   // bits 11..14
+    u32 hi = __dp4a(newline_flags(v.z), 0x08040201u, 0u);
+    hi = __dp4a(newline_flags(v.w), 0x80402010u, hi);
+    return (acc >> 7) | (hi << 1);
 }
 
 struct Pair {

@@ -433,9 +433,13 @@ __global__ void __launch_bounds__(kParseThreads) k_parse(const __grid_constant__
     // ---- pack two symbols per byte and write the slot ----
     const u32 nw = (S_tile + 7u) >> 3;
     u32 *gw = job.sym + (u64)t * kSlotWords;
-    for (u32 w = tid; w < nw; w += kParseThreads) {
-        const uint2 s2 = *reinterpret_cast<const uint2 *>(sh.sym + 8 * w);
-        gw[w] = s2.x | (s2.y << 4);
+#pragma unroll
+    for (int i = 0; i < (kSlotWords + kParseThreads - 1) / kParseThreads; i++) {
+        const u32 w = tid + i * kParseThreads;
+        if (w < nw) {
+            const uint2 s2 = *reinterpret_cast<const uint2 *>(sh.sym + 8 * w);
+            gw[w] = s2.x | (s2.y << 4);
+        }
     }
     if (tid == 0) {
         TileInfo ti;
