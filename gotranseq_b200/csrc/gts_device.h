@@ -62,7 +62,7 @@ constexpr int kScanThreads = 256;
 constexpr int kScanPerThread = 8;
 constexpr int kScanTile = kScanThreads * kScanPerThread;  // parse tiles per scan tile
 constexpr int kSizeThreads = 256;
-constexpr int kSizePerThread = 4;
+constexpr int kSizePerThread = 1;
 constexpr int kSizeTile = kSizeThreads * kSizePerThread;  // record slots per scan tile
 
 // Chained-scan status: 4 words per tile {agg.a, agg.b, inc.a, inc.b}; bit 63 of the .a words
