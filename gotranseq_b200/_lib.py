@@ -36,6 +36,22 @@ class gts_stats(ctypes.Structure):
         "records", "nucleotides", "in_bytes", "out_bytes", "kernel_launches", "h2d_bytes", "d2h_bytes", "passes")]
 
 
+class gts_piece_info(ctypes.Structure):
+    _fields_ = [("nucleotides", ctypes.c_uint64), ("headers", ctypes.c_uint64), ("header_len", ctypes.c_uint32),
+                ("tail", ctypes.c_uint8 * 2), ("reserved", ctypes.c_uint8 * 2)]
+
+
+class gts_piece(ctypes.Structure):
+    _fields_ = [("nt_before", ctypes.c_uint64), ("nt_total", ctypes.c_uint64), ("header_len", ctypes.c_uint32),
+                ("carry", ctypes.c_uint8 * 2), ("first", ctypes.c_uint8), ("last", ctypes.c_uint8)]
+
+
+class gts_segment(ctypes.Structure):
+    _fields_ = [("offset", ctypes.c_uint64), ("length", ctypes.c_uint64)]
+
+
+GTS_MAX_SEGMENTS = 12
+
 EXPORTS = {
     # name: (restype, argtypes)
     "gts_create": (ctypes.c_int, [ctypes.POINTER(gts_options), ctypes.POINTER(ctypes.c_void_p)]),
@@ -60,6 +76,17 @@ EXPORTS = {
     "gts_set_profiling": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "gts_kernel_times": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]),
     "gts_set_max_line_length": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t]),
+    "gts_piece_scan_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
+                                             ctypes.POINTER(gts_piece_info), ctypes.c_void_p]),
+    "gts_piece_translate_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                                  ctypes.POINTER(gts_piece), ctypes.c_void_p, ctypes.c_size_t,
+                                                  ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(gts_segment),
+                                                  ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]),
+    "gts_piece_scan": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
+                                      ctypes.POINTER(gts_piece_info)]),
+    "gts_piece_translate": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(gts_piece), ctypes.POINTER(ctypes.c_size_t),
+                                           ctypes.POINTER(gts_segment), ctypes.POINTER(ctypes.c_void_p),
+                                           ctypes.POINTER(ctypes.c_int)]),
     "gts_host_alloc": (ctypes.c_void_p, [ctypes.c_size_t]),
     "gts_host_free": (None, [ctypes.c_void_p]),
 }

@@ -74,6 +74,12 @@ struct gts_ctx {
     gts::Job job;
     cudaStream_t job_stream = nullptr;
 
+    // ---- piece of a split record (gts_piece_*) ----
+    bool piece_on = false;
+    gts::Job piece_job;      // only the piece fields are used
+    size_t piece_n = 0;      // bytes of the piece kept in d_in by gts_piece_scan
+    bool piece_first = false;
+
     // ---- per-kernel timing ----
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;  // 5 per recorded pass
@@ -221,6 +227,14 @@ int enqueue_pass(gts_ctx *ctx, const uint8_t *d_in, u64 n, uint8_t *d_out, u64 c
     job.alternative = ctx->opt.alternative ? 1 : 0;
     job.trim = ctx->opt.trim ? 1 : 0;
     job.more_follows = more_follows ? 1 : 0;
+    job.piece = 0; job.no_end_pads = 0; job.has_carry = 0; job.carry = 0; job.no_headers = 0; job.ov_H = 0;
+    job.t0_base = 0; job.win_lo = 0; job.ov_slot = 0; job.ov_n = 0; job.ov_dbase = 0;
+    if (ctx->piece_on) {
+        const gts::Job &p = ctx->piece_job;
+        job.piece = p.piece; job.no_end_pads = p.no_end_pads; job.has_carry = p.has_carry; job.carry = p.carry;
+        job.no_headers = p.no_headers; job.ov_H = p.ov_H; job.t0_base = p.t0_base; job.win_lo = p.win_lo;
+        job.ov_slot = p.ov_slot; job.ov_n = p.ov_n; job.ov_dbase = p.ov_dbase;
+    }
     job.lut = ctx->lut;
     ctx->job_stream = stream;
     cudaEvent_t *ev = nullptr;
@@ -451,6 +465,66 @@ int translate_host(gts_ctx *ctx, const uint8_t *in, size_t n, size_t *out_n) {
     ctx->stats.out_bytes = out_off;
     *out_n = out_off;
     return GTS_OK;
+}
+
+// ---- split record: which bytes of the record's output a piece writes --------------------------
+// Same arithmetic as build_runs (gts_translate.cu) / tests/gpu_model.py, for the whole piece at once.
+u64 host_reverse_start(u64 n, int i, bool alternative) {
+    if (alternative) return (u64)i;
+    int r = (int)(n % 3) - i;
+    return (u64)(r < 0 ? r + 3 : r);
+}
+void host_frame_lengths(u64 n, bool alternative, u64 L[6]) {
+    for (int k = 0; k < 3; k++) L[k] = n >= (u64)k ? (n - k + 2) / 3 : 0;
+    for (int i = 0; i < 3; i++) {
+        const u64 p = host_reverse_start(n, i, alternative);
+        L[3 + i] = n >= p ? (n - p + 2) / 3 : 0;
+    }
+}
+u64 host_run_size(u64 H, u64 L) { return H + 3 + L + (L + 59) / 60; }
+long long floordiv3(long long x) { return x >= 0 ? x / 3 : -((-x + 2) / 3); }
+long long ceildiv3(long long x) { return -floordiv3(-x); }
+
+int piece_segments(uint32_t mask, bool alternative, const gts_piece &p, u64 n_piece, gts_segment *segs, u64 *total) {
+    const u64 n = p.nt_total, H = p.header_len;
+    u64 L[6];
+    host_frame_lengths(n, alternative, L);
+    // windows (by start q) owned by the piece: those whose last nucleotide i = q + 2 lies in it;
+    // the last piece also owns the two windows that end on the pads behind the record
+    const long long q_lo = (long long)p.nt_before - 2;
+    const long long q_hi = (long long)(p.nt_before + n_piece + (p.last ? 2 : 0)) - 3;
+    std::vector<gts_segment> v;
+    u64 run_base = 0;
+    for (int f = 0; f < 6; f++) {
+        if (!((mask >> f) & 1u)) continue;
+        const u64 Lf = L[f];
+        const u64 body = run_base + H + 3;
+        if (p.first) v.push_back({run_base, H + 3});
+        run_base += host_run_size(H, Lf);
+        long long j_lo, j_hi;
+        if (f < 3) {
+            j_lo = std::max<long long>(0, ceildiv3(q_lo - f));
+            j_hi = q_hi >= f ? floordiv3(q_hi - f) + 1 : 0;
+        } else {
+            const long long Q = (long long)n - 3 - (long long)host_reverse_start(n, f - 3, alternative);
+            j_lo = std::max<long long>(0, ceildiv3(Q - q_hi));
+            j_hi = Q >= q_lo ? floordiv3(Q - q_lo) + 1 : 0;
+        }
+        if (j_hi > (long long)Lf) j_hi = (long long)Lf;
+        if (j_hi <= j_lo) continue;
+        const u64 a = body + (u64)j_lo + (u64)j_lo / 60;
+        const u64 b = body + (u64)j_hi + (u64)j_hi / 60 + (((u64)j_hi == Lf && Lf % 60 != 0) ? 1 : 0);
+        v.push_back({a, b - a});
+    }
+    *total = run_base;
+    std::sort(v.begin(), v.end(), [](const gts_segment &x, const gts_segment &y) { return x.offset < y.offset; });
+    int m = 0;
+    for (const gts_segment &s : v) {
+        if (s.length == 0) continue;
+        if (m && segs[m - 1].offset + segs[m - 1].length == s.offset) segs[m - 1].length += s.length;
+        else segs[m++] = s;
+    }
+    return m;
 }
 
 }  // namespace
@@ -751,6 +825,130 @@ int gts_kernel_times(gts_ctx *ctx, double ms[4], uint64_t *passes) {
     }
     if (passes) *passes = np;
     ctx->prof_used = 0;
+    return GTS_OK;
+}
+
+// ---- one record split over several GPUs ---------------------------------------------------
+
+int gts_piece_scan_device(gts_ctx *ctx, const void *d_in, size_t n, int first, gts_piece_info *info, void *stream) {
+    if (!ctx || !info) return GTS_ERR_ARG;
+    if (n && !d_in) return fail(ctx, GTS_ERR_ARG, "d_in is NULL");
+    if (ctx->opt.trim) return fail(ctx, GTS_ERR_ARG, "a split record cannot be trimmed");
+    CU(cudaSetDevice(ctx->device));
+    ctx->piece_on = true;
+    ctx->piece_job = gts::Job();
+    ctx->piece_job.no_end_pads = 1;  // count only: no pass of its own end
+    ctx->last_truncated = false;
+    int rc = enqueue_pass(ctx, static_cast<const uint8_t *>(d_in), n, nullptr, 0, static_cast<cudaStream_t>(stream), true);
+    if (!rc) rc = finish_pass(ctx, true);
+    ctx->piece_on = false;
+    if (rc) return rc;
+    const gts::Totals &t = *ctx->h_totals;
+    if (ctx->last_truncated) return fail(ctx, GTS_ERR_ARG, "a split record cannot hold an over-long line");
+    info->headers = t.n_headers;
+    info->nucleotides = t.total_sym - 2 - 2 * t.n_headers;
+    info->tail[0] = (uint8_t)(t.tail & 0xF);
+    info->tail[1] = (uint8_t)((t.tail >> 4) & 0xF);
+    info->reserved[0] = info->reserved[1] = 0;
+    info->header_len = 0;
+    if (first) {
+        if (t.n_headers != 1) return fail(ctx, GTS_ERR_ARG, "the first piece must hold exactly one header line");
+        u64 hoff = 0, hinfo = 0;
+        CU(cudaMemcpy(&hoff, ctx->d_hdr_off + 1, sizeof(u64), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(&hinfo, ctx->d_hinfo + 1, sizeof(u64), cudaMemcpyDeviceToHost));
+        if (hoff != 0) return fail(ctx, GTS_ERR_ARG, "the first piece must start with the header line");
+        info->header_len = (uint32_t)(hinfo & 0xFFFFFFFFull);
+    } else if (t.n_headers != 0) {
+        return fail(ctx, GTS_ERR_ARG, "only the first piece of a split record may hold a header line");
+    }
+    return GTS_OK;
+}
+
+int gts_piece_translate_device(gts_ctx *ctx, const void *d_in, size_t n, const gts_piece *piece, void *d_out,
+                               size_t cap, size_t *out_total, gts_segment segs[GTS_MAX_SEGMENTS], int *nseg,
+                               void *stream) {
+    if (!ctx || !piece || !segs || !nseg) return GTS_ERR_ARG;
+    if (n && !d_in) return fail(ctx, GTS_ERR_ARG, "d_in is NULL");
+    if (ctx->opt.trim) return fail(ctx, GTS_ERR_ARG, "a split record cannot be trimmed");
+    CU(cudaSetDevice(ctx->device));
+    gts::Job &p = ctx->piece_job;
+    p = gts::Job();
+    p.piece = 1;
+    p.no_end_pads = piece->last ? 0 : 1;
+    p.no_headers = piece->first ? 0 : 1;
+    p.ov_H = piece->header_len;
+    p.ov_n = piece->nt_total;
+    p.ov_dbase = 4;  // stream of the whole record: slot 0's pads, the record's pads, its nucleotides
+    if (piece->first) {
+        p.ov_slot = 1;
+    } else {
+        // the buffer's first two symbols stand in for the two nucleotides before the piece
+        p.ov_slot = 0;
+        p.has_carry = 1;
+        p.carry = (u32)(piece->carry[0] & 0xF) | (u32)(piece->carry[1] & 0xF) << 4;
+        p.t0_base = piece->nt_before + 2;
+        p.win_lo = p.t0_base + 2;
+    }
+    ctx->piece_on = true;
+    int rc = enqueue_pass(ctx, static_cast<const uint8_t *>(d_in), n, static_cast<uint8_t *>(d_out), cap,
+                          static_cast<cudaStream_t>(stream), false);
+    if (!rc) rc = finish_pass(ctx, false);
+    ctx->piece_on = false;
+    if (rc) return rc;
+    const gts::Totals &t = *ctx->h_totals;
+    if (out_total) *out_total = t.out_total;
+    if (t.flags & gts::kFlagOutOverflow)
+        return fail(ctx, GTS_ERR_CAPACITY, "output buffer too small: need " + std::to_string(t.out_total) + " bytes");
+    const u64 n_piece = t.total_sym - 2 - (piece->first ? 2 : 0);
+    u64 total = 0;
+    *nseg = piece_segments(ctx->mask, ctx->opt.alternative != 0, *piece, n_piece, segs, &total);
+    if (total != t.out_total) return fail(ctx, GTS_ERR_ARG, "split record: host and device output sizes differ");
+    return GTS_OK;
+}
+
+int gts_piece_scan(gts_ctx *ctx, const uint8_t *in, size_t n, int first, gts_piece_info *info) {
+    if (!ctx || !info) return GTS_ERR_ARG;
+    if (n && !in) return fail(ctx, GTS_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    int rc = ensure_dev_buffer(ctx, &ctx->d_in, &ctx->d_in_cap, n + 64);
+    if (rc) return rc;
+    if (n) CU(cudaMemcpyAsync(ctx->d_in, in, n, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes += n;
+    ctx->piece_n = n;
+    ctx->piece_first = first != 0;
+    return gts_piece_scan_device(ctx, ctx->d_in, n, first, info, ctx->stream);
+}
+
+int gts_piece_translate(gts_ctx *ctx, const gts_piece *piece, size_t *out_total, gts_segment segs[GTS_MAX_SEGMENTS],
+                        const uint8_t *data[GTS_MAX_SEGMENTS], int *nseg) {
+    if (!ctx || !piece || !segs || !data || !nseg) return GTS_ERR_ARG;
+    if ((piece->first != 0) != ctx->piece_first) return fail(ctx, GTS_ERR_ARG, "gts_piece_translate: not the piece last scanned");
+    CU(cudaSetDevice(ctx->device));
+    // the whole record's output size is known from the counts alone
+    u64 L[6], total = 0;
+    host_frame_lengths(piece->nt_total, ctx->opt.alternative != 0, L);
+    for (int f = 0; f < 6; f++)
+        if ((ctx->mask >> f) & 1u) total += host_run_size(piece->header_len, L[f]);
+    int rc = ensure_dev_buffer(ctx, &ctx->d_out, &ctx->d_out_cap, total + 64);
+    if (rc) return rc;
+    if (ctx->poison && total) CU(cudaMemsetAsync(ctx->d_out, 0xEE, total, ctx->stream));
+    size_t tot = 0;
+    rc = gts_piece_translate_device(ctx, ctx->d_in, ctx->piece_n, piece, ctx->d_out, ctx->d_out_cap, &tot, segs, nseg,
+                                    ctx->stream);
+    if (rc) return rc;
+    size_t bytes = 0;
+    for (int i = 0; i < *nseg; i++) bytes += round_up(segs[i].length, 16);
+    rc = ensure_pinned(ctx, &ctx->h_out, &ctx->h_out_cap, bytes + 64, 0);
+    if (rc) return rc;
+    size_t off = 0;
+    for (int i = 0; i < *nseg; i++) {
+        CU(cudaMemcpyAsync(ctx->h_out + off, ctx->d_out + segs[i].offset, segs[i].length, cudaMemcpyDeviceToHost, ctx->stream));
+        data[i] = ctx->h_out + off;
+        off += round_up(segs[i].length, 16);
+        ctx->stats.d2h_bytes += segs[i].length;
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (out_total) *out_total = tot;
     return GTS_OK;
 }
 

@@ -78,7 +78,7 @@ struct Totals {  // device-resident result block, copied to pinned host memory a
     u64 records;      // records emitted
     u64 nucleotides;  // nucleotides in emitted records
     u64 cut;          // with kFlagLongLine: the reference stops reading at this offset
-    u64 pad[1];
+    u64 tail;         // the stream's last two symbols (end pads excluded): last | second-to-last << 4
 };
 constexpr u64 kFlagRecOverflow = 1;  // record table too small (n_headers is still exact)
 constexpr u64 kFlagOutOverflow = 2;  // output buffer too small (out_total is still exact)
@@ -161,6 +161,21 @@ struct Job {  // kernel argument block (by value)
     u32 alternative;
     u32 trim;
     u32 more_follows;  // this buffer is not the end of the stream: an empty slot 0 is never emitted
+
+    // ---- a piece of ONE record split over several passes / GPUs (gts_piece_*) ----
+    // The piece's symbols keep their index in the whole record's stream: t0_base is the stream index
+    // of the buffer's first symbol, and one record slot is given the whole record's geometry.
+    u32 piece;         // 0 = an ordinary pass
+    u32 no_end_pads;   // the stream goes on after this buffer: no end pads
+    u32 has_carry;     // the two symbols in front of the buffer are `carry` (they replace slot 0's pads)
+    u32 carry;         // last | second-to-last << 4
+    u32 no_headers;    // the record's header lines are written by the first piece only
+    u32 ov_H;          // the record's header line bytes
+    u64 t0_base;
+    u64 win_lo;        // windows ending below this stream index belong to the piece before
+    u64 ov_slot;       // the record's slot in this pass; every other slot is silent
+    u64 ov_n;          // the whole record's nucleotides
+    u64 ov_dbase;      // stream index of its first nucleotide
     Lut lut;
 };
 

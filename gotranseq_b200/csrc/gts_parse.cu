@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(kParseThreads) k_parse(const __grid_constant__
     }
     const bool last_tile = (t + 1 == job.ntiles);
     const u32 S_own = tile_total & 0xFFFFu, R_tile = tile_total >> 16;
-    const u32 S_tile = S_own + (last_tile ? 2u : 0u);  // the last tile owns the two end pads
+    const u32 S_tile = S_own + (last_tile && !job.no_end_pads ? 2u : 0u);  // the last tile owns the two end pads
     const u32 d = excl & 0xFFFFu;                      // slot index of the chunk's first symbol
     if (tid == 0 && R_tile) {
         // one slot range of the event list for the tile's header lines
@@ -381,8 +381,8 @@ __global__ void __launch_bounds__(kParseThreads) k_parse(const __grid_constant__
             const u32 lead = c_first ? 2u : 0u;
             const u32 off = lead + (u32)__popc(keepm & lt) + 2u * (u32)__popc(hs & lt);
             if (c_first && lane == 0) {  // pads of slot 0 (the bytes before the first header line)
-                sh.sym[0] = 0;
-                sh.sym[1] = 0;
+                sh.sym[0] = job.has_carry ? (uint8_t)((job.carry >> 4) & 0xFu) : 0;
+                sh.sym[1] = job.has_carry ? (uint8_t)(job.carry & 0xFu) : 0;
             }
             if (keep) sh.sym[c_d + off] = sh.enc[b];
             if (hstart) {

@@ -109,14 +109,28 @@ __global__ void __launch_bounds__(kScanThreads) k_tile_scan(const __grid_constan
                 if (st + 1 == nscan) {
                     // totals; the last tile's two end pads are not counted as stream symbols
                     const u64 S2 = ex.a + tot_s, R = ex.b + tot_r;
-                    job.totals->total_sym = S2 - 2;
+                    const u64 S = S2 - (job.no_end_pads ? 0 : 2);
+                    job.totals->total_sym = S;
+                    {   // the stream's last two symbols (a later piece of the same record needs them)
+                        u32 got = 0, tail = 0;
+                        for (i64 u = (i64)ntiles - 1; got < 2 && u >= 0; u--) {
+                            const TileInfo ti = job.tile_info[u];
+                            // the last tile's end pads are not part of the record
+                            const u32 ns_u = ti.nsym - ((u32)u == ntiles - 1 && !job.no_end_pads ? 2u : 0u);
+                            for (u32 k = 0; k < ns_u && got < 2; k++) {
+                                tail |= slot_symbol(job.sym, (u32)u, ns_u - 1 - k) << (4 * got);
+                                got++;
+                            }
+                        }
+                        job.totals->tail = tail;
+                    }
                     job.totals->n_headers = R;
                     if (R + 2 <= job.rec_cap) {
                         // slot 0 (bytes before the first header line) and the sentinel after the last record
                         job.hdr_off[0] = 0;
-                        job.dbase[0] = 2;
+                        job.dbase[0] = job.t0_base + 2;
                         job.loc[0] = 2;
-                        job.dbase[R + 1] = S2;
+                        job.dbase[R + 1] = job.t0_base + S + 2;
                         job.loc[R + 1] = (u64)(ntiles - 1) << 16 | job.tile_info[ntiles - 1].nsym;
                     } else {
                         atomicOr(&job.totals->flags, kFlagRecOverflow);
@@ -125,7 +139,7 @@ __global__ void __launch_bounds__(kScanThreads) k_tile_scan(const __grid_constan
             }
         }
         __syncthreads();
-        u64 T = s_excl_s + ex_s, Rr = s_excl_r + ex_r;
+        u64 T = job.t0_base + s_excl_s + ex_s, Rr = s_excl_r + ex_r;
 #pragma unroll
         for (int i = 0; i < kScanPerThread; i++) {
             const u32 t = t0 + i;
@@ -308,8 +322,12 @@ __global__ void __launch_bounds__(kSizeThreads) k_size(const __grid_constant__ J
             const u64 s = t * kSizeTile + (u64)tid * kSizePerThread + i;
             size[i] = 0;
             if (s < nslots) {
-                const u64 D = job.dbase[s];
-                const u64 n = job.dbase[s + 1] - 2 - D;
+                u64 D = job.dbase[s];
+                u64 n = job.dbase[s + 1] - 2 - D;
+                if (job.piece && s == job.ov_slot) {  // the whole record's geometry
+                    D = job.ov_dbase;
+                    n = job.ov_n;
+                }
                 u64 L[6];
                 frame_lengths(n, job.alternative != 0, L);
                 if (job.trim) {
@@ -317,8 +335,12 @@ __global__ void __launch_bounds__(kSizeThreads) k_size(const __grid_constant__ J
 #pragma unroll
                     for (int f = 0; f < 6; f++) job.trim_len[s * 6 + f] = (u32)L[f];
                 }
-                const u64 H = s >= 1 ? (job.hinfo[s] & 0xFFFFFFFFull) : 0;
-                const bool em = record_emitted(s, n, R, job.more_follows != 0);
+                u64 H = s >= 1 ? (job.hinfo[s] & 0xFFFFFFFFull) : 0;
+                bool em = record_emitted(s, n, R, job.more_follows != 0);
+                if (job.piece) {
+                    em = s == job.ov_slot;
+                    if (em) H = job.ov_H;
+                }
                 if (em) {
 #pragma unroll
                     for (int f = 0; f < 6; f++)

@@ -153,7 +153,9 @@ __device__ __forceinline__ void build_runs(const Job &job, RunTable &ws, u64 R, 
         }
         // windows (by start q) of this record whose last symbol lies in the chunk
         const i64 dq = (i64)D - (i64)T0;  // local index of the record's first symbol
-        const i64 q_lo = -dq - 2 > -2 ? -dq - 2 : -2;
+        const u64 Tlo = T0 > job.win_lo ? T0 : job.win_lo;  // (a piece leaves its first windows to the piece before)
+        const i64 q_first = (i64)Tlo - (i64)D - 2;
+        const i64 q_lo = q_first > -2 ? q_first : -2;
         const i64 q_hi = ((i64)n - 1 < (i64)(Tend - T0) - 1 - dq - 2) ? (i64)n - 1 : (i64)(Tend - T0) - 1 - dq - 2;
         u64 run_base = ri.out_off;
 #pragma unroll
@@ -431,7 +433,7 @@ __global__ void __launch_bounds__(kTransBlock, 4) k_translate(const __grid_const
 __global__ void __launch_bounds__(256) k_headers(const __grid_constant__ Job job) {
     const int lane = threadIdx.x & 31, sub = lane & 15, half = lane >> 4;
     const u64 R = job.totals->n_headers;
-    if (job.totals->flags != 0) return;
+    if (job.totals->flags != 0 || job.no_headers) return;
     const u64 nhalf = (u64)gridDim.x * (blockDim.x >> 4);
     for (u64 s = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 4; s <= R; s += nhalf) {
         const RecInfo ri = job.rec[s];

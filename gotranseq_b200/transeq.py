@@ -130,6 +130,60 @@ class Translator:
         self._check(self._L.gts_kernel_times(self._h, ms, ctypes.byref(n)))
         return list(ms), n.value
 
+    # ---- one record split over several GPUs (gotranseq_b200/split.py drives these) ----
+    def piece_scan(self, data, first):
+        """Parse a piece of a split record (host bytes; they stay on the device for piece_translate).
+        Returns dict(nucleotides, headers, header_len, tail)."""
+        n = len(data)
+        buf = (ctypes.c_char * max(n, 1)).from_buffer_copy(bytes(data) if n else b"\0")
+        info = _lib.gts_piece_info()
+        self._check(self._L.gts_piece_scan(self._h, ctypes.cast(buf, ctypes.c_void_p), n, 1 if first else 0,
+                                           ctypes.byref(info)))
+        return dict(nucleotides=info.nucleotides, headers=info.headers, header_len=info.header_len,
+                    tail=(info.tail[0], info.tail[1]))
+
+    @staticmethod
+    def _piece_struct(piece):
+        p = _lib.gts_piece()
+        p.nt_before, p.nt_total, p.header_len = piece["nt_before"], piece["nt_total"], piece["header_len"]
+        p.carry[0], p.carry[1] = piece["carry"]
+        p.first, p.last = (1 if piece["first"] else 0), (1 if piece["last"] else 0)
+        return p
+
+    def piece_translate(self, piece):
+        """Translate the piece last scanned.  Returns (size of the whole record's output,
+        [(offset, bytes), ...]): the byte ranges of that output this piece produces."""
+        p = self._piece_struct(piece)
+        segs = (_lib.gts_segment * _lib.GTS_MAX_SEGMENTS)()
+        data = (ctypes.c_void_p * _lib.GTS_MAX_SEGMENTS)()
+        nseg = ctypes.c_int()
+        total = ctypes.c_size_t()
+        self._check(self._L.gts_piece_translate(self._h, ctypes.byref(p), ctypes.byref(total), segs, data,
+                                                ctypes.byref(nseg)))
+        return total.value, [(segs[i].offset, ctypes.string_at(data[i], segs[i].length)) for i in range(nseg.value)]
+
+    def piece_scan_device(self, d_in, n, first, stream=0):
+        info = _lib.gts_piece_info()
+        self._check(self._L.gts_piece_scan_device(self._h, ctypes.c_void_p(d_in), n, 1 if first else 0,
+                                                  ctypes.byref(info), ctypes.c_void_p(stream)))
+        return dict(nucleotides=info.nucleotides, headers=info.headers, header_len=info.header_len,
+                    tail=(info.tail[0], info.tail[1]))
+
+    def piece_translate_device(self, d_in, n, piece, d_out, cap, stream=0):
+        """Device-resident piece: writes its segments into d_out (the whole record's output buffer).
+        Returns (size of the whole output, [(offset, length), ...])."""
+        p = self._piece_struct(piece)
+        segs = (_lib.gts_segment * _lib.GTS_MAX_SEGMENTS)()
+        nseg = ctypes.c_int()
+        total = ctypes.c_size_t()
+        rc = self._L.gts_piece_translate_device(self._h, ctypes.c_void_p(d_in), n, ctypes.byref(p),
+                                                ctypes.c_void_p(d_out), cap, ctypes.byref(total), segs,
+                                                ctypes.byref(nseg), ctypes.c_void_p(stream))
+        if rc == _lib.GTS_ERR_CAPACITY:
+            raise TranseqError(rc, f"output buffer too small: need {total.value} bytes")
+        self._check(rc)
+        return total.value, [(segs[i].offset, segs[i].length) for i in range(nseg.value)]
+
     # ---- streaming (what the Go shim's Translate loop does, INTEGRATION.md) ----
     def translate_stream(self, reader, writer):
         L, h = self._L, self._h

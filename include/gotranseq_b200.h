@@ -170,6 +170,63 @@ int gts_kernel_times(gts_ctx *ctx, double ms[4], uint64_t *passes);
  */
 int gts_set_max_line_length(gts_ctx *ctx, size_t n);
 
+/*
+ * One record split over several GPUs (BASELINE config 4: a chromosome-sized record; the reference
+ * translates a record on ONE worker, writer.go:57-117, so this has no counterpart there).  The
+ * caller cuts the record's FASTA bytes into pieces at line starts (the first piece begins with the
+ * header line) and gives each piece to one GPU / context:
+ *
+ *   1. gts_piece_scan*       parses the piece: its nucleotide count, the codes of its last two
+ *                            nucleotides, the header line's length (first piece)
+ *   2. the caller adds the counts up (an all-gather of three integers between the ranks) and
+ *      fills gts_piece for every piece: nucleotides before it, nucleotides of the whole record,
+ *      the two nucleotides in front of it (carry), the header length
+ *   3. gts_piece_translate*  writes the piece's share of the record's protein FASTA at its
+ *                            FINAL offsets: at most 12 byte ranges (one per requested frame, plus
+ *                            the header lines on the first piece), returned as segments
+ *
+ * The pieces' segments are disjoint and cover the record's output exactly; every residue is
+ * computed by the piece that holds the LAST nucleotide of its codon (the carry supplies the other
+ * two), so no piece needs bytes of another.  --trim is not supported here (GTS_ERR_ARG).
+ */
+typedef struct gts_piece_info {
+    uint64_t nucleotides; /* nucleotides in the piece                                          */
+    uint64_t headers;     /* header lines seen: must be 1 for the first piece, 0 for the others */
+    uint32_t header_len;  /* bytes of the header line, CR dropped (first piece)                */
+    uint8_t tail[2];      /* codes (N=0 A=1 C=2 T=3 G=4) of its last / second-to-last nucleotide */
+    uint8_t reserved[2];
+} gts_piece_info;
+
+typedef struct gts_piece {
+    uint64_t nt_before;   /* nucleotides of the record in the pieces before this one            */
+    uint64_t nt_total;    /* nucleotides of the whole record                                    */
+    uint32_t header_len;  /* gts_piece_info.header_len of the first piece                       */
+    uint8_t carry[2];     /* codes of the two nucleotides before the piece: [0] last, [1] second to last */
+    uint8_t first;        /* this piece starts with the record's header line                    */
+    uint8_t last;         /* this piece ends the record                                         */
+} gts_piece;
+
+typedef struct gts_segment {
+    uint64_t offset;      /* offset in the record's protein FASTA                               */
+    uint64_t length;
+} gts_segment;
+#define GTS_MAX_SEGMENTS 12
+
+/* Device-resident: d_in as for gts_translate_device.  d_out holds the WHOLE record's output
+ * (*out_total bytes, reported also on GTS_ERR_CAPACITY); the piece writes its segments only. */
+int gts_piece_scan_device(gts_ctx *ctx, const void *d_in, size_t n, int first, gts_piece_info *info,
+                          void *stream);
+int gts_piece_translate_device(gts_ctx *ctx, const void *d_in, size_t n, const gts_piece *piece,
+                               void *d_out, size_t cap, size_t *out_total,
+                               gts_segment segs[GTS_MAX_SEGMENTS], int *nseg, void *stream);
+/* Host buffers: gts_piece_scan copies the piece to the device and keeps it there for
+ * gts_piece_translate, which hands segment i back as data[i] (pinned, owned by ctx, valid until
+ * the next call on ctx). */
+int gts_piece_scan(gts_ctx *ctx, const uint8_t *in, size_t n, int first, gts_piece_info *info);
+int gts_piece_translate(gts_ctx *ctx, const gts_piece *piece, size_t *out_total,
+                        gts_segment segs[GTS_MAX_SEGMENTS], const uint8_t *data[GTS_MAX_SEGMENTS],
+                        int *nseg);
+
 /* Pinned host memory for callers of gts_translate_buffer that want full-speed PCIe copies. */
 void *gts_host_alloc(size_t bytes);
 void gts_host_free(void *p);

@@ -1,0 +1,217 @@
+"""One record split into pieces (gotranseq_b200/split.py).
+
+CPU part: the host logic (cuts, carry planning, assembly) against a fake translator that answers
+from the oracle, with the segment geometry restated here in Python.  GPU part: the real pieces
+through the C ABI, assembled, against the oracle."""
+import random
+
+import pytest
+
+import oracle
+from gotranseq_b200 import split
+
+CODES = {c: 0 for c in range(256)}
+for ch, v in (("A", 1), ("C", 2), ("T", 3), ("U", 3), ("G", 4)):
+    CODES[ord(ch)] = v
+    CODES[ord(ch.lower())] = v
+
+FRAME_MASKS = {"1": [0], "2": [1], "3": [2], "F": [0, 1, 2], "-1": [3], "-2": [4], "-3": [5], "R": [3, 4, 5],
+               "6": [0, 1, 2, 3, 4, 5]}
+
+
+def nucleotides(piece, first):
+    """Bytes of a piece that the reference keeps as nucleotides (transeq.go:183-216): header line
+    dropped, line ends ('\\n', '\\r\\n') dropped."""
+    lines = piece.split(b"\n")
+    if first:
+        lines = lines[1:]
+    out = bytearray()
+    for k, ln in enumerate(lines):
+        last = k == len(lines) - 1
+        if ln.endswith(b"\r") and not last:
+            ln = ln[:-1]
+        elif ln.endswith(b"\r") and last:
+            ln = ln[:-1]  # bufio.ScanLines drops a CR at EOF too
+        out += ln
+    return bytes(out)
+
+
+def reverse_start(n, i, alt):
+    return i if alt else (n % 3 - i) % 3
+
+
+def frame_lengths(n, alt):
+    L = [(n - k + 2) // 3 if n >= k else 0 for k in range(3)]
+    for i in range(3):
+        p = reverse_start(n, i, alt)
+        L.append((n - p + 2) // 3 if n >= p else 0)
+    return L
+
+
+def segments(frames, alt, H, n, before, m, first, last):
+    """Byte ranges of the record's output owned by the piece holding nucleotides [before, before+m)."""
+    L = frame_lengths(n, alt)
+    q_lo, q_hi = before - 2, before + m + (2 if last else 0) - 3
+    segs, base = [], 0
+    for f in frames:
+        body = base + H + 3
+        if first:
+            segs.append((base, H + 3))
+        base += H + 3 + L[f] + (L[f] + 59) // 60
+        if f < 3:
+            j_lo, j_hi = max(0, -((f - q_lo) // 3)), ((q_hi - f) // 3 + 1 if q_hi >= f else 0)
+        else:
+            Q = n - 3 - reverse_start(n, f - 3, alt)
+            j_lo, j_hi = max(0, -((q_hi - Q) // 3)), ((Q - q_lo) // 3 + 1 if Q >= q_lo else 0)
+        j_hi = min(j_hi, L[f])
+        if j_hi <= j_lo:
+            continue
+        a = body + j_lo + j_lo // 60
+        b = body + j_hi + j_hi // 60 + (1 if j_hi == L[f] and L[f] % 60 else 0)
+        segs.append((a, b - a))
+    return base, [s for s in segs if s[1]]
+
+
+class FakeTranslator:
+    """Answers piece_scan / piece_translate from the oracle's output of the WHOLE record."""
+
+    def __init__(self, whole, frame, alt):
+        self.whole, self.frame, self.alt = whole, frame, alt
+
+    def piece_scan(self, data, first):
+        self.nts = nucleotides(data, first)
+        hl = 0
+        if first:
+            h = data.split(b"\n")[0]
+            hl = len(h[:-1] if h.endswith(b"\r") else h)
+        codes = [CODES[c] for c in self.nts[-2:]]
+        tail = (codes[-1] if codes else 0, codes[-2] if len(codes) > 1 else 0)
+        return dict(nucleotides=len(self.nts), headers=1 if first else 0, header_len=hl, tail=tail)
+
+    def piece_translate(self, p):
+        want = oracle.translate(self.whole, frame=self.frame, alternative=self.alt)
+        total, segs = segments(FRAME_MASKS[self.frame], self.alt, p["header_len"], p["nt_total"], p["nt_before"],
+                               len(self.nts), p["first"], p["last"])
+        assert total == len(want)
+        return total, [(o, want[o:o + n]) for o, n in segs]
+
+    def close(self):
+        pass
+
+
+def one_record(seed, n, width=60, crlf=False, header=b">chr1 test record"):
+    rng = random.Random(seed)
+    seq = bytes(rng.choice(b"ACGTNacgtRYK") for _ in range(n))
+    eol = b"\r\n" if crlf else b"\n"
+    body = eol.join(seq[i:i + width] for i in range(0, n, width))
+    return header + eol + body + (eol if rng.random() < 0.5 else b"")
+
+
+def test_piece_ranges_cover_and_cut_at_line_starts():
+    for seed in range(20):
+        buf = one_record(seed, 50 + 37 * seed, width=7 + seed)
+        for k in (1, 2, 3, 8, 40):
+            r = split.piece_ranges(buf, k)
+            assert r[0][0] == 0 and r[-1][1] == len(buf)
+            assert all(r[i][1] == r[i + 1][0] for i in range(k - 1))
+            hdr_end = buf.find(b"\n") + 1
+            for lo, _ in r[1:]:
+                assert lo >= hdr_end and (lo == len(buf) or buf[lo - 1:lo] == b"\n")
+
+
+def test_plan_pieces_carry():
+    infos = [dict(nucleotides=5, headers=1, header_len=4, tail=(3, 2)), dict(nucleotides=0, headers=0, header_len=0, tail=(0, 0)),
+             dict(nucleotides=1, headers=0, header_len=0, tail=(4, 0)), dict(nucleotides=7, headers=0, header_len=0, tail=(1, 1))]
+    p = split.plan_pieces(infos)
+    assert [x["nt_before"] for x in p] == [0, 5, 5, 6]
+    assert all(x["nt_total"] == 13 and x["header_len"] == 4 for x in p)
+    assert [x["carry"] for x in p] == [(0, 0), (3, 2), (3, 2), (4, 3)]
+    assert [x["first"] for x in p] == [True, False, False, False] and p[-1]["last"] and not p[0]["last"]
+
+
+@pytest.mark.parametrize("frame", ["1", "2", "3", "F", "-1", "-2", "-3", "R", "6"])
+def test_split_host_logic_against_oracle(frame):
+    for seed in range(12):
+        n = [0, 1, 2, 3, 5, 59, 60, 61, 179, 180, 181, 1000][seed]
+        buf = one_record(seed, n, width=(60, 7, 13)[seed % 3], crlf=seed % 4 == 1)
+        for alt in (False, True):
+            want = oracle.translate(buf, frame=frame, alternative=alt)
+            for k in (1, 2, 3, 5):
+                got = split.translate_split(buf, k, lambda: FakeTranslator(buf, frame, alt))
+                assert got == want, (seed, frame, alt, k)
+
+
+def test_assemble_rejects_gaps():
+    with pytest.raises(ValueError):
+        split.assemble(10, [[(0, b"abc")], [(4, b"defghi")]])
+    with pytest.raises(ValueError):
+        split.assemble(10, [[(0, b"abc")], [(3, b"def")]])
+
+
+# ---- GPU: the real pieces ----
+
+def make_gpu(frame, alt, table=0, clean=False, trim=False):
+    import gotranseq_b200
+    return lambda: gotranseq_b200.Translator(gotranseq_b200.Options(Frame=frame, Alternative=alt, Table=table,
+                                                                    Clean=clean, Trim=trim))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("frame", ["1", "2", "3", "F", "-1", "-2", "-3", "R", "6"])
+def test_gpu_split_small(frame):
+    for seed in range(12):
+        n = [0, 1, 2, 3, 5, 59, 60, 61, 179, 180, 181, 1000][seed]
+        buf = one_record(seed, n, width=(60, 7, 13)[seed % 3], crlf=seed % 4 == 1)
+        for alt in (False, True):
+            want = oracle.translate(buf, frame=frame, alternative=alt)
+            for k in (1, 2, 3, 5):
+                assert split.translate_split(buf, k, make_gpu(frame, alt)) == want, (seed, frame, alt, k)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("npieces", [1, 2, 3, 8])
+def test_gpu_split_chromosome_shaped(npieces):
+    """BASELINE config 4's shape (-f R -a, one long record, 60-column lines), and all six frames."""
+    buf = one_record(77, 3_000_003 + npieces, width=60, header=b">chr21 Homo sapiens chromosome 21")
+    for frame, alt, table, clean in (("R", True, 0, False), ("6", False, 11, True), ("F", False, 0, False)):
+        want = oracle.translate(buf, frame=frame, alternative=alt, table=table, clean=clean)
+        assert split.translate_split(buf, npieces, make_gpu(frame, alt, table=table, clean=clean)) == want
+
+
+@pytest.mark.gpu
+def test_gpu_split_ragged_lines_and_tiny_pieces():
+    rng = random.Random(5)
+    for seed in range(30):
+        n = rng.randrange(0, 40000)
+        lines, seq = [], bytes(rng.choice(b"ACGTN") for _ in range(n))
+        i = 0
+        while i < n:
+            w = rng.choice((1, 2, 3, 10, 61, 500, 9000))
+            lines.append(seq[i:i + w])
+            if rng.random() < 0.05:
+                lines.append(b"")  # blank line
+            i += w
+        eol = b"\r\n" if seed % 3 == 0 else b"\n"
+        buf = b">r" + str(seed).encode() + b" x y" + eol + eol.join(lines) + (eol if seed % 2 else b"")
+        frame = rng.choice(["6", "R", "F", "-2", "3"])
+        alt = rng.random() < 0.5
+        want = oracle.translate(buf, frame=frame, alternative=alt)
+        for k in (2, 4, 7):
+            assert split.translate_split(buf, k, make_gpu(frame, alt)) == want, (seed, frame, alt, k)
+
+
+@pytest.mark.gpu
+def test_gpu_split_argument_errors():
+    import gotranseq_b200
+    tr = make_gpu("6", False)()
+    with pytest.raises(gotranseq_b200.TranseqError, match="exactly one header"):
+        tr.piece_scan(b">a\nACG\n>b\nAC\n", True)
+    with pytest.raises(gotranseq_b200.TranseqError, match="start with the header"):
+        tr.piece_scan(b"ACG\n>b\nAC\n", True)
+    with pytest.raises(gotranseq_b200.TranseqError, match="only the first piece"):
+        tr.piece_scan(b"ACG\n>b\nAC\n", False)
+    tr.close()
+    tr = make_gpu("6", False, trim=True)()
+    with pytest.raises(gotranseq_b200.TranseqError, match="cannot be trimmed"):
+        tr.piece_scan(b">a\nACG\n", True)
+    tr.close()
