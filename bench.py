@@ -166,6 +166,107 @@ def workload_config(args, nbytes):
             "sharding": "one independent batch per GPU, no collective"}
 
 
+def run_split(args, rank, local_rank, world):
+    """--workload chromosome_split (BASELINE config 4 at N GPUs): ONE record cut into N pieces, one per
+    rank.  A step = every rank scans its piece, the ranks all-gather three integers (NCCL), every rank
+    translates its piece into its byte ranges of the record's output.  Strong scaling: the record is
+    the same at every N."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import gotranseq_b200
+    import workloads
+    from gotranseq_b200 import split
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    gen, opts = workloads.WORKLOADS["chromosome"]
+    data = gen()
+    lo, hi = split.piece_ranges(data, world)[rank]
+    piece_bytes = data[lo:hi]
+    n = len(piece_bytes)
+    O = gotranseq_b200.Options(Frame=opts["frame"], Alternative=opts.get("alternative", False))
+    tr = gotranseq_b200.Translator(O, device=local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+    d_in = torch.from_numpy(np.frombuffer(piece_bytes, dtype=np.uint8).copy()).cuda()
+    cap = len(data) * 2 + 4096  # three frames of n/3 residues + newlines + headers
+    d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    mine = torch.zeros(4, dtype=torch.int64, device="cuda")
+    every = torch.zeros(4 * world, dtype=torch.int64, device="cuda")
+
+    def step():
+        info = tr.piece_scan_device(d_in.data_ptr(), n, rank == 0, stream)
+        mine.copy_(torch.tensor([info["nucleotides"], info["header_len"], info["tail"][0], info["tail"][1]]))
+        if world > 1:
+            dist.all_gather_into_tensor(every, mine)
+            rows = every.view(world, 4).tolist()
+        else:
+            rows = [mine.tolist()]
+        infos = [dict(nucleotides=r[0], header_len=r[1], tail=(r[2], r[3])) for r in rows]
+        piece = split.plan_pieces(infos)[rank]
+        return tr.piece_translate_device(d_in.data_ptr(), n, piece, d_out.data_ptr(), cap, stream), infos
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        (total, segs), infos = step()
+    launches0 = tr.stats()["kernel_launches"]
+    sampler = ClockSampler(local_rank)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    dev_s = ev0.elapsed_time(ev1) / 1e3
+    launches = tr.stats()["kernel_launches"] - launches0
+    nt_total = sum(i["nucleotides"] for i in infos)
+
+    # every rank checks its own byte ranges against the oracle's output of the whole record
+    ok = True
+    if args.verify:
+        import oracle
+        want = oracle.translate(np.frombuffer(data, dtype=np.uint8), num_worker=1, **opts)
+        ok = total == len(want)
+        host = d_out[:total].cpu().numpy().tobytes() if ok else b""
+        for off, length in segs:
+            ok = ok and host[off:off + length] == want[off:off + length]
+    seg_bytes = sum(length for _, length in segs)
+    t = torch.tensor([dev_s, 0.0 if ok else 1.0], dtype=torch.float64, device="cuda")
+    sb = torch.tensor([seg_bytes], dtype=torch.int64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(sb, op=dist.ReduceOp.SUM)
+    dev_s = float(t[0])
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        line = {
+            "metric": METRIC, "value": nt_total * args.steps / dev_s / 1e9, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": warm, "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "chromosome_split: one %d-byte record (%d nt, 60-column lines), flags -f R -a, cut "
+                                   "into %d pieces at line starts, one per GPU" % (len(data), nt_total, world),
+                       "l2": "piece + output per step exceed the 126 MB L2 at N <= 2; no explicit flush",
+                       "sharding": "intra-record split; exchange = one all-gather of 4 integers per rank per step"},
+            "e2e": None, "gpu_launches": launches, "clocks": clocks,
+            "segments_cover_output": int(sb[0]) == total,
+            "verified": (float(t[1]) == 0.0) if args.verify else None,
+            "bytes": {"in": len(data), "out": total, "nucleotides": nt_total, "records": 1},
+            "peak_GBps": peak, "peak_source": peak_src,
+        }
+        print(json.dumps(line))
+    tr.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -178,10 +279,17 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the end-to-end loop (default: min(steps, 10))")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end loop (profiling runs)")
     ap.add_argument("--chunk-mb", type=float, default=0, help="pipeline chunk of the host entry point (0 = library default)")
+    ap.add_argument("--verify", action="store_true", help="chromosome_split: compare every rank's byte ranges with the oracle")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank, local_rank, world = env_rank()
 
+    if args.workload == "chromosome_split":
+        if args.impl == "reference":
+            args.workload = "chromosome"
+        else:
+            run_split(args, rank, local_rank, world)
+            return
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

@@ -148,6 +148,48 @@ def test_assemble_rejects_gaps():
         split.assemble(10, [[(0, b"abc")], [(3, b"def")]])
 
 
+def _split_worker(rank, world, port, buf, frame, alt, q):
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def all_gather(obj):
+        objs = [None] * world
+        dist.all_gather_object(objs, obj)
+        return objs
+
+    total, segs = split.translate_split_rank(buf, rank, world, FakeTranslator(buf, frame, alt), all_gather)
+    q.put((rank, total, segs))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_split_two_ranks_gloo():
+    """The exchange between the ranks of a split record (three integers per piece), world_size 2."""
+    import socket
+    import torch.multiprocessing as mp
+    buf = one_record(3, 5000, width=60)
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_split_worker, args=(r, 2, port, buf, "6", False, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == res[1][1]
+    assert split.assemble(res[0][1], [r[2] for r in res]) == oracle.translate(buf, frame="6")
+
+
 # ---- GPU: the real pieces ----
 
 def make_gpu(frame, alt, table=0, clean=False, trim=False):
