@@ -169,4 +169,42 @@ __device__ __forceinline__ u32 slot_symbol(const u32 *sym, u32 tile, u32 i) {
     return (w >> (8 * (b & 3) + 4 * (b >> 2))) & 0xFu;
 }
 
+// ---- shared-memory output image -> global memory ----
+__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, u32 bytes) {
+    const u32 saddr = (u32)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr), "r"(bytes)
+                 : "memory");
+}
+
+// Copy the bytes [lo, hi) of the image (hi - lo < 16, both inside one aligned 16-byte slot) to
+// global memory with naturally aligned stores; g is the global address of image byte 0.
+__device__ __forceinline__ void store_edge(const uint8_t *image, uint8_t *g, u32 lo, u32 hi) {
+    u32 x = lo;
+    if ((x & 1u) && x + 1u <= hi) { g[x] = image[x]; x += 1u; }
+    if ((x & 2u) && x + 2u <= hi) { *reinterpret_cast<uint16_t *>(g + x) = *reinterpret_cast<const uint16_t *>(image + x); x += 2u; }
+    if ((x & 4u) && x + 4u <= hi) { *reinterpret_cast<u32 *>(g + x) = *reinterpret_cast<const u32 *>(image + x); x += 4u; }
+    if (x + 8u <= hi) { *reinterpret_cast<uint2 *>(g + x) = *reinterpret_cast<const uint2 *>(image + x); x += 8u; }
+    if (x + 4u <= hi) { *reinterpret_cast<u32 *>(g + x) = *reinterpret_cast<const u32 *>(image + x); x += 4u; }
+    if (x + 2u <= hi) { *reinterpret_cast<uint16_t *>(g + x) = *reinterpret_cast<const uint16_t *>(image + x); x += 2u; }
+    if (x + 1u <= hi) { g[x] = image[x]; }
+}
+// The 1..15 bytes in front of the 16-byte aligned image offset `end`: one store per set bit of the length.
+__device__ __forceinline__ void store_head(const uint8_t *image, uint8_t *g, u32 lo, u32 end) {
+    const u32 h = end - lo;
+    u32 x = end;
+    if (h & 8u) { x -= 8u; *reinterpret_cast<uint2 *>(g + x) = *reinterpret_cast<const uint2 *>(image + x); }
+    if (h & 4u) { x -= 4u; *reinterpret_cast<u32 *>(g + x) = *reinterpret_cast<const u32 *>(image + x); }
+    if (h & 2u) { x -= 2u; *reinterpret_cast<uint16_t *>(g + x) = *reinterpret_cast<const uint16_t *>(image + x); }
+    if (h & 1u) { x -= 1u; g[x] = image[x]; }
+}
+// The 1..15 bytes behind the 16-byte aligned image offset `lo`.
+__device__ __forceinline__ void store_tail(const uint8_t *image, uint8_t *g, u32 lo, u32 end) {
+    const u32 t = end - lo;
+    u32 x = lo;
+    if (t & 8u) { *reinterpret_cast<uint2 *>(g + x) = *reinterpret_cast<const uint2 *>(image + x); x += 8u; }
+    if (t & 4u) { *reinterpret_cast<u32 *>(g + x) = *reinterpret_cast<const u32 *>(image + x); x += 4u; }
+    if (t & 2u) { *reinterpret_cast<uint16_t *>(g + x) = *reinterpret_cast<const uint16_t *>(image + x); x += 2u; }
+    if (t & 1u) { g[x] = image[x]; }
+}
+
 }  // namespace gts

@@ -6,6 +6,8 @@
 //                the fused table holds the reverse-strand residue of every window)
 //   k_headers    writeHeader            transeq/writer.go:120-131
 // tests/gpu_model.py is the executable specification of the index arithmetic used here.
+#include <cstdlib>
+
 #include "gts_common.cuh"
 #include "gts_kernels.h"
 
@@ -55,6 +57,7 @@ __device__ __forceinline__ u32 lds32(const uint8_t *base, u32 off) {
 __device__ __forceinline__ void copy_line(WarpShared &ws, const Run &r, u32 ln) {
     const uint8_t *ph = ws.phase;
     const u32 col0 = r.col0, naa = r.naa;
+    if (ln * 60u >= col0 + naa) return;  // a lane in the gap between the forward and the reverse line jobs
     const u32 start = ln == 0 ? 0 : (60 - col0) + 60 * (ln - 1);
     const u32 cnt = min(60u - (ln == 0 ? col0 : 0u), naa - start);
     // the newline after column 60; a frame's final newline elsewhere is patched in by the run's
@@ -110,12 +113,6 @@ __device__ __forceinline__ void copy_line(WarpShared &ws, const Run &r, u32 ln) 
     }
 }
 
-__device__ __forceinline__ void bulk_store(void *gdst, const void *ssrc, u32 bytes) {
-    const u32 saddr = (u32)__cvta_generic_to_shared(ssrc);
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr), "r"(bytes)
-                 : "memory");
-}
-
 // Run table of one batch of record pieces of one chunk.  Called by a group of `width` (4 or 32)
 // consecutive lanes, lane `gl` of the group handling record slot s0 + gl (gl < kRecBatch); lane
 // kRecBatch of the group, when present, only looks whether the chunk has more record pieces.
@@ -142,7 +139,7 @@ __device__ __forceinline__ void build_runs(const Job &job, RunTable &ws, u64 R, 
         if (gl == kRecBatch - 1 && s + 1 <= R) next_dbase = job.rec[s + 1].dbase;
     }
     const bool valid = ri.dbase < Tend;  // slots past R keep dbase = ~0
-    u32 nlines = 0, img_need = 0;
+    u32 nlines_f = 0, nlines_r = 0, img_need = 0;
     if (valid && ri.emitted) {
         const u64 D = ri.dbase, n = ri.n, H = ri.H;
         u64 L[6];
@@ -195,73 +192,51 @@ __device__ __forceinline__ void build_runs(const Job &job, RunTable &ws, u64 R, 
             runs[f].nbytes = (uint16_t)nb;
             runs[f].col0 = (uint8_t)col0;
             runs[f].flags = (uint8_t)((fin ? 1 : 0) | (f < 3 ? 0 : 2));
-            nlines += (col0 + naa + 59u) / 60u;
+            (f < 3 ? nlines_f : nlines_r) += (col0 + naa + 59u) / 60u;
             // image space: 16-byte congruent start, then room for the last word's overhang
             const u32 mis = (u32)((out_mis + runs[f].g0) & 15u);
             img_need += (mis + nb + 3u + 15u) & ~15u;
         }
     }
-    // exclusive scans over the group's records: line jobs and image space
+    // Exclusive scans over the group's records: line jobs and image space.  The table lists the
+    // forward runs of all records first and the reverse runs after them, and the reverse runs' line
+    // jobs start at a multiple of 32: a round of 32 line jobs is then all forward or all reverse, so
+    // copy_line's two strands never diverge inside a warp.
     const unsigned gmask = width == 32 ? 0xFFFFFFFFu : (0xFu << ((threadIdx.x & 31) & ~3));
-    u32 lp = nlines, ip = img_need;
+    u32 lf = nlines_f, lr = nlines_r, ip = img_need;
 #pragma unroll
     for (int o = 1; o < kRecBatch; o <<= 1) {
-        const u32 y = __shfl_up_sync(gmask, lp, o, width);
+        const u32 x = __shfl_up_sync(gmask, lf, o, width);
+        const u32 y = __shfl_up_sync(gmask, lr, o, width);
         const u32 z = __shfl_up_sync(gmask, ip, o, width);
-        if (gl >= o) { lp += y; ip += z; }
+        if (gl >= o) { lf += x; lr += y; ip += z; }
     }
-    const u32 total_lines = __shfl_sync(gmask, lp, kRecBatch - 1, width);
-    lp -= nlines;
+    const u32 total_f = __shfl_sync(gmask, lf, kRecBatch - 1, width);
+    const u32 total_r = __shfl_sync(gmask, lr, kRecBatch - 1, width);
+    const u32 base_r = total_r ? (total_f + 31u) & ~31u : total_f;
+    lf -= nlines_f;
+    lr += base_r - nlines_r;
     ip -= img_need;
     if (gl < kRecBatch) {
 #pragma unroll
         for (int f = 0; f < 6; f++) {
-            ws.line_pre[gl * 6 + f] = lp;
+            const int idx = (f < 3 ? 0 : kRecBatch * 3) + gl * 3 + (f < 3 ? f : f - 3);
+            u32 &lp = f < 3 ? lf : lr;
+            ws.line_pre[idx] = lp;
             if (runs[f].naa) {
                 const u32 mis = (u32)((out_mis + runs[f].g0) & 15u);
                 runs[f].img = ip + mis;
                 ip += (mis + runs[f].nbytes + 3u + 15u) & ~15u;
                 lp += (runs[f].col0 + runs[f].naa + 59u) / 60u;
             }
-            ws.runs[gl * 6 + f] = runs[f];
+            ws.runs[idx] = runs[f];
         }
-        if (gl == 0) ws.line_pre[kRunsPerBatch] = total_lines;
+        if (gl == 0) ws.line_pre[kRunsPerBatch] = base_r + total_r;
         if (gl == kRecBatch - 1) {
             ws.more = (valid && next_dbase < Tend) ? 1u : 0u;
             ws.next_slot = (u32)(s + 1);
         }
     }
-}
-
-// Copy the bytes [lo, hi) of the image (hi - lo < 16, both inside one aligned 16-byte slot) to
-// global memory with naturally aligned stores; g is the global address of image byte 0.
-__device__ __forceinline__ void store_edge(const uint8_t *image, uint8_t *g, u32 lo, u32 hi) {
-    u32 x = lo;
-    if ((x & 1u) && x + 1u <= hi) { g[x] = image[x]; x += 1u; }
-    if ((x & 2u) && x + 2u <= hi) { *reinterpret_cast<uint16_t *>(g + x) = *reinterpret_cast<const uint16_t *>(image + x); x += 2u; }
-    if ((x & 4u) && x + 4u <= hi) { *reinterpret_cast<u32 *>(g + x) = *reinterpret_cast<const u32 *>(image + x); x += 4u; }
-    if (x + 8u <= hi) { *reinterpret_cast<uint2 *>(g + x) = *reinterpret_cast<const uint2 *>(image + x); x += 8u; }
-    if (x + 4u <= hi) { *reinterpret_cast<u32 *>(g + x) = *reinterpret_cast<const u32 *>(image + x); x += 4u; }
-    if (x + 2u <= hi) { *reinterpret_cast<uint16_t *>(g + x) = *reinterpret_cast<const uint16_t *>(image + x); x += 2u; }
-    if (x + 1u <= hi) { g[x] = image[x]; }
-}
-// The 1..15 bytes in front of the 16-byte aligned image offset `end`: one store per set bit of the length.
-__device__ __forceinline__ void store_head(const uint8_t *image, uint8_t *g, u32 lo, u32 end) {
-    const u32 h = end - lo;
-    u32 x = end;
-    if (h & 8u) { x -= 8u; *reinterpret_cast<uint2 *>(g + x) = *reinterpret_cast<const uint2 *>(image + x); }
-    if (h & 4u) { x -= 4u; *reinterpret_cast<u32 *>(g + x) = *reinterpret_cast<const u32 *>(image + x); }
-    if (h & 2u) { x -= 2u; *reinterpret_cast<uint16_t *>(g + x) = *reinterpret_cast<const uint16_t *>(image + x); }
-    if (h & 1u) { x -= 1u; g[x] = image[x]; }
-}
-// The 1..15 bytes behind the 16-byte aligned image offset `lo`.
-__device__ __forceinline__ void store_tail(const uint8_t *image, uint8_t *g, u32 lo, u32 end) {
-    const u32 t = end - lo;
-    u32 x = lo;
-    if (t & 8u) { *reinterpret_cast<uint2 *>(g + x) = *reinterpret_cast<const uint2 *>(image + x); x += 8u; }
-    if (t & 4u) { *reinterpret_cast<u32 *>(g + x) = *reinterpret_cast<const u32 *>(image + x); x += 4u; }
-    if (t & 2u) { *reinterpret_cast<uint16_t *>(g + x) = *reinterpret_cast<const uint16_t *>(image + x); x += 2u; }
-    if (t & 1u) { g[x] = image[x]; }
 }
 
 // Persistent CTAs, one parse tile (slot) per iteration.  Warps 0..kTransWarps-1 translate one
@@ -470,9 +445,23 @@ __global__ void __launch_bounds__(256) k_headers(const __grid_constant__ Job job
 // =====================================================================================
 // launch
 // =====================================================================================
+cudaError_t init_lines();
+cudaError_t launch_lines(const Job &job, cudaStream_t stream);
+
 cudaError_t init_kernels() {
+    cudaError_t e = init_lines();
+    if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_translate, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)sizeof(TransShared));
+}
+
+static cudaError_t launch_residues(const Job &job, u32 grid, cudaStream_t stream) {
+    static const bool old = getenv("GTS_OLD_TRANSLATE") != nullptr;
+    if (job.piece || old) {
+        k_translate<<<grid, kTransBlock, sizeof(TransShared), stream>>>(job);
+        return cudaGetLastError();
+    }
+    return launch_lines(job, stream);
 }
 
 // k_headers only needs the record table, so it runs on `side` (when given) next to k_translate: the
@@ -491,11 +480,11 @@ cudaError_t launch_emit(const Job &job, int sm_count, cudaStream_t stream, cudaE
         cudaStreamWaitEvent(side, ev_fork, 0);
         k_headers<<<sm_count * 4, 256, 0, side>>>(job);
         cudaEventRecord(ev_join, side);
-        k_translate<<<grid, kTransBlock, sizeof(TransShared), stream>>>(job);
+        launch_residues(job, grid, stream);
         if (ev_mid) cudaEventRecord(ev_mid, stream);
         cudaStreamWaitEvent(stream, ev_join, 0);
     } else {
-        k_translate<<<grid, kTransBlock, sizeof(TransShared), stream>>>(job);
+        launch_residues(job, grid, stream);
         if (ev_mid) cudaEventRecord(ev_mid, stream);
         k_headers<<<sm_count * 4, 256, 0, stream>>>(job);
     }
