@@ -236,6 +236,15 @@ int enqueue_pass(gts_ctx *ctx, const uint8_t *d_in, u64 n, uint8_t *d_out, u64 c
         job.ov_slot = p.ov_slot; job.ov_n = p.ov_n; job.ov_dbase = p.ov_dbase;
     }
     job.lut = ctx->lut;
+    {
+        uint8_t *bf = reinterpret_cast<uint8_t *>(job.lutb.f), *br = reinterpret_cast<uint8_t *>(job.lutb.r);
+        for (int e = 0; e < 128; e++) {
+            const int x = e < 125 ? e : 0;
+            const int s0 = x % 5, s1 = (x / 5) % 5, s2 = x / 25;
+            bf[e] = (uint8_t)(ctx->lut.v[x] & 0xFF);
+            br[e] = (uint8_t)(ctx->lut.v[s2 + 5 * s1 + 25 * s0] >> 8);
+        }
+    }
     ctx->job_stream = stream;
     cudaEvent_t *ev = nullptr;
     if (ctx->profiling && !sizes_only) {

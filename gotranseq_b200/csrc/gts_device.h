@@ -126,6 +126,11 @@ struct Lut {  // 125 used entries: forward residue | reverse-strand residue << 8
     uint16_t v[128];
 };
 
+struct LutBytes {  // k_lines' tables, one residue per byte (125 used entries each)
+    u32 f[32];     // forward residue of the codon s0 + 5 s1 + 25 s2
+    u32 r[32];     // reverse-strand residue of the codon read downwards: index s2 + 5 s1 + 25 s0
+};
+
 struct Job {  // kernel argument block (by value)
     const uint8_t *in;  // raw FASTA, 16-byte aligned
     u64 n;
@@ -177,6 +182,7 @@ struct Job {  // kernel argument block (by value)
     u64 ov_n;          // the whole record's nucleotides
     u64 ov_dbase;      // stream index of its first nucleotide
     Lut lut;
+    LutBytes lutb;
 };
 
 }  // namespace gts
