@@ -5,7 +5,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgotranseq_b200.so")
+LIB_PATH = os.environ.get("GOTRANSEQ_B200_LIB") or os.path.join(_HERE, "libgotranseq_b200.so")
 
 GTS_OK = 0
 GTS_ERR_FRAME = -1

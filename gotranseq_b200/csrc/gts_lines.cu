@@ -20,7 +20,13 @@
 
 namespace gts {
 
-constexpr int kLinesThreads = 288;  // >= kLineRuns
+#ifndef GTS_LINES_THREADS
+#define GTS_LINES_THREADS 96
+#endif
+#ifndef GTS_LINES_CTAS
+#define GTS_LINES_CTAS 5
+#endif
+constexpr int kLinesThreads = GTS_LINES_THREADS;  // >= kLineRuns
 constexpr int kHalo = 192;                              // symbols staged before / after the tile's own
 constexpr int kSymArr = kHalo + kSlotSyms + kHalo;      // bytes per staged array
 constexpr int kMirror = kSlotSyms + kHalo - 1;          // mirror index of local symbol x = kMirror - x; = 7 (mod 8)
@@ -49,10 +55,11 @@ struct LinesShared {
     u32 line_pre[kLineRuns];
     alignas(16) uint8_t line_run[kLineMaxLines];  // run of each line job
     u32 scan_l[4], scan_i[4];
-    u32 take, total_lines;
+    u32 piece_need[kLineBatch];
+    u32 total_lines;
     alignas(16) uint8_t lutf[128];      // forward residue of s0 + 5 s1 + 25 s2
     alignas(16) uint8_t lutr[128];      // reverse-strand residue of the window read downwards: s2 + 5 s1 + 25 s0
-    u32 nruns, npieces_done;
+    u32 npieces_done;
 };
 
 __device__ __forceinline__ i64 floordiv180(i64 a) {
@@ -98,7 +105,7 @@ __device__ __forceinline__ void emit_line(uint8_t *smem, u32 symoff, u32 lut, u3
     for (int g = 1; g < 16; g++) dw[g] = prmt(z[g - 1], z[g], sela);
 }
 
-__global__ void __launch_bounds__(kLinesThreads, 3) k_lines(const __grid_constant__ Job job) {
+__global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const __grid_constant__ Job job) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     LinesShared &sh = *reinterpret_cast<LinesShared *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -128,6 +135,7 @@ __global__ void __launch_bounds__(kLinesThreads, 3) k_lines(const __grid_constan
     const uintptr_t out_mis = (uintptr_t)job.out & 15u;
 
     // ---- stage: tables, margins, the tile's symbols ----
+    if (tid < kLineBatch) sh.piece_need[tid] = 0;
     if (tid < 32) {
         reinterpret_cast<u32 *>(sh.lutf)[tid] = job.lutb.f[tid];
         reinterpret_cast<u32 *>(sh.lutr)[tid] = job.lutb.r[tid];
@@ -198,12 +206,14 @@ __global__ void __launch_bounds__(kLinesThreads, 3) k_lines(const __grid_constan
     while (done < npieces) {
         // ---- build: one thread per (record piece, frame), kLineBatch pieces per batch ----
         if (tid < kLineRuns) {
-            const u32 p = (u32)tid / 6u, f = (u32)tid - 6u * p;
+            // thread order = forward runs of all pieces, then reverse runs: the line jobs of a warp
+            // then read one residue table (no bank conflicts between the two)
+            const u32 strand = (u32)tid / (3u * kLineBatch), rem = (u32)tid - strand * (3u * kLineBatch);
+            const u32 p = rem / 3u, f = 3u * strand + (rem - 3u * p);
             const u64 s = (u64)tp.R0 + done + p;
             LineRun run;
             run.g0 = 0; run.img = 0; run.nbytes = 0; run.sym = 0; run.lut = 0; run.flags = 0; run.pad = 0;
             u32 nl = 0, need = 0;
-            if (tid == 0) sh.take = kLineBatch;
             if (done + p < npieces && s <= R && ((job.frame_mask >> f) & 1u)) {
                 const RecInfo ri = job.rec[s];
                 if (ri.emitted) {
@@ -272,7 +282,21 @@ __global__ void __launch_bounds__(kLinesThreads, 3) k_lines(const __grid_constan
                     }
                 }
             }
-            // inclusive scans over the batch's runs (thread order = piece-major): line jobs, image space
+            // pieces taken: as many as fit the image (a single piece always fits)
+            if (need) atomicAdd(&sh.piece_need[p], need);
+            asm volatile("bar.sync 1, %0;" ::"r"(kLineRuns) : "memory");
+            u32 take = kLineBatch;
+            {
+                u32 acc = 0;
+#pragma unroll
+                for (int k = 0; k < kLineBatch; k++) {
+                    acc += sh.piece_need[k];
+                    if (acc > (u32)kLineImage && take == (u32)kLineBatch) take = k;
+                }
+            }
+            if (take > npieces - done) take = npieces - done;
+            if (p >= take) { nl = 0; need = 0; run.nbytes = 0; }
+            // inclusive scans over the batch's runs: line jobs, image space
             u32 lp = nl, ip = need;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -283,28 +307,21 @@ __global__ void __launch_bounds__(kLinesThreads, 3) k_lines(const __grid_constan
             if (lane == 31) { sh.scan_l[warp] = lp; sh.scan_i[warp] = ip; }
             asm volatile("bar.sync 1, %0;" ::"r"(kLineRuns) : "memory");
             for (int w = 0; w < warp; w++) { lp += sh.scan_l[w]; ip += sh.scan_i[w]; }
-            // pieces taken: as many as fit the image (a single piece always fits)
-            if (ip > (u32)kLineImage) atomicMin(&sh.take, p);
-            asm volatile("bar.sync 1, %0;" ::"r"(kLineRuns) : "memory");
-            u32 take = sh.take;
-            if (take > npieces - done) take = npieces - done;
-            if (p < take) {
-                sh.line_pre[tid] = lp - nl;
-                if (nl) {
-                    const u32 mis = (u32)((out_mis + run.g0) & 15u);
-                    run.img = ip - need + mis;
-                    for (u32 i = 0; i < nl; i++) sh.line_run[lp - nl + i] = (uint8_t)tid;
-                }
-                sh.runs[tid] = run;
-                if ((u32)tid == take * 6u - 1u) {
-                    sh.total_lines = lp;
-                    sh.nruns = take * 6u;
-                    sh.npieces_done = done + take;
-                }
+            if (tid < kLineBatch) sh.piece_need[tid] = 0;  // for the next batch
+            sh.line_pre[tid] = lp - nl;
+            if (nl) {
+                const u32 mis = (u32)((out_mis + run.g0) & 15u);
+                run.img = ip - need + mis;
+                for (u32 i = 0; i < nl; i++) sh.line_run[lp - nl + i] = (uint8_t)tid;
+            }
+            sh.runs[tid] = run;
+            if (tid == kLineRuns - 1) {
+                sh.total_lines = lp;
+                sh.npieces_done = done + take;
             }
         }
         __syncthreads();  // symbols staged, run table built
-        const u32 nruns = sh.nruns;
+        const u32 nruns = kLineRuns;
         const u32 total = sh.total_lines;
         for (u32 job_i = tid; job_i < total; job_i += blockDim.x) {
             const u32 ridx = sh.line_run[job_i];
