@@ -49,6 +49,7 @@ struct gts_ctx {
     u64 *d_hdr_off = nullptr, *d_dbase = nullptr, *d_loc = nullptr, *d_hinfo = nullptr;
     gts::RecInfo *d_rec = nullptr;
     u32 *d_trim = nullptr;
+    gts::FrameTab *d_ftab = nullptr;
     gts::Totals *h_totals = nullptr;  // pinned
     u64 *d_dbg = nullptr;             // phase timing sums (GTS_PHASE_TIMING builds with GTS_PHASE_TIMING=1 set)
 
@@ -132,7 +133,8 @@ ZeroLayout zero_layout(u64 ntiles, u64 rec_cap) {
 
 int free_rec(gts_ctx *ctx) {
     cudaFree(ctx->d_events); cudaFree(ctx->d_hdr_off); cudaFree(ctx->d_dbase); cudaFree(ctx->d_loc); cudaFree(ctx->d_hinfo);
-    cudaFree(ctx->d_rec); cudaFree(ctx->d_trim);
+    cudaFree(ctx->d_rec); cudaFree(ctx->d_trim); cudaFree(ctx->d_ftab);
+    ctx->d_ftab = nullptr;
     ctx->d_events = nullptr;
     ctx->d_hdr_off = ctx->d_dbase = ctx->d_loc = ctx->d_hinfo = nullptr;
     ctx->d_rec = nullptr;
@@ -150,6 +152,7 @@ int alloc_rec(gts_ctx *ctx, u64 rec_cap) {
     CU(cudaMalloc(&ctx->d_hinfo, rec_cap * sizeof(u64)));
     CU(cudaMalloc(&ctx->d_rec, rec_cap * sizeof(gts::RecInfo)));
     if (ctx->opt.trim) CU(cudaMalloc(&ctx->d_trim, rec_cap * 6 * sizeof(u32)));
+    CU(cudaMalloc(&ctx->d_ftab, rec_cap * sizeof(gts::FrameTab)));
     ctx->rec_cap = rec_cap;
     return GTS_OK;
 }
@@ -214,7 +217,7 @@ int enqueue_pass(gts_ctx *ctx, const uint8_t *d_in, u64 n, uint8_t *d_out, u64 c
     job.chunk_hint = ctx->d_chunk_hint;
     job.events = ctx->d_events;
     job.hdr_off = ctx->d_hdr_off; job.dbase = ctx->d_dbase; job.loc = ctx->d_loc; job.hinfo = ctx->d_hinfo;
-    job.rec = ctx->d_rec; job.trim_len = ctx->d_trim; job.rec_cap = ctx->rec_cap;
+    job.rec = ctx->d_rec; job.trim_len = ctx->d_trim; job.ftab = ctx->d_ftab; job.rec_cap = ctx->rec_cap;
     job.t_status = reinterpret_cast<u64 *>(ctx->d_zero + z.t_status);
     job.s_status = reinterpret_cast<u64 *>(ctx->d_zero + z.s_status);
     job.totals = reinterpret_cast<gts::Totals *>(ctx->d_zero + z.totals);

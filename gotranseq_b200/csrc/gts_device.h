@@ -122,6 +122,12 @@ struct RecInfo {  // 32 bytes per record slot, written by k_size, read by k_tran
     u32 emitted;  // 0: the record produces no output (empty slot 0)
 };
 
+struct FrameTab {  // 80 bytes per record slot, written by k_size, read by k_lines
+    u64 body[6];   // output offset of the first residue of each requested frame
+    u32 len[6];    // residues of the frame (after --trim); 0 for frames not requested / records not emitted
+    u32 pad[2];
+};
+
 struct Lut {  // 125 used entries: forward residue | reverse-strand residue << 8
     uint16_t v[128];
 };
@@ -151,6 +157,7 @@ struct Job {  // kernel argument block (by value)
     u64 *hinfo;     // header line bytes (CR dropped) | index of its first space << 32
     RecInfo *rec;   // per record summary (+1 sentinel: dbase = end of stream, out_off = total)
     u32 *trim_len;  // [slot*6 + frame] residues kept after --trim (only with trim)
+    FrameTab *ftab; // per record: where each frame's residues go and how many there are
     u64 rec_cap;    // entries in each of the arrays above
 
     u64 *t_status;  // [tile-scan tiles * 4] chained scan of the parse tiles' counts

@@ -53,9 +53,9 @@ struct LinesShared {
     alignas(16) uint8_t image[kLineImage];
     alignas(16) LineRun runs[kLineRuns];
     u32 line_pre[kLineRuns];
-    alignas(16) uint8_t line_run[kLineMaxLines];  // run of each line job
-    u32 scan_l[4], scan_i[4];
-    u32 piece_need[kLineBatch];
+    alignas(16) uint8_t line_run[kLineRuns];  // the runs that have lines, in line job order
+    u32 scan_l[6], scan_i[6], scan_c[6];
+    u32 nlisted;
     u32 total_lines;
     alignas(16) uint8_t lutf[128];      // forward residue of s0 + 5 s1 + 25 s2
     alignas(16) uint8_t lutr[128];      // reverse-strand residue of the window read downwards: s2 + 5 s1 + 25 s0
@@ -134,8 +134,36 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
     const u64 T0 = tp.T0, Tend = tp.T0 + nsym;
     const uintptr_t out_mis = (uintptr_t)job.out & 15u;
 
+    // Record pieces of the tile: the record open at its first byte, then one per header line.  A
+    // builder thread handles one (piece, frame) of a batch of kLineBatch pieces; thread order =
+    // forward runs of all pieces, then the reverse runs, so that the line jobs of a warp read one
+    // residue table (no bank conflicts between the two).  The record data of the first batch is
+    // requested here, before the staging, so that its latency is hidden.
+    const u32 npieces = (u32)ti.nhdr + 1u;
+    u32 done = 0;
+    const u32 strand = (u32)tid / (3u * kLineBatch), rem = (u32)tid - strand * (3u * kLineBatch);
+    const u32 bp = rem / 3u, bf = 3u * strand + (rem - 3u * bp);
+    RecInfo ri;
+    ri.emitted = 0; ri.dbase = 0; ri.n = 0; ri.H = 0; ri.out_off = 0;
+    u32 Lf = 0;
+    u64 body = 0;
+    bool have = false;
+    auto fetch = [&](u32 from) {
+        have = false;
+        Lf = 0;
+        if (tid < kLineRuns && from + bp < npieces) {
+            const u64 s = (u64)tp.R0 + from + bp;
+            if (s <= R && ((job.frame_mask >> bf) & 1u)) {
+                ri = job.rec[s];
+                Lf = job.ftab[s].len[bf];
+                body = job.ftab[s].body[bf];
+                have = true;
+            }
+        }
+    };
+    fetch(0);
+
     // ---- stage: tables, margins, the tile's symbols ----
-    if (tid < kLineBatch) sh.piece_need[tid] = 0;
     if (tid < 32) {
         reinterpret_cast<u32 *>(sh.lutf)[tid] = job.lutb.f[tid];
         reinterpret_cast<u32 *>(sh.lutr)[tid] = job.lutb.r[tid];
@@ -200,133 +228,133 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
     const u32 lutr_addr = (u32)offsetof(LinesShared, lutr);
     const u32 image_addr = (u32)offsetof(LinesShared, image);
 
-    // record pieces of the tile: the record open at its first byte, then one per header line
-    const u32 npieces = (u32)ti.nhdr + 1u;
-    u32 done = 0;
     while (done < npieces) {
         // ---- build: one thread per (record piece, frame), kLineBatch pieces per batch ----
         if (tid < kLineRuns) {
-            // thread order = forward runs of all pieces, then reverse runs: the line jobs of a warp
-            // then read one residue table (no bank conflicts between the two)
-            const u32 strand = (u32)tid / (3u * kLineBatch), rem = (u32)tid - strand * (3u * kLineBatch);
-            const u32 p = rem / 3u, f = 3u * strand + (rem - 3u * p);
-            const u64 s = (u64)tp.R0 + done + p;
             LineRun run;
             run.g0 = 0; run.img = 0; run.nbytes = 0; run.sym = 0; run.lut = 0; run.flags = 0; run.pad = 0;
             u32 nl = 0, need = 0;
-            if (done + p < npieces && s <= R && ((job.frame_mask >> f) & 1u)) {
-                const RecInfo ri = job.rec[s];
-                if (ri.emitted) {
-                    const i64 D = (i64)ri.dbase;
-                    const u64 n = ri.n, H = ri.H;
-                    u64 L[6];
-                    frame_lengths(n, job.alternative != 0, L);
-                    if (job.trim) {
-#pragma unroll
-                        for (int k = 0; k < 6; k++) L[k] = job.trim_len[s * 6 + k];
-                    }
-                    u64 run_base = ri.out_off, Lf = 0;
-#pragma unroll
-                    for (int k = 0; k < 6; k++) {
-                        if ((u32)k == f) Lf = L[k];
-                        if ((u32)k < f && ((job.frame_mask >> k) & 1u)) run_base += run_size(H, L[k]);
-                    }
-                    const u64 body = run_base + H + 3;
-                    const i64 NL = (i64)udiv60(Lf + 59);
-                    i64 lo = 0, hi = 0, sym0 = 0;  // lines [lo, hi); sym0 = staged index of line 0's first symbol
-                    u32 base_addr;
-                    if (f < 3) {
-                        // line b: codons start at nucleotide f + 180 b; its first codon ends at D + f + 2 + 180 b
-                        const i64 k0 = D + (i64)f + 2;
-                        lo = ceildiv180((i64)T0 - k0);
-                        hi = ceildiv180((i64)Tend - k0);
-                        sym0 = kHalo + (k0 - 2 - (i64)T0);
-                        base_addr = symf_addr;
+            if (have && ri.emitted && Lf) {
+                const i64 d = (i64)ri.dbase - (i64)T0;  // the record's first nucleotide, relative to the tile
+                const u64 n = ri.n;
+                const u32 NL = (Lf + 59u) / 60u;
+                u64 lo = 0, hi = 0;  // lines [lo, hi)
+                i64 symrel;          // index, in its staged array, of the first symbol of line lo
+                if (bf < 3) {
+                    // line b: codons start at nucleotide f + 180 b; its first codon ends at k0 + 180 b, k0 = D + f + 2
+                    const i64 x = -(d + (i64)bf + 2);  // T0 - k0
+                    if (x > 0) {
+                        const u64 q = (u64)(x - 1) / 180u;
+                        const u32 rem = (u32)((u64)(x - 1) - 180u * q);
+                        lo = q + 1;
+                        hi = q + (rem + nsym + 180u) / 180u;
+                        symrel = kHalo + 177 - (i64)rem;
                     } else {
-                        // line b: residues 60 b .. are the codons starting at Q - 180 b, Q - 180 b - 3, ...;
-                        // the lowest one used (residue 60 b + 62) ends at D + Q - 180 b - 184, unless the
-                        // record starts above it: then at D + 2 + qmod (its lowest codon of this phase)
-                        const i64 Q = (i64)n - 3 - reverse_start(n, (int)f - 3, job.alternative != 0);
-                        const i64 qmod = -2 + (Q + 2) % 3;
-                        i64 Lc = floordiv180(Q - 186 - qmod) + 1;  // first line whose lowest codon is clipped
-                        if (Lc < 0) Lc = 0;
-                        if (Lc > NL) Lc = NL;
-                        const i64 K0 = D + Q - 184;
-                        lo = floordiv180(K0 - (i64)Tend) + 1;
-                        hi = floordiv180(K0 - (i64)T0) + 1;
-                        if (lo < 0) lo = 0;
-                        if (hi > Lc) hi = Lc;
-                        const i64 kc = D + 2 + qmod;
-                        if (Lc < NL && kc >= (i64)T0 && kc < (i64)Tend) {
-                            if (hi > lo) hi = NL;
-                            else { lo = Lc; hi = NL; }
+                        const i64 e = x + (i64)nsym;
+                        hi = e > 0 ? ((u32)e + 179u) / 180u : 0u;
+                        symrel = kHalo - x - 2;
+                    }
+                } else {
+                    // line b: residues 60 b .. are the codons starting at Q - 180 b, Q - 180 b - 3, ...; the
+                    // lowest one used (residue 60 b + 62) ends at D + Q - 180 b - 184, unless the record
+                    // starts above it: then at D + 2 + qmod (its lowest codon of this phase).  Such
+                    // "clipped" lines are the last one or two of the frame: b >= Lc.
+                    const u32 n3 = (u32)(n - 3u * udiv3(n));
+                    const u32 i3 = bf - 3u;
+                    const u32 pstart = job.alternative ? i3 : (n3 + 3u - i3) % 3u;  // reverse_start
+                    const i64 qmod = -2 + (i64)((n3 + 5u - pstart) % 3u);          // (Q + 2) mod 3 - 2
+                    u32 Lc = Lf >= 63u ? (Lf - 63u) / 60u + 1u : 0u;
+                    if (Lc > NL) Lc = NL;
+                    const i64 y = d + (i64)n - 3 - (i64)pstart - 184;  // D + Q - 184 - T0
+                    if (y >= 0) {
+                        const u64 qy = (u64)y / 180u;
+                        const u32 ry = (u32)((u64)y - 180u * qy);
+                        hi = qy + 1;
+                        if (nsym > ry) {
+                            const u32 c1 = (nsym - ry + 179u) / 180u;
+                            lo = qy + 1 >= c1 ? qy + 1 - c1 : 0;
+                        } else {
+                            lo = hi;
                         }
-                        // the line's highest symbol D + Q + 2 - 180 b is read first, then downwards
-                        sym0 = kMirror - (D + Q + 2 - (i64)T0);
-                        base_addr = symr_addr;
                     }
-                    if (lo < 0) lo = 0;
-                    if (hi > NL) hi = NL;
-                    if (hi > lo) {
-                        const u32 c = (u32)(hi - lo);
-                        const bool last = hi == NL;
-                        const u32 cut = last ? (u32)(60 * (u64)NL - Lf) : 0u;  // residues missing in the frame's last line
-                        run.g0 = body + 61ull * (u64)lo;
-                        run.nbytes = 61u * c - cut;
-                        run.sym = base_addr + (u32)(sym0 + 180 * lo);
-                        run.lut = f < 3 ? lutf_addr : lutr_addr;
-                        run.flags = (last && cut) ? 1u : 0u;
-                        nl = c;
-                        const u32 mis = (u32)((out_mis + run.g0) & 15u);
-                        need = (mis + 61u * c + 3u + 15u) & ~15u;
+                    if (hi > Lc) hi = Lc;
+                    const i64 kcr = d + 2 + qmod;
+                    if (Lc < NL && kcr >= 0 && kcr < (i64)nsym) {
+                        if (hi <= lo) lo = Lc;
+                        hi = NL;
                     }
+                    // the line's highest symbol D + Q + 2 - 180 b is read first, then downwards
+                    symrel = (i64)kMirror - (y + 186) + 180 * (i64)lo;
+                }
+                if (hi > NL) hi = NL;
+                if (hi > lo) {
+                    const u32 c = (u32)(hi - lo);
+                    const bool last = hi == NL;
+                    const u32 cut = last ? 60u * NL - Lf : 0u;  // residues missing in the frame's last line
+                    run.g0 = body + 61ull * lo;
+                    run.nbytes = 61u * c - cut;
+                    run.sym = (bf < 3 ? symf_addr : symr_addr) + (u32)symrel;
+                    run.lut = bf < 3 ? lutf_addr : lutr_addr;
+                    run.flags = (last && cut) ? 1u : 0u;
+                    nl = c;
+                    const u32 mis = (u32)((out_mis + run.g0) & 15u);
+                    need = (mis + 61u * c + 3u + 15u) & ~15u;
                 }
             }
-            // pieces taken: as many as fit the image (a single piece always fits)
-            if (need) atomicAdd(&sh.piece_need[p], need);
-            asm volatile("bar.sync 1, %0;" ::"r"(kLineRuns) : "memory");
-            u32 take = kLineBatch;
-            {
-                u32 acc = 0;
+            // Inclusive scans over the batch's runs: line jobs, image space, runs that have lines.
+            // Pieces taken: all of the batch, unless the image is too small for them: then half as
+            // many, and so on (a single piece always fits).
+            u32 take = npieces - done < (u32)kLineBatch ? npieces - done : (u32)kLineBatch;
+            u32 lp, ip, cp;
+            for (int pass = 0;; pass++) {
+                if (bp >= take) { nl = 0; need = 0; run.nbytes = 0; }
+                lp = nl; ip = need; cp = nl ? 1u : 0u;
 #pragma unroll
-                for (int k = 0; k < kLineBatch; k++) {
-                    acc += sh.piece_need[k];
-                    if (acc > (u32)kLineImage && take == (u32)kLineBatch) take = k;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const u32 y = __shfl_up_sync(0xFFFFFFFFu, lp, o);
+                    const u32 z = __shfl_up_sync(0xFFFFFFFFu, ip, o);
+                    const u32 c = __shfl_up_sync(0xFFFFFFFFu, cp, o);
+                    if (lane >= o) { lp += y; ip += z; cp += c; }
                 }
+                const int sl = 3 * (pass & 1);  // two sets of slots: no barrier between a read and the next pass's write
+                if (lane == 31) { sh.scan_l[sl + warp] = lp; sh.scan_i[sl + warp] = ip; sh.scan_c[sl + warp] = cp; }
+                asm volatile("bar.sync 1, %0;" ::"r"(kLineRuns) : "memory");
+                const u32 total_need = sh.scan_i[sl] + sh.scan_i[sl + 1] + sh.scan_i[sl + 2];
+                for (int w = 0; w < warp; w++) { lp += sh.scan_l[sl + w]; ip += sh.scan_i[sl + w]; cp += sh.scan_c[sl + w]; }
+                if (total_need <= (u32)kLineImage || take == 1) break;
+                take = (take + 1) >> 1;
             }
-            if (take > npieces - done) take = npieces - done;
-            if (p >= take) { nl = 0; need = 0; run.nbytes = 0; }
-            // inclusive scans over the batch's runs: line jobs, image space
-            u32 lp = nl, ip = need;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const u32 y = __shfl_up_sync(0xFFFFFFFFu, lp, o);
-                const u32 z = __shfl_up_sync(0xFFFFFFFFu, ip, o);
-                if (lane >= o) { lp += y; ip += z; }
-            }
-            if (lane == 31) { sh.scan_l[warp] = lp; sh.scan_i[warp] = ip; }
-            asm volatile("bar.sync 1, %0;" ::"r"(kLineRuns) : "memory");
-            for (int w = 0; w < warp; w++) { lp += sh.scan_l[w]; ip += sh.scan_i[w]; }
-            if (tid < kLineBatch) sh.piece_need[tid] = 0;  // for the next batch
-            sh.line_pre[tid] = lp - nl;
             if (nl) {
                 const u32 mis = (u32)((out_mis + run.g0) & 15u);
                 run.img = ip - need + mis;
-                for (u32 i = 0; i < nl; i++) sh.line_run[lp - nl + i] = (uint8_t)tid;
+                sh.line_pre[cp - 1u] = lp - nl;  // the runs that have lines, in line job order
+                sh.line_run[cp - 1u] = (uint8_t)tid;
             }
             sh.runs[tid] = run;
             if (tid == kLineRuns - 1) {
                 sh.total_lines = lp;
+                sh.nlisted = cp;
                 sh.npieces_done = done + take;
             }
         }
         __syncthreads();  // symbols staged, run table built
         const u32 nruns = kLineRuns;
         const u32 total = sh.total_lines;
-        for (u32 job_i = tid; job_i < total; job_i += blockDim.x) {
-            const u32 ridx = sh.line_run[job_i];
-            const LineRun &r = sh.runs[ridx];
-            const u32 i = job_i - sh.line_pre[ridx];
+        const u32 nlisted = sh.nlisted;
+        for (u32 j0 = (u32)warp * 32u; j0 < total; j0 += kLinesThreads) {
+            // The warp takes line jobs j0 .. j0 + 31.  Listed run of a job: the last one that starts
+            // at or before it = (runs starting at or before j0) + (runs starting in (j0, job]).
+            const u32 job_i = j0 + lane;
+            u32 before = 0, starts = 0;
+            for (u32 c0 = 0; c0 < nlisted; c0 += 32) {
+                const u32 st = c0 + lane < nlisted ? sh.line_pre[c0 + lane] : 0xFFFFFFFFu;
+                before += __popc(__ballot_sync(0xFFFFFFFFu, st <= j0));
+                starts |= __reduce_or_sync(0xFFFFFFFFu, (st > j0 && st - j0 < 32u) ? 1u << (st - j0) : 0u);
+            }
+            if (job_i >= total) continue;
+            const u32 lo = before - 1u + __popc(starts & (0xFFFFFFFFu >> (31 - lane)));
+            const LineRun &r = sh.runs[sh.line_run[lo]];
+            const u32 i = job_i - sh.line_pre[lo];
             emit_line(smem_raw, r.sym + 180u * i, r.lut, image_addr + r.img + 61u * i, i == 0);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // image writes -> visible to the bulk copy engine
@@ -355,6 +383,7 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // image may be reused / CTA may exit
         done = sh.npieces_done;
+        fetch(done);
         __syncthreads();
     }
 }

@@ -315,6 +315,7 @@ __global__ void __launch_bounds__(kSizeThreads) k_size(const __grid_constant__ J
         if (t >= ntiles) return;
         u64 size[kSizePerThread];
         RecInfo ri[kSizePerThread];
+        u32 flen[kSizePerThread][6];
         u64 sum = 0, nt = 0;
         u32 nrec = 0;
 #pragma unroll
@@ -348,6 +349,8 @@ __global__ void __launch_bounds__(kSizeThreads) k_size(const __grid_constant__ J
                     nt += n;
                     nrec++;
                 }
+#pragma unroll
+                for (int f = 0; f < 6; f++) flen[i][f] = (em && ((job.frame_mask >> f) & 1u)) ? (u32)L[f] : 0u;
                 ri[i].dbase = D;
                 ri[i].n = n;
                 ri[i].H = (u32)H;
@@ -408,6 +411,16 @@ __global__ void __launch_bounds__(kSizeThreads) k_size(const __grid_constant__ J
             if (s < nslots) {
                 ri[i].out_off = off;
                 job.rec[s] = ri[i];
+                FrameTab ft;
+                u64 base = off;
+#pragma unroll
+                for (int f = 0; f < 6; f++) {
+                    ft.body[f] = base + ri[i].H + 3;
+                    ft.len[f] = flen[i][f];
+                    if (ri[i].emitted && ((job.frame_mask >> f) & 1u)) base += run_size(ri[i].H, flen[i][f]);
+                }
+                ft.pad[0] = ft.pad[1] = 0;
+                job.ftab[s] = ft;
             }
             off += size[i];
         }
