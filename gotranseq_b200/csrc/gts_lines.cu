@@ -109,7 +109,22 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
     extern __shared__ __align__(16) uint8_t smem_raw[];
     LinesShared &sh = *reinterpret_cast<LinesShared *>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const u32 tile = blockIdx.x;
+    // tables and margins that no tile overwrites (ordered before their first use by the staging barrier)
+    if (tid < 32) {
+        reinterpret_cast<u32 *>(sh.lutf)[tid] = job.lutb.f[tid];
+        reinterpret_cast<u32 *>(sh.lutr)[tid] = job.lutb.r[tid];
+    }
+    // margins that are read but never hold a tile's data: below the two carried symbols
+    for (int i = tid; i < (kHalo - 2) / 2; i += kLinesThreads) {
+        reinterpret_cast<uint16_t *>(sh.symf)[i] = 0;
+        reinterpret_cast<uint16_t *>(sh.symr + kMirror + 3)[i] = 0;  // mirror of locals -3, -4, ...
+    }
+    const u64 flags = job.totals->flags;
+    const u64 R = job.totals->n_headers;
+    if (flags != 0) return;
+
+    // persistent CTAs: the grid is one wave, each CTA takes every gridDim.x-th tile
+    for (u32 tile = blockIdx.x; tile < job.ntiles; tile += gridDim.x) {
     // ---- loads that depend on nothing go first: the slot's words (all of them: words past the
     // tile's symbols hold stale but valid symbols), the start of the next slot, the tile's scalars ----
     constexpr int kWordsPerThread = (kSlotWords + kLinesThreads - 1) / kLinesThreads;
@@ -124,13 +139,10 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
     u32 hw = 0;
     if (tid < kHalo / 8 && has_next) hw = gw[kSlotWords + tid];
     const u32 next_nsym = has_next ? job.tile_info[tile + 1].nsym : 0u;
-    const u64 flags = job.totals->flags;
-    const u64 R = job.totals->n_headers;
     const TileInfo ti = job.tile_info[tile];
     const TilePrefix tp = job.tile_pre[tile];
-    if (flags != 0) return;
     const u32 nsym = ti.nsym;
-    if (nsym == 0) return;
+    if (nsym == 0) continue;
     const u64 T0 = tp.T0, Tend = tp.T0 + nsym;
     const uintptr_t out_mis = (uintptr_t)job.out & 15u;
 
@@ -163,16 +175,7 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
     };
     fetch(0);
 
-    // ---- stage: tables, margins, the tile's symbols ----
-    if (tid < 32) {
-        reinterpret_cast<u32 *>(sh.lutf)[tid] = job.lutb.f[tid];
-        reinterpret_cast<u32 *>(sh.lutr)[tid] = job.lutb.r[tid];
-    }
-    // margins that are read but never hold the tile's data: below the two carried symbols
-    for (int i = tid; i < (kHalo - 2) / 2; i += kLinesThreads) {
-        reinterpret_cast<uint16_t *>(sh.symf)[i] = 0;
-        reinterpret_cast<uint16_t *>(sh.symr + kMirror + 3)[i] = 0;  // mirror of locals -3, -4, ...
-    }
+    // ---- stage: the tile's symbols ----
     if (tid == 0) {
         const u32 c = tp.carry;  // last | second-to-last << 4
         sh.symf[kHalo - 1] = (uint8_t)(c & 0xFu);
@@ -191,6 +194,18 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
         }
     }
     __syncthreads();  // the halo overwrites what the slot holds behind the tile's symbols
+    {
+        // pull the CTA's next tile towards the SM while this one is being translated
+        const u32 nt = tile + gridDim.x;
+        if (nt < job.ntiles) {
+            const char *base = reinterpret_cast<const char *>(job.sym + (u64)nt * kSlotWords);
+            const char *pf = nullptr;
+            if (tid < (kSlotWords * 4 + 96 + 127) / 128) pf = base + 128 * tid;
+            else if (tid == 40) pf = reinterpret_cast<const char *>(job.tile_info + nt);
+            else if (tid == 41) pf = reinterpret_cast<const char *>(job.tile_pre + nt);
+            if (pf) asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+        }
+    }
     // the 192 symbols after the tile: the stream goes on in the next slot ...
     if (!has_next || next_nsym >= (u32)kHalo) {
         if (tid < kHalo / 8) {
@@ -386,14 +401,16 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
         fetch(done);
         __syncthreads();
     }
+    }  // tiles
 }
 
 cudaError_t init_lines() {
     return cudaFuncSetAttribute(k_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LinesShared));
 }
 
-cudaError_t launch_lines(const Job &job, cudaStream_t stream) {
-    k_lines<<<job.ntiles, kLinesThreads, sizeof(LinesShared), stream>>>(job);
+cudaError_t launch_lines(const Job &job, int sm_count, cudaStream_t stream) {
+    const u32 wave = (u32)sm_count * GTS_LINES_CTAS;
+    k_lines<<<job.ntiles < wave ? job.ntiles : wave, kLinesThreads, sizeof(LinesShared), stream>>>(job);
     return cudaGetLastError();
 }
 

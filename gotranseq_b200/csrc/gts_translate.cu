@@ -446,7 +446,7 @@ __global__ void __launch_bounds__(256) k_headers(const __grid_constant__ Job job
 // launch
 // =====================================================================================
 cudaError_t init_lines();
-cudaError_t launch_lines(const Job &job, cudaStream_t stream);
+cudaError_t launch_lines(const Job &job, int sm_count, cudaStream_t stream);
 
 cudaError_t init_kernels() {
     cudaError_t e = init_lines();
@@ -455,13 +455,13 @@ cudaError_t init_kernels() {
                                 (int)sizeof(TransShared));
 }
 
-static cudaError_t launch_residues(const Job &job, u32 grid, cudaStream_t stream) {
+static cudaError_t launch_residues(const Job &job, u32 grid, int sm_count, cudaStream_t stream) {
     static const bool old = getenv("GTS_OLD_TRANSLATE") != nullptr;
     if (job.piece || old) {
         k_translate<<<grid, kTransBlock, sizeof(TransShared), stream>>>(job);
         return cudaGetLastError();
     }
-    return launch_lines(job, stream);
+    return launch_lines(job, sm_count, stream);
 }
 
 // k_headers only needs the record table, so it runs on `side` (when given) next to k_translate: the
@@ -480,11 +480,11 @@ cudaError_t launch_emit(const Job &job, int sm_count, cudaStream_t stream, cudaE
         cudaStreamWaitEvent(side, ev_fork, 0);
         k_headers<<<sm_count * 4, 256, 0, side>>>(job);
         cudaEventRecord(ev_join, side);
-        launch_residues(job, grid, stream);
+        launch_residues(job, grid, sm_count, stream);
         if (ev_mid) cudaEventRecord(ev_mid, stream);
         cudaStreamWaitEvent(stream, ev_join, 0);
     } else {
-        launch_residues(job, grid, stream);
+        launch_residues(job, grid, sm_count, stream);
         if (ev_mid) cudaEventRecord(ev_mid, stream);
         k_headers<<<sm_count * 4, 256, 0, stream>>>(job);
     }
