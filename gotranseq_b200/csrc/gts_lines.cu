@@ -1,18 +1,21 @@
-// gts_lines.cu -- k_lines: symbols -> residue lines, one lane per 60-column output line.
+// gts_lines.cu -- k_lines: symbols -> residue lines, one lane per 180-nucleotide block of one strand.
 //
 // Reference behaviour reproduced (feliixx/gotranseq): translate / translate3Frames / writeAA /
 // newLine, transeq/writer.go:57-157; reverseComplement, transeq/encodedSequence.go:71-97 (never
 // materialised).
 //
-// One CTA per parse tile.  The tile's symbols are staged in shared memory one per byte, twice: in
-// stream order (forward frames) and mirrored (reverse frames read the mirror upwards, which is the
-// stream downwards), with the two symbols before the tile and 192 symbols after it, so that every
-// output line whose FIRST codon ends in the tile can be produced by one lane from 189 consecutive
-// staged bytes: 63 codons (the line's 60 residues and the first 3 of the next line) through one
-// integer dot product and one byte-table load each, '\n' at a fixed position, one byte funnel for
-// the line's alignment in the output, 16 word stores into the tile's output image.  Nothing in
-// the lane's work depends on the strand except two base addresses.  The image is written out
-// with TMA bulk stores as in k_translate.
+// Persistent CTAs, one parse tile per iteration.  The tile's symbols are staged in shared memory
+// one per byte, twice: in stream order (forward frames) and mirrored (reverse frames read the
+// mirror upwards, which is the stream downwards), with the two symbols before the tile and 192
+// symbols after it.  A lane then takes one BLOCK: 180 nucleotides of one record and strand, i.e.
+// output line b of the strand's three frames.  It loads the block's 194 symbols once; frame k is
+// the codons at byte offsets k, k+3, ... of them: 63 codons (the line's 60 residues and the first 3
+// of the next line) through one integer dot product and one byte-table load each, '\n' at a
+// fixed position, one byte funnel for the line's alignment in the output, 16 word stores into
+// the tile's output image.  Nothing in the lane's work depends on the strand except two base
+// addresses.  A block belongs to the tile that holds the last symbol of its lowest codon, so the
+// tile's two carried symbols and the 192 after it are all a lane ever needs.  The image is
+// written out with TMA bulk stores.
 #include <cstddef>
 
 #include "gts_common.cuh"
@@ -26,75 +29,83 @@ namespace gts {
 #ifndef GTS_LINES_CTAS
 #define GTS_LINES_CTAS 5
 #endif
-constexpr int kLinesThreads = GTS_LINES_THREADS;  // >= kLineRuns
+constexpr int kLinesThreads = GTS_LINES_THREADS;  // >= 3 * kBlockRuns
 constexpr int kHalo = 192;                              // symbols staged before / after the tile's own
-constexpr int kSymArr = kHalo + kSlotSyms + kHalo;      // bytes per staged array
+constexpr int kSymArr = kHalo + kSlotSyms + kHalo + 16; // bytes per staged array
 constexpr int kMirror = kSlotSyms + kHalo - 1;          // mirror index of local symbol x = kMirror - x; = 7 (mod 8)
 constexpr int kLineBatch = 16;                          // record pieces per batch
-constexpr int kLineRuns = kLineBatch * 6;
+constexpr int kBlockRuns = kLineBatch * 2;              // (piece, strand) entries per batch: one builder lane each
 constexpr int kLineImage = 20480;                       // output image bytes (one piece needs < 17.8 KB)
-constexpr int kLineMaxLines = kLineImage / 61 + 1;      // line jobs per batch
 static_assert(kMirror % 8 == 7, "mirror stores are 8-byte aligned");
 static_assert(kMirror + kHalo + 1 <= kSymArr, "mirror array too small");
+static_assert(kBlockRuns == 32, "the run table is built by one warp");
+static_assert(kLinesThreads >= 3 * kBlockRuns, "one thread per frame run in the copy-out");
 
-struct LineRun {     // the lines of one (record, frame) whose first codon ends in the tile
+struct FrameRun {    // lines of one frame among a BlockRun's blocks
     u64 g0;          // output offset of its first byte
     u32 img;         // byte offset of its first byte in the image
     u32 nbytes;      // bytes to copy out
-    u32 sym;         // shared-memory offset of the first line's first symbol (+180 per line)
-    u32 lut;         // shared-memory offset of the strand's residue table
+    u32 nl;          // lines: the first nl blocks of the BlockRun have a line in this frame
     u32 flags;       // bit 0: ends the frame with a partial line (the final newline is patched in)
+};
+
+struct BlockRun {    // the blocks of one (record piece, strand) that belong to the tile
+    u32 sym;         // shared-memory offset of the first block's first symbol (+180 per block)
+    u32 lut;         // shared-memory offset of the strand's residue table
+    u32 nblk;
     u32 pad;
+    FrameRun fr[3];  // by codon phase: forward frame k; reverse frame that starts k nucleotides from the end
 };
 
 struct LinesShared {
     alignas(16) uint8_t symf[kSymArr];  // [kHalo - 2 .. ) = the two symbols before the tile, the tile, the halo
     alignas(16) uint8_t symr[kSymArr];  // symr[kMirror - x] = local symbol x
     alignas(16) uint8_t image[kLineImage];
-    alignas(16) LineRun runs[kLineRuns];
-    u32 line_pre[kLineRuns];
-    alignas(16) uint8_t line_run[kLineRuns];  // the runs that have lines, in line job order
-    u32 scan_l[6], scan_i[6], scan_c[6];
-    u32 nlisted;
-    u32 total_lines;
+    alignas(16) BlockRun runs[kBlockRuns];
+    u32 job_pre[kBlockRuns];            // first block job of the runs that have blocks, in job order
+    uint8_t job_run[kBlockRuns];        // their index in runs[]
     alignas(16) uint8_t lutf[128];      // forward residue of s0 + 5 s1 + 25 s2
-    alignas(16) uint8_t lutr[128];      // reverse-strand residue of the window read downwards: s2 + 5 s1 + 25 s0
-    u32 npieces_done;
+    alignas(16) uint8_t lutr[128];      // reverse-strand residue of the codon read downwards: s2 + 5 s1 + 25 s0
+    u32 total_jobs, nlisted, npieces_done;
 };
 
-__device__ __forceinline__ i64 floordiv180(i64 a) {
-    i64 q = a / 180;
-    if (a - q * 180 < 0) q--;
-    return q;
+// dp4a weights (1, 5, 25 for a codon's three symbols) of codon j of phase k inside word `word` of
+// a 12-symbol group (word 3 = the first word of the next group); 0 = the codon has no symbol there
+__host__ __device__ constexpr u32 codon_weights(int k, int j, int word) {
+    u32 m = 0;
+    for (int t = 0; t < 3; t++) {
+        const int b = k + 3 * j + t;
+        if ((b >> 2) == word) m |= (t == 0 ? 1u : t == 1 ? 5u : 25u) << (8 * (b & 3));
+    }
+    return m;
 }
-__device__ __forceinline__ i64 ceildiv180(i64 a) { return -floordiv180(-a); }
 
-// One output line: 189 staged symbols -> 64 image bytes (60 residues, '\n', 3 residues of the next line).
-// All offsets are relative to the start of the CTA's shared memory.  The loads of all 16 codon
-// groups come before the first store so that they can be in flight together.
-__device__ __forceinline__ void emit_line(uint8_t *smem, u32 symoff, u32 lut, u32 dst, bool first) {
-    const u32 sbase = symoff & ~3u;
-    const u32 sels = 0x3210u + 0x1111u * (symoff & 3u);
+// Line i of one frame of a block run: 63 codons of phase K from the block's symbols c[] -> 64 image
+// bytes (60 residues, '\n', 3 residues of the next line).
+template <int K>
+__device__ __forceinline__ void emit_frame(uint8_t *smem, const u32 (&c)[49], u32 lut, u32 dst, bool first) {
     const u32 a = dst & 3u;
     const u32 sela = 0x3210u + 0x1111u * ((4u - a) & 7u);
-    const u32 *sw = reinterpret_cast<const u32 *>(smem + sbase);
     u32 z[16];
-    u32 wprev = sw[0];
 #pragma unroll
     for (int g = 0; g < 16; g++) {
-        const u32 w1 = sw[3 * g + 1], w2 = sw[3 * g + 2], w3 = sw[3 * g + 3];
-        const u32 c0 = prmt(wprev, w1, sels), c1 = prmt(w1, w2, sels), c2 = prmt(w2, w3, sels);
-        wprev = w3;
-        // table offsets of the four codons in these 12 symbols
-        const u32 a0 = __dp4a(c0, 0x00190501u, lut);
-        const u32 a1 = __dp4a(c1, 0x00001905u, __dp4a(c0, 0x01000000u, lut));
-        const u32 a2 = __dp4a(c2, 0x00000019u, __dp4a(c1, 0x05010000u, lut));
-        const u32 a3 = __dp4a(c2, 0x19050100u, lut);
-        const u32 r0 = smem[a0], r1 = smem[a1], r2 = smem[a2], r3 = smem[a3];
+        u32 r[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            u32 addr = lut;  // table offset of the codon: lut + s0 + 5 s1 + 25 s2
+#pragma unroll
+            for (int w = 0; w < 4; w++) {
+                constexpr int dummy = 0;
+                (void)dummy;
+                const u32 m = codon_weights(K, j, w);
+                if (m != 0 && 3 * g + w < 49) addr = __dp4a(c[3 * g + w], m, addr);
+            }
+            r[j] = smem[addr];
+        }
         if (g < 15) {
-            z[g] = prmt(prmt(r0, r1, 0x0040u), prmt(r2, r3, 0x0040u), 0x5410u);
+            z[g] = prmt(prmt(r[0], r[1], 0x0040u), prmt(r[2], r[3], 0x0040u), 0x5410u);
         } else {  // residues 60..62 belong to the next line: they follow this line's newline
-            z[g] = prmt(prmt(0x0Au, r0, 0x0040u), prmt(r1, r2, 0x0040u), 0x5410u);
+            z[g] = prmt(prmt(0x0Au, r[0], 0x0040u), prmt(r[1], r[2], 0x0040u), 0x5410u);
         }
     }
     // image word g holds line bytes 4g - a .. 4g - a + 3; a lane owns the words that start in its
@@ -115,7 +126,7 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
         reinterpret_cast<u32 *>(sh.lutr)[tid] = job.lutb.r[tid];
     }
     // margins that are read but never hold a tile's data: below the two carried symbols
-    for (int i = tid; i < (kHalo - 2) / 2; i += kLinesThreads) {
+    for (int i = tid; i < (kSymArr - kMirror - 3) / 2; i += kLinesThreads) {
         reinterpret_cast<uint16_t *>(sh.symf)[i] = 0;
         reinterpret_cast<uint16_t *>(sh.symr + kMirror + 3)[i] = 0;  // mirror of locals -3, -4, ...
     }
@@ -147,29 +158,29 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
     const uintptr_t out_mis = (uintptr_t)job.out & 15u;
 
     // Record pieces of the tile: the record open at its first byte, then one per header line.  A
-    // builder thread handles one (piece, frame) of a batch of kLineBatch pieces; thread order =
-    // forward runs of all pieces, then the reverse runs, so that the line jobs of a warp read one
-    // residue table (no bank conflicts between the two).  The record data of the first batch is
-    // requested here, before the staging, so that its latency is hidden.
+    // builder lane (warp 0) handles one (piece, strand) of a batch of kLineBatch pieces; lane order =
+    // forward runs of all pieces, then the reverse runs, so that the block jobs of a warp mostly
+    // read one residue table (no bank conflicts between the two).  The record data of the first
+    // batch is requested here, before the staging, so that its latency is hidden.
     const u32 npieces = (u32)ti.nhdr + 1u;
     u32 done = 0;
-    const u32 strand = (u32)tid / (3u * kLineBatch), rem = (u32)tid - strand * (3u * kLineBatch);
-    const u32 bp = rem / 3u, bf = 3u * strand + (rem - 3u * bp);
+    const u32 bp = (u32)lane & (kLineBatch - 1), bs = (u32)lane / kLineBatch;
     RecInfo ri;
     ri.emitted = 0; ri.dbase = 0; ri.n = 0; ri.H = 0; ri.out_off = 0;
-    u32 Lf = 0;
-    u64 body = 0;
-    bool have = false;
+    u32 flen[3] = {0, 0, 0};   // the strand's three frames, in frame order
+    u64 fbody[3] = {0, 0, 0};
     auto fetch = [&](u32 from) {
-        have = false;
-        Lf = 0;
-        if (tid < kLineRuns && from + bp < npieces) {
+        ri.emitted = 0;
+        if (warp == 0 && from + bp < npieces) {
             const u64 s = (u64)tp.R0 + from + bp;
-            if (s <= R && ((job.frame_mask >> bf) & 1u)) {
+            if (s <= R) {
                 ri = job.rec[s];
-                Lf = job.ftab[s].len[bf];
-                body = job.ftab[s].body[bf];
-                have = true;
+                const FrameTab *ft = job.ftab + s;
+#pragma unroll
+                for (int i = 0; i < 3; i++) {
+                    flen[i] = ft->len[3 * bs + i];
+                    fbody[i] = ft->body[3 * bs + i];
+                }
             }
         }
     };
@@ -244,138 +255,181 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
     const u32 image_addr = (u32)offsetof(LinesShared, image);
 
     while (done < npieces) {
-        // ---- build: one thread per (record piece, frame), kLineBatch pieces per batch ----
-        if (tid < kLineRuns) {
-            LineRun run;
-            run.g0 = 0; run.img = 0; run.nbytes = 0; run.sym = 0; run.lut = 0; run.flags = 0; run.pad = 0;
-            u32 nl = 0, need = 0;
-            if (have && ri.emitted && Lf) {
+        // ---- build (warp 0): one lane per (record piece, strand) ----
+        if (warp == 0) {
+            BlockRun run;
+            run.sym = 0; run.lut = 0; run.nblk = 0; run.pad = 0;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                run.fr[k].g0 = 0; run.fr[k].img = 0; run.fr[k].nbytes = 0; run.fr[k].nl = 0; run.fr[k].flags = 0;
+            }
+            u32 need = 0;
+            if (ri.emitted) {
                 const i64 d = (i64)ri.dbase - (i64)T0;  // the record's first nucleotide, relative to the tile
                 const u64 n = ri.n;
-                const u32 NL = (Lf + 59u) / 60u;
-                u64 lo = 0, hi = 0;  // lines [lo, hi)
-                i64 symrel;          // index, in its staged array, of the first symbol of line lo
-                if (bf < 3) {
-                    // line b: codons start at nucleotide f + 180 b; its first codon ends at k0 + 180 b, k0 = D + f + 2
-                    const i64 x = -(d + (i64)bf + 2);  // T0 - k0
-                    if (x > 0) {
-                        const u64 q = (u64)(x - 1) / 180u;
-                        const u32 rem = (u32)((u64)(x - 1) - 180u * q);
-                        lo = q + 1;
-                        hi = q + (rem + nsym + 180u) / 180u;
-                        symrel = kHalo + 177 - (i64)rem;
-                    } else {
-                        const i64 e = x + (i64)nsym;
-                        hi = e > 0 ? ((u32)e + 179u) / 180u : 0u;
-                        symrel = kHalo - x - 2;
-                    }
+                // the strand's frames by codon phase k: forward frame k; the reverse frame whose first
+                // codon starts k nucleotides from the record's end (reverse_start == k)
+                u32 Lk[3];
+                u64 Bk[3];
+                if (bs == 0 || job.alternative) {
+#pragma unroll
+                    for (int k = 0; k < 3; k++) { Lk[k] = flen[k]; Bk[k] = fbody[k]; }
                 } else {
-                    // line b: residues 60 b .. are the codons starting at Q - 180 b, Q - 180 b - 3, ...; the
-                    // lowest one used (residue 60 b + 62) ends at D + Q - 180 b - 184, unless the record
-                    // starts above it: then at D + 2 + qmod (its lowest codon of this phase).  Such
-                    // "clipped" lines are the last one or two of the frame: b >= Lc.
-                    const u32 n3 = (u32)(n - 3u * udiv3(n));
-                    const u32 i3 = bf - 3u;
-                    const u32 pstart = job.alternative ? i3 : (n3 + 3u - i3) % 3u;  // reverse_start
-                    const i64 qmod = -2 + (i64)((n3 + 5u - pstart) % 3u);          // (Q + 2) mod 3 - 2
-                    u32 Lc = Lf >= 63u ? (Lf - 63u) / 60u + 1u : 0u;
-                    if (Lc > NL) Lc = NL;
-                    const i64 y = d + (i64)n - 3 - (i64)pstart - 184;  // D + Q - 184 - T0
-                    if (y >= 0) {
-                        const u64 qy = (u64)y / 180u;
-                        const u32 ry = (u32)((u64)y - 180u * qy);
-                        hi = qy + 1;
-                        if (nsym > ry) {
-                            const u32 c1 = (nsym - ry + 179u) / 180u;
-                            lo = qy + 1 >= c1 ? qy + 1 - c1 : 0;
-                        } else {
-                            lo = hi;
-                        }
+                    const u32 n3 = (u32)(n - 3u * udiv3(n));  // frame i starts at (n3 - i) mod 3
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        const u32 i = (n3 + 3u - (u32)k) % 3u;
+                        Lk[k] = i == 0 ? flen[0] : i == 1 ? flen[1] : flen[2];
+                        Bk[k] = i == 0 ? fbody[0] : i == 1 ? fbody[1] : fbody[2];
                     }
-                    if (hi > Lc) hi = Lc;
-                    const i64 kcr = d + 2 + qmod;
-                    if (Lc < NL && kcr >= 0 && kcr < (i64)nsym) {
-                        if (hi <= lo) lo = Lc;
-                        hi = NL;
-                    }
-                    // the line's highest symbol D + Q + 2 - 180 b is read first, then downwards
-                    symrel = (i64)kMirror - (y + 186) + 180 * (i64)lo;
                 }
-                if (hi > NL) hi = NL;
+                u32 NLk[3], NLmax = 0;
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    NLk[k] = (Lk[k] + 59u) / 60u;
+                    NLmax = NLk[k] > NLmax ? NLk[k] : NLmax;
+                }
+                u64 lo = 0, hi = 0;  // blocks [lo, hi)
+                i64 symrel = 0;      // index, in its staged array, of the first symbol of block lo
+                if (NLmax) {
+                    if (bs == 0) {
+                        // block b = nucleotides 180 b ..; its lowest codon (frame 1) ends at k0 + 180 b, k0 = D + 2
+                        const i64 x = -(d + 2);  // T0 - k0
+                        if (x > 0) {
+                            const u64 q = (u64)(x - 1) / 180u;
+                            const u32 rem = (u32)((u64)(x - 1) - 180u * q);
+                            lo = q + 1;
+                            hi = q + (rem + nsym + 180u) / 180u;
+                            symrel = kHalo + 177 - (i64)rem;
+                        } else {
+                            const i64 e = x + (i64)nsym;
+                            hi = e > 0 ? ((u32)e + 179u) / 180u : 0u;
+                            symrel = kHalo - x - 2;
+                        }
+                    } else {
+                        // block b is read downwards from nucleotide n - 1 - 180 b; its lowest codon (phase 2,
+                        // residue 60 b + 62) ends at D + n - 189 - 180 b, unless the record starts above it:
+                        // then ("clipped", b >= Lc) at D, the end of the codon made of the record's pads
+                        u64 Lc = n >= 189 ? (n - 189) / 180u + 1 : 0;
+                        if (Lc > NLmax) Lc = NLmax;
+                        const i64 y = d + (i64)n - 189;
+                        if (y >= 0) {
+                            const u64 qy = (u64)y / 180u;
+                            const u32 ry = (u32)((u64)y - 180u * qy);
+                            hi = qy + 1;
+                            if (nsym > ry) {
+                                const u32 c1 = (nsym - ry + 179u) / 180u;
+                                lo = qy + 1 >= c1 ? qy + 1 - c1 : 0;
+                            } else {
+                                lo = hi;
+                            }
+                        }
+                        if (hi > Lc) hi = Lc;
+                        if (Lc < NLmax && d >= 0 && d < (i64)nsym) {
+                            if (hi <= lo) lo = Lc;
+                            hi = NLmax;
+                        }
+                        symrel = (i64)kMirror - (y + 188) + 180 * (i64)lo;
+                    }
+                    if (hi > NLmax) hi = NLmax;
+                }
                 if (hi > lo) {
                     const u32 c = (u32)(hi - lo);
-                    const bool last = hi == NL;
-                    const u32 cut = last ? 60u * NL - Lf : 0u;  // residues missing in the frame's last line
-                    run.g0 = body + 61ull * lo;
-                    run.nbytes = 61u * c - cut;
-                    run.sym = (bf < 3 ? symf_addr : symr_addr) + (u32)symrel;
-                    run.lut = bf < 3 ? lutf_addr : lutr_addr;
-                    run.flags = (last && cut) ? 1u : 0u;
-                    nl = c;
-                    const u32 mis = (u32)((out_mis + run.g0) & 15u);
-                    need = (mis + 61u * c + 3u + 15u) & ~15u;
+                    run.sym = (bs == 0 ? symf_addr : symr_addr) + (u32)symrel;
+                    run.lut = bs == 0 ? lutf_addr : lutr_addr;
+                    run.nblk = c;
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        if ((u64)NLk[k] <= lo) continue;  // (also frames that were not requested: no lines)
+                        const u64 left = (u64)NLk[k] - lo;
+                        const u32 nl = left < c ? (u32)left : c;
+                        const bool last = lo + nl == NLk[k];
+                        const u32 cut = last ? 60u * NLk[k] - Lk[k] : 0u;  // residues missing in the frame's last line
+                        run.fr[k].g0 = Bk[k] + 61ull * lo;
+                        run.fr[k].nbytes = 61u * nl - cut;
+                        run.fr[k].nl = nl;
+                        run.fr[k].flags = (last && cut) ? 1u : 0u;
+                        const u32 mis = (u32)((out_mis + run.fr[k].g0) & 15u);
+                        need += (mis + 61u * nl + 3u + 15u) & ~15u;
+                    }
                 }
             }
-            // Inclusive scans over the batch's runs: line jobs, image space, runs that have lines.
+            // Inclusive scans over the batch's runs: block jobs, image space, runs that have blocks.
             // Pieces taken: all of the batch, unless the image is too small for them: then half as
             // many, and so on (a single piece always fits).
             u32 take = npieces - done < (u32)kLineBatch ? npieces - done : (u32)kLineBatch;
-            u32 lp, ip, cp;
-            for (int pass = 0;; pass++) {
-                if (bp >= take) { nl = 0; need = 0; run.nbytes = 0; }
-                lp = nl; ip = need; cp = nl ? 1u : 0u;
+            u32 jp, ip, cp;
+            while (true) {
+                if (bp >= take) { run.nblk = 0; need = 0; run.fr[0].nbytes = run.fr[1].nbytes = run.fr[2].nbytes = 0; }
+                jp = run.nblk; ip = need; cp = run.nblk ? 1u : 0u;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
-                    const u32 y = __shfl_up_sync(0xFFFFFFFFu, lp, o);
+                    const u32 y = __shfl_up_sync(0xFFFFFFFFu, jp, o);
                     const u32 z = __shfl_up_sync(0xFFFFFFFFu, ip, o);
                     const u32 c = __shfl_up_sync(0xFFFFFFFFu, cp, o);
-                    if (lane >= o) { lp += y; ip += z; cp += c; }
+                    if (lane >= o) { jp += y; ip += z; cp += c; }
                 }
-                const int sl = 3 * (pass & 1);  // two sets of slots: no barrier between a read and the next pass's write
-                if (lane == 31) { sh.scan_l[sl + warp] = lp; sh.scan_i[sl + warp] = ip; sh.scan_c[sl + warp] = cp; }
-                asm volatile("bar.sync 1, %0;" ::"r"(kLineRuns) : "memory");
-                const u32 total_need = sh.scan_i[sl] + sh.scan_i[sl + 1] + sh.scan_i[sl + 2];
-                for (int w = 0; w < warp; w++) { lp += sh.scan_l[sl + w]; ip += sh.scan_i[sl + w]; cp += sh.scan_c[sl + w]; }
+                const u32 total_need = __shfl_sync(0xFFFFFFFFu, ip, 31);
                 if (total_need <= (u32)kLineImage || take == 1) break;
                 take = (take + 1) >> 1;
             }
-            if (nl) {
-                const u32 mis = (u32)((out_mis + run.g0) & 15u);
-                run.img = ip - need + mis;
-                sh.line_pre[cp - 1u] = lp - nl;  // the runs that have lines, in line job order
-                sh.line_run[cp - 1u] = (uint8_t)tid;
+            if (run.nblk) {
+                u32 img = ip - need;
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    if (run.fr[k].nl) {
+                        const u32 mis = (u32)((out_mis + run.fr[k].g0) & 15u);
+                        run.fr[k].img = img + mis;
+                        img += (mis + 61u * run.fr[k].nl + 3u + 15u) & ~15u;
+                    }
+                }
+                sh.job_pre[cp - 1u] = jp - run.nblk;  // the runs that have blocks, in job order
+                sh.job_run[cp - 1u] = (uint8_t)lane;
             }
-            sh.runs[tid] = run;
-            if (tid == kLineRuns - 1) {
-                sh.total_lines = lp;
+            sh.runs[lane] = run;
+            if (lane == 31) {
+                sh.total_jobs = jp;
                 sh.nlisted = cp;
                 sh.npieces_done = done + take;
             }
         }
         __syncthreads();  // symbols staged, run table built
-        const u32 nruns = kLineRuns;
-        const u32 total = sh.total_lines;
+        const u32 total = sh.total_jobs;
         const u32 nlisted = sh.nlisted;
         for (u32 j0 = (u32)warp * 32u; j0 < total; j0 += kLinesThreads) {
-            // The warp takes line jobs j0 .. j0 + 31.  Listed run of a job: the last one that starts
+            // The warp takes block jobs j0 .. j0 + 31.  Listed run of a job: the last one that starts
             // at or before it = (runs starting at or before j0) + (runs starting in (j0, job]).
             const u32 job_i = j0 + lane;
-            u32 before = 0, starts = 0;
-            for (u32 c0 = 0; c0 < nlisted; c0 += 32) {
-                const u32 st = c0 + lane < nlisted ? sh.line_pre[c0 + lane] : 0xFFFFFFFFu;
-                before += __popc(__ballot_sync(0xFFFFFFFFu, st <= j0));
-                starts |= __reduce_or_sync(0xFFFFFFFFu, (st > j0 && st - j0 < 32u) ? 1u << (st - j0) : 0u);
-            }
+            const u32 st = (u32)lane < nlisted ? sh.job_pre[lane] : 0xFFFFFFFFu;
+            const u32 before = __popc(__ballot_sync(0xFFFFFFFFu, st <= j0));
+            const u32 starts = __reduce_or_sync(0xFFFFFFFFu, (st > j0 && st - j0 < 32u) ? 1u << (st - j0) : 0u);
             if (job_i >= total) continue;
-            const u32 lo = before - 1u + __popc(starts & (0xFFFFFFFFu >> (31 - lane)));
-            const LineRun &r = sh.runs[sh.line_run[lo]];
-            const u32 i = job_i - sh.line_pre[lo];
-            emit_line(smem_raw, r.sym + 180u * i, r.lut, image_addr + r.img + 61u * i, i == 0);
+            const u32 li = before - 1u + __popc(starts & (0xFFFFFFFFu >> (31 - lane)));
+            const BlockRun &r = sh.runs[sh.job_run[li]];
+            const u32 i = job_i - sh.job_pre[li];
+            // the block's 194 symbols, four per word
+            const u32 symoff = r.sym + 180u * i;
+            const u32 sels = 0x3210u + 0x1111u * (symoff & 3u);
+            const u32 *sw = reinterpret_cast<const u32 *>(smem_raw + (symoff & ~3u));
+            u32 c[49];
+            {
+                u32 wprev = sw[0];
+#pragma unroll
+                for (int m = 0; m < 49; m++) {
+                    const u32 w = sw[m + 1];
+                    c[m] = prmt(wprev, w, sels);
+                    wprev = w;
+                }
+            }
+            const u32 lut = r.lut;
+            if (i < r.fr[0].nl) emit_frame<0>(smem_raw, c, lut, image_addr + r.fr[0].img + 61u * i, i == 0);
+            if (i < r.fr[1].nl) emit_frame<1>(smem_raw, c, lut, image_addr + r.fr[1].img + 61u * i, i == 0);
+            if (i < r.fr[2].nl) emit_frame<2>(smem_raw, c, lut, image_addr + r.fr[2].img + 61u * i, i == 0);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // image writes -> visible to the bulk copy engine
         __syncthreads();                                               // image complete
-        for (u32 ri = tid; ri < nruns; ri += blockDim.x) {
-            const LineRun r = sh.runs[ri];
+        if (tid < 3 * kBlockRuns) {
+            const FrameRun r = sh.runs[tid / 3].fr[tid % 3];
             if (r.nbytes) {
                 const u32 lo16 = (r.img + 15u) & ~15u, end = r.img + r.nbytes, hi16 = end & ~15u;
                 uint8_t *g = job.out + r.g0 - r.img;  // global address of image byte 0 (16-byte congruent)
@@ -396,7 +450,7 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
             }
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // image may be reused / CTA may exit
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // image may be reused
         done = sh.npieces_done;
         fetch(done);
         __syncthreads();
