@@ -640,7 +640,7 @@ void gts_destroy(gts_ctx *ctx) {
         cudaDeviceSynchronize();
         cudaMemcpy(h, ctx->d_dbg, sizeof(h), cudaMemcpyDeviceToHost);
         std::fprintf(stderr, "[gts phase timing, ns summed over tiles, %llu passes]", (unsigned long long)ctx->stats.passes);
-        for (int i = 0; i < 16; i++) std::fprintf(stderr, " p%d=%llu", i, (unsigned long long)h[i]);
+        for (int i = 0; i < 24; i++) std::fprintf(stderr, " p%d=%llu", i, (unsigned long long)h[i]);
         std::fprintf(stderr, "\n");
         cudaFree(ctx->d_dbg);
     }

@@ -136,6 +136,9 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
 
     // persistent CTAs: the grid is one wave, each CTA takes every gridDim.x-th tile
     for (u32 tile = blockIdx.x; tile < job.ntiles; tile += gridDim.x) {
+#ifdef GTS_PHASE_TIMING
+    u64 tprev = gtime();
+#endif
     // ---- loads that depend on nothing go first: the slot's words (all of them: words past the
     // tile's symbols hold stale but valid symbols), the start of the next slot, the tile's scalars ----
     constexpr int kWordsPerThread = (kSlotWords + kLinesThreads - 1) / kLinesThreads;
@@ -205,6 +208,7 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
         }
     }
     __syncthreads();  // the halo overwrites what the slot holds behind the tile's symbols
+    PHASE_MARK(job, 16, tprev);  // loads + staging
     {
         // pull the CTA's next tile towards the SM while this one is being translated
         const u32 nt = tile + gridDim.x;
@@ -394,6 +398,7 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
             }
         }
         __syncthreads();  // symbols staged, run table built
+        PHASE_MARK(job, 17, tprev);  // halo + build
         const u32 total = sh.total_jobs;
         const u32 nlisted = sh.nlisted;
         for (u32 j0 = (u32)warp * 32u; j0 < total; j0 += kLinesThreads) {
@@ -428,6 +433,7 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // image writes -> visible to the bulk copy engine
         __syncthreads();                                               // image complete
+        PHASE_MARK(job, 18, tprev);  // block jobs
         if (tid < 3 * kBlockRuns) {
             const FrameRun r = sh.runs[tid / 3].fr[tid % 3];
             if (r.nbytes) {
@@ -454,6 +460,7 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
         done = sh.npieces_done;
         fetch(done);
         __syncthreads();
+        PHASE_MARK(job, 19, tprev);  // copy-out
     }
     }  // tiles
 }
