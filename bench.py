@@ -7,7 +7,7 @@ A step is one pass of the whole hot path (parse -> encode -> translate all six f
 over one batch of FASTA (BASELINE.json configs[1]: 189 MB, multi-record, -f 6 -t 0).
   value   device-resident Gbp/s (input and output in HBM, CUDA events on the launch stream)
   e2e     the same metric through gts_translate_buffer with pinned HOST buffers, PCIe copies timed
-  roofline  the dominant kernel (k_translate) against the measured HBM copy rate
+  roofline  the dominant kernel (k_lines) against the measured HBM copy rate
   cpu_baseline / --impl reference  the restated reference (oracle/, all host threads)
 Under torchrun (N > 1) every rank translates its own batch (independent shards, no collective);
 the time is the max over ranks and the value the sum of the nucleotides over that time.
@@ -24,9 +24,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "6-frame Gbp/s device-resident"
-# DRAM bytes of one k_translate launch on the default workload, from the committed ncu capture
-# (profiles/r1c_ncu_full_summary.txt: 134.43 MB read + 339.85 MB written); null for other workloads
-NCU_TRAFFIC = {"readme189": 134429696 + 339853312}
+# DRAM bytes of one k_lines launch on the default workload, from the committed ncu capture
+# (profiles/r1f_ncu_full_summary.txt: 140.69 MB read + 328.65 MB written); null for other workloads
+NCU_TRAFFIC = {"readme189": 140689152 + 328648192}
 UNIT = "Gbp/s"
 
 
@@ -382,7 +382,7 @@ def main():
         peak, peak_src = measured_peak()
         value = nt_all * args.steps / dev_s / 1e9
         e2e_v = nt_all * e2e_steps / e2e_s / 1e9 if e2e_s > 0 else None
-        # algorithmic bytes of one k_translate launch: the packed symbol stream it reads (4 bits per
+        # algorithmic bytes of one k_lines launch: the packed symbol stream it reads (4 bits per
         # symbol: nucleotides + 2 pads per record) + the residue lines it writes (output - headers)
         st = tr.stats()
         nrec = st["records"]
@@ -405,16 +405,16 @@ def main():
                     "api": "gts_translate_buffer (pinned host buffers)"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "k_translate", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "k_lines", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": NCU_TRAFFIC.get(args.workload), "peak_source": peak_src,
-                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one k_translate launch, "
-                                           "ncu --set full capture profiles/r1c_ncu_full_summary.txt",
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one k_lines launch, "
+                                           "ncu --set full capture profiles/r1f_ncu_full_summary.txt",
                          "algorithmic_bytes_per_launch": trans_bytes, "ms_per_launch": trans_ms},
             "path": {"bytes_per_step_per_gpu": path_bytes, "achieved_GBps_per_gpu": path_gbs, "frac_of_peak": path_gbs / peak,
                      "note": "(FASTA in + protein FASTA out) / device time of the whole path"},
             "kernels_ms_per_step": {"reset+k_parse": kms[0] / max(kpasses, 1),
                                     "k_tile_scan+k_records+k_size": kms[1] / max(kpasses, 1),
-                                    "k_translate": kms[2] / max(kpasses, 1), "k_headers": kms[3] / max(kpasses, 1)},
+                                    "k_lines": kms[2] / max(kpasses, 1), "k_headers": kms[3] / max(kpasses, 1)},
             "bytes": {"in": nbytes, "out": out_n, "nucleotides": nt, "records": nrec},
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -1,15 +1,16 @@
 // gts_device.h -- data layout in HBM shared by the host API (gts_api.cu) and the kernels.
 // See DESIGN.md "Data layout" for the narrative.
 //
-// One device pass turns a FASTA buffer into protein FASTA with six kernels:
+// One device pass turns a FASTA buffer into protein FASTA with six kernels (k_lines; k_translate is
+// the residue kernel of the split-record path, gts_piece_*):
 //
 //   k_parse      raw bytes -> per-tile 4-bit symbol slots + header events   (transeq.go:183-216,
 //                                                                            encodedSequence.go:17-43)
 //   k_tile_scan  per-tile symbol / header counts -> stream offsets of the tiles
 //   k_records    header events + tile offsets -> record table (header offset, stream base)
 //   k_size       record table -> frame lengths (trim), output offsets       (writer.go:85-116,159-169)
-//   k_translate  symbols -> residues of all requested frames, laid out as
-//                60-column lines at their final output offsets              (writer.go:57-157,
+//   k_lines      symbols -> residues of all requested frames, laid out as
+//   (k_translate) 60-column lines at their final output offsets             (writer.go:57-157,
 //                                                                            encodedSequence.go:71-97)
 //   k_headers    record table + raw header bytes -> ">id_N rest" lines      (writer.go:120-131)
 //
@@ -40,7 +41,7 @@ constexpr int kParseTile = kParseThreads * kParseBytesPerThread;  // 8192 raw by
 constexpr int kSlotSyms = kParseTile + 64;  // symbols a slot can hold: the tile's bytes + 2 leading + 2 end pads
 constexpr int kSlotWords = kSlotSyms / 8;   // 1032 stream words per slot
 
-// ---- k_translate geometry: one CTA per parse tile, one warp per chunk of its symbols ----
+// ---- k_translate geometry (split-record path): one warp per chunk of a parse tile's symbols ----
 constexpr int kTransSymPerThread = 48;
 constexpr int kTransSub = 32 * kTransSymPerThread;        // 1536 symbols per warp ("chunk")
 constexpr int kTransSubWords = kTransSub / 8;             // 192 stream words

@@ -1,13 +1,15 @@
 // gts_translate.cu -- k_translate and k_headers: symbols -> protein FASTA bytes.
 //
+// k_translate is the residue kernel of the split-record path (gts_piece_*): every residue is produced
+// by the tile that holds the LAST symbol of its codon, so a piece needs only the two symbols in front
+// of it.  Ordinary passes use k_lines (gts_lines.cu), which needs the 192 symbols behind a tile instead.
+//
 // Reference behaviour reproduced (feliixx/gotranseq):
 //   k_translate  translate / translate3Frames / writeAA / newLine   transeq/writer.go:57-157,
 //                reverseComplement      transeq/encodedSequence.go:71-97 (never materialised:
 //                the fused table holds the reverse-strand residue of every window)
 //   k_headers    writeHeader            transeq/writer.go:120-131
 // tests/gpu_model.py is the executable specification of the index arithmetic used here.
-#include <cstdlib>
-
 #include "gts_common.cuh"
 #include "gts_kernels.h"
 
@@ -456,8 +458,7 @@ cudaError_t init_kernels() {
 }
 
 static cudaError_t launch_residues(const Job &job, u32 grid, int sm_count, cudaStream_t stream) {
-    static const bool old = getenv("GTS_OLD_TRANSLATE") != nullptr;
-    if (job.piece || old) {
+    if (job.piece) {
         k_translate<<<grid, kTransBlock, sizeof(TransShared), stream>>>(job);
         return cudaGetLastError();
     }

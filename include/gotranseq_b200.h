@@ -156,7 +156,7 @@ int gts_get_stats(const gts_ctx *ctx, gts_stats *st);
 /*
  * Per-kernel timing (bench.py's roofline numbers).  While enabled, CUDA events are recorded on
  * the pass's stream around each kernel.  gts_kernel_times waits for the recorded passes, adds
- * their durations up in ms -- [0] scratch reset + k_parse, [1] k_size, [2] k_translate,
+ * their durations up in ms -- [0] scratch reset + k_parse, [1] k_size, [2] k_lines (k_translate for a piece of a split record),
  * [3] k_headers -- reports how many passes that covers and starts a new accumulation.
  */
 int gts_set_profiling(gts_ctx *ctx, int enable);
