@@ -196,3 +196,66 @@ def test_over_long_lines():
                     assert out.getvalue() == want, name + " (stream)"
     finally:
         oracle.set_max_line_length(100 << 20)
+
+
+# ---- shapes that stress k_lines' tile / block / batch geometry ----
+
+def _seq(rng, n):
+    return bytes(rng.choice(b"ACGTN") for _ in range(n))
+
+
+def test_tiles_without_symbols_and_short_tiles():
+    """Header lines longer than a parse tile (8192 bytes): tiles with no symbols at all, and the
+    192 symbols behind a tile have to be collected from several later slots."""
+    import random
+    rng = random.Random(11)
+    parts = []
+    for r in range(12):
+        hdr = b">" + bytes(rng.choice(b"abcdefgh ") for _ in range(rng.choice((5, 9000, 17000, 8191, 8192, 8193))))
+        parts.append(hdr + b"\n" + _seq(rng, rng.choice((0, 1, 2, 50, 179, 180, 181, 400, 9000))) + b"\n")
+    data = b"".join(parts)
+    for kw in (dict(frame="6"), dict(frame="6", trim=True, alternative=True), dict(frame="R"), dict(frame="2")):
+        assert gpu(data, **kw) == oracle.translate(data, **kw), kw
+
+
+def test_thousands_of_tiny_records_per_tile():
+    """More record pieces in a tile than one batch of the run table holds (16), up to 4096 empty ones."""
+    import random
+    rng = random.Random(12)
+    parts = []
+    for r in range(9000):
+        parts.append(b">" + (b"r%d" % r if r % 3 else b"") + b"\n" + _seq(rng, rng.choice((0, 0, 0, 1, 2, 3, 4, 7))) +
+                     (b"\n" if r % 5 else b""))
+    data = b"".join(parts)
+    for kw in (dict(frame="6"), dict(frame="6", trim=True), dict(frame="F", table=4), dict(frame="-2", alternative=True)):
+        assert gpu(data, **kw) == oracle.translate(data, **kw), kw
+
+
+def test_image_capacity_batches():
+    """Sixteen record pieces of a tile whose lines do not fit the output image together."""
+    import random
+    rng = random.Random(13)
+    parts = []
+    for r in range(400):
+        n = rng.choice((420, 480, 500, 511, 540, 600))
+        parts.append(b">q%d\n" % r + _seq(rng, n) + b"\n")  # one-line records: 16+ of them per 8 KB tile
+    data = b"".join(parts)
+    for kw in (dict(frame="6"), dict(frame="6", trim=True, clean=True)):
+        assert gpu(data, **kw) == oracle.translate(data, **kw), kw
+
+
+@pytest.mark.parametrize("frame", ["6", "F", "R", "1", "-3"])
+def test_block_and_tile_boundary_sweep(frame):
+    """One record whose length moves the 180-nucleotide blocks and the ends of the frames across the
+    8192-byte tile boundaries, with and without a second record behind it."""
+    import random
+    rng = random.Random(14)
+    base = _seq(rng, 3 * 8192 + 400)
+    for n in list(range(8180, 8200)) + list(range(16370, 16392)) + [8192 + 177, 8192 + 180, 8192 + 183, 24576, 24577]:
+        for width in (10 ** 9, 60):
+            seq = base[:n]
+            body = b"\n".join(seq[i:i + width] for i in range(0, n, width))
+            data = b">x\n" + body + b"\n>y\nACGTAC\n"
+            for alt in (False, True):
+                want = oracle.translate(data, frame=frame, alternative=alt, trim=(n % 2 == 0))
+                assert gpu(data, frame=frame, alternative=alt, trim=(n % 2 == 0)) == want, (n, width, alt)
