@@ -192,18 +192,20 @@ def run_split(args, rank, local_rank, world):
     d_in = torch.from_numpy(np.frombuffer(piece_bytes, dtype=np.uint8).copy()).cuda()
     cap = len(data) * 2 + 4096  # three frames of n/3 residues + newlines + headers
     d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
-    mine = torch.zeros(4, dtype=torch.int64, device="cuda")
-    every = torch.zeros(4 * world, dtype=torch.int64, device="cuda")
+    W = 4 + 192  # nucleotide count, header length, last two codes, first 192 codes
+    mine = torch.zeros(W, dtype=torch.int64, device="cuda")
+    every = torch.zeros(W * world, dtype=torch.int64, device="cuda")
 
     def step():
         info = tr.piece_scan_device(d_in.data_ptr(), n, rank == 0, stream)
-        mine.copy_(torch.tensor([info["nucleotides"], info["header_len"], info["tail"][0], info["tail"][1]]))
+        mine.copy_(torch.tensor([info["nucleotides"], info["header_len"], info["tail"][0], info["tail"][1]] +
+                                list(info["head"])))
         if world > 1:
             dist.all_gather_into_tensor(every, mine)
-            rows = every.view(world, 4).tolist()
+            rows = every.view(world, W).tolist()
         else:
             rows = [mine.tolist()]
-        infos = [dict(nucleotides=r[0], header_len=r[1], tail=(r[2], r[3])) for r in rows]
+        infos = [dict(nucleotides=r[0], header_len=r[1], tail=(r[2], r[3]), head=bytes(r[4:])) for r in rows]
         piece = split.plan_pieces(infos)[rank]
         return tr.piece_translate_device(d_in.data_ptr(), n, piece, d_out.data_ptr(), cap, stream), infos
 
@@ -254,7 +256,7 @@ def run_split(args, rank, local_rank, world):
             "config": {"workload": "chromosome_split: one %d-byte record (%d nt, 60-column lines), flags -f R -a, cut "
                                    "into %d pieces at line starts, one per GPU" % (len(data), nt_total, world),
                        "l2": "piece + output per step exceed the 126 MB L2 at N <= 2; no explicit flush",
-                       "sharding": "intra-record split; exchange = one all-gather of 4 integers per rank per step"},
+                       "sharding": "intra-record split; exchange = one all-gather of 196 small integers per rank per step"},
             "e2e": None, "gpu_launches": launches, "clocks": clocks,
             "segments_cover_output": int(sb[0]) == total,
             "verified": (float(t[1]) == 0.0) if args.verify else None,

@@ -38,12 +38,13 @@ class gts_stats(ctypes.Structure):
 
 class gts_piece_info(ctypes.Structure):
     _fields_ = [("nucleotides", ctypes.c_uint64), ("headers", ctypes.c_uint64), ("header_len", ctypes.c_uint32),
-                ("tail", ctypes.c_uint8 * 2), ("reserved", ctypes.c_uint8 * 2)]
+                ("tail", ctypes.c_uint8 * 2), ("reserved", ctypes.c_uint8 * 2), ("head", ctypes.c_uint8 * 192)]
 
 
 class gts_piece(ctypes.Structure):
     _fields_ = [("nt_before", ctypes.c_uint64), ("nt_total", ctypes.c_uint64), ("header_len", ctypes.c_uint32),
-                ("carry", ctypes.c_uint8 * 2), ("first", ctypes.c_uint8), ("last", ctypes.c_uint8)]
+                ("carry", ctypes.c_uint8 * 2), ("first", ctypes.c_uint8), ("last", ctypes.c_uint8),
+                ("next_head", ctypes.c_uint8 * 192)]
 
 
 class gts_segment(ctypes.Structure):

@@ -3,7 +3,7 @@
 //
 // This file replaces the orchestration of transeq.Translate (transeq/transeq.go:114-173): where
 // the reference runs one reader goroutine feeding NumWorker translate goroutines, a gts_ctx cuts
-// the byte stream at record boundaries and runs one device pass (four kernels, gts_kernels.cu)
+// the byte stream at record boundaries and runs one device pass (six kernels, gts_kernels.h)
 // per cut, handing the results back strictly in input order.
 #include <cuda_runtime.h>
 
@@ -33,7 +33,7 @@ struct gts_ctx {
     int device = 0;
     int sm_count = 148;
     cudaStream_t stream = nullptr;  // used by the host-buffer entry points
-    cudaStream_t s_side = nullptr;  // k_headers runs here, next to k_translate
+    cudaStream_t s_side = nullptr;  // k_headers runs here, next to k_lines
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
     // ---- device scratch (grows, never shrinks) ----
@@ -41,7 +41,6 @@ struct gts_ctx {
     u32 *d_sym = nullptr;
     gts::TileInfo *d_tile_info = nullptr;
     gts::TilePrefix *d_tile_pre = nullptr;
-    uint16_t *d_chunk_hint = nullptr;
     uint8_t *d_zero = nullptr;  // per-pass zeroed block: scan status, tickets, totals
     size_t zero_cap = 0;
     u64 rec_cap = 0;
@@ -80,6 +79,7 @@ struct gts_ctx {
     gts::Job piece_job;      // only the piece fields are used
     size_t piece_n = 0;      // bytes of the piece kept in d_in by gts_piece_scan
     bool piece_first = false;
+    uint8_t *d_head = nullptr;  // 192 codes written by the scan pass of a piece
 
     // ---- per-kernel timing ----
     bool profiling = false;
@@ -164,8 +164,8 @@ int ensure_scratch(gts_ctx *ctx, u64 n) {
     if (n > ctx->cap_n || ctx->d_sym == nullptr) {
         const u64 cap = std::max<u64>(n + n / 8, 1u << 20);
         const u64 tiles = parse_tiles(cap);
-        cudaFree(ctx->d_sym); cudaFree(ctx->d_tile_info); cudaFree(ctx->d_tile_pre); cudaFree(ctx->d_chunk_hint);
-        ctx->d_sym = nullptr; ctx->d_tile_info = nullptr; ctx->d_tile_pre = nullptr; ctx->d_chunk_hint = nullptr;
+        cudaFree(ctx->d_sym); cudaFree(ctx->d_tile_info); cudaFree(ctx->d_tile_pre);
+        ctx->d_sym = nullptr; ctx->d_tile_info = nullptr; ctx->d_tile_pre = nullptr;
         ctx->cap_n = 0;
         const size_t sym_bytes = (tiles + 2) * gts::kSlotWords * sizeof(u32);
         CU(cudaMalloc(&ctx->d_sym, sym_bytes));
@@ -176,7 +176,6 @@ int ensure_scratch(gts_ctx *ctx, u64 n) {
         CU(cudaDeviceSynchronize());
         CU(cudaMalloc(&ctx->d_tile_info, tiles * sizeof(gts::TileInfo)));
         CU(cudaMalloc(&ctx->d_tile_pre, tiles * sizeof(gts::TilePrefix)));
-        CU(cudaMalloc(&ctx->d_chunk_hint, tiles * gts::kTransWarps * sizeof(uint16_t)));
         ctx->cap_n = cap;
     }
     const u64 want_rec = n / 128 + 4096;
@@ -214,7 +213,6 @@ int enqueue_pass(gts_ctx *ctx, const uint8_t *d_in, u64 n, uint8_t *d_out, u64 c
     job.sym = ctx->d_sym;
     job.tile_info = ctx->d_tile_info;
     job.tile_pre = ctx->d_tile_pre;
-    job.chunk_hint = ctx->d_chunk_hint;
     job.events = ctx->d_events;
     job.hdr_off = ctx->d_hdr_off; job.dbase = ctx->d_dbase; job.loc = ctx->d_loc; job.hinfo = ctx->d_hinfo;
     job.rec = ctx->d_rec; job.trim_len = ctx->d_trim; job.ftab = ctx->d_ftab; job.rec_cap = ctx->rec_cap;
@@ -232,11 +230,15 @@ int enqueue_pass(gts_ctx *ctx, const uint8_t *d_in, u64 n, uint8_t *d_out, u64 c
     job.more_follows = more_follows ? 1 : 0;
     job.piece = 0; job.no_end_pads = 0; job.has_carry = 0; job.carry = 0; job.no_headers = 0; job.ov_H = 0;
     job.t0_base = 0; job.win_lo = 0; job.ov_slot = 0; job.ov_n = 0; job.ov_dbase = 0;
+    job.head_out = nullptr;
+    std::memset(job.head, 0, sizeof(job.head));
     if (ctx->piece_on) {
         const gts::Job &p = ctx->piece_job;
         job.piece = p.piece; job.no_end_pads = p.no_end_pads; job.has_carry = p.has_carry; job.carry = p.carry;
         job.no_headers = p.no_headers; job.ov_H = p.ov_H; job.t0_base = p.t0_base; job.win_lo = p.win_lo;
         job.ov_slot = p.ov_slot; job.ov_n = p.ov_n; job.ov_dbase = p.ov_dbase;
+        job.head_out = p.head_out;
+        std::memcpy(job.head, p.head, sizeof(job.head));
     }
     job.lut = ctx->lut;
     {
@@ -480,7 +482,7 @@ int translate_host(gts_ctx *ctx, const uint8_t *in, size_t n, size_t *out_n) {
 }
 
 // ---- split record: which bytes of the record's output a piece writes --------------------------
-// Same arithmetic as build_runs (gts_translate.cu) / tests/gpu_model.py, for the whole piece at once.
+// Same frame arithmetic as the kernels (gts_common.cuh), for the whole piece at once.
 u64 host_reverse_start(u64 n, int i, bool alternative) {
     if (alternative) return (u64)i;
     int r = (int)(n % 3) - i;
@@ -501,10 +503,20 @@ int piece_segments(uint32_t mask, bool alternative, const gts_piece &p, u64 n_pi
     const u64 n = p.nt_total, H = p.header_len;
     u64 L[6];
     host_frame_lengths(n, alternative, L);
-    // windows (by start q) owned by the piece: those whose last nucleotide i = q + 2 lies in it;
-    // the last piece also owns the two windows that end on the pads behind the record
-    const long long q_lo = (long long)p.nt_before - 2;
-    const long long q_hi = (long long)(p.nt_before + n_piece + (p.last ? 2 : 0)) - 3;
+    // Output line b of a strand's frames is one block of 180 nucleotides; the block belongs to the
+    // piece that holds its anchor, the last symbol of its lowest codon (k_lines, gts_lines.cu).
+    // Anchors as indices into the record's nucleotides (n, n + 1 = the two pads behind it):
+    // forward 2 + 180 b; reverse n - 189 - 180 b, or 0 for the blocks b >= Lc at the record's start.
+    const u64 a = p.nt_before, e = p.nt_before + n_piece + (p.last ? 2 : 0);
+    const u64 f_lo = a > 2 ? (a - 2 + 179) / 180 : 0, f_hi = e > 2 ? (e - 2 + 179) / 180 : 0;
+    const u64 Lc = n >= 189 ? (n - 189) / 180 + 1 : 0;
+    u64 r_lo = (n >= 189 && n - 189 >= e) ? (n - 189 - e) / 180 + 1 : 0;
+    u64 r_hi = (n >= 189 && n - 189 >= a) ? (n - 189 - a) / 180 + 1 : 0;
+    if (r_hi > Lc) r_hi = Lc;
+    if (a == 0 && e > 0) {  // the blocks at the record's start
+        if (r_hi <= r_lo) r_lo = Lc;
+        r_hi = ~0ull;
+    }
     std::vector<gts_segment> v;
     u64 run_base = 0;
     for (int f = 0; f < 6; f++) {
@@ -513,20 +525,12 @@ int piece_segments(uint32_t mask, bool alternative, const gts_piece &p, u64 n_pi
         const u64 body = run_base + H + 3;
         if (p.first) v.push_back({run_base, H + 3});
         run_base += host_run_size(H, Lf);
-        long long j_lo, j_hi;
-        if (f < 3) {
-            j_lo = std::max<long long>(0, ceildiv3(q_lo - f));
-            j_hi = q_hi >= f ? floordiv3(q_hi - f) + 1 : 0;
-        } else {
-            const long long Q = (long long)n - 3 - (long long)host_reverse_start(n, f - 3, alternative);
-            j_lo = std::max<long long>(0, ceildiv3(Q - q_hi));
-            j_hi = Q >= q_lo ? floordiv3(Q - q_lo) + 1 : 0;
-        }
-        if (j_hi > (long long)Lf) j_hi = (long long)Lf;
-        if (j_hi <= j_lo) continue;
-        const u64 a = body + (u64)j_lo + (u64)j_lo / 60;
-        const u64 b = body + (u64)j_hi + (u64)j_hi / 60 + (((u64)j_hi == Lf && Lf % 60 != 0) ? 1 : 0);
-        v.push_back({a, b - a});
+        const u64 NL = (Lf + 59) / 60;
+        u64 lo = f < 3 ? f_lo : r_lo, hi = f < 3 ? f_hi : r_hi;
+        if (hi > NL) hi = NL;
+        if (hi <= lo) continue;
+        const u64 bytes = 61 * (hi - lo) - (hi == NL ? 60 * NL - Lf : 0);
+        v.push_back({body + 61 * lo, bytes});
     }
     *total = run_base;
     std::sort(v.begin(), v.end(), [](const gts_segment &x, const gts_segment &y) { return x.offset < y.offset; });
@@ -644,10 +648,10 @@ void gts_destroy(gts_ctx *ctx) {
         std::fprintf(stderr, "\n");
         cudaFree(ctx->d_dbg);
     }
-    cudaFree(ctx->d_sym); cudaFree(ctx->d_tile_info); cudaFree(ctx->d_tile_pre); cudaFree(ctx->d_chunk_hint);
+    cudaFree(ctx->d_sym); cudaFree(ctx->d_tile_info); cudaFree(ctx->d_tile_pre);
     cudaFree(ctx->d_zero); cudaFree(ctx->d_scan_nl);
     free_rec(ctx);
-    cudaFree(ctx->d_in); cudaFree(ctx->d_out);
+    cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_head);
     for (int b = 0; b < 2; b++) {
         cudaFree(ctx->p_in[b]); cudaFree(ctx->p_out[b]);
         if (ctx->ev_h2d[b]) cudaEventDestroy(ctx->ev_h2d[b]);
@@ -850,6 +854,8 @@ int gts_piece_scan_device(gts_ctx *ctx, const void *d_in, size_t n, int first, g
     ctx->piece_on = true;
     ctx->piece_job = gts::Job();
     ctx->piece_job.no_end_pads = 1;  // count only: no pass of its own end
+    if (!ctx->d_head) CU(cudaMalloc(&ctx->d_head, 256));
+    ctx->piece_job.head_out = ctx->d_head;
     ctx->last_truncated = false;
     int rc = enqueue_pass(ctx, static_cast<const uint8_t *>(d_in), n, nullptr, 0, static_cast<cudaStream_t>(stream), true);
     if (!rc) rc = finish_pass(ctx, true);
@@ -863,6 +869,7 @@ int gts_piece_scan_device(gts_ctx *ctx, const void *d_in, size_t n, int first, g
     info->tail[1] = (uint8_t)((t.tail >> 4) & 0xF);
     info->reserved[0] = info->reserved[1] = 0;
     info->header_len = 0;
+    CU(cudaMemcpy(info->head, ctx->d_head, sizeof(info->head), cudaMemcpyDeviceToHost));
     if (first) {
         if (t.n_headers != 1) return fail(ctx, GTS_ERR_ARG, "the first piece must hold exactly one header line");
         u64 hoff = 0, hinfo = 0;
@@ -891,6 +898,8 @@ int gts_piece_translate_device(gts_ctx *ctx, const void *d_in, size_t n, const g
     p.ov_H = piece->header_len;
     p.ov_n = piece->nt_total;
     p.ov_dbase = 4;  // stream of the whole record: slot 0's pads, the record's pads, its nucleotides
+    std::memcpy(p.head, piece->next_head, sizeof(p.head));
+    for (uint8_t &c : p.head) c = c > 4 ? 0 : c;
     if (piece->first) {
         p.ov_slot = 1;
     } else {

@@ -1,8 +1,7 @@
 // gts_device.h -- data layout in HBM shared by the host API (gts_api.cu) and the kernels.
 // See DESIGN.md "Data layout" for the narrative.
 //
-// One device pass turns a FASTA buffer into protein FASTA with six kernels (k_lines; k_translate is
-// the residue kernel of the split-record path, gts_piece_*):
+// One device pass turns a FASTA buffer into protein FASTA with six kernels:
 //
 //   k_parse      raw bytes -> per-tile 4-bit symbol slots + header events   (transeq.go:183-216,
 //                                                                            encodedSequence.go:17-43)
@@ -10,7 +9,7 @@
 //   k_records    header events + tile offsets -> record table (header offset, stream base)
 //   k_size       record table -> frame lengths (trim), output offsets       (writer.go:85-116,159-169)
 //   k_lines      symbols -> residues of all requested frames, laid out as
-//   (k_translate) 60-column lines at their final output offsets             (writer.go:57-157,
+//                60-column lines at their final output offsets              (writer.go:57-157,
 //                                                                            encodedSequence.go:71-97)
 //   k_headers    record table + raw header bytes -> ">id_N rest" lines      (writer.go:120-131)
 //
@@ -40,23 +39,6 @@ constexpr int kParseBytesPerThread = 32;
 constexpr int kParseTile = kParseThreads * kParseBytesPerThread;  // 8192 raw bytes
 constexpr int kSlotSyms = kParseTile + 64;  // symbols a slot can hold: the tile's bytes + 2 leading + 2 end pads
 constexpr int kSlotWords = kSlotSyms / 8;   // 1032 stream words per slot
-
-// ---- k_translate geometry (split-record path): one warp per chunk of a parse tile's symbols ----
-constexpr int kTransSymPerThread = 48;
-constexpr int kTransSub = 32 * kTransSymPerThread;        // 1536 symbols per warp ("chunk")
-constexpr int kTransSubWords = kTransSub / 8;             // 192 stream words
-constexpr int kTransWarps = (kSlotSyms + kTransSub - 1) / kTransSub;  // 6 chunks cover a slot
-constexpr int kTransBlock = (kTransWarps + 1) * 32;       // + 1 builder warp
-constexpr int kPhaseLen = kTransSub / 3;                  // residues per phase array (per warp)
-constexpr int kPhaseGuard = 16;
-constexpr int kPhasePad = 0;                              // extra bytes that rotate the arrays over the banks
-constexpr int kPhaseStride = kPhaseLen + 2 * kPhaseGuard + kPhasePad; // bytes per phase array in smem
-constexpr int kRecBatch = 4;                              // record pieces per chunk and format batch
-constexpr int kRunsPerBatch = kRecBatch * 6;
-// Output image of one chunk batch in shared memory: the residue lines a chunk writes (at most
-// 2 * kTransSub * 61 / 60 bytes + one final newline per run) plus up to 34 bytes of 16-byte
-// alignment padding per run.
-constexpr int kImageBytes = (2 * kTransSub * 61 / 60 + kRunsPerBatch * 35 + 128 + 15) / 16 * 16;
 
 // ---- k_tile_scan / k_size geometry ----
 constexpr int kScanThreads = 256;
@@ -115,7 +97,7 @@ struct HeaderEvent {  // 16 bytes per header line, appended by k_parse in no par
     uint16_t pos;  // slot index of the record's first nucleotide (its pads sit at pos-2, pos-1)
 };
 
-struct RecInfo {  // 32 bytes per record slot, written by k_size, read by k_translate / k_headers
+struct RecInfo {  // 32 bytes per record slot, written by k_size, read by k_lines / k_headers
     u64 out_off;  // offset of the record's first output byte
     u64 dbase;    // stream index of the record's first nucleotide
     u64 n;        // nucleotides
@@ -147,8 +129,6 @@ struct Job {  // kernel argument block (by value)
     u32 *sym;              // [ntiles * kSlotWords] symbol slots
     TileInfo *tile_info;   // [ntiles]
     TilePrefix *tile_pre;  // [ntiles]
-    uint16_t *chunk_hint;  // [ntiles * kTransWarps] header lines of the tile whose record starts at
-                           // or before the chunk's first symbol
     HeaderEvent *events;   // [rec_cap]
 
     // record table, slots 0..R (+1 sentinel)
@@ -189,6 +169,8 @@ struct Job {  // kernel argument block (by value)
     u64 ov_slot;       // the record's slot in this pass; every other slot is silent
     u64 ov_n;          // the whole record's nucleotides
     u64 ov_dbase;      // stream index of its first nucleotide
+    uint8_t *head_out; // scan pass: receives the codes of the buffer's first 192 nucleotides
+    uint8_t head[192]; // the 192 symbols behind the buffer (the record goes on in the next piece)
     Lut lut;
     LutBytes lutb;
 };

@@ -1,0 +1,82 @@
+// gts_headers.cu -- k_headers and the launch of the emit stage (k_lines + k_headers).
+//
+// Reference behaviour reproduced (feliixx/gotranseq):
+//   k_headers    writeHeader            transeq/writer.go:120-131
+#include "gts_common.cuh"
+#include "gts_kernels.h"
+
+namespace gts {
+
+// =====================================================================================
+// k_headers
+// =====================================================================================
+// Header line of one frame (writer.go:120-131): the header's bytes with '_' and the frame digit
+// inserted before its first space (or appended), then '\n'.  Half a warp per record, lane i holding
+// output bytes i, i+16, ...: the line is assembled once (only the digit differs between frames)
+// and stored once per requested frame.
+__global__ void __launch_bounds__(256) k_headers(const __grid_constant__ Job job) {
+    const int lane = threadIdx.x & 31, sub = lane & 15, half = lane >> 4;
+    const u64 R = job.totals->n_headers;
+    if (job.totals->flags != 0 || job.no_headers) return;
+    const u64 nhalf = (u64)gridDim.x * (blockDim.x >> 4);
+    for (u64 s = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 4; s <= R; s += nhalf) {
+        const RecInfo ri = job.rec[s];
+        if (!ri.emitted) continue;
+        const u32 H = ri.H;
+        const u32 sp = s >= 1 ? (u32)(job.hinfo[s] >> 32) : 0u;
+        const uint8_t *hdr = job.in + job.hdr_off[s];
+        // run sizes of the six frames
+        u64 L[6];
+        frame_lengths(ri.n, job.alternative != 0, L);
+        if (job.trim) {
+#pragma unroll
+            for (int f = 0; f < 6; f++) L[f] = job.trim_len[s * 6 + f];
+        }
+        for (u32 i = sub; i < H + 3; i += 16) {
+            // byte i of the line; the digit at sp+1 is patched per frame
+            uint8_t c = '\n';
+            if (i < sp) c = hdr[i];
+            else if (i == sp) c = '_';
+            else if (i > sp + 1 && i < H + 2) c = hdr[i - 2];
+            const bool digit = i == sp + 1;
+            u64 run_base = ri.out_off;
+#pragma unroll
+            for (int f = 0; f < 6; f++) {
+                if (!((job.frame_mask >> f) & 1u)) continue;
+                job.out[run_base + i] = digit ? (uint8_t)('1' + f) : c;
+                run_base += run_size(H, L[f]);
+            }
+        }
+    }
+    (void)half;
+}
+
+// =====================================================================================
+// launch
+// =====================================================================================
+cudaError_t init_lines();
+cudaError_t launch_lines(const Job &job, int sm_count, cudaStream_t stream);
+
+cudaError_t init_kernels() { return init_lines(); }
+
+// k_headers only needs the record table, so it runs on `side` (when given) next to k_lines: the
+// persistent k_lines grid leaves room for its small CTAs on every SM.
+cudaError_t launch_emit(const Job &job, int sm_count, cudaStream_t stream, cudaEvent_t ev_mid, cudaStream_t side,
+                        cudaEvent_t ev_fork, cudaEvent_t ev_join) {
+    if (side) {
+        cudaEventRecord(ev_fork, stream);
+        cudaStreamWaitEvent(side, ev_fork, 0);
+        k_headers<<<sm_count * 4, 256, 0, side>>>(job);
+        cudaEventRecord(ev_join, side);
+        launch_lines(job, sm_count, stream);
+        if (ev_mid) cudaEventRecord(ev_mid, stream);
+        cudaStreamWaitEvent(stream, ev_join, 0);
+    } else {
+        launch_lines(job, sm_count, stream);
+        if (ev_mid) cudaEventRecord(ev_mid, stream);
+        k_headers<<<sm_count * 4, 256, 0, stream>>>(job);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace gts

@@ -1,5 +1,5 @@
 // gts_kernels.h -- host-callable launchers of the kernels (gts_parse.cu, gts_size.cu,
-// gts_lines.cu, gts_translate.cu).
+// gts_lines.cu, gts_headers.cu).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -7,13 +7,13 @@
 
 namespace gts {
 
-// Per-device one-time kernel attribute setup (dynamic shared memory of k_lines / k_translate).
+// Per-device one-time kernel attribute setup (dynamic shared memory of k_lines).
 cudaError_t init_kernels();
 
 cudaError_t launch_parse(const Job &job, cudaStream_t stream);                // k_parse
 cudaError_t launch_sizes(const Job &job, int sm_count, cudaStream_t stream);  // k_tile_scan, k_records, k_size
-// k_lines (k_translate for a piece of a split record) and k_headers; with a side stream (and two events to fork / join) the two run
-// concurrently; ev_mid (optional) is recorded on `stream` after k_translate
+// k_lines and k_headers; with a side stream (and two events to fork / join) the two run
+// concurrently; ev_mid (optional) is recorded on `stream` after k_lines
 cudaError_t launch_emit(const Job &job, int sm_count, cudaStream_t stream, cudaEvent_t ev_mid,
                         cudaStream_t side = nullptr, cudaEvent_t ev_fork = nullptr, cudaEvent_t ev_join = nullptr);
 

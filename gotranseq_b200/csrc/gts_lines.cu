@@ -158,6 +158,7 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
     const u32 nsym = ti.nsym;
     if (nsym == 0) continue;
     const u64 T0 = tp.T0, Tend = tp.T0 + nsym;
+    const u32 tlo = job.win_lo > T0 ? (u32)(job.win_lo - T0) : 0u;  // 2 in the first tile of a later piece of a split record
     const uintptr_t out_mis = (uintptr_t)job.out & 15u;
 
     // Record pieces of the tile: the record open at its first byte, then one per header line.  A
@@ -222,7 +223,8 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
         }
     }
     // the 192 symbols after the tile: the stream goes on in the next slot ...
-    if (!has_next || next_nsym >= (u32)kHalo) {
+    const bool from_head = job.piece && job.no_end_pads;  // a split record goes on in the next piece
+    if (has_next ? next_nsym >= (u32)kHalo : !from_head) {
         if (tid < kHalo / 8) {
             const u32 lo4 = hw & 0x0F0F0F0Fu, hi4 = (hw >> 4) & 0x0F0F0F0Fu;
 #pragma unroll
@@ -237,15 +239,18 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
         // ... or, when that one is short, in the slots after it
         for (u32 i = tid; i < (u32)kHalo; i += kLinesThreads) {
             u32 u = tile + 1, off = i, v = 0;
+            bool found = false;
             while (u < job.ntiles) {
                 const u32 nu = job.tile_info[u].nsym;
                 if (off < nu) {
                     v = slot_symbol(job.sym, u, off);
+                    found = true;
                     break;
                 }
                 off -= nu;
                 u++;
             }
+            if (!found && from_head) v = job.head[off];  // off < kHalo symbols past the end of the piece
             sh.symf[kHalo + nsym + i] = (uint8_t)v;
             sh.symr[kMirror - (int)(nsym + i)] = (uint8_t)v;
         }
@@ -298,38 +303,33 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
                 if (NLmax) {
                     if (bs == 0) {
                         // block b = nucleotides 180 b ..; its lowest codon (frame 1) ends at k0 + 180 b, k0 = D + 2
-                        const i64 x = -(d + 2);  // T0 - k0
-                        if (x > 0) {
-                            const u64 q = (u64)(x - 1) / 180u;
-                            const u32 rem = (u32)((u64)(x - 1) - 180u * q);
-                            lo = q + 1;
-                            hi = q + (rem + nsym + 180u) / 180u;
-                            symrel = kHalo + 177 - (i64)rem;
-                        } else {
-                            const i64 e = x + (i64)nsym;
-                            hi = e > 0 ? ((u32)e + 179u) / 180u : 0u;
-                            symrel = kHalo - x - 2;
-                        }
+                        // (tlo: a piece of a split record leaves the anchors on its first two symbols,
+                        // the stand-ins for the nucleotides before it, to the piece before)
+                        const i64 x = -(d + 2) + (i64)tlo;  // first anchor position of the tile - k0
+                        if (x > 0) lo = (u64)(x - 1) / 180u + 1;
+                        const i64 e = (i64)nsym - (d + 2) - 180 * (i64)lo;  // anchors k0 + 180 b < T0 + nsym
+                        hi = lo + (e > 0 ? ((u32)e + 179u) / 180u : 0u);
+                        symrel = kHalo + d + 180 * (i64)lo;
                     } else {
                         // block b is read downwards from nucleotide n - 1 - 180 b; its lowest codon (phase 2,
                         // residue 60 b + 62) ends at D + n - 189 - 180 b, unless the record starts above it:
                         // then ("clipped", b >= Lc) at D, the end of the codon made of the record's pads
                         u64 Lc = n >= 189 ? (n - 189) / 180u + 1 : 0;
                         if (Lc > NLmax) Lc = NLmax;
-                        const i64 y = d + (i64)n - 189;
-                        if (y >= 0) {
-                            const u64 qy = (u64)y / 180u;
-                            const u32 ry = (u32)((u64)y - 180u * qy);
+                        const i64 y = d + (i64)n - 189;  // anchor of block 0, relative to the tile
+                        if (y >= (i64)tlo) {
+                            const u64 qy = (u64)(y - tlo) / 180u;
+                            const u32 ry = (u32)((u64)(y - tlo) - 180u * qy);
                             hi = qy + 1;
-                            if (nsym > ry) {
-                                const u32 c1 = (nsym - ry + 179u) / 180u;
+                            if (nsym - tlo > ry) {
+                                const u32 c1 = (nsym - tlo - ry + 179u) / 180u;
                                 lo = qy + 1 >= c1 ? qy + 1 - c1 : 0;
                             } else {
                                 lo = hi;
                             }
                         }
                         if (hi > Lc) hi = Lc;
-                        if (Lc < NLmax && d >= 0 && d < (i64)nsym) {
+                        if (Lc < NLmax && d >= (i64)tlo && d < (i64)nsym) {
                             if (hi <= lo) lo = Lc;
                             hi = NLmax;
                         }

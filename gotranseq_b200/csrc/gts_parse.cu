@@ -402,30 +402,9 @@ __global__ void __launch_bounds__(kParseThreads) k_parse(const __grid_constant__
                     job.events[base + k] = ev;
                 }
             }
-            // header lines of the tile whose record starts at or before the first symbol of a
-            // translate chunk that starts in this chunk's symbols
-            const u32 c_nsym = __shfl_sync(0xFFFFFFFFu, nsym, c);
-            const u32 x = (c_d + kTransSub - 1) / kTransSub;
-            if (c_nsym > 0 && x * kTransSub < c_d + c_nsym) {
-                const u32 xs = x * kTransSub;
-                const unsigned le = __ballot_sync(0xFFFFFFFFu, hstart && c_d + off + 2 <= xs);
-                if (lane == 0) job.chunk_hint[(u64)t * kTransWarps + x] = (uint16_t)(c_rec + (u32)__popc(le));
-            }
         }
-    }
-    // chunk starts inside fast chunks (no header line there: the record open at the chunk)
-    if (fast) {
-        const u32 x = (d + kTransSub - 1) / kTransSub;
-        if (x * kTransSub < d + nsym) job.chunk_hint[(u64)t * kTransWarps + x] = (uint16_t)(excl >> 16);
     }
     if (tid < 32) sh.sym[S_own + tid] = 0;  // end pads (last tile) and zero fill of the last word
-    if (tid == 0) {
-        if (last_tile) {
-            // the two end pads may open a translate chunk of their own
-            const u32 x = (S_own + kTransSub - 1) / kTransSub;
-            if (x * kTransSub < S_tile) job.chunk_hint[(u64)t * kTransWarps + x] = (uint16_t)R_tile;
-        }
-    }
     PHASE_MARK(job, 4, tprev);  // slow chunks, hints
     __syncthreads();  // all symbols staged
     PHASE_MARK(job, 5, tprev);  // barrier

@@ -124,6 +124,18 @@ __global__ void __launch_bounds__(kScanThreads) k_tile_scan(const __grid_constan
                         }
                         job.totals->tail = tail;
                     }
+                    if (job.head_out) {
+                        // codes of the buffer's first 192 nucleotides (a piece of a split record: the
+                        // piece before it needs them); slot 0's pads and a header's pads are skipped
+                        const u32 skip = 2u + 2u * (u32)R;
+                        u32 seen = 0, got = 0;
+                        for (u32 u = 0; u < ntiles && got < 192u; u++) {
+                            const u32 ns_u = job.tile_info[u].nsym - (u == ntiles - 1 && !job.no_end_pads ? 2u : 0u);
+                            for (u32 k = 0; k < ns_u && got < 192u; k++, seen++)
+                                if (seen >= skip) job.head_out[got++] = (uint8_t)slot_symbol(job.sym, u, k);
+                        }
+                        for (; got < 192u; got++) job.head_out[got] = 0;
+                    }
                     job.totals->n_headers = R;
                     if (R + 2 <= job.rec_cap) {
                         // slot 0 (bytes before the first header line) and the sentinel after the last record

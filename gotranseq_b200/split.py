@@ -2,10 +2,11 @@
 
 Record sharding (shard.py) cannot spread ONE record; the reference translates a record on one
 worker (writer.go:57-117).  Here the record's FASTA bytes are cut into pieces at line starts, every
-rank parses its piece, the ranks exchange three integers per piece (nucleotide count and the codes
-of the piece's last two nucleotides; the header length comes from piece 0), and every rank then
-writes its share of the protein FASTA at its final offsets: every residue is computed by the piece
-that holds the last nucleotide of its codon, so no sequence bytes travel between the ranks.
+rank parses its piece, the ranks exchange ~200 bytes per piece (nucleotide count, the codes of the
+piece's first 192 and last two nucleotides; the header length comes from piece 0), and every rank
+then writes its share of the protein FASTA at its final offsets.  Output lines are never shared:
+a 60-residue line (180 nucleotides) is computed by the piece that holds the last nucleotide of the
+line's lowest codon, with the two nucleotides before the piece and the 192 behind it as context.
 """
 
 
@@ -33,8 +34,14 @@ def plan_pieces(infos):
     before = 0
     last, second = 0, 0  # codes of the two nucleotides before the current piece (0 = the pads)
     for k, inf in enumerate(infos):
+        # the 192 nucleotides behind the piece: the heads of the pieces after it, as far as needed
+        nxt = b""
+        for later in infos[k + 1:]:
+            if len(nxt) >= 192:
+                break
+            nxt += bytes(later["head"])[:min(192, later["nucleotides"])]
         pieces.append(dict(nt_before=before, nt_total=total, header_len=H, carry=(last, second),
-                           first=(k == 0), last=(k == len(infos) - 1)))
+                           first=(k == 0), last=(k == len(infos) - 1), next_head=nxt[:192]))
         m = inf["nucleotides"]
         if m >= 2:
             last, second = inf["tail"]

@@ -140,7 +140,7 @@ class Translator:
         self._check(self._L.gts_piece_scan(self._h, ctypes.cast(buf, ctypes.c_void_p), n, 1 if first else 0,
                                            ctypes.byref(info)))
         return dict(nucleotides=info.nucleotides, headers=info.headers, header_len=info.header_len,
-                    tail=(info.tail[0], info.tail[1]))
+                    tail=(info.tail[0], info.tail[1]), head=bytes(info.head))
 
     @staticmethod
     def _piece_struct(piece):
@@ -148,6 +148,8 @@ class Translator:
         p.nt_before, p.nt_total, p.header_len = piece["nt_before"], piece["nt_total"], piece["header_len"]
         p.carry[0], p.carry[1] = piece["carry"]
         p.first, p.last = (1 if piece["first"] else 0), (1 if piece["last"] else 0)
+        nh = bytes(piece.get("next_head", b""))[:192]
+        ctypes.memmove(p.next_head, nh + bytes(192 - len(nh)), 192)
         return p
 
     def piece_translate(self, piece):
@@ -167,7 +169,7 @@ class Translator:
         self._check(self._L.gts_piece_scan_device(self._h, ctypes.c_void_p(d_in), n, 1 if first else 0,
                                                   ctypes.byref(info), ctypes.c_void_p(stream)))
         return dict(nucleotides=info.nucleotides, headers=info.headers, header_len=info.header_len,
-                    tail=(info.tail[0], info.tail[1]))
+                    tail=(info.tail[0], info.tail[1]), head=bytes(info.head))
 
     def piece_translate_device(self, d_in, n, piece, d_out, cap, stream=0):
         """Device-resident piece: writes its segments into d_out (the whole record's output buffer).

@@ -156,7 +156,7 @@ int gts_get_stats(const gts_ctx *ctx, gts_stats *st);
 /*
  * Per-kernel timing (bench.py's roofline numbers).  While enabled, CUDA events are recorded on
  * the pass's stream around each kernel.  gts_kernel_times waits for the recorded passes, adds
- * their durations up in ms -- [0] scratch reset + k_parse, [1] k_size, [2] k_lines (k_translate for a piece of a split record),
+ * their durations up in ms -- [0] scratch reset + k_parse, [1] k_size, [2] k_lines,
  * [3] k_headers -- reports how many passes that covers and starts a new accumulation.
  */
 int gts_set_profiling(gts_ctx *ctx, int enable);
@@ -176,18 +176,20 @@ int gts_set_max_line_length(gts_ctx *ctx, size_t n);
  * caller cuts the record's FASTA bytes into pieces at line starts (the first piece begins with the
  * header line) and gives each piece to one GPU / context:
  *
- *   1. gts_piece_scan*       parses the piece: its nucleotide count, the codes of its last two
- *                            nucleotides, the header line's length (first piece)
- *   2. the caller adds the counts up (an all-gather of three integers between the ranks) and
- *      fills gts_piece for every piece: nucleotides before it, nucleotides of the whole record,
- *      the two nucleotides in front of it (carry), the header length
+ *   1. gts_piece_scan*       parses the piece: its nucleotide count, the codes of its first 192
+ *                            and last two nucleotides, the header line's length (first piece)
+ *   2. the caller adds the counts up (an all-gather of ~200 bytes between the ranks) and fills
+ *      gts_piece for every piece: nucleotides before it, nucleotides of the whole record, the two
+ *      nucleotides in front of it (carry), the 192 behind it (next_head), the header length
  *   3. gts_piece_translate*  writes the piece's share of the record's protein FASTA at its
  *                            FINAL offsets: at most 12 byte ranges (one per requested frame, plus
  *                            the header lines on the first piece), returned as segments
  *
- * The pieces' segments are disjoint and cover the record's output exactly; every residue is
- * computed by the piece that holds the LAST nucleotide of its codon (the carry supplies the other
- * two), so no piece needs bytes of another.  --trim is not supported here (GTS_ERR_ARG).
+ * The pieces' segments are disjoint and cover the record's output exactly.  Output lines are
+ * never shared: a 60-residue line (180 nucleotides) is computed by the piece that holds the last
+ * nucleotide of the line's lowest codon; carry and next_head supply what the line needs from the
+ * neighbouring pieces, so no sequence bytes travel besides those ~200.  --trim is not supported
+ * here (GTS_ERR_ARG).
  */
 typedef struct gts_piece_info {
     uint64_t nucleotides; /* nucleotides in the piece                                          */
@@ -195,6 +197,7 @@ typedef struct gts_piece_info {
     uint32_t header_len;  /* bytes of the header line, CR dropped (first piece)                */
     uint8_t tail[2];      /* codes (N=0 A=1 C=2 T=3 G=4) of its last / second-to-last nucleotide */
     uint8_t reserved[2];
+    uint8_t head[192];    /* codes of its first 192 nucleotides (0 beyond the piece's end)      */
 } gts_piece_info;
 
 typedef struct gts_piece {
@@ -204,6 +207,7 @@ typedef struct gts_piece {
     uint8_t carry[2];     /* codes of the two nucleotides before the piece: [0] last, [1] second to last */
     uint8_t first;        /* this piece starts with the record's header line                    */
     uint8_t last;         /* this piece ends the record                                         */
+    uint8_t next_head[192]; /* codes of the 192 nucleotides behind the piece (0 beyond the record) */
 } gts_piece;
 
 typedef struct gts_segment {

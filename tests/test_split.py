@@ -49,26 +49,33 @@ def frame_lengths(n, alt):
 
 
 def segments(frames, alt, H, n, before, m, first, last):
-    """Byte ranges of the record's output owned by the piece holding nucleotides [before, before+m)."""
+    """Byte ranges of the record's output owned by the piece holding nucleotides [before, before+m).
+    Output line b of a strand = one block of 180 nucleotides, owned by the piece that holds the
+    block's anchor (the last symbol of its lowest codon): forward 2 + 180 b; reverse n - 189 - 180 b,
+    or 0 for the blocks at the record's start (gts_lines.cu)."""
     L = frame_lengths(n, alt)
-    q_lo, q_hi = before - 2, before + m + (2 if last else 0) - 3
+    a, e = before, before + m + (2 if last else 0)
+    f_lo = -((2 - a) // 180) if a > 2 else 0
+    f_hi = -((2 - e) // 180) if e > 2 else 0
+    Lc = (n - 189) // 180 + 1 if n >= 189 else 0
+    r_lo = (n - 189 - e) // 180 + 1 if n - 189 >= e else 0
+    r_hi = min((n - 189 - a) // 180 + 1 if n - 189 >= a else 0, Lc)
+    if a == 0 and e > 0:
+        if r_hi <= r_lo:
+            r_lo = Lc
+        r_hi = 1 << 62
     segs, base = [], 0
     for f in frames:
         body = base + H + 3
         if first:
             segs.append((base, H + 3))
-        base += H + 3 + L[f] + (L[f] + 59) // 60
-        if f < 3:
-            j_lo, j_hi = max(0, -((f - q_lo) // 3)), ((q_hi - f) // 3 + 1 if q_hi >= f else 0)
-        else:
-            Q = n - 3 - reverse_start(n, f - 3, alt)
-            j_lo, j_hi = max(0, -((q_hi - Q) // 3)), ((Q - q_lo) // 3 + 1 if Q >= q_lo else 0)
-        j_hi = min(j_hi, L[f])
-        if j_hi <= j_lo:
+        NL = (L[f] + 59) // 60
+        base += H + 3 + L[f] + NL
+        lo, hi = (f_lo, f_hi) if f < 3 else (r_lo, r_hi)
+        hi = min(hi, NL)
+        if hi <= lo:
             continue
-        a = body + j_lo + j_lo // 60
-        b = body + j_hi + j_hi // 60 + (1 if j_hi == L[f] and L[f] % 60 else 0)
-        segs.append((a, b - a))
+        segs.append((body + 61 * lo, 61 * (hi - lo) - (60 * NL - L[f] if hi == NL else 0)))
     return base, [s for s in segs if s[1]]
 
 
@@ -86,7 +93,9 @@ class FakeTranslator:
             hl = len(h[:-1] if h.endswith(b"\r") else h)
         codes = [CODES[c] for c in self.nts[-2:]]
         tail = (codes[-1] if codes else 0, codes[-2] if len(codes) > 1 else 0)
-        return dict(nucleotides=len(self.nts), headers=1 if first else 0, header_len=hl, tail=tail)
+        head = bytes(CODES[c] for c in self.nts[:192])
+        return dict(nucleotides=len(self.nts), headers=1 if first else 0, header_len=hl, tail=tail,
+                    head=head + bytes(192 - len(head)))
 
     def piece_translate(self, p):
         want = oracle.translate(self.whole, frame=self.frame, alternative=self.alt)
@@ -120,13 +129,17 @@ def test_piece_ranges_cover_and_cut_at_line_starts():
 
 
 def test_plan_pieces_carry():
-    infos = [dict(nucleotides=5, headers=1, header_len=4, tail=(3, 2)), dict(nucleotides=0, headers=0, header_len=0, tail=(0, 0)),
-             dict(nucleotides=1, headers=0, header_len=0, tail=(4, 0)), dict(nucleotides=7, headers=0, header_len=0, tail=(1, 1))]
+    infos = [dict(nucleotides=5, headers=1, header_len=4, tail=(3, 2), head=bytes([1, 2, 3, 2, 3]) + bytes(187)),
+             dict(nucleotides=0, headers=0, header_len=0, tail=(0, 0), head=bytes(192)),
+             dict(nucleotides=1, headers=0, header_len=0, tail=(4, 0), head=bytes([4]) + bytes(191)),
+             dict(nucleotides=7, headers=0, header_len=0, tail=(1, 1), head=bytes([2, 2, 2, 2, 2, 1, 1]) + bytes(185))]
     p = split.plan_pieces(infos)
     assert [x["nt_before"] for x in p] == [0, 5, 5, 6]
     assert all(x["nt_total"] == 13 and x["header_len"] == 4 for x in p)
     assert [x["carry"] for x in p] == [(0, 0), (3, 2), (3, 2), (4, 3)]
     assert [x["first"] for x in p] == [True, False, False, False] and p[-1]["last"] and not p[0]["last"]
+    assert [x["next_head"] for x in p] == [bytes([4, 2, 2, 2, 2, 2, 1, 1]), bytes([4, 2, 2, 2, 2, 2, 1, 1]),
+                                           bytes([2, 2, 2, 2, 2, 1, 1]), b""]
 
 
 @pytest.mark.parametrize("frame", ["1", "2", "3", "F", "-1", "-2", "-3", "R", "6"])
