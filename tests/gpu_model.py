@@ -1,7 +1,6 @@
 """Executable specification of the GPU data flow (TEST INFRASTRUCTURE, pure Python, small inputs).
 
-This mirrors, formula for formula, what the CUDA kernels in gotranseq_b200/csrc/gts_kernels.cu
-compute -- it is NOT the oracle (that is oracle/transeq_oracle.c, a restatement of the Go code).
+This mirrors, formula for formula, what the CUDA kernels in gotranseq_b200/csrc/ compute -- it is NOT the oracle (that is oracle/transeq_oracle.c, a restatement of the Go code).
 Its job is to let the index arithmetic of the kernels (symbol stream with pads, window -> frame
 routing, run geometry, 60-column line jobs, tile boundaries) be checked against the oracle on the
 CPU, with deliberately tiny tile sizes so that every tile-boundary case is hit.
@@ -10,9 +9,15 @@ Stages (DESIGN.md has the narrative):
   parse      raw FASTA -> dense symbol stream (codes N=0 A=1 C=2 T=3 G=4; two 0 pads in front of
              every record, two more at the end) + record table (hdr_off, hdr_end, dbase)
   size       per record: nucleotide count, frame lengths (optionally trimmed), output offsets
-  translate  per tile of `tile` symbols: one LUT lookup per symbol e for the window (e-2, e-1, e),
-             results spread over 3 phase arrays (e mod 3) x {forward, reverse}; then for every
-             (record piece, frame) a "run" whose 60-column lines are copied to the output
+  residues   two formulations of the same output, both checked against the oracle:
+             "windows" (round 1's first residue kernel): per tile of `tile` symbols one LUT lookup per
+             symbol e for the window (e-2, e-1, e), results spread over 3 phase arrays (e mod 3) x
+             {forward, reverse}; then for every (record piece, frame) a "run" whose 60-column lines
+             are copied to the output;
+             "lines" (k_lines, gts_lines.cu): per tile, record piece and strand the BLOCKS of 180
+             nucleotides whose anchor (last symbol of the block's lowest codon) lies in the tile; a
+             block is output line b of the strand's three frames, 60 codons each read straight
+             from the stream
   headers    per record and frame: header bytes with _N inserted before the first space
 """
 
@@ -154,7 +159,90 @@ def fdiv(a, b):
     return a // b  # python floors; the kernels use an explicit floor division helper
 
 
-def translate(raw, aa64, mask, clean=False, alternative=False, trim=False, tile=48):
+def lines_stage(out, sym, lut, dbase, hdr_off, hdr_end, Lp, out_off, emitted, mask, alternative, tile, S2):
+    """k_lines: block ranges per (tile, record piece, strand) with the kernel's tile-relative
+    arithmetic (build step of gts_lines.cu), then every owned line written residue by residue."""
+    nslots = len(dbase) - 1
+
+    def symbol(e):
+        return sym[e] if 0 <= e < len(sym) else 0  # the staged halo is zero past the end of the stream
+
+    ntiles = (S2 + tile - 1) // tile
+    for t in range(ntiles):
+        T0 = t * tile
+        nsym = min(T0 + tile, S2) - T0
+        s = 0
+        while dbase[s + 1] <= T0:
+            s += 1
+        while s < nslots and dbase[s] < T0 + nsym:
+            D = dbase[s]
+            n = dbase[s + 1] - 2 - D
+            if emitted(s):
+                H = hdr_end[s] - hdr_off[s]
+                d = D - T0
+                bodies, base = [], out_off[s]
+                for f in range(6):
+                    bodies.append(base + H + 3)
+                    if (mask >> f) & 1:
+                        base += run_size(H, Lp[s][f])
+                for strand in (0, 1):
+                    # the strand's frames by codon phase k
+                    if strand == 0:
+                        fr = [0, 1, 2]
+                    else:
+                        fr = [3 + (k if alternative else (n % 3 - k) % 3) for k in range(3)]
+                    Lk = [Lp[s][f] if (mask >> f) & 1 else 0 for f in fr]
+                    NLk = [(L + 59) // 60 for L in Lk]
+                    NLmax = max(NLk)
+                    lo = hi = 0
+                    if NLmax:
+                        if strand == 0:
+                            x = -(d + 2)
+                            if x > 0:
+                                lo = (x - 1) // 180 + 1
+                            e = nsym - (d + 2) - 180 * lo
+                            hi = lo + ((e + 179) // 180 if e > 0 else 0)
+                        else:
+                            Lc = min((n - 189) // 180 + 1 if n >= 189 else 0, NLmax)
+                            y = d + n - 189
+                            if y >= 0:
+                                qy = y // 180
+                                ry = y - 180 * qy
+                                hi = qy + 1
+                                if nsym > ry:
+                                    lo = max(qy + 1 - (nsym - ry + 179) // 180, 0)
+                                else:
+                                    lo = hi
+                            hi = min(hi, Lc)
+                            if Lc < NLmax and 0 <= d < nsym:
+                                if hi <= lo:
+                                    lo = Lc
+                                hi = NLmax
+                        hi = min(hi, NLmax)
+                    for b in range(lo, hi):
+                        for k in range(3):
+                            if b >= NLk[k]:
+                                continue
+                            f = fr[k]
+                            dst = bodies[f] + 61 * b
+                            cnt = min(60, Lk[k] - 60 * b)
+                            for x in range(cnt):
+                                if strand == 0:
+                                    q = k + 180 * b + 3 * x  # codon = nucleotides q, q+1, q+2
+                                    idx = symbol(D + q) + 5 * symbol(D + q + 1) + 25 * symbol(D + q + 2)
+                                    aa = lut[idx] & 0xFF
+                                else:
+                                    top = n - 1 - 180 * b - k - 3 * x  # read downwards: top, top-1, top-2
+                                    idx = symbol(D + top - 2) + 5 * symbol(D + top - 1) + 25 * symbol(D + top)
+                                    aa = lut[idx] >> 8
+                                assert out[dst + x] == ord("?")
+                                out[dst + x] = aa
+                            assert out[dst + cnt] == ord("?")
+                            out[dst + cnt] = 0x0A
+            s += 1
+
+
+def translate(raw, aa64, mask, clean=False, alternative=False, trim=False, tile=48, residues="windows"):
     assert tile % 3 == 0
     lut = build_lut(aa64, clean)
     sym, hdr_off, hdr_end, dbase, total = parse(raw)
@@ -184,8 +272,11 @@ def translate(raw, aa64, mask, clean=False, alternative=False, trim=False, tile=
         n = dbase[s + 1] - 2 - dbase[s]
         return s >= 1 or n > 0 or R == 0
 
-    # ---- k_translate ----
+    # ---- residues ----
     ntiles = (S2 + tile - 1) // tile
+    if residues == "lines":
+        lines_stage(out, sym, lut, dbase, hdr_off, hdr_end, Lp, out_off, emitted, mask, alternative, tile, S2)
+        ntiles = 0
     for t in range(ntiles):
         T0 = t * tile
         Tend = min(T0 + tile, S2)
