@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(kScanThreads) k_tile_scan(const __grid_constan
         const u32 st = s_tile;
         if (st >= nscan) return;
         const u32 t0 = st * kScanTile + tid * kScanPerThread;
-        u32 ns[kScanPerThread], nh[kScanPerThread];
+        u32 ns[kScanPerThread], nh[kScanPerThread], tl[kScanPerThread];
         u64 sum_s = 0, sum_r = 0;
         const bool track_nl = job.n >= job.max_line;
         NlPart mine;
@@ -49,11 +49,12 @@ __global__ void __launch_bounds__(kScanThreads) k_tile_scan(const __grid_constan
         mine.pad = 0;
 #pragma unroll
         for (int i = 0; i < kScanPerThread; i++) {
-            ns[i] = nh[i] = 0;
+            ns[i] = nh[i] = tl[i] = 0;
             if (t0 + i < ntiles) {
                 const TileInfo ti = job.tile_info[t0 + i];
                 ns[i] = ti.nsym;
                 nh[i] = ti.nhdr;
+                tl[i] = ti.tail;
                 if (track_nl && ti.has_nl) {
                     // inside one tile no line can reach the limit (it is at least two tiles long)
                     NlPart p;
@@ -152,29 +153,35 @@ __global__ void __launch_bounds__(kScanThreads) k_tile_scan(const __grid_constan
         }
         __syncthreads();
         u64 T = job.t0_base + s_excl_s + ex_s, Rr = s_excl_r + ex_r;
+        // the two symbols before the thread's first tile (windows reach back two symbols): from the
+        // tiles before it; for its other tiles they follow from its own tiles' tails
+        u32 carry = 0;
+        if (t0 < ntiles) {
+            u32 got = 0;
+            for (i64 u = (i64)t0 - 1; got < 2 && u >= 0; u--) {
+                const TileInfo ti = job.tile_info[u];
+                if (ti.nsym >= 1) {
+                    carry |= (u32)(ti.tail & 0xFu) << (4 * got);
+                    got++;
+                    if (got < 2 && ti.nsym >= 2) {
+                        carry |= (u32)(ti.tail >> 4) << (4 * got);
+                        got++;
+                    }
+                }
+            }
+        }
 #pragma unroll
         for (int i = 0; i < kScanPerThread; i++) {
             const u32 t = t0 + i;
             if (t < ntiles) {
-                // the two symbols before the tile (windows reach back two symbols)
-                u32 got = 0, carry = 0;
-                for (i64 u = (i64)t - 1; got < 2 && u >= 0; u--) {
-                    const TileInfo ti = job.tile_info[u];
-                    if (ti.nsym >= 1) {
-                        carry |= (u32)(ti.tail & 0xFu) << (4 * got);
-                        got++;
-                        if (got < 2 && ti.nsym >= 2) {
-                            carry |= (u32)(ti.tail >> 4) << (4 * got);
-                            got++;
-                        }
-                    }
-                }
                 TilePrefix tp;
                 tp.T0 = T;
                 tp.R0 = (u32)Rr;
                 tp.carry = carry;
                 job.tile_pre[t] = tp;
             }
+            if (ns[i] >= 2) carry = tl[i];
+            else if (ns[i] == 1) carry = (tl[i] & 0xFu) | (carry & 0xFu) << 4;
             T += ns[i];
             Rr += nh[i];
         }
