@@ -42,10 +42,16 @@ constexpr int kSlotWords = kSlotSyms / 8;   // 1032 stream words per slot
 
 // ---- k_tile_scan / k_size geometry ----
 constexpr int kScanThreads = 256;
-constexpr int kScanPerThread = 8;
+#ifndef GTS_SCAN_PER_THREAD
+#define GTS_SCAN_PER_THREAD 4
+#endif
+constexpr int kScanPerThread = GTS_SCAN_PER_THREAD;
 constexpr int kScanTile = kScanThreads * kScanPerThread;  // parse tiles per scan tile
 constexpr int kSizeThreads = 256;
-constexpr int kSizePerThread = 1;
+#ifndef GTS_SIZE_PER_THREAD
+#define GTS_SIZE_PER_THREAD 1
+#endif
+constexpr int kSizePerThread = GTS_SIZE_PER_THREAD;
 constexpr int kSizeTile = kSizeThreads * kSizePerThread;  // record slots per scan tile
 
 // Chained-scan status: 4 words per tile {agg.a, agg.b, inc.a, inc.b}; bit 63 of the .a words
