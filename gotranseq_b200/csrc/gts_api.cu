@@ -8,6 +8,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -57,10 +60,32 @@ struct gts_ctx {
     size_t d_in_cap = 0, d_out_cap = 0;
     uint8_t *h_out = nullptr;
     size_t h_out_cap = 0;
-    uint8_t *h_in = nullptr;  // streaming input (pinned)
-    size_t h_in_cap = 0, h_in_fill = 0;
-    bool stream_first_pass = true, stream_eof = false, stream_out_ready = false, stream_done = false;
-    size_t stream_out_n = 0;
+    // ---- streaming host interface: the caller fills one pinned input buffer while a worker thread
+    // translates the other; two output buffers, handed back in order ----
+    struct StreamJob {
+        int in_idx = 0;    // input buffer
+        size_t n = 0;      // bytes to translate: [0, n) of it
+    };
+    uint8_t *s_in[2] = {nullptr, nullptr};   // pinned
+    size_t s_in_cap[2] = {0, 0};
+    int s_fill_idx = 0;                      // the buffer the caller is filling
+    size_t s_fill = 0;                       // bytes in it
+    const uint8_t *s_rest_src = nullptr;     // unfinished record of the buffer submitted last: copied
+    size_t s_rest_len = 0;                   //   to the front of the next buffer when it is acquired
+    uint8_t *s_out[2] = {nullptr, nullptr};  // pinned
+    size_t s_out_cap[2] = {0, 0}, s_out_n[2] = {0, 0};
+    int s_out_state[2] = {0, 0};             // 0 free, 1 being written, 2 ready for the caller
+    int s_out_head = 0, s_out_tail = 0;      // next buffer for the caller / for the worker
+    bool s_has_running = false, s_has_pending = false;
+    StreamJob s_running, s_pending;
+    int s_running_out = 0;
+    std::thread s_worker;
+    std::mutex s_mu;
+    std::condition_variable s_cv;
+    bool s_worker_started = false, s_worker_exit = false;
+    int s_rc = 0;                            // first error of the worker
+    std::string s_err;
+    bool stream_first_pass = true, stream_eof = false;
 
     // ---- chunk pipeline of the host entry points: H2D / kernels / D2H overlap ----
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;  // `stream` above runs the kernels
@@ -637,6 +662,14 @@ int gts_create(const gts_options *opt, gts_ctx **out) {
 
 void gts_destroy(gts_ctx *ctx) {
     if (!ctx) return;
+    if (ctx->s_worker_started) {
+        {
+            std::lock_guard<std::mutex> lk(ctx->s_mu);
+            ctx->s_worker_exit = true;
+        }
+        ctx->s_cv.notify_all();
+        ctx->s_worker.join();
+    }
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->d_dbg) {
@@ -661,8 +694,11 @@ void gts_destroy(gts_ctx *ctx) {
     if (ctx->h_totals2) cudaFreeHost(ctx->h_totals2);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+    for (int b = 0; b < 2; b++) {
+        if (ctx->s_in[b]) cudaFreeHost(ctx->s_in[b]);
+        if (ctx->s_out[b] && ctx->s_out[b] != ctx->h_out) cudaFreeHost(ctx->s_out[b]);
+    }
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
-    if (ctx->h_in) cudaFreeHost(ctx->h_in);
     if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -721,47 +757,116 @@ int gts_translate_buffer(gts_ctx *ctx, const uint8_t *in, size_t n, const uint8_
 
 // ---- streaming host interface ----------------------------------------------------------
 
+// The worker: translates the running job into its output buffer, then promotes the pending job.
+static void stream_try_start_locked(gts_ctx *ctx) {
+    if (ctx->s_has_running || !ctx->s_has_pending) return;
+    if (ctx->s_out_state[ctx->s_out_tail] != 0) return;  // both output buffers are still with the caller
+    ctx->s_running = ctx->s_pending;
+    ctx->s_has_pending = false;
+    ctx->s_has_running = true;
+    ctx->s_running_out = ctx->s_out_tail;
+    ctx->s_out_state[ctx->s_out_tail] = 1;
+    ctx->s_out_tail ^= 1;
+}
+
+static void stream_worker(gts_ctx *ctx) {
+    cudaSetDevice(ctx->device);
+    std::unique_lock<std::mutex> lk(ctx->s_mu);
+    while (true) {
+        ctx->s_cv.wait(lk, [&] { return ctx->s_worker_exit || ctx->s_has_running; });
+        if (ctx->s_worker_exit) return;
+        const gts_ctx::StreamJob job = ctx->s_running;
+        const int o = ctx->s_running_out;
+        const bool skip = ctx->stream_truncated || ctx->s_rc != 0;
+        lk.unlock();
+        size_t total = 0;
+        int rc = GTS_OK;
+        if (!skip) {
+            // translate_host writes into ctx->h_out: lend it this job's output buffer
+            uint8_t *keep = ctx->h_out;
+            const size_t keep_cap = ctx->h_out_cap;
+            ctx->h_out = ctx->s_out[o];
+            ctx->h_out_cap = ctx->s_out_cap[o];
+            rc = translate_host(ctx, ctx->s_in[job.in_idx], job.n, &total);
+            ctx->s_out[o] = ctx->h_out;
+            ctx->s_out_cap[o] = ctx->h_out_cap;
+            ctx->h_out = keep;
+            ctx->h_out_cap = keep_cap;
+        }
+        lk.lock();
+        if (rc != GTS_OK && ctx->s_rc == 0) {
+            ctx->s_rc = rc;
+            ctx->s_err = ctx->err;
+        }
+        if (!skip && rc == GTS_OK && ctx->last_truncated) ctx->stream_truncated = true;  // the reference stopped reading here
+        ctx->s_out_n[o] = rc == GTS_OK ? total : 0;
+        if (ctx->s_out_n[o]) {
+            ctx->s_out_state[o] = 2;
+        } else {
+            // nothing to hand back: the buffer is free again (it was the last one taken)
+            ctx->s_out_state[o] = 0;
+            ctx->s_out_tail = o;
+        }
+        ctx->s_has_running = false;
+        stream_try_start_locked(ctx);
+        ctx->s_cv.notify_all();
+    }
+}
+
+static int stream_error_locked(gts_ctx *ctx) {
+    if (ctx->s_rc == 0) return GTS_OK;
+    ctx->err = ctx->s_err;
+    return ctx->s_rc;
+}
+
 int gts_acquire_input(gts_ctx *ctx, uint8_t **buf, size_t *cap) {
     if (!ctx || !buf || !cap) return GTS_ERR_ARG;
     if (ctx->stream_eof) return fail(ctx, GTS_ERR_ARG, "gts_acquire_input after eof");
     CU(cudaSetDevice(ctx->device));
+    const int k = ctx->s_fill_idx;
+    {
+        // the buffer may still be the input of a job (the one submitted two submits ago)
+        std::unique_lock<std::mutex> lk(ctx->s_mu);
+        ctx->s_cv.wait(lk, [&] {
+            return !(ctx->s_has_running && ctx->s_running.in_idx == k) && !(ctx->s_has_pending && ctx->s_pending.in_idx == k);
+        });
+        int rc = stream_error_locked(ctx);
+        if (rc) return rc;
+    }
     const size_t chunk = ctx->opt.chunk_bytes ? (size_t)ctx->opt.chunk_bytes : (size_t)64 << 20;
     // keep at least half a chunk of free space; a record larger than the buffer makes it grow
-    size_t need = ctx->h_in_fill + std::max<size_t>(chunk / 2, 4096);
+    size_t need = ctx->s_fill + ctx->s_rest_len + std::max<size_t>(chunk / 2, 4096);
     if (need < chunk) need = chunk;
-    int rc = ensure_pinned(ctx, &ctx->h_in, &ctx->h_in_cap, need, ctx->h_in_fill);
+    int rc = ensure_pinned(ctx, &ctx->s_in[k], &ctx->s_in_cap[k], need, ctx->s_fill);
     if (rc) return rc;
-    *buf = ctx->h_in + ctx->h_in_fill;
-    *cap = ctx->h_in_cap - ctx->h_in_fill;
+    if (ctx->s_rest_len) {  // the unfinished record of the buffer submitted last (that buffer is only read by its job)
+        std::memcpy(ctx->s_in[k], ctx->s_rest_src, ctx->s_rest_len);
+        ctx->s_fill = ctx->s_rest_len;
+        ctx->s_rest_len = 0;
+        ctx->s_rest_src = nullptr;
+    }
+    *buf = ctx->s_in[k] + ctx->s_fill;
+    *cap = ctx->s_in_cap[k] - ctx->s_fill;
     return GTS_OK;
 }
 
 int gts_submit(gts_ctx *ctx, size_t nbytes, int eof) {
     if (!ctx) return GTS_ERR_ARG;
     if (ctx->stream_eof) return fail(ctx, GTS_ERR_ARG, "gts_submit after eof");
-    if (ctx->stream_out_ready) return fail(ctx, GTS_ERR_ARG, "gts_submit before the previous output was released");
-    if (ctx->h_in_fill + nbytes > ctx->h_in_cap) return fail(ctx, GTS_ERR_ARG, "gts_submit: more bytes than acquired");
-    CU(cudaSetDevice(ctx->device));
-    ctx->h_in_fill += nbytes;
+    const int k = ctx->s_fill_idx;
+    if (ctx->s_fill + nbytes > ctx->s_in_cap[k]) return fail(ctx, GTS_ERR_ARG, "gts_submit: more bytes than acquired");
+    ctx->s_fill += nbytes;
     if (eof) ctx->stream_eof = true;
-    if (ctx->stream_truncated) {  // the reference has stopped reading: the rest of the stream is ignored
-        ctx->h_in_fill = 0;
-        if (eof) ctx->stream_done = true;
-        return GTS_OK;
-    }
     const size_t chunk = ctx->opt.chunk_bytes ? (size_t)ctx->opt.chunk_bytes : (size_t)64 << 20;
     size_t cut = 0;
     if (eof) {
-        cut = ctx->h_in_fill;
-        if (cut == 0 && !ctx->stream_first_pass) {  // nothing left after the last record boundary
-            ctx->stream_done = true;
-            return GTS_OK;
-        }
+        cut = ctx->s_fill;
+        if (cut == 0 && !ctx->stream_first_pass) return GTS_OK;  // nothing left after the last record boundary
     } else {
-        if (ctx->h_in_fill < chunk) return GTS_OK;  // keep filling
+        if (ctx->s_fill < chunk) return GTS_OK;  // keep filling
         // last record boundary: a '>' that starts a line (transeq.go:198)
-        const uint8_t *p = ctx->h_in;
-        for (size_t i = ctx->h_in_fill; i-- > 1;) {
+        const uint8_t *p = ctx->s_in[k];
+        for (size_t i = ctx->s_fill; i-- > 1;) {
             if (p[i] == '>' && p[i - 1] == '\n') {
                 cut = i;
                 break;
@@ -769,47 +874,64 @@ int gts_submit(gts_ctx *ctx, size_t nbytes, int eof) {
         }
         if (cut == 0) return GTS_OK;  // one record larger than the buffer: keep reading (buffer grows)
     }
-    size_t total = 0;
-    int rc = translate_host(ctx, ctx->h_in, cut, &total);
-    if (rc) return rc;
     ctx->stream_first_pass = false;
-    if (ctx->last_truncated) {
-        ctx->stream_truncated = true;
-        ctx->h_in_fill = cut;  // nothing is carried over
+    std::unique_lock<std::mutex> lk(ctx->s_mu);
+    int rc = stream_error_locked(ctx);
+    if (rc) return rc;
+    if (!ctx->s_worker_started) {
+        ctx->s_worker = std::thread(stream_worker, ctx);
+        ctx->s_worker_started = true;
     }
-    // carry the unfinished record over
-    const size_t rest = ctx->h_in_fill - cut;
-    if (rest) std::memmove(ctx->h_in, ctx->h_in + cut, rest);
-    ctx->h_in_fill = rest;
-    ctx->stream_out_n = total;
-    ctx->stream_out_ready = total > 0;
-    if (eof) ctx->stream_done = true;
+    ctx->s_cv.wait(lk, [&] { return !ctx->s_has_pending; });  // at most one job waits behind the running one
+    ctx->s_pending.in_idx = k;
+    ctx->s_pending.n = cut;
+    ctx->s_has_pending = true;
+    stream_try_start_locked(ctx);
+    ctx->s_cv.notify_all();
+    // the caller goes on with the other buffer; the unfinished record moves there when it is acquired
+    ctx->s_rest_src = ctx->s_in[k] + cut;
+    ctx->s_rest_len = ctx->s_fill - cut;
+    ctx->s_fill_idx = k ^ 1;
+    ctx->s_fill = 0;
     return GTS_OK;
 }
 
 int gts_next_output(gts_ctx *ctx, const uint8_t **buf, size_t *n) {
     if (!ctx || !buf || !n) return GTS_ERR_ARG;
-    if (ctx->stream_out_ready) {
-        *buf = ctx->h_out;
-        *n = ctx->stream_out_n;
-    } else {
-        *buf = nullptr;
-        *n = 0;
-        if (ctx->stream_done) {  // drained: ready for another stream
-            ctx->stream_truncated = false;
-            ctx->stream_done = false;
-            ctx->stream_eof = false;
-            ctx->stream_first_pass = true;
-            ctx->h_in_fill = 0;
-        }
+    *buf = nullptr;
+    *n = 0;
+    std::unique_lock<std::mutex> lk(ctx->s_mu);
+    const int h = ctx->s_out_head;
+    if (ctx->stream_eof)  // drain: wait for the next result, or for the worker to run dry
+        ctx->s_cv.wait(lk, [&] { return ctx->s_out_state[h] == 2 || (!ctx->s_has_running && !ctx->s_has_pending); });
+    int rc = stream_error_locked(ctx);
+    if (rc) return rc;
+    if (ctx->s_out_state[h] == 2) {
+        *buf = ctx->s_out[h];
+        *n = ctx->s_out_n[h];
+        return GTS_OK;
+    }
+    if (ctx->stream_eof) {  // drained: ready for another stream
+        ctx->stream_truncated = false;
+        ctx->stream_eof = false;
+        ctx->stream_first_pass = true;
+        ctx->s_fill = 0;
+        ctx->s_rest_len = 0;
+        ctx->s_rest_src = nullptr;
     }
     return GTS_OK;
 }
 
 int gts_release_output(gts_ctx *ctx) {
     if (!ctx) return GTS_ERR_ARG;
-    ctx->stream_out_ready = false;
-    ctx->stream_out_n = 0;
+    std::unique_lock<std::mutex> lk(ctx->s_mu);
+    const int h = ctx->s_out_head;
+    if (ctx->s_out_state[h] != 2) return GTS_OK;
+    ctx->s_out_state[h] = 0;
+    ctx->s_out_n[h] = 0;
+    ctx->s_out_head ^= 1;
+    stream_try_start_locked(ctx);
+    ctx->s_cv.notify_all();
     return GTS_OK;
 }
 

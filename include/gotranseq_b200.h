@@ -131,9 +131,14 @@ int gts_translate_buffer(gts_ctx *ctx, const uint8_t *in, size_t n, const uint8_
  *   }
  *
  * The library cuts the byte stream at record boundaries ("\n>"), carries the unfinished last
- * record over to the next pass, keeps one pass in flight while the caller reads / writes, and
- * hands results back strictly in input order.  After gts_submit(..., eof=1) the
- * gts_next_output loop drains everything; n == 0 then means "done".
+ * record over to the next pass and hands results back strictly in input order.  gts_submit only
+ * queues the pass: a worker thread owned by ctx runs it (H2D, kernels, D2H) while the caller reads
+ * the next chunk into the other pinned input buffer and writes the previous result, so reading,
+ * translating and writing overlap.  Before eof gts_next_output does not block: n == 0 means
+ * "nothing finished yet, go on reading".  After gts_submit(..., eof=1) it waits for each remaining
+ * result; n == 0 then means "done" (and ctx is ready for another stream).  At most two results wait
+ * for the caller: drain gts_next_output after every gts_submit, as in the loop above.  The other
+ * entry points of ctx must not be called while a stream is in progress.
  */
 int gts_acquire_input(gts_ctx *ctx, uint8_t **buf, size_t *cap);
 int gts_submit(gts_ctx *ctx, size_t nbytes, int eof);

@@ -87,6 +87,44 @@ def test_translate_stream_matches_one_shot():
         assert out2.getvalue() == want
 
 
+def test_translate_stream_overlapped_pipeline():
+    """The streaming interface keeps a worker translating while the caller reads and writes: small
+    reads (the input buffer fills over many calls), records larger than a chunk (the buffer grows),
+    a writer that lags, and more data behind the last record boundary of every chunk."""
+    import random
+    import time
+    import gotranseq_b200
+
+    class Dribble:
+        def __init__(self, data, rng):
+            self.data, self.pos, self.rng = data, 0, rng
+
+        def read(self, n):
+            k = min(n, self.rng.choice((1, 100, 4096, 70000, 1 << 20)))
+            out = self.data[self.pos:self.pos + k]
+            self.pos += len(out)
+            return out
+
+    class SlowWriter:
+        def __init__(self):
+            self.parts = []
+
+        def write(self, b):
+            time.sleep(0.002)
+            self.parts.append(bytes(b))
+
+    rng = random.Random(21)
+    data = regular_fasta(8, 400, 100, 3000) + regular_fasta(9, 2, 300_000, 400_000) + regular_fasta(10, 300, 10, 900)
+    for kw, okw in ((dict(Frame="6"), dict(frame="6")), (dict(Frame="R", Alternative=True, Trim=True),
+                                                          dict(frame="R", alternative=True, trim=True))):
+        want = oracle.translate(data, **okw)
+        with gotranseq_b200.Translator(gotranseq_b200.Options(**kw), chunk_bytes=1 << 17) as t:
+            for _ in range(2):
+                w = SlowWriter()
+                t.translate_stream(Dribble(data, rng), w)
+                assert b"".join(w.parts) == want
+
+
 def test_translate_api():
     import gotranseq_b200
     data = nasty_fasta(5)
