@@ -833,7 +833,7 @@ int gts_acquire_input(gts_ctx *ctx, uint8_t **buf, size_t *cap) {
         int rc = stream_error_locked(ctx);
         if (rc) return rc;
     }
-    const size_t chunk = ctx->opt.chunk_bytes ? (size_t)ctx->opt.chunk_bytes : (size_t)64 << 20;
+    const size_t chunk = ctx->opt.chunk_bytes ? (size_t)ctx->opt.chunk_bytes : (size_t)16 << 20;
     // keep at least half a chunk of free space; a record larger than the buffer makes it grow
     size_t need = ctx->s_fill + ctx->s_rest_len + std::max<size_t>(chunk / 2, 4096);
     if (need < chunk) need = chunk;
@@ -857,7 +857,7 @@ int gts_submit(gts_ctx *ctx, size_t nbytes, int eof) {
     if (ctx->s_fill + nbytes > ctx->s_in_cap[k]) return fail(ctx, GTS_ERR_ARG, "gts_submit: more bytes than acquired");
     ctx->s_fill += nbytes;
     if (eof) ctx->stream_eof = true;
-    const size_t chunk = ctx->opt.chunk_bytes ? (size_t)ctx->opt.chunk_bytes : (size_t)64 << 20;
+    const size_t chunk = ctx->opt.chunk_bytes ? (size_t)ctx->opt.chunk_bytes : (size_t)16 << 20;
     size_t cut = 0;
     if (eof) {
         cut = ctx->s_fill;
