@@ -27,17 +27,16 @@ namespace gts {
 #define GTS_LINES_THREADS 96
 #endif
 #ifndef GTS_LINES_CTAS
-#define GTS_LINES_CTAS 5
+#define GTS_LINES_CTAS 7
 #endif
 constexpr int kLinesThreads = GTS_LINES_THREADS;  // >= 3 * kBlockRuns
-constexpr int kHalo = 192;                              // symbols staged before / after the tile's own
-constexpr int kSymArr = kHalo + kSlotSyms + kHalo + 16; // bytes per staged array
-constexpr int kMirror = kSlotSyms + kHalo - 1;          // mirror index of local symbol x = kMirror - x; = 7 (mod 8)
+constexpr int kHalo = 192;                              // symbols staged behind the tile's own
+constexpr int kLeft = 208;                              // margin in front of them: zeros and the two carried symbols
+constexpr int kSymArr = kLeft + kSlotSyms + kHalo + 16;  // bytes of the staged array
 constexpr int kLineBatch = 16;                          // record pieces per batch
 constexpr int kBlockRuns = kLineBatch * 2;              // (piece, strand) entries per batch: one builder lane each
-constexpr int kLineImage = 20480;                       // output image bytes (one piece needs < 17.8 KB)
-static_assert(kMirror % 8 == 7, "mirror stores are 8-byte aligned");
-static_assert(kMirror + kHalo + 1 <= kSymArr, "mirror array too small");
+constexpr int kLineImage = 18432;                       // output image bytes (one piece needs < 17.8 KB)
+static_assert(kLeft % 16 == 0, "staging stores are 8-byte aligned");
 static_assert(kBlockRuns == 32, "the run table is built by one warp");
 static_assert(kLinesThreads >= 3 * kBlockRuns, "one thread per frame run in the copy-out");
 
@@ -50,16 +49,16 @@ struct FrameRun {    // lines of one frame among a BlockRun's blocks
 };
 
 struct BlockRun {    // the blocks of one (record piece, strand) that belong to the tile
-    u32 sym;         // shared-memory offset of the first block's first symbol (+180 per block)
+    u32 sym;         // shared-memory offset of the first block's first symbol: forward its lowest one
+                     // (+180 per block, read upwards), reverse its highest one (-180 per block, read downwards)
     u32 lut;         // shared-memory offset of the strand's residue table
     u32 nblk;
-    u32 pad;
+    int dir;         // +1 forward, -1 reverse
     FrameRun fr[3];  // by codon phase: forward frame k; reverse frame that starts k nucleotides from the end
 };
 
 struct LinesShared {
-    alignas(16) uint8_t symf[kSymArr];  // [kHalo - 2 .. ) = the two symbols before the tile, the tile, the halo
-    alignas(16) uint8_t symr[kSymArr];  // symr[kMirror - x] = local symbol x
+    alignas(16) uint8_t symf[kSymArr];  // [kLeft - 2 .. ) = the two symbols before the tile, the tile, the halo
     alignas(16) uint8_t image[kLineImage];
     alignas(16) BlockRun runs[kBlockRuns];
     u32 job_pre[kBlockRuns];            // first block job of the runs that have blocks, in job order
@@ -126,10 +125,7 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
         reinterpret_cast<u32 *>(sh.lutr)[tid] = job.lutb.r[tid];
     }
     // margins that are read but never hold a tile's data: below the two carried symbols
-    for (int i = tid; i < (kSymArr - kMirror - 3) / 2; i += kLinesThreads) {
-        reinterpret_cast<uint16_t *>(sh.symf)[i] = 0;
-        reinterpret_cast<uint16_t *>(sh.symr + kMirror + 3)[i] = 0;  // mirror of locals -3, -4, ...
-    }
+    for (int i = tid; i < (kLeft - 2) / 2; i += kLinesThreads) reinterpret_cast<uint16_t *>(sh.symf)[i] = 0;
     const u64 flags = job.totals->flags;
     const u64 R = job.totals->n_headers;
     if (flags != 0) return;
@@ -193,19 +189,15 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
     // ---- stage: the tile's symbols ----
     if (tid == 0) {
         const u32 c = tp.carry;  // last | second-to-last << 4
-        sh.symf[kHalo - 1] = (uint8_t)(c & 0xFu);
-        sh.symf[kHalo - 2] = (uint8_t)((c >> 4) & 0xFu);
-        sh.symr[kMirror + 1] = (uint8_t)(c & 0xFu);
-        sh.symr[kMirror + 2] = (uint8_t)((c >> 4) & 0xFu);
+        sh.symf[kLeft - 1] = (uint8_t)(c & 0xFu);
+        sh.symf[kLeft - 2] = (uint8_t)((c >> 4) & 0xFu);
     }
 #pragma unroll
     for (int k = 0; k < kWordsPerThread; k++) {
         const u32 w = tid + k * kLinesThreads;
         if (w < (u32)kSlotWords) {
             const u32 lo4 = xw[k] & 0x0F0F0F0Fu, hi4 = (xw[k] >> 4) & 0x0F0F0F0Fu;
-            *reinterpret_cast<uint2 *>(sh.symf + kHalo + 8u * w) = make_uint2(lo4, hi4);
-            *reinterpret_cast<uint2 *>(sh.symr + kMirror - 7 - 8u * w) =
-                make_uint2(prmt(hi4, 0u, 0x0123u), prmt(lo4, 0u, 0x0123u));
+            *reinterpret_cast<uint2 *>(sh.symf + kLeft + 8u * w) = make_uint2(lo4, hi4);
         }
     }
     __syncthreads();  // the halo overwrites what the slot holds behind the tile's symbols
@@ -231,8 +223,7 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
             for (int j = 0; j < 8; j++) {
                 const uint8_t v = (uint8_t)(((j < 4 ? lo4 : hi4) >> (8 * (j & 3))) & 0xFFu);
                 const u32 x = nsym + 8u * tid + j;
-                sh.symf[kHalo + x] = v;
-                sh.symr[kMirror - (int)x] = v;
+                sh.symf[kLeft + x] = v;
             }
         }
     } else {
@@ -251,14 +242,12 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
                 u++;
             }
             if (!found && from_head) v = job.head[off];  // off < kHalo symbols past the end of the piece
-            sh.symf[kHalo + nsym + i] = (uint8_t)v;
-            sh.symr[kMirror - (int)(nsym + i)] = (uint8_t)v;
+            sh.symf[kLeft + nsym + i] = (uint8_t)v;
         }
     }
 
     // offsets in the CTA's shared memory
     const u32 symf_addr = (u32)offsetof(LinesShared, symf);
-    const u32 symr_addr = (u32)offsetof(LinesShared, symr);
     const u32 lutf_addr = (u32)offsetof(LinesShared, lutf);
     const u32 lutr_addr = (u32)offsetof(LinesShared, lutr);
     const u32 image_addr = (u32)offsetof(LinesShared, image);
@@ -267,7 +256,7 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
         // ---- build (warp 0): one lane per (record piece, strand) ----
         if (warp == 0) {
             BlockRun run;
-            run.sym = 0; run.lut = 0; run.nblk = 0; run.pad = 0;
+            run.sym = 0; run.lut = 0; run.nblk = 0; run.dir = 1;
 #pragma unroll
             for (int k = 0; k < 3; k++) {
                 run.fr[k].g0 = 0; run.fr[k].img = 0; run.fr[k].nbytes = 0; run.fr[k].nl = 0; run.fr[k].flags = 0;
@@ -309,7 +298,7 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
                         if (x > 0) lo = (u64)(x - 1) / 180u + 1;
                         const i64 e = (i64)nsym - (d + 2) - 180 * (i64)lo;  // anchors k0 + 180 b < T0 + nsym
                         hi = lo + (e > 0 ? ((u32)e + 179u) / 180u : 0u);
-                        symrel = kHalo + d + 180 * (i64)lo;
+                        symrel = kLeft + d + 180 * (i64)lo;
                     } else {
                         // block b is read downwards from nucleotide n - 1 - 180 b; its lowest codon (phase 2,
                         // residue 60 b + 62) ends at D + n - 189 - 180 b, unless the record starts above it:
@@ -333,13 +322,14 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
                             if (hi <= lo) lo = Lc;
                             hi = NLmax;
                         }
-                        symrel = (i64)kMirror - (y + 188) + 180 * (i64)lo;
+                        symrel = kLeft + (y + 188) - 180 * (i64)lo;  // the block's highest symbol
                     }
                     if (hi > NLmax) hi = NLmax;
                 }
                 if (hi > lo) {
                     const u32 c = (u32)(hi - lo);
-                    run.sym = (bs == 0 ? symf_addr : symr_addr) + (u32)symrel;
+                    run.sym = symf_addr + (u32)symrel;
+                    run.dir = bs == 0 ? 1 : -1;
                     run.lut = bs == 0 ? lutf_addr : lutr_addr;
                     run.nblk = c;
 #pragma unroll
@@ -412,16 +402,28 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
             const u32 li = before - 1u + __popc(starts & (0xFFFFFFFFu >> (31 - lane)));
             const BlockRun &r = sh.runs[sh.job_run[li]];
             const u32 i = job_i - sh.job_pre[li];
-            // the block's 194 symbols, four per word
-            const u32 symoff = r.sym + 180u * i;
-            const u32 sels = 0x3210u + 0x1111u * (symoff & 3u);
-            const u32 *sw = reinterpret_cast<const u32 *>(smem_raw + (symoff & ~3u));
+            // the block's 194 symbols, four per word, in the order the strand reads them: 50 words at
+            // x0, x0 + step, ...; symbol 4m..4m+3 = a byte window of words m, m+1
+            const int dir = r.dir;
+            const u32 symoff = r.sym + (u32)(dir * 180 * (int)i);
+            u32 x0, sels;
+            if (dir > 0) {
+                x0 = symoff & ~3u;
+                sels = 0x3210u + 0x1111u * (symoff & 3u);
+            } else {
+                const u32 a = symoff - 3u;  // lowest byte of the first group of four
+                x0 = (a & ~3u) + 4u;
+                sels = (0x0123u + 0x1111u * (a & 3u)) ^ 0x4444u;  // bytes reversed; word m is the HIGH word of pair m
+            }
+            const int step = 4 * dir;
             u32 c[49];
             {
-                u32 wprev = sw[0];
+                const uint8_t *sp = smem_raw + x0;
+                u32 wprev = *reinterpret_cast<const u32 *>(sp);
 #pragma unroll
                 for (int m = 0; m < 49; m++) {
-                    const u32 w = sw[m + 1];
+                    sp += step;
+                    const u32 w = *reinterpret_cast<const u32 *>(sp);
                     c[m] = prmt(wprev, w, sels);
                     wprev = w;
                 }
