@@ -5,17 +5,16 @@
 // materialised).
 //
 // Persistent CTAs, one parse tile per iteration.  The tile's symbols are staged in shared memory
-// one per byte, twice: in stream order (forward frames) and mirrored (reverse frames read the
-// mirror upwards, which is the stream downwards), with the two symbols before the tile and 192
-// symbols after it.  A lane then takes one BLOCK: 180 nucleotides of one record and strand, i.e.
-// output line b of the strand's three frames.  It loads the block's 194 symbols once; frame k is
-// the codons at byte offsets k, k+3, ... of them: 63 codons (the line's 60 residues and the first 3
-// of the next line) through one integer dot product and one byte-table load each, '\n' at a
-// fixed position, one byte funnel for the line's alignment in the output, 16 word stores into
-// the tile's output image.  Nothing in the lane's work depends on the strand except two base
-// addresses.  A block belongs to the tile that holds the last symbol of its lowest codon, so the
-// tile's two carried symbols and the 192 after it are all a lane ever needs.  The image is
-// written out with TMA bulk stores.
+// one per byte, with the two symbols before the tile and 192 symbols after it.  A lane then takes
+// one BLOCK: 180 nucleotides of one record and strand, i.e. output line b of the strand's three
+// frames.  It loads the block's 194 symbols once -- upwards for the forward strand, downwards for
+// the reverse strand (word step +-4 and a byte-reversing funnel selector are the only difference);
+// frame k is the codons at byte offsets k, k+3, ... of them: 63 codons (the line's 60 residues and
+// the first 3 of the next line) through one integer dot product and one byte-table load each,
+// '\n' at a fixed position, one byte funnel for the line's alignment in the output, 16 word
+// stores into the tile's output image.  A block belongs to the tile that holds the last symbol of
+// its lowest codon, so the tile's two carried symbols and the 192 after it are all a lane ever
+// needs.  The image is written out with TMA bulk stores.
 #include <cstddef>
 
 #include "gts_common.cuh"
@@ -288,7 +287,7 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
                     NLmax = NLk[k] > NLmax ? NLk[k] : NLmax;
                 }
                 u64 lo = 0, hi = 0;  // blocks [lo, hi)
-                i64 symrel = 0;      // index, in its staged array, of the first symbol of block lo
+                i64 symrel = 0;      // index, in the staged array, of the first symbol block lo reads
                 if (NLmax) {
                     if (bs == 0) {
                         // block b = nucleotides 180 b ..; its lowest codon (frame 1) ends at k0 + 180 b, k0 = D + 2
