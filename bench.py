@@ -367,7 +367,7 @@ def main():
             optr, on = tr.translate_host_ptr(h_in, nbytes)
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
-        host_out = ctypes.string_at(optr, on)
+        host_out = bytes((ctypes.c_char * on).from_address(optr))
 
     # ---- max over ranks, sum of the work ----
     if world > 1:

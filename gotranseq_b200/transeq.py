@@ -10,6 +10,11 @@ from dataclasses import dataclass
 from . import _lib
 
 
+def _bytes_at(ptr, n):
+    """n bytes at address ptr as a bytes object (ctypes.string_at takes the size as a C int: wrong beyond 2 GiB)."""
+    return bytes((ctypes.c_char * n).from_address(ptr)) if n else b""
+
+
 class TranseqError(Exception):
     """Mirrors the `error` returned by transeq.Translate; .code is the C ABI return code."""
 
@@ -83,7 +88,7 @@ class Translator:
         out_n = ctypes.c_size_t()
         self._check(self._L.gts_translate_buffer(self._h, ctypes.cast(buf, ctypes.c_void_p), n,
                                                  ctypes.byref(out), ctypes.byref(out_n)))
-        return ctypes.string_at(out.value, out_n.value) if out_n.value else b""
+        return _bytes_at(out.value, out_n.value)
 
     def translate_host_ptr(self, ptr, n):
         """Host pointer in, (pointer, size) of the pinned result out (valid until the next call)."""
@@ -162,7 +167,7 @@ class Translator:
         total = ctypes.c_size_t()
         self._check(self._L.gts_piece_translate(self._h, ctypes.byref(p), ctypes.byref(total), segs, data,
                                                 ctypes.byref(nseg)))
-        return total.value, [(segs[i].offset, ctypes.string_at(data[i], segs[i].length)) for i in range(nseg.value)]
+        return total.value, [(segs[i].offset, _bytes_at(data[i], segs[i].length)) for i in range(nseg.value)]
 
     def piece_scan_device(self, d_in, n, first, stream=0):
         info = _lib.gts_piece_info()
@@ -209,7 +214,7 @@ class Translator:
                 if on.value == 0:
                     break
                 try:
-                    writer.write(ctypes.string_at(obuf.value, on.value))
+                    writer.write(_bytes_at(obuf.value, on.value))
                 except Exception as e:  # writer.go:175
                     L.gts_release_output(h)
                     raise TranseqError(_lib.GTS_ERR_WRITE, f"fail to write to output file: {e}") from e

@@ -86,7 +86,8 @@ def translate(data, frame="1", table=0, clean=False, alternative=False, trim=Fal
     if rc != 0:
         raise OracleError(err.value.decode())
     try:
-        res = ctypes.string_at(out.value, out_n.value)
+        # (ctypes.string_at takes the size as a C int: wrong beyond 2 GiB)
+        res = bytes((ctypes.c_char * out_n.value).from_address(out.value)) if out_n.value else b""
     finally:
         L.to_free(out)
     return (res, warns.value) if return_warnings else res

@@ -297,3 +297,27 @@ def test_block_and_tile_boundary_sweep(frame):
             for alt in (False, True):
                 want = oracle.translate(data, frame=frame, alternative=alt, trim=(n % 2 == 0))
                 assert gpu(data, frame=frame, alternative=alt, trim=(n % 2 == 0)) == want, (n, width, alt)
+
+
+def test_offsets_beyond_32_bits():
+    """2.2 GB in, 4.4 GB out in one device pass: input offsets beyond 2^31, output offsets beyond 2^32."""
+    import hashlib
+    import numpy as np
+    import torch
+    import gotranseq_b200
+    import workloads
+    data = workloads.contigs(n_records=430, len_lo=4_500_000, len_hi=5_500_000, seed=7)
+    cut = 1_000_000_007
+    data = data[:cut] + b"\n>tiny x\r\nACGTNACG\r\n>e\n\n" + data[cut:]  # small records between the big offsets
+    n = len(data)
+    arr = np.frombuffer(data, dtype=np.uint8)
+    with gotranseq_b200.Translator(gotranseq_b200.Options(Frame="6", Table=11, Clean=True)) as tr:
+        d_in = torch.from_numpy(arr.copy()).cuda()
+        cap = 2 * n + n // 8 + (1 << 20)
+        d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+        out_n = tr.translate_device(d_in.data_ptr(), n, d_out.data_ptr(), cap, torch.cuda.current_stream().cuda_stream)
+        got = d_out[:out_n].cpu().numpy()
+        del d_in, d_out
+    want = oracle.translate(arr, frame="6", table=11, clean=True)
+    assert n > 2 ** 31 and out_n > 2 ** 32 and out_n == len(want)
+    assert hashlib.sha256(got.tobytes()).digest() == hashlib.sha256(want).digest()
