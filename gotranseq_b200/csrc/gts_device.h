@@ -151,7 +151,7 @@ struct Job {  // kernel argument block (by value)
     NlPart *scan_nl;// [tile-scan tiles] newline summaries (only used when n >= max_line)
     u64 max_line;   // bufio.Scanner token limit of the reference: 100 MiB (transeq.go:27)
     u64 *s_status;  // [size tiles * 4] chained scan of output sizes
-    u32 *counters;  // [0] tile-scan ticket, [1] size ticket, [2] header events appended
+    u32 *counters;  // [0] tile-scan ticket, [1] size ticket, [2] header events appended, [3] k_lines tile ticket
     Totals *totals;
     u64 *dbg;       // optional phase timing sums (GTS_PHASE_TIMING builds), else nullptr
 

@@ -64,7 +64,7 @@ struct LinesShared {
     uint8_t job_run[kBlockRuns];        // their index in runs[]
     alignas(16) uint8_t lutf[128];      // forward residue of s0 + 5 s1 + 25 s2
     alignas(16) uint8_t lutr[128];      // reverse-strand residue of the codon read downwards: s2 + 5 s1 + 25 s0
-    u32 total_jobs, nlisted, npieces_done;
+    u32 total_jobs, nlisted, npieces_done, next_tile;
 };
 
 // dp4a weights (1, 5, 25 for a codon's three symbols) of codon j of phase k inside word `word` of
@@ -129,11 +129,13 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
     const u64 R = job.totals->n_headers;
     if (flags != 0) return;
 
-    // persistent CTAs: the grid is one wave, each CTA takes every gridDim.x-th tile
-    for (u32 tile = blockIdx.x; tile < job.ntiles; tile += gridDim.x) {
+    // persistent CTAs: the grid is one wave; a CTA starts with tile blockIdx.x and claims its next
+    // tile from a counter one iteration ahead (tiles differ in cost: the wave stays balanced)
+    for (u32 tile = blockIdx.x, tile_next = 0; tile < job.ntiles; tile = tile_next) {
 #ifdef GTS_PHASE_TIMING
     u64 tprev = gtime();
 #endif
+    if (tid == 0) sh.next_tile = gridDim.x + atomicAdd(&job.counters[3], 1u);
     // ---- loads that depend on nothing go first: the slot's words (all of them: words past the
     // tile's symbols hold stale but valid symbols), the start of the next slot, the tile's scalars ----
     constexpr int kWordsPerThread = (kSlotWords + kLinesThreads - 1) / kLinesThreads;
@@ -151,7 +153,12 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
     const TileInfo ti = job.tile_info[tile];
     const TilePrefix tp = job.tile_pre[tile];
     const u32 nsym = ti.nsym;
-    if (nsym == 0) continue;
+    if (nsym == 0) {  // nothing ends in this tile
+        __syncthreads();
+        tile_next = sh.next_tile;
+        __syncthreads();
+        continue;
+    }
     const u64 T0 = tp.T0, Tend = tp.T0 + nsym;
     const u32 tlo = job.win_lo > T0 ? (u32)(job.win_lo - T0) : 0u;  // 2 in the first tile of a later piece of a split record
     const uintptr_t out_mis = (uintptr_t)job.out & 15u;
@@ -203,7 +210,7 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
     PHASE_MARK(job, 16, tprev);  // loads + staging
     {
         // pull the CTA's next tile towards the SM while this one is being translated
-        const u32 nt = tile + gridDim.x;
+        const u32 nt = tile_next = sh.next_tile;
         if (nt < job.ntiles) {
             const char *base = reinterpret_cast<const char *>(job.sym + (u64)nt * kSlotWords);
             const char *pf = nullptr;
