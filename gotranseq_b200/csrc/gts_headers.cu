@@ -5,6 +5,10 @@
 #include "gts_common.cuh"
 #include "gts_kernels.h"
 
+#ifndef GTS_HDR_BLOCKS
+#define GTS_HDR_BLOCKS 8
+#endif
+
 namespace gts {
 
 // =====================================================================================
@@ -13,8 +17,8 @@ namespace gts {
 // Header line of one frame (writer.go:120-131): the header's bytes with '_' and the frame digit
 // inserted before its first space (or appended), then '\n'.  Half a warp per record, lane i holding
 // output bytes i, i+16, ...: the line is assembled once (only the digit differs between frames)
-// and stored once per requested frame.
-__global__ void __launch_bounds__(256) k_headers(const __grid_constant__ Job job) {
+// and stored once per requested frame, in front of the frame's residues (frame table of k_size).
+__global__ void __launch_bounds__(128) k_headers(const __grid_constant__ Job job) {
     const int lane = threadIdx.x & 31, sub = lane & 15, half = lane >> 4;
     const u64 R = job.totals->n_headers;
     if (job.totals->flags != 0 || job.no_headers) return;
@@ -25,13 +29,11 @@ __global__ void __launch_bounds__(256) k_headers(const __grid_constant__ Job job
         const u32 H = ri.H;
         const u32 sp = s >= 1 ? (u32)(job.hinfo[s] >> 32) : 0u;
         const uint8_t *hdr = job.in + job.hdr_off[s];
-        // run sizes of the six frames
-        u64 L[6];
-        frame_lengths(ri.n, job.alternative != 0, L);
-        if (job.trim) {
+        // each frame's header line ends where its residues begin (frame table of k_size)
+        const FrameTab *ft = job.ftab + s;
+        u64 base[6];
 #pragma unroll
-            for (int f = 0; f < 6; f++) L[f] = job.trim_len[s * 6 + f];
-        }
+        for (int f = 0; f < 6; f++) base[f] = ft->body[f] - (H + 3);
         for (u32 i = sub; i < H + 3; i += 16) {
             // byte i of the line; the digit at sp+1 is patched per frame
             uint8_t c = '\n';
@@ -39,13 +41,9 @@ __global__ void __launch_bounds__(256) k_headers(const __grid_constant__ Job job
             else if (i == sp) c = '_';
             else if (i > sp + 1 && i < H + 2) c = hdr[i - 2];
             const bool digit = i == sp + 1;
-            u64 run_base = ri.out_off;
 #pragma unroll
-            for (int f = 0; f < 6; f++) {
-                if (!((job.frame_mask >> f) & 1u)) continue;
-                job.out[run_base + i] = digit ? (uint8_t)('1' + f) : c;
-                run_base += run_size(H, L[f]);
-            }
+            for (int f = 0; f < 6; f++)
+                if ((job.frame_mask >> f) & 1u) job.out[base[f] + i] = digit ? (uint8_t)('1' + f) : c;
         }
     }
     (void)half;
@@ -66,7 +64,7 @@ cudaError_t launch_emit(const Job &job, int sm_count, cudaStream_t stream, cudaE
     if (side) {
         cudaEventRecord(ev_fork, stream);
         cudaStreamWaitEvent(side, ev_fork, 0);
-        k_headers<<<sm_count * 4, 256, 0, side>>>(job);
+        k_headers<<<sm_count * GTS_HDR_BLOCKS, 128, 0, side>>>(job);
         cudaEventRecord(ev_join, side);
         launch_lines(job, sm_count, stream);
         if (ev_mid) cudaEventRecord(ev_mid, stream);
@@ -74,7 +72,7 @@ cudaError_t launch_emit(const Job &job, int sm_count, cudaStream_t stream, cudaE
     } else {
         launch_lines(job, sm_count, stream);
         if (ev_mid) cudaEventRecord(ev_mid, stream);
-        k_headers<<<sm_count * 4, 256, 0, stream>>>(job);
+        k_headers<<<sm_count * GTS_HDR_BLOCKS, 128, 0, stream>>>(job);
     }
     return cudaGetLastError();
 }
