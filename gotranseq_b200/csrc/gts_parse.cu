@@ -13,6 +13,10 @@
 #include "gts_common.cuh"
 #include "gts_kernels.h"
 
+#ifndef GTS_PARSE_CTAS
+#define GTS_PARSE_CTAS 8
+#endif
+
 namespace gts {
 
 enum { LS = 0, SEQ = 1, HDR = 2 };
@@ -91,7 +95,7 @@ __device__ __forceinline__ void remove_byte(u32 (&C)[9], int p) {
     }
 }
 
-__global__ void __launch_bounds__(kParseThreads) k_parse(const __grid_constant__ Job job) {
+__global__ void __launch_bounds__(kParseThreads, GTS_PARSE_CTAS) k_parse(const __grid_constant__ Job job) {
     __shared__ ParseShared sh;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
