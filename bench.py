@@ -25,8 +25,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "6-frame Gbp/s device-resident"
 # DRAM bytes of one k_lines launch on the default workload, from the committed ncu capture
-# (profiles/r1g_ncu_full_summary.txt: 141.08 MB read + 334.91 MB written); null for other workloads
-NCU_TRAFFIC = {"readme189": 141075968 + 334907904}
+# (profiles/r1h_ncu_full_summary.txt: 140.83 MB read + 334.67 MB written); null for other workloads
+NCU_TRAFFIC = {"readme189": 140825600 + 334672640}
 UNIT = "Gbp/s"
 
 
@@ -410,7 +410,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": "k_lines", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": NCU_TRAFFIC.get(args.workload), "peak_source": peak_src,
                          "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one k_lines launch, "
-                                           "ncu --set full capture profiles/r1g_ncu_full_summary.txt",
+                                           "ncu --set full capture profiles/r1h_ncu_full_summary.txt",
                          "algorithmic_bytes_per_launch": trans_bytes, "ms_per_launch": trans_ms},
             "path": {"bytes_per_step_per_gpu": path_bytes, "achieved_GBps_per_gpu": path_gbs, "frac_of_peak": path_gbs / peak,
                      "note": "(FASTA in + protein FASTA out) / device time of the whole path"},
