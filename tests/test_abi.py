@@ -93,3 +93,16 @@ def test_no_gpu_fails_loudly():
     import gotranseq_b200
     with pytest.raises(gotranseq_b200.TranseqError, match="no CPU fallback"):
         gotranseq_b200.translate_bytes(b">a\nACG\n")
+
+
+def test_header_compiles_as_c_and_links(tmp_path):
+    """include/gotranseq_b200.h from plain C (what a cgo shim compiles), linked against the library."""
+    import subprocess
+    exe = tmp_path / "abi_smoke"
+    lib_dir = os.path.join(ROOT, "gotranseq_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c", "abi_smoke.c"), "-o", str(exe), "-L", lib_dir, "-lgotranseq_b200",
+                    "-Wl,-rpath," + lib_dir], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert r.stdout.startswith("abi ok")
