@@ -5,6 +5,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
+# GOTRANSEQ_B200_LIB: another build of the same library (kernel tuning sweeps)
 LIB_PATH = os.environ.get("GOTRANSEQ_B200_LIB") or os.path.join(_HERE, "libgotranseq_b200.so")
 
 GTS_OK = 0
