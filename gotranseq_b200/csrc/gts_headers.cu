@@ -24,16 +24,20 @@ __global__ void __launch_bounds__(128) k_headers(const __grid_constant__ Job job
     if (job.totals->flags != 0 || job.no_headers) return;
     const u64 nhalf = (u64)gridDim.x * (blockDim.x >> 4);
     for (u64 s = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 4; s <= R; s += nhalf) {
+        // everything that is indexed by the record goes first, in one round of loads
         const RecInfo ri = job.rec[s];
-        if (!ri.emitted) continue;
-        const u32 H = ri.H;
-        const u32 sp = s >= 1 ? (u32)(job.hinfo[s] >> 32) : 0u;
-        const uint8_t *hdr = job.in + job.hdr_off[s];
-        // each frame's header line ends where its residues begin (frame table of k_size)
-        const FrameTab *ft = job.ftab + s;
+        const u64 hinf = s >= 1 ? job.hinfo[s] : 0;
+        const u64 hoff = s >= 1 ? job.hdr_off[s] : 0;
+        const FrameTab *ft = job.ftab + s;  // each frame's header line ends where its residues begin
         u64 base[6];
 #pragma unroll
-        for (int f = 0; f < 6; f++) base[f] = ft->body[f] - (H + 3);
+        for (int f = 0; f < 6; f++) base[f] = ft->body[f];
+        if (!ri.emitted) continue;
+        const u32 H = ri.H;
+        const u32 sp = (u32)(hinf >> 32);
+        const uint8_t *hdr = job.in + hoff;
+#pragma unroll
+        for (int f = 0; f < 6; f++) base[f] -= H + 3;
         for (u32 i = sub; i < H + 3; i += 16) {
             // byte i of the line; the digit at sp+1 is patched per frame
             uint8_t c = '\n';
