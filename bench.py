@@ -99,6 +99,26 @@ def env_rank():
     return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 
 
+def bind_to_gpu_numa_node(index):
+    """Run this rank on the CPUs next to its GPU (NVML's affinity mask), before any pinned memory is
+    allocated: first touch then puts the host buffers on the GPU's NUMA node.  Returns the CPU count
+    or None when NVML / the scheduler call is not available."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def record_cut(buf, limit):
     """Largest prefix of buf of at most `limit` bytes that ends at a record boundary."""
     if len(buf) <= limit:
@@ -304,6 +324,7 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (gotranseq_b200 has no CPU fallback)")
+    numa_cpus = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -404,7 +425,8 @@ def main():
             "dtype": "u8", "data": "synthetic", "config": workload_config(args, nbytes),
             "e2e": {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": out_n + 64,
                     "ms_per_step": e2e_s / e2e_steps * 1e3 if e2e_s > 0 else None, "steps": e2e_steps,
-                    "api": "gts_translate_buffer (pinned host buffers)"},
+                    "api": "gts_translate_buffer (pinned host buffers)",
+                    "cpus_per_rank": numa_cpus},
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "k_lines", "achieved": achieved, "peak": peak, "unit": "GB/s",
