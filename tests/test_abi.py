@@ -106,3 +106,19 @@ def test_header_compiles_as_c_and_links(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     assert r.stdout.startswith("abi ok")
+
+
+def test_cli_reports_option_errors_like_the_reference(tmp_path):
+    """main.go prints the error of transeq.Translate and returns (exit status 0); the option errors
+    come before any device is touched, so this runs without a GPU."""
+    import subprocess
+    exe = os.path.join(ROOT, "gotranseq_b200", "bin", "gotranseq")
+    src = tmp_path / "t.fna"
+    src.write_bytes(b">a\nACG\n")
+    for flags, text in ((["-f", "7"], "wrong value for -f | --frame parameter: 7"),
+                        (["-f", "6", "-t", "1"], "invalid table code: 1")):
+        r = subprocess.run([exe, "-s", str(src), "-o", str(tmp_path / "o.faa")] + flags, capture_output=True, text=True)
+        assert text in r.stdout + r.stderr, (flags, r.stdout, r.stderr)
+    r = subprocess.run([exe, "--help"], capture_output=True, text=True)
+    for flag in ("--sequence", "--outseq", "--frame", "--table", "--clean", "--alternative", "--trim", "--numcpu"):
+        assert flag in r.stdout + r.stderr, flag
