@@ -82,6 +82,33 @@ def regular_fasta(seed, n_records, len_lo, len_hi, width=60, header="seq", n_fra
     return "".join(out).encode("ascii")
 
 
+def mid_fasta(seed):
+    """0.02-1.5 MB of records with heavy-tailed lengths (0 .. 120 k), odd line widths, header lines from
+    empty to longer than a parse tile, CRLF, blank lines, data before the first header: many tiles, many
+    record pieces per tile, blocks and frames ending everywhere."""
+    rng = random.Random(seed)
+    parts = []
+    target = rng.choice((20_000, 200_000, 1_500_000))
+    size = 0
+    if rng.random() < 0.3:
+        parts.append(bytes(rng.choice(b"ACGTN") for _ in range(rng.randint(0, 500))) + b"\n")
+    while size < target:
+        hl = rng.choice((0, 1, 5, 20, 60, 61, 64, 65, 120, 300, 9000)) if rng.random() < 0.3 else rng.randint(1, 40)
+        hdr = b">" + bytes(rng.choice(b"abcXYZ01 _|") for _ in range(hl))
+        n = int(rng.choice((0, 1, 2, 3, 59, 60, 61, 179, 180, 181, 189, 190, rng.paretovariate(0.7) * 50))) % 120_000
+        alpha = rng.choice((b"ACGT", b"ACGTN", b"ACGTUacgtunRYKM", b"AC"))
+        seq = bytes(rng.choice(alpha) for _ in range(n))
+        w = rng.choice((60, 70, 80, 1, 7, 10 ** 9, rng.randint(1, 200)))
+        eol = b"\r\n" if rng.random() < 0.2 else b"\n"
+        lines = [seq[i:i + w] for i in range(0, n, w)]
+        if rng.random() < 0.1 and lines:
+            lines.insert(rng.randrange(len(lines) + 1), b"")
+        rec = hdr + eol + eol.join(lines) + (eol if rng.random() < 0.9 else b"")
+        parts.append(rec)
+        size += len(rec)
+    return b"".join(parts)
+
+
 ALL_FRAMES = ["1", "2", "3", "F", "-1", "-2", "-3", "R", "6"]
 ALL_TABLES = [0, 2, 3, 4, 5, 6, 9, 10, 11, 12, 13, 14, 16, 21, 22, 23, 24, 25, 26, 29, 30]
 

@@ -4,7 +4,7 @@ import io
 import pytest
 
 import oracle
-from fasta_gen import nasty_fasta, random_options, regular_fasta, ALL_FRAMES, ALL_TABLES
+from fasta_gen import mid_fasta, nasty_fasta, random_options, regular_fasta, ALL_FRAMES, ALL_TABLES
 from optparse_ref import parse_option_string
 
 pytestmark = pytest.mark.gpu
@@ -36,6 +36,13 @@ def test_quirks():
 def test_random_nasty(seed):
     data = nasty_fasta(seed)
     kw = random_options(seed)
+    assert gpu(data, **kw) == oracle.translate(data, **kw), (seed, kw)
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_mid_size(seed):
+    data = mid_fasta(5000 + seed)
+    kw = random_options(5000 + seed)
     assert gpu(data, **kw) == oracle.translate(data, **kw), (seed, kw)
 
 
