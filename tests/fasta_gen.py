@@ -82,13 +82,14 @@ def regular_fasta(seed, n_records, len_lo, len_hi, width=60, header="seq", n_fra
     return "".join(out).encode("ascii")
 
 
-def mid_fasta(seed):
+def mid_fasta(seed, target=None):
     """0.02-1.5 MB of records with heavy-tailed lengths (0 .. 120 k), odd line widths, header lines from
     empty to longer than a parse tile, CRLF, blank lines, data before the first header: many tiles, many
     record pieces per tile, blocks and frames ending everywhere."""
     rng = random.Random(seed)
     parts = []
-    target = rng.choice((20_000, 200_000, 1_500_000))
+    pick = rng.choice((20_000, 200_000, 1_500_000))
+    target = target or pick
     size = 0
     if rng.random() < 0.3:
         parts.append(bytes(rng.choice(b"ACGTN") for _ in range(rng.randint(0, 500))) + b"\n")

@@ -5,7 +5,7 @@ import pytest
 
 import oracle
 import gpu_model
-from fasta_gen import nasty_fasta, random_options
+from fasta_gen import mid_fasta, nasty_fasta, random_options
 from optparse_ref import parse_option_string
 
 MASKS = {"1": 1, "2": 2, "3": 4, "F": 7, "-1": 8, "-2": 16, "-3": 32, "R": 56, "6": 63}
@@ -89,3 +89,13 @@ def test_lines_model_quirks():
             for trim in (False, True):
                 got = model(data, frame=frame, trim=trim, tile=3, residues="lines")
                 assert got == oracle.translate(data, frame=frame, trim=trim), (data, frame, trim)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_lines_model_mid_size(seed):
+    """Several kilobytes with long headers, many short records and a few long ones, tiles of 8 KB like the kernel's."""
+    data = mid_fasta(7000 + seed, target=12_000)
+    kw = random_options(7000 + seed)
+    want = oracle.translate(data, **kw)
+    for tile in (8256, 600):
+        assert model(data, tile=tile, residues="lines", **kw) == want, (seed, tile, kw)
