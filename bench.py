@@ -435,6 +435,7 @@ def main():
                                            "ncu --set full capture profiles/r1h_ncu_full_summary.txt",
                          "algorithmic_bytes_per_launch": trans_bytes, "ms_per_launch": trans_ms},
             "path": {"bytes_per_step_per_gpu": path_bytes, "achieved_GBps_per_gpu": path_gbs, "frac_of_peak": path_gbs / peak,
+                     "frac_of_nominal_8TBps": path_gbs / 8000.0,
                      "note": "(FASTA in + protein FASTA out) / device time of the whole path"},
             "kernels_ms_per_step": {"reset+k_parse": kms[0] / max(kpasses, 1),
                                     "k_tile_scan+k_records+k_size": kms[1] / max(kpasses, 1),
