@@ -16,6 +16,7 @@ GTS_ERR_NOMEM = -4
 GTS_ERR_CAPACITY = -5
 GTS_ERR_ARG = -6
 GTS_ERR_WRITE = -7
+GTS_ERR_CANCELLED = -8
 
 
 class gts_options(ctypes.Structure):
@@ -29,7 +30,15 @@ class gts_options(ctypes.Structure):
         ("num_worker", ctypes.c_int32),
         ("device", ctypes.c_int32),
         ("chunk_bytes", ctypes.c_uint64),
+        ("num_gpus", ctypes.c_int32),
+        ("device_ids", ctypes.c_int32 * 8),
+        ("reserved1", ctypes.c_int32),
     ]
+
+
+# typedef void (*gts_warning_fn)(void *user, const uint8_t *header, size_t header_len, uint8_t byte, uint64_t pos)
+gts_warning_fn = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint8), ctypes.c_size_t,
+                                  ctypes.c_uint8, ctypes.c_uint64)
 
 
 class gts_stats(ctypes.Structure):
@@ -74,6 +83,14 @@ EXPORTS = {
     "gts_submit": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]),
     "gts_next_output": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]),
     "gts_release_output": (ctypes.c_int, [ctypes.c_void_p]),
+    "gts_wait_output": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t)]),
+    "gts_report_write_error": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_char_p]),
+    "gts_cancel": (ctypes.c_int, [ctypes.c_void_p]),
+    "gts_stream_reset": (ctypes.c_int, [ctypes.c_void_p]),
+    "gts_num_devices": (ctypes.c_int, [ctypes.c_void_p]),
+    "gts_set_warning_callback": (ctypes.c_int, [ctypes.c_void_p, gts_warning_fn, ctypes.c_void_p]),
+    "gts_format_warning": (ctypes.c_size_t, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_uint8, ctypes.c_uint64,
+                                             ctypes.c_void_p, ctypes.c_size_t]),
     "gts_get_stats": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(gts_stats)]),
     "gts_set_profiling": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "gts_kernel_times": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]),

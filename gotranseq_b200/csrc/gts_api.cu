@@ -1,20 +1,29 @@
-// gts_api.cu -- the C ABI of include/gotranseq_b200.h: option decoding, scratch management,
-// device passes, the one-shot host call and the streaming host interface.
+// gts_api.cu -- the C ABI of include/gotranseq_b200.h: option decoding, per-GPU scratch, device
+// passes, and the host chunk engine behind the one-shot and the streaming entry points.
 //
-// This file replaces the orchestration of transeq.Translate (transeq/transeq.go:114-173): where
-// the reference runs one reader goroutine feeding NumWorker translate goroutines, a gts_ctx cuts
-// the byte stream at record boundaries and runs one device pass (six kernels, gts_kernels.h)
-// per cut, handing the results back strictly in input order.
+// This file replaces the orchestration of transeq.Translate (transeq/transeq.go:114-173).  Where
+// the reference runs one reader goroutine feeding NumWorker translate goroutines over a channel
+// (transeq.go:126-160) and lets every worker flush to the writer (writer.go:171-181), a gts_ctx
+//   * cuts the byte stream into chunks at record boundaries ('>' at a line start, transeq.go:198),
+//   * deals the chunks to its GPUs in turn; every GPU has an issuer thread (H2D copy + the six
+//     kernels of gts_kernels.h, enqueued without waiting) and a retirer thread (exact output size,
+//     D2H copy), so that the copies of neighbouring chunks overlap the kernels of the current one,
+//   * hands the results back strictly in input order (the reference's -n 1 order),
+//   * carries the reference's failure semantics: the first write error cancels everything
+//     (writer.go:171-179, transeq.go:145-149,200-204).
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <condition_variable>
-#include <mutex>
-#include <thread>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/gotranseq_b200.h"
@@ -27,19 +36,64 @@ using gts::u64;
 
 static thread_local std::string g_create_error;
 
-struct gts_ctx {
-    gts_options opt;
-    std::string frame;
-    uint32_t mask = 0;
-    bool reverse = false;
-    gts::Lut lut;
+namespace {
+
+constexpr int kSlots = 3;  // chunks in flight per GPU: one in H2D, one in the kernels, one in D2H
+
+size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct HostBuf {  // pinned host memory of the chunk pools
+    uint8_t *p = nullptr;
+    size_t cap = 0;
+};
+
+struct WarnOut {  // one WARNING line of encodedSequence.go:39, ready for the callback
+    std::string header;
+    uint64_t pos = 0;
+    uint8_t byte = 0;
+};
+
+struct XJob {  // one chunk on its way through the engine
+    uint64_t seq = 0;
+    const uint8_t *in = nullptr;
+    size_t n = 0;
+    bool last = false;         // the stream ends with this chunk
+    HostBuf *inbuf = nullptr;  // pool buffer holding `in`; nullptr = caller memory
+    int dev = 0, slot = -1;
+    bool skipped = false;      // cancelled / behind the point where the reference stops reading
+    // ---- result ----
+    HostBuf *outbuf = nullptr;
+    const uint8_t *out = nullptr;
+    size_t out_n = 0;
+    uint64_t records = 0, nucleotides = 0;
+    bool truncated = false;    // a line of >= 100 MiB: the reference stops reading inside this chunk
+    std::vector<WarnOut> warns;
+    bool warned = false;
+    int rc = 0;
+    std::string err;
+    bool done = false;
+};
+
+struct PassSlot {  // device side of one chunk in flight
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    size_t d_in_cap = 0, d_out_cap = 0;
+    gts::Totals *h_totals = nullptr;  // pinned
+    u64 *d_warn = nullptr;
+    gts::WarnRec *d_wres = nullptr;
+    size_t warn_cap = 0;
+    cudaEvent_t ev_h2d = nullptr, ev_comp = nullptr;
+    bool busy = false;
+};
+
+struct DevCtx {  // one GPU: streams, scratch of a device pass, chunk slots, worker threads
     int device = 0;
     int sm_count = 148;
-    cudaStream_t stream = nullptr;  // used by the host-buffer entry points
+    cudaStream_t stream = nullptr;  // kernels of the host entry points
     cudaStream_t s_side = nullptr;  // k_headers runs here, next to k_lines
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
-    // ---- device scratch (grows, never shrinks) ----
+    // ---- scratch of a device pass (grows, never shrinks) ----
     u64 cap_n = 0;  // raw bytes the per-tile scratch is sized for
     u32 *d_sym = nullptr;
     gts::TileInfo *d_tile_info = nullptr;
@@ -52,71 +106,85 @@ struct gts_ctx {
     gts::RecInfo *d_rec = nullptr;
     u32 *d_trim = nullptr;
     gts::FrameTab *d_ftab = nullptr;
-    gts::Totals *h_totals = nullptr;  // pinned
-    u64 *d_dbg = nullptr;             // phase timing sums (GTS_PHASE_TIMING builds with GTS_PHASE_TIMING=1 set)
+    gts::NlPart *d_scan_nl = nullptr;
+    size_t scan_nl_cap = 0;
+    gts::Totals *h_totals = nullptr;  // pinned (device-resident entry points)
+    u64 *d_dbg = nullptr;             // phase timing sums (GTS_PHASE_TIMING builds)
+    double rec_per_byte = 1.0 / 128;  // record table sizing, raised when a pass overflows
 
-    // ---- buffers of the host entry points ----
-    uint8_t *d_in = nullptr, *d_out = nullptr;
+    // ---- buffers of the piece entry points ----
+    uint8_t *d_in = nullptr, *d_out = nullptr, *d_head = nullptr;
     size_t d_in_cap = 0, d_out_cap = 0;
-    uint8_t *h_out = nullptr;
-    size_t h_out_cap = 0;
-    // ---- streaming host interface: the caller fills one pinned input buffer while a worker thread
-    // translates the other; two output buffers, handed back in order ----
-    struct StreamJob {
-        int in_idx = 0;    // input buffer
-        size_t n = 0;      // bytes to translate: [0, n) of it
-    };
-    uint8_t *s_in[2] = {nullptr, nullptr};   // pinned
-    size_t s_in_cap[2] = {0, 0};
-    int s_fill_idx = 0;                      // the buffer the caller is filling
-    size_t s_fill = 0;                       // bytes in it
-    const uint8_t *s_rest_src = nullptr;     // unfinished record of the buffer submitted last: copied
-    size_t s_rest_len = 0;                   //   to the front of the next buffer when it is acquired
-    uint8_t *s_out[2] = {nullptr, nullptr};  // pinned
-    size_t s_out_cap[2] = {0, 0}, s_out_n[2] = {0, 0};
-    int s_out_state[2] = {0, 0};             // 0 free, 1 being written, 2 ready for the caller
-    int s_out_head = 0, s_out_tail = 0;      // next buffer for the caller / for the worker
-    bool s_has_running = false, s_has_pending = false;
-    StreamJob s_running, s_pending;
-    int s_running_out = 0;
-    std::thread s_worker;
-    std::mutex s_mu;
-    std::condition_variable s_cv;
-    bool s_worker_started = false, s_worker_exit = false;
-    int s_rc = 0;                            // first error of the worker
-    std::string s_err;
-    bool stream_first_pass = true, stream_eof = false;
 
-    // ---- chunk pipeline of the host entry points: H2D / kernels / D2H overlap ----
-    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;  // `stream` above runs the kernels
-    uint8_t *p_in[2] = {nullptr, nullptr}, *p_out[2] = {nullptr, nullptr};
-    size_t p_in_cap[2] = {0, 0}, p_out_cap[2] = {0, 0};
-    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_d2h[2] = {nullptr, nullptr};
-    gts::Totals *h_totals2 = nullptr;  // pinned, one per pipeline slot
-
-    // ---- last enqueued device pass ----
+    // ---- last enqueued device pass (device-resident entry points) ----
     bool pending = false;
     gts::Job job;
     cudaStream_t job_stream = nullptr;
 
-    // ---- piece of a split record (gts_piece_*) ----
-    bool piece_on = false;
-    gts::Job piece_job;      // only the piece fields are used
-    size_t piece_n = 0;      // bytes of the piece kept in d_in by gts_piece_scan
-    bool piece_first = false;
-    uint8_t *d_head = nullptr;  // 192 codes written by the scan pass of a piece
-
     // ---- per-kernel timing ----
-    bool profiling = false;
     std::vector<cudaEvent_t> prof_events;  // 5 per recorded pass
     size_t prof_used = 0;
 
+    // ---- chunk engine ----
+    std::mutex mu;  // enqueue / scratch reallocation: the issuer and the retirer both use the scratch
+    PassSlot slots[kSlots];
+    std::deque<XJob *> inq, inflight;
+    std::thread issuer, retirer;
+};
+
+}  // namespace
+
+struct gts_ctx {
+    gts_options opt;
+    std::string frame;
+    uint32_t mask = 0;
+    bool reverse = false;
+    gts::Lut lut;
+    gts::LutBytes lutb;
+    std::vector<std::unique_ptr<DevCtx>> devs;
+    size_t chunk = (size_t)16 << 20;
     u64 max_line = 100ull << 20;  // bufio.Scanner token limit of the reference (transeq.go:27)
-    gts::NlPart *d_scan_nl = nullptr;
-    size_t scan_nl_cap = 0;
-    bool last_truncated = false;  // the last host translation stopped at an over-long line
-    bool stream_truncated = false;
-    bool poison = false;  // GTS_POISON_OUTPUT=1: fill the output with 0xEE first (tests: no byte left unwritten)
+    bool poison = false;          // GTS_POISON_OUTPUT=1: fill the output with 0xEE first (tests)
+    bool profiling = false;
+
+    // ---- piece of a split record (gts_piece_*) ----
+    bool piece_on = false;
+    gts::Job piece_job;  // only the piece fields are used
+    size_t piece_n = 0;
+    bool piece_first = false;
+    bool last_truncated = false;
+
+    // ---- chunk engine (streaming and one-shot host entry points) ----
+    std::mutex mu;
+    std::condition_variable cv;
+    bool workers_started = false, exiting = false;
+    std::vector<HostBuf *> in_free, out_free;
+    size_t in_count = 0, out_count = 0, in_max = 0, out_max = 0;
+    std::deque<XJob *> window;  // submitted and not yet consumed, in input order
+    uint64_t next_seq = 0, consume_seq = 0;
+    uint64_t trunc_seq = ~0ull;  // chunk in which the reference stops reading
+    bool cancelled = false;
+    int e_rc = 0;  // first error of the stream (sticky until gts_stream_reset)
+    std::string e_err;
+    XJob *handed = nullptr;  // result currently with the caller
+    // producer side (touched by the submitting thread only)
+    HostBuf *fill = nullptr;
+    size_t fill_n = 0, scan_from = 1, last_boundary = 0;
+    bool eof = false, first_job = true;
+    // one-shot mode: results go straight to their final place in h_out
+    bool direct = false;
+    uint8_t *h_out = nullptr;
+    size_t h_out_cap = 0;
+    uint64_t direct_turn = 0;
+    size_t direct_off = 0;
+    int direct_active = 0;
+    bool direct_growing = false;
+    // piece entry points
+    uint8_t *h_piece = nullptr;
+    size_t h_piece_cap = 0;
+
+    gts_warning_fn warn_fn = nullptr;
+    void *warn_user = nullptr;
 
     gts_stats stats;
     std::string err;
@@ -128,17 +196,24 @@ int fail(gts_ctx *ctx, int code, const std::string &msg) {
     if (ctx) ctx->err = msg; else g_create_error = msg;
     return code;
 }
+int cuda_code(cudaError_t e) { return e == cudaErrorMemoryAllocation ? GTS_ERR_NOMEM : GTS_ERR_CUDA; }
 int cuda_fail(gts_ctx *ctx, cudaError_t e, const char *what) {
-    return fail(ctx, e == cudaErrorMemoryAllocation ? GTS_ERR_NOMEM : GTS_ERR_CUDA,
-                std::string(what) + ": " + cudaGetErrorString(e));
+    return fail(ctx, cuda_code(e), std::string(what) + ": " + cudaGetErrorString(e));
 }
+// CU: inside API functions (message goes to ctx->err); CUE: inside helpers with a `std::string *err`
 #define CU(call)                                                   \
     do {                                                           \
         cudaError_t e_ = (call);                                   \
         if (e_ != cudaSuccess) return cuda_fail(ctx, e_, #call);   \
     } while (0)
-
-size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+#define CUE(call)                                                                  \
+    do {                                                                           \
+        cudaError_t e_ = (call);                                                   \
+        if (e_ != cudaSuccess) {                                                   \
+            if (err) *err = std::string(#call) + ": " + cudaGetErrorString(e_);    \
+            return cuda_code(e_);                                                  \
+        }                                                                          \
+    } while (0)
 
 struct ZeroLayout {
     size_t t_status, s_status, totals, counters, bytes;
@@ -151,108 +226,133 @@ ZeroLayout zero_layout(u64 ntiles, u64 rec_cap) {
     z.t_status = off; off += scan_tiles * 4 * sizeof(u64);
     z.s_status = off; off += size_tiles * 4 * sizeof(u64);
     z.totals = off;   off += sizeof(gts::Totals);
-    z.counters = off; off += 16;
+    z.counters = off; off += 32;
     z.bytes = round_up(off, 16);
     return z;
 }
 
-int free_rec(gts_ctx *ctx) {
-    cudaFree(ctx->d_events); cudaFree(ctx->d_hdr_off); cudaFree(ctx->d_dbase); cudaFree(ctx->d_loc); cudaFree(ctx->d_hinfo);
-    cudaFree(ctx->d_rec); cudaFree(ctx->d_trim); cudaFree(ctx->d_ftab);
-    ctx->d_ftab = nullptr;
-    ctx->d_events = nullptr;
-    ctx->d_hdr_off = ctx->d_dbase = ctx->d_loc = ctx->d_hinfo = nullptr;
-    ctx->d_rec = nullptr;
-    ctx->d_trim = nullptr;
-    ctx->rec_cap = 0;
-    return 0;
+void free_rec(DevCtx *dev) {
+    cudaFree(dev->d_events); cudaFree(dev->d_hdr_off); cudaFree(dev->d_dbase); cudaFree(dev->d_loc); cudaFree(dev->d_hinfo);
+    cudaFree(dev->d_rec); cudaFree(dev->d_trim); cudaFree(dev->d_ftab);
+    dev->d_ftab = nullptr;
+    dev->d_events = nullptr;
+    dev->d_hdr_off = dev->d_dbase = dev->d_loc = dev->d_hinfo = nullptr;
+    dev->d_rec = nullptr;
+    dev->d_trim = nullptr;
+    dev->rec_cap = 0;
 }
 
-int alloc_rec(gts_ctx *ctx, u64 rec_cap) {
-    free_rec(ctx);
-    CU(cudaMalloc(&ctx->d_events, rec_cap * sizeof(gts::HeaderEvent)));
-    CU(cudaMalloc(&ctx->d_hdr_off, rec_cap * sizeof(u64)));
-    CU(cudaMalloc(&ctx->d_dbase, rec_cap * sizeof(u64)));
-    CU(cudaMalloc(&ctx->d_loc, rec_cap * sizeof(u64)));
-    CU(cudaMalloc(&ctx->d_hinfo, rec_cap * sizeof(u64)));
-    CU(cudaMalloc(&ctx->d_rec, rec_cap * sizeof(gts::RecInfo)));
-    if (ctx->opt.trim) CU(cudaMalloc(&ctx->d_trim, rec_cap * 6 * sizeof(u32)));
-    CU(cudaMalloc(&ctx->d_ftab, rec_cap * sizeof(gts::FrameTab)));
-    ctx->rec_cap = rec_cap;
+// (the caller has made sure that no pass is in flight on this device)
+int alloc_rec(gts_ctx *ctx, DevCtx *dev, u64 rec_cap, std::string *err) {
+    free_rec(dev);
+    CUE(cudaMalloc(&dev->d_events, rec_cap * sizeof(gts::HeaderEvent)));
+    CUE(cudaMalloc(&dev->d_hdr_off, rec_cap * sizeof(u64)));
+    CUE(cudaMalloc(&dev->d_dbase, rec_cap * sizeof(u64)));
+    CUE(cudaMalloc(&dev->d_loc, rec_cap * sizeof(u64)));
+    CUE(cudaMalloc(&dev->d_hinfo, rec_cap * sizeof(u64)));
+    CUE(cudaMalloc(&dev->d_rec, rec_cap * sizeof(gts::RecInfo)));
+    if (ctx->opt.trim) CUE(cudaMalloc(&dev->d_trim, rec_cap * 6 * sizeof(u32)));
+    CUE(cudaMalloc(&dev->d_ftab, rec_cap * sizeof(gts::FrameTab)));
+    dev->rec_cap = rec_cap;
     return GTS_OK;
 }
 
 u64 parse_tiles(u64 n) { return std::max<u64>(1, (n + gts::kParseTile - 1) / gts::kParseTile); }
 
-// Size the scratch for a pass over n raw bytes.
-int ensure_scratch(gts_ctx *ctx, u64 n) {
-    if (n > ctx->cap_n || ctx->d_sym == nullptr) {
+// Size the scratch for a pass over n raw bytes.  Growing it frees the old blocks, so every stream
+// of the device is drained first: a pass enqueued earlier (on any stream) may still be using them.
+int ensure_scratch(gts_ctx *ctx, DevCtx *dev, u64 n, std::string *err) {
+    const u64 want_rec = (u64)((double)n * dev->rec_per_byte) + 4096;
+    const bool grow_tiles = n > dev->cap_n || dev->d_sym == nullptr;
+    const bool grow_rec = want_rec > dev->rec_cap;
+    if (!grow_tiles && !grow_rec) return GTS_OK;
+    CUE(cudaDeviceSynchronize());
+    if (grow_tiles) {
         const u64 cap = std::max<u64>(n + n / 8, 1u << 20);
         const u64 tiles = parse_tiles(cap);
-        cudaFree(ctx->d_sym); cudaFree(ctx->d_tile_info); cudaFree(ctx->d_tile_pre);
-        ctx->d_sym = nullptr; ctx->d_tile_info = nullptr; ctx->d_tile_pre = nullptr;
-        ctx->cap_n = 0;
+        cudaFree(dev->d_sym); cudaFree(dev->d_tile_info); cudaFree(dev->d_tile_pre);
+        dev->d_sym = nullptr; dev->d_tile_info = nullptr; dev->d_tile_pre = nullptr;
+        dev->cap_n = 0;
         const size_t sym_bytes = (tiles + 2) * gts::kSlotWords * sizeof(u32);
-        CU(cudaMalloc(&ctx->d_sym, sym_bytes));
+        CUE(cudaMalloc(&dev->d_sym, sym_bytes));
         // zero once: stale words past the end of a slot must still hold valid symbols (<= 4)
-        CU(cudaMemset(ctx->d_sym, 0, sym_bytes));
+        CUE(cudaMemset(dev->d_sym, 0, sym_bytes));
         // the memset runs on the legacy stream, the passes on non-blocking streams: without this
         // it can land after the first k_parse has written its slots
-        CU(cudaDeviceSynchronize());
-        CU(cudaMalloc(&ctx->d_tile_info, tiles * sizeof(gts::TileInfo)));
-        CU(cudaMalloc(&ctx->d_tile_pre, tiles * sizeof(gts::TilePrefix)));
-        ctx->cap_n = cap;
+        CUE(cudaDeviceSynchronize());
+        CUE(cudaMalloc(&dev->d_tile_info, tiles * sizeof(gts::TileInfo)));
+        CUE(cudaMalloc(&dev->d_tile_pre, tiles * sizeof(gts::TilePrefix)));
+        dev->cap_n = cap;
     }
-    const u64 want_rec = n / 128 + 4096;
-    if (want_rec > ctx->rec_cap) {
-        int rc = alloc_rec(ctx, want_rec + want_rec / 8);
+    if (grow_rec) {
+        int rc = alloc_rec(ctx, dev, want_rec + want_rec / 8, err);
         if (rc) return rc;
     }
-    const size_t nscan = (parse_tiles(ctx->cap_n) + gts::kScanTile - 1) / gts::kScanTile;
-    if (nscan > ctx->scan_nl_cap) {
-        cudaFree(ctx->d_scan_nl);
-        ctx->d_scan_nl = nullptr; ctx->scan_nl_cap = 0;
-        CU(cudaMalloc(&ctx->d_scan_nl, nscan * sizeof(gts::NlPart)));
-        ctx->scan_nl_cap = nscan;
+    const size_t nscan = (parse_tiles(dev->cap_n) + gts::kScanTile - 1) / gts::kScanTile;
+    if (nscan > dev->scan_nl_cap) {
+        cudaFree(dev->d_scan_nl);
+        dev->d_scan_nl = nullptr; dev->scan_nl_cap = 0;
+        CUE(cudaMalloc(&dev->d_scan_nl, nscan * sizeof(gts::NlPart)));
+        dev->scan_nl_cap = nscan;
     }
-    const ZeroLayout z = zero_layout(parse_tiles(ctx->cap_n), ctx->rec_cap);
-    if (z.bytes > ctx->zero_cap) {
-        cudaFree(ctx->d_zero);
-        ctx->d_zero = nullptr; ctx->zero_cap = 0;
-        CU(cudaMalloc(&ctx->d_zero, z.bytes));
-        ctx->zero_cap = z.bytes;
+    const ZeroLayout z = zero_layout(parse_tiles(dev->cap_n), dev->rec_cap);
+    if (z.bytes > dev->zero_cap) {
+        cudaFree(dev->d_zero);
+        dev->d_zero = nullptr; dev->zero_cap = 0;
+        CUE(cudaMalloc(&dev->d_zero, z.bytes));
+        dev->zero_cap = z.bytes;
     }
     return GTS_OK;
 }
 
-// Enqueue one device pass on `stream` (no host synchronisation).
-int enqueue_pass(gts_ctx *ctx, const uint8_t *d_in, u64 n, uint8_t *d_out, u64 cap, cudaStream_t stream,
-                 bool sizes_only, gts::Totals *h_dst = nullptr, bool more_follows = false) {
-    if (((uintptr_t)d_in & 15) != 0) return fail(ctx, GTS_ERR_ARG, "device input must be 16-byte aligned");
-    int rc = ensure_scratch(ctx, n);
+struct PassArgs {
+    const uint8_t *d_in = nullptr;
+    u64 n = 0;
+    uint8_t *d_out = nullptr;
+    u64 cap = 0;
+    cudaStream_t stream = nullptr;
+    bool sizes_only = false;
+    gts::Totals *h_dst = nullptr;  // pinned destination of the totals (default: dev->h_totals)
+    bool more_follows = false;
+    u64 *d_warn = nullptr;         // warning list (nullptr = off)
+    gts::WarnRec *d_wres = nullptr;
+    size_t warn_cap = 0;
+};
+
+// Enqueue one device pass on a.stream (no host synchronisation).
+int enqueue_pass(gts_ctx *ctx, DevCtx *dev, const PassArgs &a, std::string *err) {
+    if (((uintptr_t)a.d_in & 15) != 0) {
+        if (err) *err = "device input must be 16-byte aligned";
+        return GTS_ERR_ARG;
+    }
+    int rc = ensure_scratch(ctx, dev, a.n, err);
     if (rc) return rc;
-    const u64 ntiles = parse_tiles(n);
-    const ZeroLayout z = zero_layout(ntiles, ctx->rec_cap);
-    gts::Job &job = ctx->job;
-    job.in = d_in; job.n = n; job.out = d_out; job.out_cap = cap;
-    job.sym = ctx->d_sym;
-    job.tile_info = ctx->d_tile_info;
-    job.tile_pre = ctx->d_tile_pre;
-    job.events = ctx->d_events;
-    job.hdr_off = ctx->d_hdr_off; job.dbase = ctx->d_dbase; job.loc = ctx->d_loc; job.hinfo = ctx->d_hinfo;
-    job.rec = ctx->d_rec; job.trim_len = ctx->d_trim; job.ftab = ctx->d_ftab; job.rec_cap = ctx->rec_cap;
-    job.t_status = reinterpret_cast<u64 *>(ctx->d_zero + z.t_status);
-    job.s_status = reinterpret_cast<u64 *>(ctx->d_zero + z.s_status);
-    job.totals = reinterpret_cast<gts::Totals *>(ctx->d_zero + z.totals);
-    job.counters = reinterpret_cast<u32 *>(ctx->d_zero + z.counters);
-    job.dbg = ctx->d_dbg;
-    job.scan_nl = ctx->d_scan_nl;
+    const u64 ntiles = parse_tiles(a.n);
+    const ZeroLayout z = zero_layout(ntiles, dev->rec_cap);
+    gts::Job &job = dev->job;
+    job.in = a.d_in; job.n = a.n; job.out = a.d_out; job.out_cap = a.cap;
+    job.sym = dev->d_sym;
+    job.tile_info = dev->d_tile_info;
+    job.tile_pre = dev->d_tile_pre;
+    job.events = dev->d_events;
+    job.hdr_off = dev->d_hdr_off; job.dbase = dev->d_dbase; job.loc = dev->d_loc; job.hinfo = dev->d_hinfo;
+    job.rec = dev->d_rec; job.trim_len = dev->d_trim; job.ftab = dev->d_ftab; job.rec_cap = dev->rec_cap;
+    job.t_status = reinterpret_cast<u64 *>(dev->d_zero + z.t_status);
+    job.s_status = reinterpret_cast<u64 *>(dev->d_zero + z.s_status);
+    job.totals = reinterpret_cast<gts::Totals *>(dev->d_zero + z.totals);
+    job.counters = reinterpret_cast<u32 *>(dev->d_zero + z.counters);
+    job.warn = a.warn_cap ? a.d_warn : nullptr;
+    job.wres = a.d_wres;
+    job.warn_cap = (u32)std::min<size_t>(a.warn_cap, 0xFFFFFFFFu);
+    job.pad0 = 0;
+    job.dbg = dev->d_dbg;
+    job.scan_nl = dev->d_scan_nl;
     job.max_line = ctx->max_line;
     job.ntiles = (u32)ntiles;
     job.frame_mask = ctx->mask;
     job.alternative = ctx->opt.alternative ? 1 : 0;
     job.trim = ctx->opt.trim ? 1 : 0;
-    job.more_follows = more_follows ? 1 : 0;
+    job.more_follows = a.more_follows ? 1 : 0;
     job.piece = 0; job.no_end_pads = 0; job.has_carry = 0; job.carry = 0; job.no_headers = 0; job.ov_H = 0;
     job.t0_base = 0; job.win_lo = 0; job.ov_slot = 0; job.ov_n = 0; job.ov_dbase = 0;
     job.head_out = nullptr;
@@ -266,95 +366,96 @@ int enqueue_pass(gts_ctx *ctx, const uint8_t *d_in, u64 n, uint8_t *d_out, u64 c
         std::memcpy(job.head, p.head, sizeof(job.head));
     }
     job.lut = ctx->lut;
-    {
-        uint8_t *bf = reinterpret_cast<uint8_t *>(job.lutb.f), *br = reinterpret_cast<uint8_t *>(job.lutb.r);
-        for (int e = 0; e < 128; e++) {
-            const int x = e < 125 ? e : 0;
-            const int s0 = x % 5, s1 = (x / 5) % 5, s2 = x / 25;
-            bf[e] = (uint8_t)(ctx->lut.v[x] & 0xFF);
-            br[e] = (uint8_t)(ctx->lut.v[s2 + 5 * s1 + 25 * s0] >> 8);
-        }
-    }
-    ctx->job_stream = stream;
+    job.lutb = ctx->lutb;
+    dev->job_stream = a.stream;
     cudaEvent_t *ev = nullptr;
-    if (ctx->profiling && !sizes_only) {
-        while (ctx->prof_events.size() < ctx->prof_used + 5) {
+    if (ctx->profiling && !a.sizes_only) {
+        while (dev->prof_events.size() < dev->prof_used + 5) {
             cudaEvent_t e;
-            CU(cudaEventCreate(&e));
-            ctx->prof_events.push_back(e);
+            CUE(cudaEventCreate(&e));
+            dev->prof_events.push_back(e);
         }
-        ev = ctx->prof_events.data() + ctx->prof_used;
-        ctx->prof_used += 5;
-        CU(cudaEventRecord(ev[0], stream));
+        ev = dev->prof_events.data() + dev->prof_used;
+        dev->prof_used += 5;
+        CUE(cudaEventRecord(ev[0], a.stream));
     }
-    CU(cudaMemsetAsync(ctx->d_zero, 0, z.bytes, stream));
-    CU(gts::launch_parse(job, stream));
-    if (ev) CU(cudaEventRecord(ev[1], stream));
-    CU(gts::launch_sizes(job, ctx->sm_count, stream));
-    if (ev) CU(cudaEventRecord(ev[2], stream));
-    ctx->stats.kernel_launches += 4;
-    if (!sizes_only) {
-        CU(gts::launch_emit(job, ctx->sm_count, stream, ev ? ev[3] : nullptr, ctx->s_side, ctx->ev_fork, ctx->ev_join));
-        if (ev) CU(cudaEventRecord(ev[4], stream));
-        ctx->stats.kernel_launches += 2;
+    CUE(cudaMemsetAsync(dev->d_zero, 0, z.bytes, a.stream));
+    CUE(gts::launch_parse(job, a.stream));
+    if (ev) CUE(cudaEventRecord(ev[1], a.stream));
+    CUE(gts::launch_sizes(job, dev->sm_count, a.stream));
+    u64 launches = 4;
+    if (job.warn) {
+        CUE(gts::launch_warn(job, dev->sm_count, a.stream));
+        launches++;
     }
-    CU(cudaMemcpyAsync(h_dst ? h_dst : ctx->h_totals, job.totals, sizeof(gts::Totals), cudaMemcpyDeviceToHost, stream));
-    ctx->pending = true;
-    ctx->stats.passes++;
+    if (ev) CUE(cudaEventRecord(ev[2], a.stream));
+    if (!a.sizes_only) {
+        CUE(gts::launch_emit(job, dev->sm_count, a.stream, ev ? ev[3] : nullptr, dev->s_side, dev->ev_fork, dev->ev_join));
+        if (ev) CUE(cudaEventRecord(ev[4], a.stream));
+        launches += 2;
+    }
+    CUE(cudaMemcpyAsync(a.h_dst ? a.h_dst : dev->h_totals, job.totals, sizeof(gts::Totals), cudaMemcpyDeviceToHost, a.stream));
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->stats.kernel_launches += launches;
+        ctx->stats.passes++;
+    }
     return GTS_OK;
 }
 
-// Wait for the enqueued pass; grow the record table and redo the pass if it was too small.
-int finish_pass(gts_ctx *ctx, bool sizes_only) {
-    if (!ctx->pending) return fail(ctx, GTS_ERR_ARG, "no device pass enqueued");
+// Device-resident entry points: wait for the enqueued pass; grow the record table and redo the
+// pass if it was too small; redo it on the bytes in front of an over-long line.
+int finish_pass(gts_ctx *ctx, DevCtx *dev, bool sizes_only) {
+    if (!dev->pending) return fail(ctx, GTS_ERR_ARG, "no device pass enqueued");
+    std::string emsg, *err = &emsg;
     for (int attempt = 0;; attempt++) {
-        CU(cudaStreamSynchronize(ctx->job_stream));
-        const gts::Totals &t = *ctx->h_totals;
+        CU(cudaStreamSynchronize(dev->job_stream));
+        const gts::Totals &t = *dev->h_totals;
+        PassArgs a;
+        a.d_in = dev->job.in; a.n = dev->job.n; a.d_out = dev->job.out; a.cap = dev->job.out_cap;
+        a.stream = dev->job_stream; a.sizes_only = sizes_only;
         if (t.flags & gts::kFlagLongLine) {
             // the reference stops reading at a line of >= 100 MiB (transeq.go:186): redo the pass on
             // the bytes in front of that line
             if (attempt >= 3) return fail(ctx, GTS_ERR_ARG, "over-long line handling did not converge");
-            const gts::Job j = ctx->job;
             ctx->last_truncated = true;
-            int rc = enqueue_pass(ctx, j.in, t.cut, j.out, j.out_cap, ctx->job_stream, sizes_only);
-            if (rc) return rc;
-            continue;
-        }
-        if (t.flags & gts::kFlagRecOverflow) {
+            a.n = t.cut;
+        } else if (t.flags & gts::kFlagRecOverflow) {
             if (attempt >= 3) return fail(ctx, GTS_ERR_NOMEM, "record table overflow persists");
             const u64 need = t.n_headers + 2;
-            int rc = alloc_rec(ctx, need + need / 16 + 1024);
-            if (rc) return rc;
-            const gts::Job j = ctx->job;
-            rc = enqueue_pass(ctx, j.in, j.n, j.out, j.out_cap, ctx->job_stream, sizes_only);
-            if (rc) return rc;
-            continue;
+            CU(cudaDeviceSynchronize());
+            int rc = alloc_rec(ctx, dev, need + need / 16 + 1024, err);
+            if (rc) return fail(ctx, rc, emsg);
+            dev->rec_per_byte = std::max(dev->rec_per_byte, 1.1 * (double)need / (double)std::max<u64>(a.n, 1));
+        } else {
+            break;
         }
-        break;
+        int rc = enqueue_pass(ctx, dev, a, err);
+        if (rc) return fail(ctx, rc, emsg);
     }
-    ctx->pending = false;
-    const gts::Totals &t = *ctx->h_totals;
+    dev->pending = false;
+    const gts::Totals &t = *dev->h_totals;
     ctx->stats.records = t.records;
     ctx->stats.nucleotides = t.nucleotides;
-    ctx->stats.in_bytes = ctx->job.n;
+    ctx->stats.in_bytes = dev->job.n;
     ctx->stats.out_bytes = t.out_total;
     return GTS_OK;
 }
 
-int ensure_dev_buffer(gts_ctx *ctx, uint8_t **p, size_t *cap, size_t need) {
+int ensure_dev_buffer(uint8_t **p, size_t *cap, size_t need, std::string *err) {
     if (need <= *cap && *p) return GTS_OK;
-    cudaFree(*p);
+    cudaFree(*p);  // (waits for the device: nothing enqueued earlier still uses the block)
     *p = nullptr; *cap = 0;
     const size_t want = round_up(need + need / 8 + 4096, 4096);
-    CU(cudaMalloc(p, want));
+    CUE(cudaMalloc(p, want));
     *cap = want;
     return GTS_OK;
 }
-int ensure_pinned(gts_ctx *ctx, uint8_t **p, size_t *cap, size_t need, size_t keep) {
+int ensure_pinned(uint8_t **p, size_t *cap, size_t need, size_t keep, std::string *err) {
     if (need <= *cap && *p) return GTS_OK;
     const size_t want = round_up(need + need / 8 + 4096, 4096);
     uint8_t *q = nullptr;
-    CU(cudaHostAlloc(&q, want, cudaHostAllocDefault));
+    CUE(cudaHostAlloc(&q, want, cudaHostAllocPortable));
     if (keep && *p) std::memcpy(q, *p, keep);
     if (*p) cudaFreeHost(*p);
     *p = q;
@@ -362,148 +463,487 @@ int ensure_pinned(gts_ctx *ctx, uint8_t **p, size_t *cap, size_t need, size_t ke
     return GTS_OK;
 }
 
-// Host bytes in pinned or pageable memory -> device pass -> pinned ctx->h_out.
-int translate_host_simple(gts_ctx *ctx, const uint8_t *in, size_t n, size_t *out_n) {
-    ctx->last_truncated = false;
-    int rc = ensure_dev_buffer(ctx, &ctx->d_in, &ctx->d_in_cap, n + 64);
-    if (rc) return rc;
-    if (n) CU(cudaMemcpyAsync(ctx->d_in, in, n, cudaMemcpyHostToDevice, ctx->stream));
-    ctx->stats.h2d_bytes += n;
-    // pass 1: parse + sizes, so that the output buffers can be sized exactly
-    rc = enqueue_pass(ctx, ctx->d_in, n, nullptr, 0, ctx->stream, true);
-    if (rc) return rc;
-    rc = finish_pass(ctx, true);
-    if (rc) return rc;
-    const size_t total = ctx->h_totals->out_total;
-    rc = ensure_dev_buffer(ctx, &ctx->d_out, &ctx->d_out_cap, total + 64);
-    if (rc) return rc;
-    rc = ensure_pinned(ctx, &ctx->h_out, &ctx->h_out_cap, total + 64, 0);
-    if (rc) return rc;
-    // pass 2: residues and headers (the parse results are still in the scratch)
-    if (ctx->poison && total) CU(cudaMemsetAsync(ctx->d_out, 0xEE, total, ctx->stream));
-    ctx->job.out = ctx->d_out;
-    ctx->job.out_cap = ctx->d_out_cap;
-    // clear the "output too small" flag left by the sizing pass
-    ctx->h_totals->flags &= ~gts::kFlagOutOverflow;
-    CU(cudaMemcpyAsync(ctx->job.totals, ctx->h_totals, sizeof(gts::Totals), cudaMemcpyHostToDevice, ctx->stream));
-    CU(gts::launch_emit(ctx->job, ctx->sm_count, ctx->stream, nullptr, ctx->s_side, ctx->ev_fork, ctx->ev_join));
-    ctx->stats.kernel_launches += 2;
-    if (total) CU(cudaMemcpyAsync(ctx->h_out, ctx->d_out, total, cudaMemcpyDeviceToHost, ctx->stream));
-    ctx->stats.d2h_bytes += total;
-    CU(cudaStreamSynchronize(ctx->stream));
-    *out_n = total;
+// ---- device contexts --------------------------------------------------------------------
+
+void dev_destroy(DevCtx *dev) {
+    cudaSetDevice(dev->device);
+    cudaDeviceSynchronize();
+    if (dev->d_dbg) {
+        u64 h[64];
+        cudaMemcpy(h, dev->d_dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        std::fprintf(stderr, "[gts phase timing, ns summed over tiles]");
+        for (int i = 0; i < 24; i++) std::fprintf(stderr, " p%d=%llu", i, (unsigned long long)h[i]);
+        std::fprintf(stderr, "\n");
+        cudaFree(dev->d_dbg);
+    }
+    cudaFree(dev->d_sym); cudaFree(dev->d_tile_info); cudaFree(dev->d_tile_pre);
+    cudaFree(dev->d_zero); cudaFree(dev->d_scan_nl);
+    free_rec(dev);
+    cudaFree(dev->d_in); cudaFree(dev->d_out); cudaFree(dev->d_head);
+    for (PassSlot &s : dev->slots) {
+        cudaFree(s.d_in); cudaFree(s.d_out); cudaFree(s.d_warn); cudaFree(s.d_wres);
+        if (s.h_totals) cudaFreeHost(s.h_totals);
+        if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
+        if (s.ev_comp) cudaEventDestroy(s.ev_comp);
+    }
+    if (dev->h_totals) cudaFreeHost(dev->h_totals);
+    for (cudaEvent_t e : dev->prof_events) cudaEventDestroy(e);
+    if (dev->stream) cudaStreamDestroy(dev->stream);
+    if (dev->s_side) cudaStreamDestroy(dev->s_side);
+    if (dev->s_h2d) cudaStreamDestroy(dev->s_h2d);
+    if (dev->s_d2h) cudaStreamDestroy(dev->s_d2h);
+    if (dev->ev_fork) cudaEventDestroy(dev->ev_fork);
+    if (dev->ev_join) cudaEventDestroy(dev->ev_join);
+}
+
+// No CPU fallback: without a usable sm_100 device creation fails.
+int dev_create(int ordinal, std::unique_ptr<DevCtx> *out, std::string *err) {
+    std::unique_ptr<DevCtx> dev(new DevCtx());
+    int d = ordinal;
+    if (d < 0) CUE(cudaGetDevice(&d)); else CUE(cudaSetDevice(d));
+    CUE(cudaFree(nullptr));  // force context creation
+    cudaDeviceProp prop;
+    CUE(cudaGetDeviceProperties(&prop, d));
+    if (prop.major < 10) {
+        *err = "gotranseq_b200 needs an sm_100a device (found sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + ")";
+        return GTS_ERR_CUDA;
+    }
+    dev->device = d;
+    dev->sm_count = prop.multiProcessorCount;
+    std::memset(&dev->job, 0, sizeof(dev->job));
+    *out = std::move(dev);
+    DevCtx *p = out->get();
+    CUE(gts::init_kernels());
+    CUE(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    CUE(cudaStreamCreateWithFlags(&p->s_side, cudaStreamNonBlocking));
+    CUE(cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking));
+    CUE(cudaStreamCreateWithFlags(&p->s_d2h, cudaStreamNonBlocking));
+    CUE(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+    CUE(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+    CUE(cudaHostAlloc(&p->h_totals, sizeof(gts::Totals), cudaHostAllocPortable));
+    for (PassSlot &s : p->slots) {
+        CUE(cudaHostAlloc(&s.h_totals, sizeof(gts::Totals), cudaHostAllocPortable));
+        CUE(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
+        CUE(cudaEventCreateWithFlags(&s.ev_comp, cudaEventDisableTiming));
+    }
+#ifdef GTS_PHASE_TIMING
+    if (std::getenv("GTS_PHASE_TIMING")) {
+        cudaMalloc(&p->d_dbg, 64 * sizeof(u64));
+        cudaMemset(p->d_dbg, 0, 64 * sizeof(u64));
+    }
+#endif
     return GTS_OK;
 }
 
+// ---- chunk engine -----------------------------------------------------------------------
 
-// Record boundary (a '>' that starts a line) closest below `pos`, searched back to `lo`; 0 = none.
+// Record boundary (a '>' that starts a line, transeq.go:198) closest below `pos`, searched back to
+// `lo` (exclusive); 0 = none.
 size_t boundary_below(const uint8_t *p, size_t lo, size_t pos) {
-    for (size_t i = pos; i > lo + 1; i--)
-        if (p[i - 1] == '>' && p[i - 2] == '\n') return i - 1;
+    size_t i = pos;
+    while (i > lo + 1) {
+        const void *q = memrchr(p + lo + 1, '>', i - (lo + 1));
+        if (!q) return 0;
+        i = (size_t)(static_cast<const uint8_t *>(q) - p);
+        if (p[i - 1] == '\n') return i;
+    }
     return 0;
 }
+// First record boundary at or above `pos` (pos >= 1), n = none.
+size_t boundary_above(const uint8_t *p, size_t pos, size_t n) {
+    size_t i = pos;
+    while (i < n) {
+        const void *q = memchr(p + i, '>', n - i);
+        if (!q) return n;
+        i = (size_t)(static_cast<const uint8_t *>(q) - p);
+        if (p[i - 1] == '\n') return i;
+        i++;
+    }
+    return n;
+}
 
-// Host bytes -> pinned ctx->h_out through a two-slot pipeline of record-aligned chunks: the copy
-// in of chunk i+1 and the copy out of chunk i-1 run while chunk i is in the kernels.  Falls back
-// to the simple two-pass path when the input is small, has a record larger than a chunk, or a
-// chunk overflows one of the (generously) estimated buffers.
-int translate_host(gts_ctx *ctx, const uint8_t *in, size_t n, size_t *out_n) {
-    const size_t chunk = ctx->opt.chunk_bytes ? (size_t)ctx->opt.chunk_bytes : (size_t)16 << 20;
-    ctx->last_truncated = false;
-    // (a chunk shorter than the line limit cannot hold an over-long line; otherwise use the simple path)
-    if (n < 2 * chunk || chunk + chunk / 2 >= ctx->max_line) return translate_host_simple(ctx, in, n, out_n);
-    // ---- cut points ----
-    std::vector<size_t> cuts;
-    cuts.push_back(0);
-    while (n - cuts.back() > chunk + chunk / 2) {
-        const size_t b = boundary_below(in, cuts.back(), cuts.back() + chunk);
-        if (b == 0) return translate_host_simple(ctx, in, n, out_n);  // a record larger than a chunk
-        cuts.push_back(b);
-    }
-    cuts.push_back(n);
-    const size_t nchunks = cuts.size() - 1;
-    // ---- resources ----
-    if (!ctx->s_h2d) {
-        CU(cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking));
-        CU(cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking));
-        for (int b = 0; b < 2; b++) {
-            CU(cudaEventCreateWithFlags(&ctx->ev_h2d[b], cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&ctx->ev_comp[b], cudaEventDisableTiming));
-            CU(cudaEventCreateWithFlags(&ctx->ev_d2h[b], cudaEventDisableTiming));
-        }
-        CU(cudaHostAlloc(&ctx->h_totals2, 2 * sizeof(gts::Totals), cudaHostAllocDefault));
-    }
-    const size_t in_need = chunk + chunk / 2 + 64, out_need = 4 * in_need;
-    for (int b = 0; b < 2; b++) {
-        int rc = ensure_dev_buffer(ctx, &ctx->p_in[b], &ctx->p_in_cap[b], in_need);
-        if (rc) return rc;
-        rc = ensure_dev_buffer(ctx, &ctx->p_out[b], &ctx->p_out_cap[b], out_need);
-        if (rc) return rc;
-    }
-    int rc = ensure_pinned(ctx, &ctx->h_out, &ctx->h_out_cap, n * 2 + n / 4 + (1 << 20), 0);
-    if (rc) return rc;
-    rc = ensure_scratch(ctx, in_need);  // no reallocation while chunks are in flight
-    if (rc) return rc;
+bool stream_dead(const gts_ctx *ctx) { return ctx->cancelled || ctx->e_rc != 0 || ctx->exiting; }
 
-    size_t out_off = 0;
-    bool fallback = false;
-    // retire chunk j: wait for its kernels, read its exact size, copy it out behind the others
-    auto retire = [&](size_t j) -> int {
-        const int b = (int)(j & 1);
-        CU(cudaEventSynchronize(ctx->ev_comp[b]));
-        const gts::Totals &t = ctx->h_totals2[b];
-        if (t.flags != 0) {  // record table or output estimate too small: redo everything the simple way
-            fallback = true;
-            return GTS_OK;
+int stream_error_locked(gts_ctx *ctx) {
+    if (ctx->e_rc) {
+        ctx->err = ctx->e_err;
+        return ctx->e_rc;
+    }
+    if (ctx->cancelled) {
+        ctx->err = "translation cancelled";
+        return GTS_ERR_CANCELLED;
+    }
+    return GTS_OK;
+}
+
+void set_stream_error_locked(gts_ctx *ctx, int rc, const std::string &msg) {
+    if (ctx->e_rc == 0) {
+        ctx->e_rc = rc;
+        ctx->e_err = msg;
+    }
+    ctx->cv.notify_all();
+}
+
+// A pinned buffer from a pool (allocated on demand up to the pool's limit); nullptr when the stream died.
+HostBuf *pool_take(gts_ctx *ctx, std::unique_lock<std::mutex> &lk, std::vector<HostBuf *> &pool, size_t &count,
+                   size_t max_count, size_t min_cap, std::string *err, int *rc) {
+    *rc = GTS_OK;
+    ctx->cv.wait(lk, [&] { return stream_dead(ctx) || !pool.empty() || count < max_count; });
+    if (stream_dead(ctx)) return nullptr;
+    HostBuf *b = nullptr;
+    if (!pool.empty()) {
+        b = pool.back();
+        pool.pop_back();
+    } else {
+        count++;
+        b = new HostBuf();
+    }
+    if (b->cap < min_cap) {
+        lk.unlock();
+        *rc = ensure_pinned(&b->p, &b->cap, min_cap, 0, err);
+        lk.lock();
+        if (*rc) {
+            pool.push_back(b);
+            return nullptr;
         }
-        if (out_off + t.out_total > ctx->h_out_cap) {
-            CU(cudaStreamSynchronize(ctx->s_d2h));
-            int r2 = ensure_pinned(ctx, &ctx->h_out, &ctx->h_out_cap, (out_off + t.out_total) * 3 / 2, out_off);
-            if (r2) return r2;
+    }
+    return b;
+}
+
+int free_slot(const DevCtx *dev) {
+    for (int i = 0; i < kSlots; i++)
+        if (!dev->slots[i].busy) return i;
+    return -1;
+}
+
+size_t out_estimate(size_t n) { return n * 4 + 4096; }
+
+// H2D copy and the kernels of one chunk, enqueued without waiting.
+int issue_job(gts_ctx *ctx, DevCtx *dev, XJob *job) {
+    std::string *err = &job->err;
+    PassSlot &s = dev->slots[job->slot];
+    std::lock_guard<std::mutex> dl(dev->mu);
+    int rc = ensure_dev_buffer(&s.d_in, &s.d_in_cap, job->n + 64, err);
+    if (rc) return rc;
+    rc = ensure_dev_buffer(&s.d_out, &s.d_out_cap, out_estimate(job->n), err);
+    if (rc) return rc;
+    if (ctx->warn_fn) {
+        const size_t want = job->n / 16 + 4096;
+        if (want > s.warn_cap) {
+            cudaFree(s.d_warn); cudaFree(s.d_wres);
+            s.d_warn = nullptr; s.d_wres = nullptr; s.warn_cap = 0;
+            CUE(cudaMalloc(&s.d_warn, want * sizeof(u64)));
+            CUE(cudaMalloc(&s.d_wres, want * sizeof(gts::WarnRec)));
+            s.warn_cap = want;
         }
-        CU(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_comp[b], 0));
-        if (t.out_total)
-            CU(cudaMemcpyAsync(ctx->h_out + out_off, ctx->p_out[b], t.out_total, cudaMemcpyDeviceToHost, ctx->s_d2h));
-        CU(cudaEventRecord(ctx->ev_d2h[b], ctx->s_d2h));
-        out_off += t.out_total;
-        ctx->stats.d2h_bytes += t.out_total;
-        ctx->stats.records += t.records;
-        ctx->stats.nucleotides += t.nucleotides;
-        return GTS_OK;
-    };
-    ctx->stats.records = 0;
-    ctx->stats.nucleotides = 0;
-    for (size_t i = 0; i < nchunks && !fallback; i++) {
-        const int b = (int)(i & 1);
-        const size_t lo = cuts[i], len = cuts[i + 1] - cuts[i];
-        if (i >= 2) CU(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_comp[b], 0));  // chunk i-2 has left p_in[b]
-        CU(cudaMemcpyAsync(ctx->p_in[b], in + lo, len, cudaMemcpyHostToDevice, ctx->s_h2d));
-        CU(cudaEventRecord(ctx->ev_h2d[b], ctx->s_h2d));
-        ctx->stats.h2d_bytes += len;
-        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[b], 0));
-        if (i >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_d2h[b], 0));  // chunk i-2 has left p_out[b]
-        if (ctx->poison) CU(cudaMemsetAsync(ctx->p_out[b], 0xEE, ctx->p_out_cap[b], ctx->stream));
-        rc = enqueue_pass(ctx, ctx->p_in[b], len, ctx->p_out[b], ctx->p_out_cap[b], ctx->stream, false,
-                          &ctx->h_totals2[b], i + 1 < nchunks);
-        if (rc) return rc;
-        CU(cudaEventRecord(ctx->ev_comp[b], ctx->stream));
-        if (i >= 1) {
-            rc = retire(i - 1);
+    }
+    rc = ensure_scratch(ctx, dev, job->n, err);  // before the copy: growing the scratch drains the device
+    if (rc) return rc;
+    if (job->n) CUE(cudaMemcpyAsync(s.d_in, job->in, job->n, cudaMemcpyHostToDevice, dev->s_h2d));
+    CUE(cudaEventRecord(s.ev_h2d, dev->s_h2d));
+    CUE(cudaStreamWaitEvent(dev->stream, s.ev_h2d, 0));
+    if (ctx->poison) CUE(cudaMemsetAsync(s.d_out, 0xEE, s.d_out_cap, dev->stream));
+    PassArgs a;
+    a.d_in = s.d_in; a.n = job->n; a.d_out = s.d_out; a.cap = s.d_out_cap; a.stream = dev->stream;
+    a.h_dst = s.h_totals; a.more_follows = !job->last;
+    if (ctx->warn_fn) { a.d_warn = s.d_warn; a.d_wres = s.d_wres; a.warn_cap = s.warn_cap; }
+    rc = enqueue_pass(ctx, dev, a, err);
+    if (rc) return rc;
+    CUE(cudaEventRecord(s.ev_comp, dev->stream));
+    return GTS_OK;
+}
+
+// Wait for a chunk's kernels, repair the rare overflows, copy the result to the host.
+int retire_job(gts_ctx *ctx, DevCtx *dev, XJob *job) {
+    std::string *err = &job->err;
+    PassSlot &s = dev->slots[job->slot];
+    CUE(cudaEventSynchronize(s.ev_comp));
+    size_t n_eff = job->n;
+    bool more_follows = !job->last;
+    for (int attempt = 0; s.h_totals->flags != 0; attempt++) {
+        // redo the pass on this slot: over-long line (the reference stops reading there), record
+        // table / output buffer / warning list too small.  The other chunks in flight on this GPU
+        // are finished first (they share the scratch).
+        const gts::Totals t = *s.h_totals;
+        if (attempt >= 6) {
+            *err = "device pass did not converge (flags " + std::to_string(t.flags) + ")";
+            return GTS_ERR_NOMEM;
+        }
+        std::lock_guard<std::mutex> dl(dev->mu);
+        CUE(cudaDeviceSynchronize());
+        if (t.flags & gts::kFlagLongLine) {
+            job->truncated = true;
+            n_eff = t.cut;
+            more_follows = false;
+        } else if (t.flags & gts::kFlagRecOverflow) {
+            const u64 need = t.n_headers + 2;
+            int rc = alloc_rec(ctx, dev, need + need / 16 + 1024, err);
+            if (rc) return rc;
+            dev->rec_per_byte = std::max(dev->rec_per_byte, 1.1 * (double)need / (double)std::max<size_t>(job->n, 1));
+        } else if (t.flags & gts::kFlagWarnOverflow) {
+            const size_t want = t.n_warn + t.n_warn / 8 + 4096;
+            cudaFree(s.d_warn); cudaFree(s.d_wres);
+            s.d_warn = nullptr; s.d_wres = nullptr; s.warn_cap = 0;
+            CUE(cudaMalloc(&s.d_warn, want * sizeof(u64)));
+            CUE(cudaMalloc(&s.d_wres, want * sizeof(gts::WarnRec)));
+            s.warn_cap = want;
+        } else if (t.flags & gts::kFlagOutOverflow) {
+            int rc = ensure_dev_buffer(&s.d_out, &s.d_out_cap, t.out_total + 64, err);
             if (rc) return rc;
         }
-    }
-    if (!fallback) {
-        rc = retire(nchunks - 1);
+        PassArgs a;
+        a.d_in = s.d_in; a.n = n_eff; a.d_out = s.d_out; a.cap = s.d_out_cap; a.stream = dev->stream;
+        a.h_dst = s.h_totals; a.more_follows = more_follows;
+        if (ctx->warn_fn) { a.d_warn = s.d_warn; a.d_wres = s.d_wres; a.warn_cap = s.warn_cap; }
+        if (ctx->poison) CUE(cudaMemsetAsync(s.d_out, 0xEE, s.d_out_cap, dev->stream));
+        int rc = enqueue_pass(ctx, dev, a, err);
         if (rc) return rc;
+        CUE(cudaStreamSynchronize(dev->stream));
     }
-    CU(cudaStreamSynchronize(ctx->stream));
-    CU(cudaStreamSynchronize(ctx->s_d2h));
-    ctx->pending = false;
-    if (fallback) return translate_host_simple(ctx, in, n, out_n);
-    ctx->stats.in_bytes = n;
-    ctx->stats.out_bytes = out_off;
-    *out_n = out_off;
+    const gts::Totals t = *s.h_totals;
+    job->records = t.records;
+    job->nucleotides = t.nucleotides;
+    size_t total = t.out_total;
+
+    // ---- where the result goes ----
+    uint8_t *dst = nullptr;
+    if (ctx->direct) {
+        // one-shot call: straight to its final place behind the chunks before it
+        std::unique_lock<std::mutex> lk(ctx->mu);
+        ctx->cv.wait(lk, [&] { return stream_dead(ctx) || ctx->direct_turn == job->seq || job->seq > ctx->trunc_seq; });
+        if (stream_dead(ctx) || job->seq > ctx->trunc_seq) return GTS_OK;  // (the reference never read this far)
+        if (job->truncated) ctx->trunc_seq = job->seq;
+        const size_t off = ctx->direct_off;
+        if (off + total > ctx->h_out_cap) {
+            ctx->direct_growing = true;
+            ctx->cv.wait(lk, [&] { return ctx->direct_active == 0; });
+            lk.unlock();
+            int rc = ensure_pinned(&ctx->h_out, &ctx->h_out_cap, (off + total) + (off + total) / 2, off, err);
+            lk.lock();
+            ctx->direct_growing = false;
+            if (rc) {
+                ctx->cv.notify_all();
+                return rc;
+            }
+        }
+        ctx->direct_off = off + total;
+        ctx->direct_turn++;
+        ctx->direct_active++;
+        dst = ctx->h_out + off;
+        ctx->cv.notify_all();
+    } else {
+        std::unique_lock<std::mutex> lk(ctx->mu);
+        // (window rule: only the out_max oldest chunks may hold an output buffer, so the chunk the
+        // caller waits for can always get one)
+        ctx->cv.wait(lk, [&] { return stream_dead(ctx) || job->seq < ctx->consume_seq + ctx->out_max; });
+        if (stream_dead(ctx)) return GTS_OK;
+        int rc = GTS_OK;
+        HostBuf *b = pool_take(ctx, lk, ctx->out_free, ctx->out_count, ctx->out_max, total + 64, err, &rc);
+        if (!b) return rc;
+        job->outbuf = b;
+        dst = b->p;
+    }
+    int rc = GTS_OK;
+    cudaError_t ce = cudaSuccess;
+    if (total) ce = cudaMemcpyAsync(dst, s.d_out, total, cudaMemcpyDeviceToHost, dev->s_d2h);
+    std::vector<gts::WarnRec> wr;
+    if (ce == cudaSuccess && ctx->warn_fn && t.n_warn) {
+        wr.resize(t.n_warn);
+        ce = cudaMemcpyAsync(wr.data(), s.d_wres, t.n_warn * sizeof(gts::WarnRec), cudaMemcpyDeviceToHost, dev->s_d2h);
+    }
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(dev->s_d2h);
+    if (ce != cudaSuccess) {
+        *err = std::string("device to host copy: ") + cudaGetErrorString(ce);
+        rc = cuda_code(ce);
+    }
+    if (ctx->direct) {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->direct_active--;
+        ctx->cv.notify_all();
+    }
+    if (rc) return rc;
+    job->out = dst;
+    job->out_n = total;
+    if (!wr.empty()) {
+        // the reader goroutine prints the warnings in input order (encodedSequence.go:39)
+        std::sort(wr.begin(), wr.end(), [](const gts::WarnRec &x, const gts::WarnRec &y) { return x.key < y.key; });
+        job->warns.reserve(wr.size());
+        for (const gts::WarnRec &w : wr) {
+            WarnOut o;
+            o.header.assign(reinterpret_cast<const char *>(job->in + w.hdr_off), w.H);
+            o.pos = w.pos;
+            o.byte = (uint8_t)w.byte;
+            job->warns.push_back(std::move(o));
+        }
+    }
     return GTS_OK;
+}
+
+void issuer_main(gts_ctx *ctx, DevCtx *dev) {
+    cudaSetDevice(dev->device);
+    std::unique_lock<std::mutex> lk(ctx->mu);
+    while (true) {
+        ctx->cv.wait(lk, [&] { return ctx->exiting || (!dev->inq.empty() && free_slot(dev) >= 0); });
+        if (ctx->exiting) return;
+        XJob *job = dev->inq.front();
+        dev->inq.pop_front();
+        job->slot = free_slot(dev);
+        dev->slots[job->slot].busy = true;
+        job->skipped = ctx->cancelled || ctx->e_rc != 0 || job->seq > ctx->trunc_seq;
+        lk.unlock();
+        if (!job->skipped) job->rc = issue_job(ctx, dev, job);
+        lk.lock();
+        dev->inflight.push_back(job);
+        ctx->cv.notify_all();
+    }
+}
+
+void retirer_main(gts_ctx *ctx, DevCtx *dev) {
+    cudaSetDevice(dev->device);
+    std::unique_lock<std::mutex> lk(ctx->mu);
+    while (true) {
+        ctx->cv.wait(lk, [&] { return ctx->exiting || !dev->inflight.empty(); });
+        if (ctx->exiting) return;
+        XJob *job = dev->inflight.front();
+        dev->inflight.pop_front();
+        const bool run = !job->skipped && job->rc == 0;
+        lk.unlock();
+        if (run) {
+            job->rc = retire_job(ctx, dev, job);
+        } else if (!job->skipped) {
+            cudaStreamSynchronize(dev->stream);  // a failed enqueue: let what was enqueued finish
+        }
+        lk.lock();
+        dev->slots[job->slot].busy = false;
+        if (job->inbuf) {
+            ctx->in_free.push_back(job->inbuf);
+            job->inbuf = nullptr;
+        }
+        if (job->rc) set_stream_error_locked(ctx, job->rc, job->err);
+        if (job->truncated && job->seq < ctx->trunc_seq) ctx->trunc_seq = job->seq;
+        ctx->stats.h2d_bytes += run ? job->n : 0;
+        ctx->stats.d2h_bytes += job->out_n;
+        if (!ctx->direct && run && job->rc == 0) {  // a stream's counters add up over its chunks
+            ctx->stats.records += job->records;
+            ctx->stats.nucleotides += job->nucleotides;
+            ctx->stats.in_bytes += job->n;
+            ctx->stats.out_bytes += job->out_n;
+        }
+        job->done = true;
+        ctx->cv.notify_all();
+    }
+}
+
+int start_workers(gts_ctx *ctx) {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (ctx->workers_started) return GTS_OK;
+    for (auto &d : ctx->devs) {
+        d->issuer = std::thread(issuer_main, ctx, d.get());
+        d->retirer = std::thread(retirer_main, ctx, d.get());
+    }
+    ctx->workers_started = true;
+    return GTS_OK;
+}
+
+// Hand a chunk to its GPU (round robin over the chunks keeps every GPU's queue equally long).
+void dispatch_locked(gts_ctx *ctx, XJob *job) {
+    job->seq = ctx->next_seq++;
+    job->dev = (int)(job->seq % ctx->devs.size());
+    ctx->window.push_back(job);
+    ctx->devs[job->dev]->inq.push_back(job);
+    ctx->cv.notify_all();
+}
+
+void recycle_job_locked(gts_ctx *ctx, XJob *job) {
+    if (job->outbuf) ctx->out_free.push_back(job->outbuf);
+    if (job->inbuf) ctx->in_free.push_back(job->inbuf);
+    delete job;
+}
+
+// Everything queued is finished (or skipped) and forgotten; the pools get their buffers back.
+void drain_and_clear_locked(gts_ctx *ctx, std::unique_lock<std::mutex> &lk) {
+    const bool was_cancelled = ctx->cancelled;
+    if (!ctx->window.empty()) ctx->cancelled = true;  // queued chunks are dropped, running ones finish
+    ctx->cv.notify_all();
+    ctx->cv.wait(lk, [&] {
+        for (XJob *j : ctx->window)
+            if (!j->done) return false;
+        return true;
+    });
+    for (XJob *j : ctx->window) recycle_job_locked(ctx, j);
+    ctx->window.clear();
+    ctx->handed = nullptr;
+    ctx->cancelled = was_cancelled;
+}
+
+void reset_stream_locked(gts_ctx *ctx) {
+    ctx->consume_seq = ctx->next_seq;
+    ctx->trunc_seq = ~0ull;
+    ctx->eof = false;
+    ctx->first_job = true;
+    if (ctx->fill) {
+        ctx->in_free.push_back(ctx->fill);
+        ctx->fill = nullptr;
+    }
+    ctx->fill_n = 0;
+    ctx->scan_from = 1;
+    ctx->last_boundary = 0;
+}
+
+void fire_warnings(gts_ctx *ctx, XJob *job) {
+    if (job->warned) return;
+    job->warned = true;
+    if (!ctx->warn_fn) return;
+    for (const WarnOut &w : job->warns)
+        ctx->warn_fn(ctx->warn_user, reinterpret_cast<const uint8_t *>(w.header.data()), w.header.size(), w.byte, w.pos);
+    job->warns.clear();
+    job->warns.shrink_to_fit();
+}
+
+// The next result in input order.  block: wait for it (after eof gts_next_output waits as well).
+int next_output(gts_ctx *ctx, const uint8_t **buf, size_t *n, bool block) {
+    *buf = nullptr;
+    *n = 0;
+    std::unique_lock<std::mutex> lk(ctx->mu);
+    while (true) {
+        int rc = stream_error_locked(ctx);
+        if (rc) return rc;
+        if (ctx->handed) {  // not released yet: the same result again
+            *buf = ctx->handed->out;
+            *n = ctx->handed->out_n;
+            return GTS_OK;
+        }
+        if (!ctx->window.empty() && ctx->window.front()->done) {
+            XJob *job = ctx->window.front();
+            if (job->seq > ctx->trunc_seq) {  // the reference stopped reading before this chunk
+                job->out_n = 0;
+                job->warns.clear();
+            }
+            if (!job->warned && !job->warns.empty()) {
+                lk.unlock();
+                fire_warnings(ctx, job);  // on the caller's thread, without the engine lock
+                lk.lock();
+                continue;
+            }
+            if (job->out_n == 0) {
+                ctx->window.pop_front();
+                ctx->consume_seq++;
+                recycle_job_locked(ctx, job);
+                ctx->cv.notify_all();
+                continue;
+            }
+            ctx->handed = job;
+            *buf = job->out;
+            *n = job->out_n;
+            return GTS_OK;
+        }
+        if (ctx->eof && ctx->window.empty()) {  // drained: ready for another stream
+            reset_stream_locked(ctx);
+            return GTS_OK;
+        }
+        if (!block && !ctx->eof) return GTS_OK;
+        ctx->cv.wait(lk);
+    }
 }
 
 // ---- split record: which bytes of the record's output a piece writes --------------------------
@@ -521,8 +961,6 @@ void host_frame_lengths(u64 n, bool alternative, u64 L[6]) {
     }
 }
 u64 host_run_size(u64 H, u64 L) { return H + 3 + L + (L + 59) / 60; }
-long long floordiv3(long long x) { return x >= 0 ? x / 3 : -((-x + 2) / 3); }
-long long ceildiv3(long long x) { return -floordiv3(-x); }
 
 int piece_segments(uint32_t mask, bool alternative, const gts_piece &p, u64 n_piece, gts_segment *segs, u64 *total) {
     const u64 n = p.nt_total, H = p.header_len;
@@ -568,6 +1006,8 @@ int piece_segments(uint32_t mask, bool alternative, const gts_piece &p, u64 n_pi
     return m;
 }
 
+DevCtx *dev0(gts_ctx *ctx) { return ctx->devs[0].get(); }
+
 }  // namespace
 
 extern "C" {
@@ -607,8 +1047,9 @@ int gts_create(const gts_options *opt, gts_ctx **out) {
         return fail(nullptr, GTS_ERR_FRAME, std::string("wrong value for -f | --frame parameter: ") + frame);
     const char *aa = gts::find_codon_table(opt->table);
     if (!aa) return fail(nullptr, GTS_ERR_TABLE, "invalid table code: " + std::to_string(opt->table));
+    if (opt->num_gpus > 8) return fail(nullptr, GTS_ERR_ARG, "num_gpus must be at most 8");
 
-    gts_ctx *ctx = new gts_ctx();
+    std::unique_ptr<gts_ctx> ctx(new gts_ctx());
     ctx->opt = *opt;
     ctx->frame = frame;
     ctx->opt.frame = ctx->frame.c_str();
@@ -616,115 +1057,110 @@ int gts_create(const gts_options *opt, gts_ctx **out) {
     ctx->reverse = reverse;
     std::memset(&ctx->lut, 0, sizeof(ctx->lut));
     gts::build_fused_lut(aa, opt->clean != 0, ctx->lut.v);
+    {   // k_lines' tables: one residue per byte, forward and (read downwards) reverse strand
+        uint8_t *bf = reinterpret_cast<uint8_t *>(ctx->lutb.f), *br = reinterpret_cast<uint8_t *>(ctx->lutb.r);
+        for (int e = 0; e < 128; e++) {
+            const int x = e < 125 ? e : 0;
+            const int s0 = x % 5, s1 = (x / 5) % 5, s2 = x / 25;
+            bf[e] = (uint8_t)(ctx->lut.v[x] & 0xFF);
+            br[e] = (uint8_t)(ctx->lut.v[s2 + 5 * s1 + 25 * s0] >> 8);
+        }
+    }
     std::memset(&ctx->stats, 0, sizeof(ctx->stats));
-    std::memset(&ctx->job, 0, sizeof(ctx->job));
+    if (opt->chunk_bytes) ctx->chunk = std::max<size_t>((size_t)opt->chunk_bytes, 4096);
 
-    // No CPU fallback: without a usable CUDA device creation fails.
-    cudaError_t e;
-    int dev = opt->device;
-    if (dev < 0) {
-        e = cudaGetDevice(&dev);
+    // ---- devices (no CPU fallback: without a usable sm_100 device creation fails) ----
+    std::vector<int> ids;
+    if (opt->num_gpus == 0) {
+        ids.push_back(opt->device);
+    } else if (opt->num_gpus > 0) {
+        for (int i = 0; i < opt->num_gpus; i++) ids.push_back(opt->device_ids[i]);
     } else {
-        e = cudaSetDevice(dev);
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count <= 0)
+            return fail(nullptr, GTS_ERR_CUDA, std::string("CUDA initialisation failed (no CPU fallback): ") +
+                                                   (e != cudaSuccess ? cudaGetErrorString(e) : "no device"));
+        for (int i = 0; i < count && i < 8; i++) ids.push_back(i);
     }
-    if (e == cudaSuccess) e = cudaFree(nullptr);  // force context creation
-    cudaDeviceProp prop;
-    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, dev);
-    if (e == cudaSuccess && prop.major < 10) {
-        delete ctx;
-        return fail(nullptr, GTS_ERR_CUDA, "gotranseq_b200 needs an sm_100a device (found sm_" +
-                                               std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+    int prev = -1;
+    cudaGetDevice(&prev);
+    for (int id : ids) {
+        std::unique_ptr<DevCtx> dev;
+        std::string emsg;
+        int rc = dev_create(id, &dev, &emsg);
+        if (rc) {
+            if (dev) dev_destroy(dev.get());
+            for (auto &d : ctx->devs) dev_destroy(d.get());
+            return fail(nullptr, rc, "CUDA initialisation failed (no CPU fallback): " + emsg);
+        }
+        ctx->devs.push_back(std::move(dev));
     }
-    if (e == cudaSuccess) e = gts::init_kernels();
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_side, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaHostAlloc(&ctx->h_totals, sizeof(gts::Totals), cudaHostAllocDefault);
-    if (e != cudaSuccess) {
-        std::string msg = std::string("CUDA initialisation failed (no CPU fallback): ") + cudaGetErrorString(e);
-        if (ctx->stream) cudaStreamDestroy(ctx->stream);
-        delete ctx;
-        return fail(nullptr, GTS_ERR_CUDA, msg);
-    }
-    ctx->device = dev;
-    ctx->sm_count = prop.multiProcessorCount;
+    if (ids.size() > 1 || ids[0] >= 0) cudaSetDevice(ctx->devs[0]->device);
+    ctx->in_max = kSlots * ctx->devs.size() + 2;
+    ctx->out_max = ctx->in_max + 1;
     ctx->poison = std::getenv("GTS_POISON_OUTPUT") != nullptr;
-#ifdef GTS_PHASE_TIMING
-    if (std::getenv("GTS_PHASE_TIMING")) {
-        cudaMalloc(&ctx->d_dbg, 64 * sizeof(u64));
-        cudaMemset(ctx->d_dbg, 0, 64 * sizeof(u64));
-    }
-#endif
-    *out = ctx;
+    *out = ctx.release();
     return GTS_OK;
 }
 
 void gts_destroy(gts_ctx *ctx) {
     if (!ctx) return;
-    if (ctx->s_worker_started) {
+    if (ctx->workers_started) {
         {
-            std::lock_guard<std::mutex> lk(ctx->s_mu);
-            ctx->s_worker_exit = true;
+            std::unique_lock<std::mutex> lk(ctx->mu);
+            ctx->cancelled = true;
+            drain_and_clear_locked(ctx, lk);
+            ctx->exiting = true;
         }
-        ctx->s_cv.notify_all();
-        ctx->s_worker.join();
+        ctx->cv.notify_all();
+        for (auto &d : ctx->devs) {
+            d->issuer.join();
+            d->retirer.join();
+        }
     }
-    cudaSetDevice(ctx->device);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    if (ctx->d_dbg) {
-        u64 h[64];
-        cudaDeviceSynchronize();
-        cudaMemcpy(h, ctx->d_dbg, sizeof(h), cudaMemcpyDeviceToHost);
-        std::fprintf(stderr, "[gts phase timing, ns summed over tiles, %llu passes]", (unsigned long long)ctx->stats.passes);
-        for (int i = 0; i < 24; i++) std::fprintf(stderr, " p%d=%llu", i, (unsigned long long)h[i]);
-        std::fprintf(stderr, "\n");
-        cudaFree(ctx->d_dbg);
-    }
-    cudaFree(ctx->d_sym); cudaFree(ctx->d_tile_info); cudaFree(ctx->d_tile_pre);
-    cudaFree(ctx->d_zero); cudaFree(ctx->d_scan_nl);
-    free_rec(ctx);
-    cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_head);
-    for (int b = 0; b < 2; b++) {
-        cudaFree(ctx->p_in[b]); cudaFree(ctx->p_out[b]);
-        if (ctx->ev_h2d[b]) cudaEventDestroy(ctx->ev_h2d[b]);
-        if (ctx->ev_comp[b]) cudaEventDestroy(ctx->ev_comp[b]);
-        if (ctx->ev_d2h[b]) cudaEventDestroy(ctx->ev_d2h[b]);
-    }
-    if (ctx->h_totals2) cudaFreeHost(ctx->h_totals2);
-    if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
-    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
-    for (int b = 0; b < 2; b++) {
-        if (ctx->s_in[b]) cudaFreeHost(ctx->s_in[b]);
-        if (ctx->s_out[b] && ctx->s_out[b] != ctx->h_out) cudaFreeHost(ctx->s_out[b]);
-    }
+    for (auto &d : ctx->devs) dev_destroy(d.get());
+    if (ctx->fill) ctx->in_free.push_back(ctx->fill);
+    for (HostBuf *b : ctx->in_free) { if (b->p) cudaFreeHost(b->p); delete b; }
+    for (HostBuf *b : ctx->out_free) { if (b->p) cudaFreeHost(b->p); delete b; }
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
-    if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
-    for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
-    if (ctx->s_side) cudaStreamDestroy(ctx->s_side);
-    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->h_piece) cudaFreeHost(ctx->h_piece);
     delete ctx;
 }
 
 const char *gts_last_error(const gts_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
+int gts_num_devices(const gts_ctx *ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+
+// ---- device-resident entry points (first device) ------------------------------------------
+
 int gts_translate_device_async(gts_ctx *ctx, const void *d_in, size_t n, void *d_out, size_t cap, void *stream) {
     if (!ctx) return GTS_ERR_ARG;
     if (n && !d_in) return fail(ctx, GTS_ERR_ARG, "d_in is NULL");
-    return enqueue_pass(ctx, static_cast<const uint8_t *>(d_in), n, static_cast<uint8_t *>(d_out), cap,
-                        static_cast<cudaStream_t>(stream), false);
+    DevCtx *dev = dev0(ctx);
+    CU(cudaSetDevice(dev->device));
+    PassArgs a;
+    a.d_in = static_cast<const uint8_t *>(d_in); a.n = n; a.d_out = static_cast<uint8_t *>(d_out); a.cap = cap;
+    a.stream = static_cast<cudaStream_t>(stream);
+    std::string emsg;
+    std::lock_guard<std::mutex> dl(dev->mu);
+    int rc = enqueue_pass(ctx, dev, a, &emsg);
+    if (rc) return fail(ctx, rc, emsg);
+    dev->pending = true;
+    return GTS_OK;
 }
 
 int gts_device_result(gts_ctx *ctx, size_t *out_n) {
     if (!ctx) return GTS_ERR_ARG;
-    int rc = finish_pass(ctx, false);
+    DevCtx *dev = dev0(ctx);
+    CU(cudaSetDevice(dev->device));
+    std::lock_guard<std::mutex> dl(dev->mu);
+    int rc = finish_pass(ctx, dev, false);
     if (rc) return rc;
-    if (out_n) *out_n = ctx->h_totals->out_total;
-    if (ctx->h_totals->flags & gts::kFlagOutOverflow)
+    if (out_n) *out_n = dev->h_totals->out_total;
+    if (dev->h_totals->flags & gts::kFlagOutOverflow)
         return fail(ctx, GTS_ERR_CAPACITY, "output buffer too small: need " +
-                                               std::to_string(ctx->h_totals->out_total) + " bytes");
+                                               std::to_string(dev->h_totals->out_total) + " bytes");
     return GTS_OK;
 }
 
@@ -740,16 +1176,91 @@ size_t gts_output_bound_hint(const gts_ctx *ctx, size_t n) {
     // by the six copies of the header.  This is a hint, not a bound: gts_translate_device reports
     // the exact size when the buffer is too small.
     (void)ctx;
-    return n * 4 + 4096;
+    return out_estimate(n);
 }
+
+// ---- one-shot host call: the chunk engine in direct mode ------------------------------------
 
 int gts_translate_buffer(gts_ctx *ctx, const uint8_t *in, size_t n, const uint8_t **out, size_t *out_n) {
     if (!ctx) return GTS_ERR_ARG;
     if ((n && !in) || !out || !out_n) return fail(ctx, GTS_ERR_ARG, "NULL argument");
-    CU(cudaSetDevice(ctx->device));
-    size_t total = 0;
-    int rc = translate_host(ctx, in, n, &total);
+    *out = nullptr;
+    *out_n = 0;
+    start_workers(ctx);
+    {
+        std::unique_lock<std::mutex> lk(ctx->mu);
+        if (!ctx->window.empty() || ctx->fill_n || ctx->eof)
+            return fail(ctx, GTS_ERR_ARG, "gts_translate_buffer: a stream is in progress on this context");
+        int rc = stream_error_locked(ctx);
+        if (rc) return rc;
+    }
+    // a first guess of the output size (grown on demand: the chunks report their exact sizes)
+    {
+        std::string emsg;
+        const size_t guess = n * 2 + n / 4 + ((size_t)1 << 20);
+        if (guess > ctx->h_out_cap) {
+            int rc = ensure_pinned(&ctx->h_out, &ctx->h_out_cap, guess, 0, &emsg);
+            if (rc) return fail(ctx, rc, emsg);
+        }
+    }
+    std::unique_lock<std::mutex> lk(ctx->mu);
+    ctx->direct = true;
+    ctx->direct_turn = ctx->next_seq;
+    ctx->direct_off = 0;
+    ctx->direct_active = 0;
+    ctx->direct_growing = false;
+    ctx->trunc_seq = ~0ull;
+    const uint64_t first_seq = ctx->next_seq;
+    // ---- cut at record boundaries and deal the chunks out ----
+    const size_t chunk = ctx->chunk;
+    size_t pos = 0;
+    uint64_t records = 0, nucleotides = 0;
+    do {
+        size_t end = n;
+        if (n - pos > chunk + chunk / 2) {
+            end = boundary_below(in, pos, pos + chunk);
+            if (end == 0) end = boundary_above(in, pos + chunk, n);  // one record larger than a chunk
+        }
+        XJob *job = new XJob();
+        job->in = in + pos;
+        job->n = end - pos;
+        job->last = end == n;
+        dispatch_locked(ctx, job);
+        pos = end;
+        // (bounded backlog: the window holds at most a few chunks per GPU)
+        ctx->cv.wait(lk, [&] {
+            return stream_dead(ctx) || ctx->trunc_seq != ~0ull || ctx->next_seq - ctx->direct_turn < 4 * ctx->devs.size() + 4;
+        });
+    } while (pos < n && !stream_dead(ctx) && ctx->trunc_seq == ~0ull);
+    ctx->cv.wait(lk, [&] {
+        for (XJob *j : ctx->window)
+            if (!j->done) return false;
+        return true;
+    });
+    int rc = stream_error_locked(ctx);
+    size_t total = ctx->direct_off;
+    ctx->last_truncated = ctx->trunc_seq != ~0ull;
+    std::vector<XJob *> jobs(ctx->window.begin(), ctx->window.end());
+    ctx->window.clear();
+    ctx->consume_seq = ctx->next_seq;
+    ctx->direct = false;
+    lk.unlock();
+    for (XJob *j : jobs) {
+        if (rc == GTS_OK && j->seq <= ctx->trunc_seq) {
+            fire_warnings(ctx, j);
+            records += j->records;
+            nucleotides += j->nucleotides;
+        }
+    }
+    lk.lock();
+    for (XJob *j : jobs) recycle_job_locked(ctx, j);
+    ctx->trunc_seq = ~0ull;
+    (void)first_seq;
     if (rc) return rc;
+    ctx->stats.records = records;
+    ctx->stats.nucleotides = nucleotides;
+    ctx->stats.in_bytes = n;
+    ctx->stats.out_bytes = total;
     *out = ctx->h_out;
     *out_n = total;
     return GTS_OK;
@@ -757,182 +1268,193 @@ int gts_translate_buffer(gts_ctx *ctx, const uint8_t *in, size_t n, const uint8_
 
 // ---- streaming host interface ----------------------------------------------------------
 
-// The worker: translates the running job into its output buffer, then promotes the pending job.
-static void stream_try_start_locked(gts_ctx *ctx) {
-    if (ctx->s_has_running || !ctx->s_has_pending) return;
-    if (ctx->s_out_state[ctx->s_out_tail] != 0) return;  // both output buffers are still with the caller
-    ctx->s_running = ctx->s_pending;
-    ctx->s_has_pending = false;
-    ctx->s_has_running = true;
-    ctx->s_running_out = ctx->s_out_tail;
-    ctx->s_out_state[ctx->s_out_tail] = 1;
-    ctx->s_out_tail ^= 1;
-}
-
-static void stream_worker(gts_ctx *ctx) {
-    cudaSetDevice(ctx->device);
-    std::unique_lock<std::mutex> lk(ctx->s_mu);
-    while (true) {
-        ctx->s_cv.wait(lk, [&] { return ctx->s_worker_exit || ctx->s_has_running; });
-        if (ctx->s_worker_exit) return;
-        const gts_ctx::StreamJob job = ctx->s_running;
-        const int o = ctx->s_running_out;
-        const bool skip = ctx->stream_truncated || ctx->s_rc != 0;
-        lk.unlock();
-        size_t total = 0;
-        int rc = GTS_OK;
-        if (!skip) {
-            // translate_host writes into ctx->h_out: lend it this job's output buffer
-            uint8_t *keep = ctx->h_out;
-            const size_t keep_cap = ctx->h_out_cap;
-            ctx->h_out = ctx->s_out[o];
-            ctx->h_out_cap = ctx->s_out_cap[o];
-            rc = translate_host(ctx, ctx->s_in[job.in_idx], job.n, &total);
-            ctx->s_out[o] = ctx->h_out;
-            ctx->s_out_cap[o] = ctx->h_out_cap;
-            ctx->h_out = keep;
-            ctx->h_out_cap = keep_cap;
-        }
-        lk.lock();
-        if (rc != GTS_OK && ctx->s_rc == 0) {
-            ctx->s_rc = rc;
-            ctx->s_err = ctx->err;
-        }
-        if (!skip && rc == GTS_OK && ctx->last_truncated) ctx->stream_truncated = true;  // the reference stopped reading here
-        ctx->s_out_n[o] = rc == GTS_OK ? total : 0;
-        if (ctx->s_out_n[o]) {
-            ctx->s_out_state[o] = 2;
-        } else {
-            // nothing to hand back: the buffer is free again (it was the last one taken)
-            ctx->s_out_state[o] = 0;
-            ctx->s_out_tail = o;
-        }
-        ctx->s_has_running = false;
-        stream_try_start_locked(ctx);
-        ctx->s_cv.notify_all();
-    }
-}
-
-static int stream_error_locked(gts_ctx *ctx) {
-    if (ctx->s_rc == 0) return GTS_OK;
-    ctx->err = ctx->s_err;
-    return ctx->s_rc;
-}
-
 int gts_acquire_input(gts_ctx *ctx, uint8_t **buf, size_t *cap) {
     if (!ctx || !buf || !cap) return GTS_ERR_ARG;
-    if (ctx->stream_eof) return fail(ctx, GTS_ERR_ARG, "gts_acquire_input after eof");
-    CU(cudaSetDevice(ctx->device));
-    const int k = ctx->s_fill_idx;
-    {
-        // the buffer may still be the input of a job (the one submitted two submits ago)
-        std::unique_lock<std::mutex> lk(ctx->s_mu);
-        ctx->s_cv.wait(lk, [&] {
-            return !(ctx->s_has_running && ctx->s_running.in_idx == k) && !(ctx->s_has_pending && ctx->s_pending.in_idx == k);
-        });
-        int rc = stream_error_locked(ctx);
-        if (rc) return rc;
-    }
-    const size_t chunk = ctx->opt.chunk_bytes ? (size_t)ctx->opt.chunk_bytes : (size_t)16 << 20;
-    // keep at least half a chunk of free space; a record larger than the buffer makes it grow
-    size_t need = ctx->s_fill + ctx->s_rest_len + std::max<size_t>(chunk / 2, 4096);
-    if (need < chunk) need = chunk;
-    int rc = ensure_pinned(ctx, &ctx->s_in[k], &ctx->s_in_cap[k], need, ctx->s_fill);
+    start_workers(ctx);
+    std::unique_lock<std::mutex> lk(ctx->mu);
+    int rc = stream_error_locked(ctx);
     if (rc) return rc;
-    if (ctx->s_rest_len) {  // the unfinished record of the buffer submitted last (that buffer is only read by its job)
-        std::memcpy(ctx->s_in[k], ctx->s_rest_src, ctx->s_rest_len);
-        ctx->s_fill = ctx->s_rest_len;
-        ctx->s_rest_len = 0;
-        ctx->s_rest_src = nullptr;
+    if (ctx->eof) return fail(ctx, GTS_ERR_ARG, "gts_acquire_input after eof");
+    const size_t chunk = ctx->chunk;
+    const size_t min_read = std::max<size_t>(chunk / 8, 4096);
+    std::string emsg;
+    if (!ctx->fill) {
+        HostBuf *b = pool_take(ctx, lk, ctx->in_free, ctx->in_count, ctx->in_max, chunk + chunk / 4 + 65536, &emsg, &rc);
+        if (!b) return rc ? fail(ctx, rc, emsg) : stream_error_locked(ctx);
+        ctx->fill = b;
+        ctx->fill_n = 0;
+        ctx->scan_from = 1;
+        ctx->last_boundary = 0;
     }
-    *buf = ctx->s_in[k] + ctx->s_fill;
-    *cap = ctx->s_in_cap[k] - ctx->s_fill;
+    if (ctx->fill->cap - ctx->fill_n < min_read) {
+        // one record larger than the buffer: grow geometrically (the bytes read so far move along)
+        lk.unlock();
+        rc = ensure_pinned(&ctx->fill->p, &ctx->fill->cap, 2 * ctx->fill->cap, ctx->fill_n, &emsg);
+        lk.lock();
+        if (rc) return fail(ctx, rc, emsg);
+    }
+    *buf = ctx->fill->p + ctx->fill_n;
+    *cap = ctx->fill->cap - ctx->fill_n;
     return GTS_OK;
 }
 
 int gts_submit(gts_ctx *ctx, size_t nbytes, int eof) {
     if (!ctx) return GTS_ERR_ARG;
-    if (ctx->stream_eof) return fail(ctx, GTS_ERR_ARG, "gts_submit after eof");
-    const int k = ctx->s_fill_idx;
-    if (ctx->s_fill + nbytes > ctx->s_in_cap[k]) return fail(ctx, GTS_ERR_ARG, "gts_submit: more bytes than acquired");
-    ctx->s_fill += nbytes;
-    if (eof) ctx->stream_eof = true;
-    const size_t chunk = ctx->opt.chunk_bytes ? (size_t)ctx->opt.chunk_bytes : (size_t)16 << 20;
-    size_t cut = 0;
-    if (eof) {
-        cut = ctx->s_fill;
-        if (cut == 0 && !ctx->stream_first_pass) return GTS_OK;  // nothing left after the last record boundary
-    } else {
-        if (ctx->s_fill < chunk) return GTS_OK;  // keep filling
-        // last record boundary: a '>' that starts a line (transeq.go:198)
-        const uint8_t *p = ctx->s_in[k];
-        for (size_t i = ctx->s_fill; i-- > 1;) {
-            if (p[i] == '>' && p[i - 1] == '\n') {
-                cut = i;
-                break;
-            }
-        }
-        if (cut == 0) return GTS_OK;  // one record larger than the buffer: keep reading (buffer grows)
-    }
-    ctx->stream_first_pass = false;
-    std::unique_lock<std::mutex> lk(ctx->s_mu);
+    std::unique_lock<std::mutex> lk(ctx->mu);
     int rc = stream_error_locked(ctx);
     if (rc) return rc;
-    if (!ctx->s_worker_started) {
-        ctx->s_worker = std::thread(stream_worker, ctx);
-        ctx->s_worker_started = true;
+    if (ctx->eof) return fail(ctx, GTS_ERR_ARG, "gts_submit after eof");
+    if (!ctx->fill) {
+        if (nbytes) return fail(ctx, GTS_ERR_ARG, "gts_submit without gts_acquire_input");
+        if (!eof) return GTS_OK;
+        lk.unlock();
+        uint8_t *b = nullptr;
+        size_t c = 0;
+        rc = gts_acquire_input(ctx, &b, &c);
+        if (rc) return rc;
+        lk.lock();
     }
-    ctx->s_cv.wait(lk, [&] { return !ctx->s_has_pending; });  // at most one job waits behind the running one
-    ctx->s_pending.in_idx = k;
-    ctx->s_pending.n = cut;
-    ctx->s_has_pending = true;
-    stream_try_start_locked(ctx);
-    ctx->s_cv.notify_all();
-    // the caller goes on with the other buffer; the unfinished record moves there when it is acquired
-    ctx->s_rest_src = ctx->s_in[k] + cut;
-    ctx->s_rest_len = ctx->s_fill - cut;
-    ctx->s_fill_idx = k ^ 1;
-    ctx->s_fill = 0;
+    HostBuf *cur = ctx->fill;
+    if (ctx->fill_n + nbytes > cur->cap) return fail(ctx, GTS_ERR_ARG, "gts_submit: more bytes than acquired");
+    const size_t old_fill = ctx->fill_n;
+    ctx->fill_n += nbytes;
+    // last record boundary among the new bytes: a '>' that starts a line (transeq.go:198); every
+    // byte is looked at once, however often a large record makes the buffer grow
+    {
+        const size_t from = std::max<size_t>(std::max<size_t>(ctx->scan_from, old_fill), 1);
+        if (ctx->fill_n > from) {
+            const size_t b = boundary_below(cur->p, from - 1, ctx->fill_n);
+            if (b) ctx->last_boundary = b;
+        }
+        ctx->scan_from = ctx->fill_n;
+    }
+    size_t cut = 0;
+    if (eof) {
+        ctx->eof = true;
+        cut = ctx->fill_n;
+        if (cut == 0 && !ctx->first_job) {  // nothing left behind the last record boundary
+            ctx->in_free.push_back(cur);
+            ctx->fill = nullptr;
+            ctx->cv.notify_all();
+            return GTS_OK;
+        }
+    } else {
+        if (ctx->fill_n < ctx->chunk || ctx->last_boundary == 0) return GTS_OK;  // keep filling
+        cut = ctx->last_boundary;
+    }
+    // the unfinished record behind the cut moves to the front of a fresh buffer
+    const size_t rest = ctx->fill_n - cut;
+    HostBuf *next = nullptr;
+    if (!eof) {
+        std::string emsg;
+        const size_t need = std::max(ctx->chunk + ctx->chunk / 4 + 65536, rest + ctx->chunk / 4);
+        next = pool_take(ctx, lk, ctx->in_free, ctx->in_count, ctx->in_max, need, &emsg, &rc);
+        if (!next) return rc ? fail(ctx, rc, emsg) : stream_error_locked(ctx);
+        if (rest) std::memcpy(next->p, cur->p + cut, rest);
+    }
+    XJob *job = new XJob();
+    job->in = cur->p;
+    job->n = cut;
+    job->last = eof != 0;
+    job->inbuf = cur;
+    if (ctx->first_job) ctx->stats.records = ctx->stats.nucleotides = ctx->stats.in_bytes = ctx->stats.out_bytes = 0;
+    ctx->first_job = false;
+    ctx->fill = next;
+    ctx->fill_n = next ? rest : 0;
+    ctx->scan_from = 1;  // (the carried bytes hold no boundary: position 0 does not count)
+    ctx->last_boundary = 0;
+    if (next && rest > 1) ctx->scan_from = rest;
+    dispatch_locked(ctx, job);
     return GTS_OK;
 }
 
 int gts_next_output(gts_ctx *ctx, const uint8_t **buf, size_t *n) {
     if (!ctx || !buf || !n) return GTS_ERR_ARG;
-    *buf = nullptr;
-    *n = 0;
-    std::unique_lock<std::mutex> lk(ctx->s_mu);
-    const int h = ctx->s_out_head;
-    if (ctx->stream_eof)  // drain: wait for the next result, or for the worker to run dry
-        ctx->s_cv.wait(lk, [&] { return ctx->s_out_state[h] == 2 || (!ctx->s_has_running && !ctx->s_has_pending); });
-    int rc = stream_error_locked(ctx);
-    if (rc) return rc;
-    if (ctx->s_out_state[h] == 2) {
-        *buf = ctx->s_out[h];
-        *n = ctx->s_out_n[h];
-        return GTS_OK;
-    }
-    if (ctx->stream_eof) {  // drained: ready for another stream
-        ctx->stream_truncated = false;
-        ctx->stream_eof = false;
-        ctx->stream_first_pass = true;
-        ctx->s_fill = 0;
-        ctx->s_rest_len = 0;
-        ctx->s_rest_src = nullptr;
-    }
-    return GTS_OK;
+    return next_output(ctx, buf, n, false);
+}
+
+int gts_wait_output(gts_ctx *ctx, const uint8_t **buf, size_t *n) {
+    if (!ctx || !buf || !n) return GTS_ERR_ARG;
+    return next_output(ctx, buf, n, true);
 }
 
 int gts_release_output(gts_ctx *ctx) {
     if (!ctx) return GTS_ERR_ARG;
-    std::unique_lock<std::mutex> lk(ctx->s_mu);
-    const int h = ctx->s_out_head;
-    if (ctx->s_out_state[h] != 2) return GTS_OK;
-    ctx->s_out_state[h] = 0;
-    ctx->s_out_n[h] = 0;
-    ctx->s_out_head ^= 1;
-    stream_try_start_locked(ctx);
-    ctx->s_cv.notify_all();
+    std::unique_lock<std::mutex> lk(ctx->mu);
+    XJob *job = ctx->handed;
+    if (!job) return GTS_OK;
+    ctx->handed = nullptr;
+    if (!ctx->window.empty() && ctx->window.front() == job) {
+        ctx->window.pop_front();
+        ctx->consume_seq++;
+        recycle_job_locked(ctx, job);
+    }
+    ctx->cv.notify_all();
     return GTS_OK;
+}
+
+int gts_report_write_error(gts_ctx *ctx, const char *msg) {
+    if (!ctx) return GTS_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    // writer.go:175: fmt.Errorf("fail to write to output file: %v", err); the first error wins
+    set_stream_error_locked(ctx, GTS_ERR_WRITE, std::string("fail to write to output file: ") + (msg ? msg : ""));
+    ctx->cancelled = true;
+    ctx->cv.notify_all();
+    return GTS_OK;
+}
+
+int gts_cancel(gts_ctx *ctx) {
+    if (!ctx) return GTS_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ctx->cancelled = true;
+    ctx->cv.notify_all();
+    return GTS_OK;
+}
+
+int gts_stream_reset(gts_ctx *ctx) {
+    if (!ctx) return GTS_ERR_ARG;
+    std::unique_lock<std::mutex> lk(ctx->mu);
+    ctx->cancelled = true;
+    drain_and_clear_locked(ctx, lk);
+    reset_stream_locked(ctx);
+    ctx->cancelled = false;
+    ctx->e_rc = 0;
+    ctx->e_err.clear();
+    ctx->direct = false;
+    ctx->cv.notify_all();
+    return GTS_OK;
+}
+
+int gts_set_warning_callback(gts_ctx *ctx, gts_warning_fn fn, void *user) {
+    if (!ctx) return GTS_ERR_ARG;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!ctx->window.empty()) return fail(ctx, GTS_ERR_ARG, "gts_set_warning_callback: a stream is in progress");
+    ctx->warn_fn = fn;
+    ctx->warn_user = user;
+    return GTS_OK;
+}
+
+size_t gts_format_warning(const uint8_t *header, size_t header_len, uint8_t byte, uint64_t pos, char *dst, size_t cap) {
+    // encodedSequence.go:39: fmt.Printf("WARNING: invalid char in sequence %s: '%s' ( pos %d), replacing
+    // with 'N'\n", string(s[:headerSize]), string(n), i) -- s[:headerSize] starts with the four raw
+    // little-endian bytes of headerSize (= header_len + 4); string(n) of a byte is the rune's UTF-8 form
+    std::string s = "WARNING: invalid char in sequence ";
+    const uint32_t hs = (uint32_t)(header_len + 4);
+    for (int i = 0; i < 4; i++) s.push_back((char)((hs >> (8 * i)) & 0xFF));
+    s.append(reinterpret_cast<const char *>(header), header_len);
+    s += ": '";
+    if (byte < 0x80) {
+        s.push_back((char)byte);
+    } else {
+        s.push_back((char)(0xC0 | (byte >> 6)));
+        s.push_back((char)(0x80 | (byte & 0x3F)));
+    }
+    s += "' ( pos " + std::to_string(pos) + "), replacing with 'N'\n";
+    if (dst && cap) {
+        const size_t m = std::min(s.size(), cap);
+        std::memcpy(dst, s.data(), m);
+    }
+    return s.size();
 }
 
 int gts_set_max_line_length(gts_ctx *ctx, size_t n) {
@@ -951,18 +1473,24 @@ int gts_set_profiling(gts_ctx *ctx, int enable) {
 int gts_kernel_times(gts_ctx *ctx, double ms[4], uint64_t *passes) {
     if (!ctx || !ms) return GTS_ERR_ARG;
     for (int k = 0; k < 4; k++) ms[k] = 0.0;
-    const size_t np = ctx->prof_used / 5;
-    for (size_t p = 0; p < np; p++) {
-        cudaEvent_t *ev = ctx->prof_events.data() + 5 * p;
-        CU(cudaEventSynchronize(ev[4]));
-        for (int k = 0; k < 4; k++) {
-            float t = 0.f;
-            CU(cudaEventElapsedTime(&t, ev[k], ev[k + 1]));
-            ms[k] += t;
+    size_t np_all = 0;
+    for (auto &d : ctx->devs) {
+        CU(cudaSetDevice(d->device));
+        const size_t np = d->prof_used / 5;
+        for (size_t p = 0; p < np; p++) {
+            cudaEvent_t *ev = d->prof_events.data() + 5 * p;
+            CU(cudaEventSynchronize(ev[4]));
+            for (int k = 0; k < 4; k++) {
+                float t = 0.f;
+                CU(cudaEventElapsedTime(&t, ev[k], ev[k + 1]));
+                ms[k] += t;
+            }
         }
+        d->prof_used = 0;
+        np_all += np;
     }
-    if (passes) *passes = np;
-    ctx->prof_used = 0;
+    CU(cudaSetDevice(dev0(ctx)->device));
+    if (passes) *passes = np_all;
     return GTS_OK;
 }
 
@@ -972,18 +1500,28 @@ int gts_piece_scan_device(gts_ctx *ctx, const void *d_in, size_t n, int first, g
     if (!ctx || !info) return GTS_ERR_ARG;
     if (n && !d_in) return fail(ctx, GTS_ERR_ARG, "d_in is NULL");
     if (ctx->opt.trim) return fail(ctx, GTS_ERR_ARG, "a split record cannot be trimmed");
-    CU(cudaSetDevice(ctx->device));
+    DevCtx *dev = dev0(ctx);
+    CU(cudaSetDevice(dev->device));
+    std::lock_guard<std::mutex> dl(dev->mu);
     ctx->piece_on = true;
     ctx->piece_job = gts::Job();
     ctx->piece_job.no_end_pads = 1;  // count only: no pass of its own end
-    if (!ctx->d_head) CU(cudaMalloc(&ctx->d_head, 256));
-    ctx->piece_job.head_out = ctx->d_head;
+    if (!dev->d_head) CU(cudaMalloc(&dev->d_head, 256));
+    ctx->piece_job.head_out = dev->d_head;
     ctx->last_truncated = false;
-    int rc = enqueue_pass(ctx, static_cast<const uint8_t *>(d_in), n, nullptr, 0, static_cast<cudaStream_t>(stream), true);
-    if (!rc) rc = finish_pass(ctx, true);
+    PassArgs a;
+    a.d_in = static_cast<const uint8_t *>(d_in); a.n = n; a.stream = static_cast<cudaStream_t>(stream);
+    a.sizes_only = true;
+    std::string emsg;
+    int rc = enqueue_pass(ctx, dev, a, &emsg);
+    if (rc) fail(ctx, rc, emsg);
+    if (!rc) {
+        dev->pending = true;
+        rc = finish_pass(ctx, dev, true);
+    }
     ctx->piece_on = false;
     if (rc) return rc;
-    const gts::Totals &t = *ctx->h_totals;
+    const gts::Totals &t = *dev->h_totals;
     if (ctx->last_truncated) return fail(ctx, GTS_ERR_ARG, "a split record cannot hold an over-long line");
     info->headers = t.n_headers;
     info->nucleotides = t.total_sym - 2 - 2 * t.n_headers;
@@ -991,12 +1529,12 @@ int gts_piece_scan_device(gts_ctx *ctx, const void *d_in, size_t n, int first, g
     info->tail[1] = (uint8_t)((t.tail >> 4) & 0xF);
     info->reserved[0] = info->reserved[1] = 0;
     info->header_len = 0;
-    CU(cudaMemcpy(info->head, ctx->d_head, sizeof(info->head), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(info->head, dev->d_head, sizeof(info->head), cudaMemcpyDeviceToHost));
     if (first) {
         if (t.n_headers != 1) return fail(ctx, GTS_ERR_ARG, "the first piece must hold exactly one header line");
         u64 hoff = 0, hinfo = 0;
-        CU(cudaMemcpy(&hoff, ctx->d_hdr_off + 1, sizeof(u64), cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(&hinfo, ctx->d_hinfo + 1, sizeof(u64), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(&hoff, dev->d_hdr_off + 1, sizeof(u64), cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(&hinfo, dev->d_hinfo + 1, sizeof(u64), cudaMemcpyDeviceToHost));
         if (hoff != 0) return fail(ctx, GTS_ERR_ARG, "the first piece must start with the header line");
         info->header_len = (uint32_t)(hinfo & 0xFFFFFFFFull);
     } else if (t.n_headers != 0) {
@@ -1011,7 +1549,9 @@ int gts_piece_translate_device(gts_ctx *ctx, const void *d_in, size_t n, const g
     if (!ctx || !piece || !segs || !nseg) return GTS_ERR_ARG;
     if (n && !d_in) return fail(ctx, GTS_ERR_ARG, "d_in is NULL");
     if (ctx->opt.trim) return fail(ctx, GTS_ERR_ARG, "a split record cannot be trimmed");
-    CU(cudaSetDevice(ctx->device));
+    DevCtx *dev = dev0(ctx);
+    CU(cudaSetDevice(dev->device));
+    std::lock_guard<std::mutex> dl(dev->mu);
     gts::Job &p = ctx->piece_job;
     p = gts::Job();
     p.piece = 1;
@@ -1033,12 +1573,19 @@ int gts_piece_translate_device(gts_ctx *ctx, const void *d_in, size_t n, const g
         p.win_lo = p.t0_base + 2;
     }
     ctx->piece_on = true;
-    int rc = enqueue_pass(ctx, static_cast<const uint8_t *>(d_in), n, static_cast<uint8_t *>(d_out), cap,
-                          static_cast<cudaStream_t>(stream), false);
-    if (!rc) rc = finish_pass(ctx, false);
+    PassArgs a;
+    a.d_in = static_cast<const uint8_t *>(d_in); a.n = n; a.d_out = static_cast<uint8_t *>(d_out); a.cap = cap;
+    a.stream = static_cast<cudaStream_t>(stream);
+    std::string emsg;
+    int rc = enqueue_pass(ctx, dev, a, &emsg);
+    if (rc) fail(ctx, rc, emsg);
+    if (!rc) {
+        dev->pending = true;
+        rc = finish_pass(ctx, dev, false);
+    }
     ctx->piece_on = false;
     if (rc) return rc;
-    const gts::Totals &t = *ctx->h_totals;
+    const gts::Totals &t = *dev->h_totals;
     if (out_total) *out_total = t.out_total;
     if (t.flags & gts::kFlagOutOverflow)
         return fail(ctx, GTS_ERR_CAPACITY, "output buffer too small: need " + std::to_string(t.out_total) + " bytes");
@@ -1052,52 +1599,56 @@ int gts_piece_translate_device(gts_ctx *ctx, const void *d_in, size_t n, const g
 int gts_piece_scan(gts_ctx *ctx, const uint8_t *in, size_t n, int first, gts_piece_info *info) {
     if (!ctx || !info) return GTS_ERR_ARG;
     if (n && !in) return fail(ctx, GTS_ERR_ARG, "NULL argument");
-    CU(cudaSetDevice(ctx->device));
-    int rc = ensure_dev_buffer(ctx, &ctx->d_in, &ctx->d_in_cap, n + 64);
-    if (rc) return rc;
-    if (n) CU(cudaMemcpyAsync(ctx->d_in, in, n, cudaMemcpyHostToDevice, ctx->stream));
+    DevCtx *dev = dev0(ctx);
+    CU(cudaSetDevice(dev->device));
+    std::string emsg;
+    int rc = ensure_dev_buffer(&dev->d_in, &dev->d_in_cap, n + 64, &emsg);
+    if (rc) return fail(ctx, rc, emsg);
+    if (n) CU(cudaMemcpyAsync(dev->d_in, in, n, cudaMemcpyHostToDevice, dev->stream));
     ctx->stats.h2d_bytes += n;
     ctx->piece_n = n;
     ctx->piece_first = first != 0;
-    return gts_piece_scan_device(ctx, ctx->d_in, n, first, info, ctx->stream);
+    return gts_piece_scan_device(ctx, dev->d_in, n, first, info, dev->stream);
 }
 
 int gts_piece_translate(gts_ctx *ctx, const gts_piece *piece, size_t *out_total, gts_segment segs[GTS_MAX_SEGMENTS],
                         const uint8_t *data[GTS_MAX_SEGMENTS], int *nseg) {
     if (!ctx || !piece || !segs || !data || !nseg) return GTS_ERR_ARG;
     if ((piece->first != 0) != ctx->piece_first) return fail(ctx, GTS_ERR_ARG, "gts_piece_translate: not the piece last scanned");
-    CU(cudaSetDevice(ctx->device));
+    DevCtx *dev = dev0(ctx);
+    CU(cudaSetDevice(dev->device));
     // the whole record's output size is known from the counts alone
     u64 L[6], total = 0;
     host_frame_lengths(piece->nt_total, ctx->opt.alternative != 0, L);
     for (int f = 0; f < 6; f++)
         if ((ctx->mask >> f) & 1u) total += host_run_size(piece->header_len, L[f]);
-    int rc = ensure_dev_buffer(ctx, &ctx->d_out, &ctx->d_out_cap, total + 64);
-    if (rc) return rc;
-    if (ctx->poison && total) CU(cudaMemsetAsync(ctx->d_out, 0xEE, total, ctx->stream));
+    std::string emsg;
+    int rc = ensure_dev_buffer(&dev->d_out, &dev->d_out_cap, total + 64, &emsg);
+    if (rc) return fail(ctx, rc, emsg);
+    if (ctx->poison && total) CU(cudaMemsetAsync(dev->d_out, 0xEE, total, dev->stream));
     size_t tot = 0;
-    rc = gts_piece_translate_device(ctx, ctx->d_in, ctx->piece_n, piece, ctx->d_out, ctx->d_out_cap, &tot, segs, nseg,
-                                    ctx->stream);
+    rc = gts_piece_translate_device(ctx, dev->d_in, ctx->piece_n, piece, dev->d_out, dev->d_out_cap, &tot, segs, nseg,
+                                    dev->stream);
     if (rc) return rc;
     size_t bytes = 0;
     for (int i = 0; i < *nseg; i++) bytes += round_up(segs[i].length, 16);
-    rc = ensure_pinned(ctx, &ctx->h_out, &ctx->h_out_cap, bytes + 64, 0);
-    if (rc) return rc;
+    rc = ensure_pinned(&ctx->h_piece, &ctx->h_piece_cap, bytes + 64, 0, &emsg);
+    if (rc) return fail(ctx, rc, emsg);
     size_t off = 0;
     for (int i = 0; i < *nseg; i++) {
-        CU(cudaMemcpyAsync(ctx->h_out + off, ctx->d_out + segs[i].offset, segs[i].length, cudaMemcpyDeviceToHost, ctx->stream));
-        data[i] = ctx->h_out + off;
+        CU(cudaMemcpyAsync(ctx->h_piece + off, dev->d_out + segs[i].offset, segs[i].length, cudaMemcpyDeviceToHost, dev->stream));
+        data[i] = ctx->h_piece + off;
         off += round_up(segs[i].length, 16);
         ctx->stats.d2h_bytes += segs[i].length;
     }
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(dev->stream));
     if (out_total) *out_total = tot;
     return GTS_OK;
 }
 
 void *gts_host_alloc(size_t bytes) {
     void *p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) return nullptr;
     return p;
 }
 void gts_host_free(void *p) {

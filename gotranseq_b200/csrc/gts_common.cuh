@@ -58,13 +58,22 @@ __device__ __forceinline__ u32 newline_flags(u32 x) {
 // Bit i of the result = byte i of the 16 bytes is '\n'.  The per-byte flags (0x80) of a word are
 // gathered with one integer dot product: flags . (1,2,4,8) = 128 * nibble, accumulated over the
 // four words with the weights shifted by the nibble position.
-__device__ __forceinline__ u32 newline_mask16(uint4 v) {
-    u32 acc = __dp4a(newline_flags(v.x), 0x08040201u, 0u);                // bits 7..10
-    acc = __dp4a(newline_flags(v.y), 0x80402010u, acc);                   // bits 11..14
-    u32 hi = __dp4a(newline_flags(v.z), 0x08040201u, 0u);
-    hi = __dp4a(newline_flags(v.w), 0x80402010u, hi);
+__device__ __forceinline__ u32 gather_flags16(u32 f0, u32 f1, u32 f2, u32 f3) {  // flags: 0x80 or 0 per byte
+    u32 acc = __dp4a(f0, 0x08040201u, 0u);                // bits 7..10
+    acc = __dp4a(f1, 0x80402010u, acc);                   // bits 11..14
+    u32 hi = __dp4a(f2, 0x08040201u, 0u);
+    hi = __dp4a(f3, 0x80402010u, hi);
     return (acc >> 7) | (hi << 1);
 }
+__device__ __forceinline__ u32 newline_mask16(uint4 v) {
+    return gather_flags16(newline_flags(v.x), newline_flags(v.y), newline_flags(v.z), newline_flags(v.w));
+}
+// 0x80 in every byte of x that is 'N' or 'n'
+__device__ __forceinline__ u32 n_flags(u32 x) {
+    return __vabsdiffu4(__vabsdiffu4(x & 0xDFDFDFDFu, 0x4E4E4E4Eu), 0x80808080u) & 0x80808080u;
+}
+// 0x80 in every byte of c (nucleotide codes 0..4) that is 0
+__device__ __forceinline__ u32 zero_code_flags(u32 c) { return (0x80808080u - c) & 0x80808080u; }
 
 struct Pair {
     u64 a, b;

@@ -68,10 +68,23 @@ struct Totals {  // device-resident result block, copied to pinned host memory a
     u64 nucleotides;  // nucleotides in emitted records
     u64 cut;          // with kFlagLongLine: the reference stops reading at this offset
     u64 tail;         // the stream's last two symbols (end pads excluded): last | second-to-last << 4
+    u64 n_warn;       // invalid nucleotides seen (WARNING lines of encodedSequence.go:39), exact even on overflow
+    u64 pad;
 };
 constexpr u64 kFlagRecOverflow = 1;  // record table too small (n_headers is still exact)
 constexpr u64 kFlagOutOverflow = 2;  // output buffer too small (out_total is still exact)
 constexpr u64 kFlagLongLine = 4;     // a line of >= max_line bytes: the pass must be redone on [0, cut)
+constexpr u64 kFlagWarnOverflow = 8; // warning list too small (n_warn is still exact)
+
+// One invalid nucleotide (anything but ACGTUN in either case, encodedSequence.go:25-41), resolved
+// to its record by k_warn: what the reference's WARNING line needs.
+struct WarnRec {   // 32 bytes
+    u64 key;       // stream index of the symbol: input order
+    u64 hdr_off;   // raw offset of the record's header line (0 with H == 0: no header line)
+    u64 pos;       // index of the nucleotide in its record
+    u32 H;         // header line bytes
+    u32 byte;      // the offending byte
+};
 
 struct TileInfo {  // 16 bytes per parse tile, written by k_parse
     uint16_t nsym;      // symbols in the tile's slot (pads included)
@@ -151,7 +164,12 @@ struct Job {  // kernel argument block (by value)
     NlPart *scan_nl;// [tile-scan tiles] newline summaries (only used when n >= max_line)
     u64 max_line;   // bufio.Scanner token limit of the reference: 100 MiB (transeq.go:27)
     u64 *s_status;  // [size tiles * 4] chained scan of output sizes
-    u32 *counters;  // [0] tile-scan ticket, [1] size ticket, [2] header events appended, [3] k_lines tile ticket
+    u32 *counters;  // [0] tile-scan ticket, [1] size ticket, [2] header events appended, [3] k_lines tile ticket,
+                    // [4] invalid nucleotides appended to `warn`
+    u64 *warn;      // [warn_cap] tile << 32 | slot index << 8 | byte, appended by k_parse (nullptr = off)
+    WarnRec *wres;  // [warn_cap] resolved by k_warn
+    u32 warn_cap;
+    u32 pad0;
     Totals *totals;
     u64 *dbg;       // optional phase timing sums (GTS_PHASE_TIMING builds), else nullptr
 

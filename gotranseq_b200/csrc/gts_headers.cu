@@ -65,20 +65,25 @@ cudaError_t init_kernels() { return init_lines(); }
 // persistent k_lines grid leaves room for its small CTAs on every SM.
 cudaError_t launch_emit(const Job &job, int sm_count, cudaStream_t stream, cudaEvent_t ev_mid, cudaStream_t side,
                         cudaEvent_t ev_fork, cudaEvent_t ev_join) {
+    cudaError_t e;
+#define GTS_TRY(call) do { e = (call); if (e != cudaSuccess) return e; } while (0)
     if (side) {
-        cudaEventRecord(ev_fork, stream);
-        cudaStreamWaitEvent(side, ev_fork, 0);
+        GTS_TRY(cudaEventRecord(ev_fork, stream));
+        GTS_TRY(cudaStreamWaitEvent(side, ev_fork, 0));
         k_headers<<<sm_count * GTS_HDR_BLOCKS, 128, 0, side>>>(job);
-        cudaEventRecord(ev_join, side);
-        launch_lines(job, sm_count, stream);
-        if (ev_mid) cudaEventRecord(ev_mid, stream);
-        cudaStreamWaitEvent(stream, ev_join, 0);
+        GTS_TRY(cudaGetLastError());
+        GTS_TRY(cudaEventRecord(ev_join, side));
+        GTS_TRY(launch_lines(job, sm_count, stream));
+        if (ev_mid) GTS_TRY(cudaEventRecord(ev_mid, stream));
+        GTS_TRY(cudaStreamWaitEvent(stream, ev_join, 0));
     } else {
-        launch_lines(job, sm_count, stream);
-        if (ev_mid) cudaEventRecord(ev_mid, stream);
+        GTS_TRY(launch_lines(job, sm_count, stream));
+        if (ev_mid) GTS_TRY(cudaEventRecord(ev_mid, stream));
         k_headers<<<sm_count * GTS_HDR_BLOCKS, 128, 0, stream>>>(job);
+        GTS_TRY(cudaGetLastError());
     }
-    return cudaGetLastError();
+#undef GTS_TRY
+    return cudaSuccess;
 }
 
 }  // namespace gts

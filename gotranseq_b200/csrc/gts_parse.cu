@@ -294,6 +294,21 @@ __global__ void __launch_bounds__(kParseThreads, GTS_PARSE_CTAS) k_parse(const _
         if (fast) {
             C[0] = encode4(v0.x); C[1] = encode4(v0.y); C[2] = encode4(v0.z); C[3] = encode4(v0.w);
             C[4] = encode4(v1.x); C[5] = encode4(v1.y); C[6] = encode4(v1.z); C[7] = encode4(v1.w);
+            if (job.warn) {
+                // invalid nucleotides (encodedSequence.go:36-40): code 0, not N/n, not a dropped byte
+                const u32 zc = gather_flags16(zero_code_flags(C[0]), zero_code_flags(C[1]), zero_code_flags(C[2]), zero_code_flags(C[3])) |
+                               gather_flags16(zero_code_flags(C[4]), zero_code_flags(C[5]), zero_code_flags(C[6]), zero_code_flags(C[7])) << 16;
+                const u32 nm = gather_flags16(n_flags(v0.x), n_flags(v0.y), n_flags(v0.z), n_flags(v0.w)) |
+                               gather_flags16(n_flags(v1.x), n_flags(v1.y), n_flags(v1.z), n_flags(v1.w)) << 16;
+                u32 inv = zc & ~nm & ~removed;
+                while (inv) {
+                    const int i = __ffs(inv) - 1;
+                    inv &= inv - 1;
+                    const u32 spos = d + (u32)i - (u32)__popc(removed & ((1u << i) - 1u));
+                    const u32 slot = atomicAdd(&job.counters[4], 1u);
+                    if (slot < job.warn_cap) job.warn[slot] = (u64)t << 32 | (u64)spos << 8 | raw[i];
+                }
+            }
             u32 rm = removed;
             while (rm) {
                 const int p = 31 - __clz(rm);
@@ -388,7 +403,14 @@ __global__ void __launch_bounds__(kParseThreads, GTS_PARSE_CTAS) k_parse(const _
                 sh.sym[0] = job.has_carry ? (uint8_t)((job.carry >> 4) & 0xFu) : 0;
                 sh.sym[1] = job.has_carry ? (uint8_t)(job.carry & 0xFu) : 0;
             }
-            if (keep) sh.sym[c_d + off] = sh.enc[b];
+            if (keep) {
+                const uint8_t code = sh.enc[b];
+                sh.sym[c_d + off] = code;
+                if (job.warn && code == 0 && (b & 0xDF) != 'N') {
+                    const u32 slot = atomicAdd(&job.counters[4], 1u);
+                    if (slot < job.warn_cap) job.warn[slot] = (u64)t << 32 | (u64)(c_d + off) << 8 | b;
+                }
+            }
             if (hstart) {
                 sh.sym[c_d + off] = 0;
                 sh.sym[c_d + off + 1] = 0;

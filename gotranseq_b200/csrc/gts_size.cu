@@ -446,6 +446,43 @@ __global__ void __launch_bounds__(kSizeThreads) k_size(const __grid_constant__ J
     }
 }
 
+// =====================================================================================
+// k_warn: invalid nucleotides -> (record, position) for the WARNING lines of encodedSequence.go:39
+// =====================================================================================
+__global__ void __launch_bounds__(256) k_warn(const __grid_constant__ Job job) {
+    const u32 n = job.counters[4];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        job.totals->n_warn = n;
+        if (n > job.warn_cap) atomicOr(&job.totals->flags, kFlagWarnOverflow);
+    }
+    const u64 R = job.totals->n_headers;
+    if (R + 2 > job.rec_cap) return;
+    const u32 m = n < job.warn_cap ? n : job.warn_cap;
+    const u32 stride = gridDim.x * blockDim.x;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += stride) {
+        const u64 ev = job.warn[i];
+        const u32 tile = (u32)(ev >> 32), spos = (u32)(ev >> 8) & 0xFFFFFFu;
+        const u64 S = job.tile_pre[tile].T0 + spos;
+        u64 lo = 0, hi = R;  // the record slot holding stream index S: largest s with dbase[s] <= S
+        while (lo < hi) {
+            const u64 mid = (lo + hi + 1) >> 1;
+            if (job.dbase[mid] <= S) lo = mid; else hi = mid - 1;
+        }
+        WarnRec w;
+        w.key = S;
+        w.pos = S - job.dbase[lo];
+        w.hdr_off = lo ? job.hdr_off[lo] : 0;
+        w.H = lo ? (u32)(job.hinfo[lo] & 0xFFFFFFFFull) : 0u;
+        w.byte = (u32)(ev & 0xFFu);
+        job.wres[i] = w;
+    }
+}
+
+cudaError_t launch_warn(const Job &job, int sm_count, cudaStream_t stream) {
+    k_warn<<<sm_count, 256, 0, stream>>>(job);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_sizes(const Job &job, int sm_count, cudaStream_t stream) {
     const u32 nscan = (job.ntiles + kScanTile - 1) / kScanTile;
     k_tile_scan<<<nscan < (u32)sm_count ? nscan : (u32)sm_count, kScanThreads, 0, stream>>>(job);

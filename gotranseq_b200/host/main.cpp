@@ -1,13 +1,21 @@
 // main.cpp -- `gotranseq` command line over the B200 path, flag for flag the reference's CLI
 // (main.go:21-91, transeq/options.go:5-10): -s/--sequence, -o/--outseq, -f/--frame, -t/--table,
 // -c/--clean, -a/--alternative, -T/--trim, -n/--numcpu, -h/--help, -v/--version.
-// Like the reference, an error from the run is printed to stdout and the exit code stays 0
-// (main.go:87-90); only flag parsing errors exit with 1 (main.go:73-76).
+// Like the reference, an error from the run is printed to stdout as "fail to translate file:\n%v"
+// and the exit code stays 0 (main.go:87-90); flag parsing errors print "wrong arguments: ..., try
+// gotranseq --help for more informations" and exit with 1 (main.go:73-76).  The flag parser of the
+// reference is go-flags v1.4.0 (go.mod:5, not vendored): its error texts are restated from memory
+// of that library and are not pinned by any reference test.
+// Environment (not flags, so that the flag set stays the reference's): GOTRANSEQ_B200_GPUS = number
+// of GPUs (default: all visible), GOTRANSEQ_B200_CHUNK_MB = chunk size.
+#include <fcntl.h>
+#include <unistd.h>
+
+#include <cerrno>
+#include <climits>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <fstream>
-#include <iostream>
 #include <string>
 
 #include "../../include/gotranseq_b200.h"
@@ -33,13 +41,37 @@ static void usage() {
         kTool, GTS_VERSION, kTool);
 }
 
+[[noreturn]] static void wrong_arguments(const std::string &what) {
+    // main.go:74
+    std::printf("wrong arguments: %s, try %s --help for more informations\n", what.c_str(), kTool);
+    std::exit(1);
+}
+
+// Go's syscall.Errno texts are the C library's with a lower-case first letter
+static std::string go_errno(int e) {
+    std::string s = std::strerror(e);
+    if (!s.empty() && s[0] >= 'A' && s[0] <= 'Z') s[0] = (char)(s[0] - 'A' + 'a');
+    return s;
+}
+
+static int parse_int(const std::string &v, const char *flag) {
+    errno = 0;
+    char *end = nullptr;
+    const long x = std::strtol(v.c_str(), &end, 10);
+    if (v.empty() || *end != 0 || errno == ERANGE || x < INT_MIN || x > INT_MAX)
+        wrong_arguments(std::string("invalid argument for flag `") + flag + "' (expected int): strconv.ParseInt: parsing \"" +
+                        v + "\": " + (errno == ERANGE ? "value out of range" : "invalid syntax"));
+    return (int)x;
+}
+
 int main(int argc, char **argv) {
     transeq::Options opt;
     std::string seq, outseq;
+    bool help = false, version = false;
     auto value = [&](int &i, const char *arg, const char *shortf, const char *longf, std::string &dst) -> bool {
         const size_t ll = std::strlen(longf);
         if (std::strcmp(arg, shortf) == 0 || std::strcmp(arg, longf) == 0) {
-            if (i + 1 >= argc) { std::printf("expected argument for flag `%s'\n", arg); std::exit(1); }
+            if (i + 1 >= argc) wrong_arguments(std::string("expected argument for flag `") + shortf + ", " + longf + "'");
             dst = argv[++i];
             return true;
         }
@@ -52,31 +84,43 @@ int main(int argc, char **argv) {
         std::string v;
         if (value(i, a, "-s", "--sequence", seq) || value(i, a, "-o", "--outseq", outseq) ||
             value(i, a, "-f", "--frame", opt.Frame)) continue;
-        if (value(i, a, "-t", "--table", v)) { opt.Table = std::atoi(v.c_str()); continue; }
-        if (value(i, a, "-n", "--numcpu", v)) { opt.NumWorker = std::atoi(v.c_str()); continue; }
+        if (value(i, a, "-t", "--table", v)) { opt.Table = parse_int(v, "-t, --table"); continue; }
+        if (value(i, a, "-n", "--numcpu", v)) { opt.NumWorker = parse_int(v, "-n, --numcpu"); continue; }
         if (!std::strcmp(a, "-c") || !std::strcmp(a, "--clean")) { opt.Clean = true; continue; }
         if (!std::strcmp(a, "-a") || !std::strcmp(a, "--alternative")) { opt.Alternative = true; continue; }
         if (!std::strcmp(a, "-T") || !std::strcmp(a, "--trim")) { opt.Trim = true; continue; }
-        if (!std::strcmp(a, "-h") || !std::strcmp(a, "--help")) { usage(); return 0; }
-        if (!std::strcmp(a, "-v") || !std::strcmp(a, "--version")) { std::printf("%s (B200) version %s\n", kTool, GTS_VERSION); return 0; }
-        std::printf("unknown flag `%s'\n", a);
-        return 1;
+        if (!std::strcmp(a, "-h") || !std::strcmp(a, "--help")) { help = true; continue; }
+        if (!std::strcmp(a, "-v") || !std::strcmp(a, "--version")) { version = true; continue; }
+        if (a[0] == '-' && a[1] != 0) wrong_arguments(std::string("unknown flag `") + (a + (a[1] == '-' ? 2 : 1)) + "'");
+        // (positional arguments are ignored, as go-flags hands them back unused)
     }
+    if (help) { usage(); return 0; }  // main.go:77-81
+    if (version) { std::printf("%s (B200) version %s\n", kTool, GTS_VERSION); return 0; }
+    if (const char *g = std::getenv("GOTRANSEQ_B200_GPUS")) opt.NumGpus = std::atoi(g);
+    if (const char *c = std::getenv("GOTRANSEQ_B200_CHUNK_MB")) opt.ChunkBytes = (unsigned long long)(std::atof(c) * (1 << 20));
+
+    // run(), main.go:39-65
     std::string err;
     if (seq.empty()) {
         err = std::string("missing required parameter -s | -sequence, try ") + kTool + " --help for details";
     } else if (outseq.empty()) {
         err = std::string("missing required parameter -o | -outseq, try ") + kTool + " --help for details";
     } else {
-        std::ifstream in(seq, std::ios::binary);
-        if (!in) {
-            err = "open " + seq + ": no such file or directory";
+        const int in = ::open(seq.c_str(), O_RDONLY);
+        if (in < 0) {
+            err = "open " + seq + ": " + go_errno(errno);  // (*os.PathError: "open <path>: <errno text>")
         } else {
-            std::ofstream out(outseq, std::ios::binary | std::ios::trunc);
-            if (!out) err = "open " + outseq + ": cannot create";
-            else err = transeq::Translate(in, out, opt);
+            const int out = ::open(outseq.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+            if (out < 0) {
+                err = "open " + outseq + ": " + go_errno(errno);
+            } else {
+                err = transeq::TranslateFd(in, out, opt);
+                ::close(out);
+            }
+            ::close(in);
         }
     }
-    if (!err.empty()) std::printf("%s\n", err.c_str());
+    if (!err.empty()) std::printf("fail to translate file:\n%s", err.c_str());  // main.go:89 (no newline)
+    std::fflush(stdout);
     return 0;
 }

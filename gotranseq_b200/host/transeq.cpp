@@ -2,11 +2,34 @@
 // worker pool / flush loop of transeq/transeq.go:126-163, writer.go:171-181).
 #include "transeq.hpp"
 
+#include <unistd.h>
+
+#include <cerrno>
+#include <cstdio>
+#include <cstring>
+#include <thread>
+#include <vector>
+
 #include "../../include/gotranseq_b200.h"
 
 namespace transeq {
 
-std::string Translate(std::istream &in, std::ostream &out, const Options &o) {
+namespace {
+
+// encodedSequence.go:39: fmt.Printf on stdout, one line per invalid nucleotide
+void print_warning(void *, const uint8_t *header, size_t header_len, uint8_t byte, uint64_t pos) {
+    char small[512];
+    const size_t need = gts_format_warning(header, header_len, byte, pos, small, sizeof(small));
+    if (need <= sizeof(small)) {
+        std::fwrite(small, 1, need, stdout);
+    } else {
+        std::vector<char> big(need);
+        gts_format_warning(header, header_len, byte, pos, big.data(), need);
+        std::fwrite(big.data(), 1, need, stdout);
+    }
+}
+
+gts_ctx *create(const Options &o, std::string *err) {
     gts_options opt{};
     opt.frame = o.Frame.c_str();
     opt.table = o.Table;
@@ -16,9 +39,23 @@ std::string Translate(std::istream &in, std::ostream &out, const Options &o) {
     opt.num_worker = o.NumWorker;
     opt.device = o.Device;
     opt.chunk_bytes = o.ChunkBytes;
+    opt.num_gpus = o.NumGpus < 0 ? -1 : o.NumGpus;
+    for (int i = 0; i < 8; i++) opt.device_ids[i] = i;
     gts_ctx *ctx = nullptr;
-    if (gts_create(&opt, &ctx) != GTS_OK) return gts_last_error(nullptr);
+    if (gts_create(&opt, &ctx) != GTS_OK) {
+        *err = gts_last_error(nullptr);
+        return nullptr;
+    }
+    if (o.Warnings) gts_set_warning_callback(ctx, print_warning, nullptr);
+    return ctx;
+}
+
+}  // namespace
+
+std::string Translate(std::istream &in, std::ostream &out, const Options &o) {
     std::string err;
+    gts_ctx *ctx = create(o, &err);
+    if (!ctx) return err;
     bool eof = false;
     while (!eof && err.empty()) {
         uint8_t *buf = nullptr;
@@ -34,9 +71,64 @@ std::string Translate(std::istream &in, std::ostream &out, const Options &o) {
             if (gts_next_output(ctx, &p, &n) != GTS_OK) { err = gts_last_error(ctx); break; }
             if (n == 0) break;
             out.write(reinterpret_cast<const char *>(p), (std::streamsize)n);
+            if (!out) {
+                // writer.go:171-179: the first failed write cancels the stream and becomes the error
+                gts_report_write_error(ctx, "stream error");
+                gts_next_output(ctx, &p, &n);
+                err = gts_last_error(ctx);
+                break;
+            }
             gts_release_output(ctx);
-            if (!out) { err = "fail to write to output file: stream error"; break; }  // writer.go:175
         }
+    }
+    gts_destroy(ctx);
+    return err;
+}
+
+std::string TranslateFd(int fd_in, int fd_out, const Options &o) {
+    std::string err;
+    gts_ctx *ctx = create(o, &err);
+    if (!ctx) return err;
+    // the writer: every finished chunk, in input order (flush, writer.go:171-181)
+    std::thread writer([&] {
+        while (true) {
+            const uint8_t *p = nullptr;
+            size_t n = 0;
+            if (gts_wait_output(ctx, &p, &n) != GTS_OK || n == 0) return;
+            size_t done = 0;
+            while (done < n) {
+                const ssize_t w = ::write(fd_out, p + done, n - done);
+                if (w < 0) {
+                    if (errno == EINTR) continue;
+                    gts_report_write_error(ctx, std::strerror(errno));
+                    return;
+                }
+                done += (size_t)w;
+            }
+            gts_release_output(ctx);
+        }
+    });
+    // the reader: this thread (readSequenceFromFasta runs on the caller's goroutine, transeq.go:161)
+    bool eof = false;
+    while (!eof) {
+        uint8_t *buf = nullptr;
+        size_t cap = 0;
+        if (gts_acquire_input(ctx, &buf, &cap) != GTS_OK) break;
+        size_t got = 0;
+        while (got < cap) {
+            const ssize_t r = ::read(fd_in, buf + got, cap - got);
+            if (r < 0 && errno == EINTR) continue;
+            if (r <= 0) { eof = true; break; }  // read errors end the stream silently (transeq.go:192-215)
+            got += (size_t)r;
+        }
+        if (gts_submit(ctx, got, eof ? 1 : 0) != GTS_OK) break;
+    }
+    if (!eof) gts_cancel(ctx);  // a failed call: make sure the writer wakes up
+    writer.join();
+    {
+        const uint8_t *p = nullptr;
+        size_t n = 0;
+        if (gts_next_output(ctx, &p, &n) != GTS_OK) err = gts_last_error(ctx);
     }
     gts_destroy(ctx);
     return err;

@@ -5,6 +5,7 @@
              (transeq/transeq.go:114): errors are raised as TranseqError with the reference's texts
 """
 import ctypes
+import sys
 from dataclasses import dataclass
 
 from . import _lib
@@ -37,12 +38,22 @@ class Options:
 class Translator:
     """One gts_ctx: a decoded option set plus its device scratch.  Not thread safe."""
 
-    def __init__(self, options=None, device=-1, chunk_bytes=0, **kw):
+    def __init__(self, options=None, device=-1, chunk_bytes=0, devices=None, warnings=None, **kw):
+        """devices: None = one GPU (`device`); "all" = every visible GPU; a list of ordinals = those GPUs
+        (record-aligned chunks are dealt to them in turn, results come back in input order).
+        warnings: a callable(bytes) receiving each WARNING line of encodedSequence.go:39 exactly as the
+        reference prints it to stdout (None = invalid nucleotides are not reported)."""
         if options is None:
             options = Options(**kw)
         self.options = options
         L = _lib.lib()
         o = _lib.gts_options()
+        if devices == "all":
+            o.num_gpus = -1
+        elif devices:
+            o.num_gpus = len(devices)
+            for i, d in enumerate(devices):
+                o.device_ids[i] = int(d)
         self._frame = options.Frame.encode()
         o.frame = self._frame
         o.table = int(options.Table)
@@ -58,6 +69,33 @@ class Translator:
             raise TranseqError(rc, L.gts_last_error(None).decode())
         self._h = h
         self._L = L
+        self._warn_cb = None
+        if warnings is not None:
+            self.set_warning_sink(warnings)
+
+    def set_warning_sink(self, sink):
+        """sink(bytes) is called with each WARNING line (formatted by gts_format_warning), in input order."""
+        L = self._L
+
+        def cb(_user, header, header_len, byte, pos):
+            need = L.gts_format_warning(header, header_len, byte, pos, None, 0)
+            buf = ctypes.create_string_buffer(need)
+            L.gts_format_warning(header, header_len, byte, pos, buf, need)
+            sink(buf.raw[:need])
+
+        self._warn_cb = _lib.gts_warning_fn(cb) if sink is not None else ctypes.cast(None, _lib.gts_warning_fn)
+        self._check(L.gts_set_warning_callback(self._h, self._warn_cb, None))
+
+    def num_devices(self):
+        return self._L.gts_num_devices(self._h)
+
+    def cancel(self):
+        """transeq.go:130: stop the stream from any thread; blocked calls raise TranseqError(GTS_ERR_CANCELLED)."""
+        self._check(self._L.gts_cancel(self._h))
+
+    def reset(self):
+        """Drop whatever is queued and clear the stream's error: ready for a new stream."""
+        self._check(self._L.gts_stream_reset(self._h))
 
     def close(self):
         if getattr(self, "_h", None):
@@ -199,32 +237,44 @@ class Translator:
         obuf = ctypes.c_void_p()
         on = ctypes.c_size_t()
         eof = False
-        while not eof:
-            self._check(L.gts_acquire_input(h, ctypes.byref(buf), ctypes.byref(cap)))
-            view = (ctypes.c_char * cap.value).from_address(buf.value)
-            got = reader.readinto(view) if hasattr(reader, "readinto") else None
-            if got is None:
-                chunk = reader.read(cap.value)
-                got = len(chunk)
-                ctypes.memmove(buf.value, chunk, got)
-            eof = got == 0
-            self._check(L.gts_submit(h, got, 1 if eof else 0))
-            while True:
-                self._check(L.gts_next_output(h, ctypes.byref(obuf), ctypes.byref(on)))
-                if on.value == 0:
-                    break
-                try:
-                    writer.write(_bytes_at(obuf.value, on.value))
-                except Exception as e:  # writer.go:175
-                    L.gts_release_output(h)
-                    raise TranseqError(_lib.GTS_ERR_WRITE, f"fail to write to output file: {e}") from e
-                self._check(L.gts_release_output(h))
+        try:
+            while not eof:
+                self._check(L.gts_acquire_input(h, ctypes.byref(buf), ctypes.byref(cap)))
+                view = (ctypes.c_char * cap.value).from_address(buf.value)
+                got = reader.readinto(view) if hasattr(reader, "readinto") else None
+                if got is None:
+                    chunk = reader.read(cap.value)
+                    got = len(chunk)
+                    ctypes.memmove(buf.value, chunk, got)
+                eof = got == 0
+                self._check(L.gts_submit(h, got, 1 if eof else 0))
+                while True:
+                    self._check(L.gts_next_output(h, ctypes.byref(obuf), ctypes.byref(on)))
+                    if on.value == 0:
+                        break
+                    try:
+                        writer.write(_bytes_at(obuf.value, on.value))
+                    except Exception as e:
+                        # writer.go:171-179: the first failed write becomes the error of Translate and
+                        # cancels everything that is still queued
+                        L.gts_report_write_error(h, str(e).encode())
+                        self._check(L.gts_next_output(h, ctypes.byref(obuf), ctypes.byref(on)))  # raises GTS_ERR_WRITE
+                    self._check(L.gts_release_output(h))
+        except TranseqError:
+            L.gts_stream_reset(h)  # the context stays usable (a Go caller gets the error and a clean shim)
+            raise
 
 
-def Translate(inputSequence, out, options):
+def _stdout_sink(line):
+    sys.stdout.buffer.write(line)
+
+
+def Translate(inputSequence, out, options, devices="all", warnings=_stdout_sink, **kw):
     """transeq.Translate (transeq/transeq.go:114): read FASTA from `inputSequence`, write the
-    protein FASTA to `out`.  Raises TranseqError instead of returning an error."""
-    with Translator(options) as t:
+    protein FASTA to `out`; WARNING lines for invalid nucleotides go to stdout like the reference's
+    (encodedSequence.go:39).  Raises TranseqError instead of returning an error.  Uses every visible
+    GPU (the reference uses Options.NumWorker goroutines; here NumWorker is ignored)."""
+    with Translator(options, devices=devices, warnings=warnings, **kw) as t:
         t.translate_stream(inputSequence, out)
 
 

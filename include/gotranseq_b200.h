@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define GTS_VERSION "0.1.0"
+#define GTS_VERSION "0.2.0"
 
 /* Return codes. 0 = success; the text for the last failure is gts_last_error(). */
 enum {
@@ -32,7 +32,8 @@ enum {
     GTS_ERR_NOMEM = -4,    /* host or device allocation failed                                  */
     GTS_ERR_CAPACITY = -5, /* caller-provided output buffer too small; needed size reported     */
     GTS_ERR_ARG = -6,      /* NULL / misaligned / out-of-range argument, wrong call order       */
-    GTS_ERR_WRITE = -7     /* "fail to write to output file: %v"             (writer.go:175)    */
+    GTS_ERR_WRITE = -7,    /* "fail to write to output file: %v"             (writer.go:175)    */
+    GTS_ERR_CANCELLED = -8 /* gts_cancel was called (the reference's ctx cancel, transeq.go:130) */
 };
 
 /*
@@ -50,6 +51,16 @@ typedef struct gts_options {
     int32_t num_worker;   /* Options.NumWorker: ignored                                       */
     int32_t device;       /* CUDA device ordinal; -1 = the calling thread's current device    */
     uint64_t chunk_bytes; /* streaming chunk size (bytes of FASTA per GPU pass); 0 = default  */
+    /* Record sharding over the GPUs of one box (replaces the worker pool of transeq.go:132-160:
+     * record-aligned chunks of the byte stream are dealt to the GPUs in turn, every GPU runs its own
+     * H2D / kernels / D2H pipeline, results are handed back strictly in input order; no collective).
+     *   num_gpus == 0   one GPU: `device`
+     *   num_gpus  > 0   device_ids[0 .. num_gpus)
+     *   num_gpus  < 0   every visible GPU
+     * The device-resident and gts_piece_* entry points use the first device only. */
+    int32_t num_gpus;
+    int32_t device_ids[8];
+    int32_t reserved1;
 } gts_options;
 
 typedef struct gts_ctx gts_ctx;
@@ -111,7 +122,10 @@ size_t gts_output_bound_hint(const gts_ctx *ctx, size_t n);
 /*
  * One-shot host call: host FASTA bytes in, host protein-FASTA bytes out (H2D, kernels, D2H).
  * *out points into a pinned buffer owned by ctx, valid until the next call on ctx.
- * The input is one complete FASTA (start of file to EOF).
+ * The input is one complete FASTA (start of file to EOF).  It runs on the same chunk pipeline as
+ * the streaming interface (record-aligned chunks dealt to the context's GPUs, H2D / kernels / D2H
+ * of different chunks overlapped), with the chunks read straight from `in` (fastest when `in` is
+ * pinned, gts_host_alloc) and copied back straight to their final place in *out.
  */
 int gts_translate_buffer(gts_ctx *ctx, const uint8_t *in, size_t n, const uint8_t **out,
                          size_t *out_n);
@@ -136,14 +150,57 @@ int gts_translate_buffer(gts_ctx *ctx, const uint8_t *in, size_t n, const uint8_
  * the next chunk into the other pinned input buffer and writes the previous result, so reading,
  * translating and writing overlap.  Before eof gts_next_output does not block: n == 0 means
  * "nothing finished yet, go on reading".  After gts_submit(..., eof=1) it waits for each remaining
- * result; n == 0 then means "done" (and ctx is ready for another stream).  At most two results wait
- * for the caller: drain gts_next_output after every gts_submit, as in the loop above.  The other
- * entry points of ctx must not be called while a stream is in progress.
+ * result; n == 0 then means "done" (and ctx is ready for another stream).  Drain gts_next_output
+ * after every gts_submit, as in the loop above (the library keeps a bounded number of chunks in
+ * flight: three per GPU).  The other entry points of ctx must not be called while a stream is in
+ * progress.  With several GPUs (gts_options.num_gpus) the chunks are dealt to them in turn.
  */
 int gts_acquire_input(gts_ctx *ctx, uint8_t **buf, size_t *cap);
 int gts_submit(gts_ctx *ctx, size_t nbytes, int eof);
 int gts_next_output(gts_ctx *ctx, const uint8_t **buf, size_t *n);
 int gts_release_output(gts_ctx *ctx);
+/* gts_next_output that always waits: for a writer thread of its own (one thread may drive
+ * gts_acquire_input / gts_submit while another drives gts_wait_output / gts_release_output).
+ * n == 0: the stream has ended and everything was handed out. */
+int gts_wait_output(gts_ctx *ctx, const uint8_t **buf, size_t *n);
+
+/*
+ * Cancellation and write errors (transeq.go:126-131,145-149,163-172; writer.go:171-179).  In the
+ * reference the first failed out.Write puts "fail to write to output file: %v" on the error
+ * channel and cancels the context; the reader and the other workers stop, Translate returns that
+ * error.  Here:
+ *   gts_report_write_error  the caller's write failed: every further call on the stream returns
+ *                           GTS_ERR_WRITE and gts_last_error() is "fail to write to output file: <msg>"
+ *   gts_cancel              stop the stream (safe from any thread): queued chunks are dropped,
+ *                           blocked calls return GTS_ERR_CANCELLED
+ *   gts_stream_reset        wait for the GPUs to go idle, drop everything queued, clear the error:
+ *                           the context is ready for a new stream (also needed after any other
+ *                           stream error)
+ */
+int gts_report_write_error(gts_ctx *ctx, const char *msg);
+int gts_cancel(gts_ctx *ctx);
+int gts_stream_reset(gts_ctx *ctx);
+
+/* GPUs the context deals chunks to. */
+int gts_num_devices(const gts_ctx *ctx);
+
+/*
+ * WARNING side channel (encodedSequence.go:36-40): the reference prints one line per nucleotide
+ * that is none of ACGTUN (either case) and translates it as N.  With a callback installed the
+ * kernels record those bytes and the library reports them in input order, on the caller's thread,
+ * from gts_next_output / gts_wait_output / gts_translate_buffer before the chunk's output is handed
+ * over.  header = the record's header line (without the line break; header_len == 0 for sequence
+ * bytes in front of the first header line), pos = index of the nucleotide in its record.
+ * gts_format_warning writes exactly the bytes the reference prints to stdout --
+ *   "WARNING: invalid char in sequence %s: '%s' ( pos %d), replacing with 'N'\n"
+ * where the first %s is s[:headerSize]: the four raw little-endian bytes of header_len + 4 followed
+ * by the header line, and the second is Go's string(byte): the UTF-8 encoding of that code point --
+ * into dst (capacity cap) and returns the length needed.  The device-resident entry points do not
+ * report warnings.
+ */
+typedef void (*gts_warning_fn)(void *user, const uint8_t *header, size_t header_len, uint8_t byte, uint64_t pos);
+int gts_set_warning_callback(gts_ctx *ctx, gts_warning_fn fn, void *user);
+size_t gts_format_warning(const uint8_t *header, size_t header_len, uint8_t byte, uint64_t pos, char *dst, size_t cap);
 
 /* Counters of the last device pass / since creation (diagnostics and bench accounting). */
 typedef struct gts_stats {

@@ -47,6 +47,12 @@ def lib():
             ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t),
             ctypes.POINTER(ctypes.c_uint64), ctypes.c_char_p, ctypes.c_size_t,
         ]
+        L.to_translate_warn.restype = ctypes.c_int
+        L.to_translate_warn.argtypes = [
+            ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(_Options),
+            ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t),
+            ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t), ctypes.c_char_p, ctypes.c_size_t,
+        ]
         L.to_free.argtypes = [ctypes.c_void_p]
         L.to_free.restype = None
         L.to_set_max_line_length.argtypes = [ctypes.c_size_t]
@@ -91,6 +97,31 @@ def translate(data, frame="1", table=0, clean=False, alternative=False, trim=Fal
     finally:
         L.to_free(out)
     return (res, warns.value) if return_warnings else res
+
+
+def translate_with_warnings(data, frame="1", table=0, clean=False, alternative=False, trim=False):
+    """(protein FASTA, stdout text of the WARNING lines) -- encodedSequence.go:39, num_worker 1."""
+    L = lib()
+    data = bytes(data)
+    n = len(data)
+    buf = (ctypes.c_char * max(n, 1)).from_buffer_copy(data if n else b"\0")
+    opt = _Options(frame.encode(), int(table), int(clean), int(alternative), int(trim), 1)
+    out, wout = ctypes.c_void_p(), ctypes.c_void_p()
+    out_n, w_n = ctypes.c_size_t(), ctypes.c_size_t()
+    err = ctypes.create_string_buffer(256)
+    rc = L.to_translate_warn(ctypes.cast(buf, ctypes.c_void_p), n, ctypes.byref(opt), ctypes.byref(out),
+                             ctypes.byref(out_n), ctypes.byref(wout), ctypes.byref(w_n), err, 256)
+    if rc != 0:
+        if wout.value:
+            L.to_free(wout)
+        raise OracleError(err.value.decode())
+    try:
+        res = bytes((ctypes.c_char * out_n.value).from_address(out.value)) if out_n.value else b""
+        wtxt = bytes((ctypes.c_char * w_n.value).from_address(wout.value)) if w_n.value else b""
+    finally:
+        L.to_free(out)
+        L.to_free(wout)
+    return res, wtxt
 
 
 def set_max_line_length(n):

@@ -171,6 +171,27 @@ static inline size_t seq_header_size(const enc_seq *e) {
 static inline size_t seq_nucl_size(const enc_seq *e) { return e->len - seq_header_size(e); }
 
 /* transeq/encodedSequence.go:17-43 newEncodedSequence */
+/* Optional capture of the reference's WARNING lines (encodedSequence.go:39), byte for byte what
+ * fmt.Printf writes to stdout: "%s" of s[:headerSize] is the 4 raw little-endian length bytes
+ * followed by the header line, and string(n) of a byte is the UTF-8 encoding of the rune n. */
+static bytes *g_warn_sink = NULL;
+
+static void warn_line(const enc_seq *e, size_t header_size, uint8_t n, size_t i) {
+    static const char a[] = "WARNING: invalid char in sequence ";
+    char tail[64];
+    bytes_append(g_warn_sink, (const uint8_t *)a, sizeof(a) - 1);
+    bytes_append(g_warn_sink, e->s, header_size);
+    bytes_append(g_warn_sink, (const uint8_t *)": '", 3);
+    if (n < 0x80) {
+        bytes_push(g_warn_sink, n);
+    } else {
+        bytes_push(g_warn_sink, (uint8_t)(0xC0 | (n >> 6)));
+        bytes_push(g_warn_sink, (uint8_t)(0x80 | (n & 0x3F)));
+    }
+    int m = snprintf(tail, sizeof(tail), "' ( pos %zu), replacing with 'N'\n", i);
+    bytes_append(g_warn_sink, (const uint8_t *)tail, (size_t)m);
+}
+
 static enc_seq new_encoded_sequence(const bytes *buf, size_t header_size, uint64_t *warnings) {
     enc_seq e;
     e.len = 4 + buf->len;
@@ -187,6 +208,7 @@ static enc_seq new_encoded_sequence(const bytes *buf, size_t header_size, uint64
         case 'T': case 'U': case 't': case 'u': e.s[i] = T_CODE; break;
         case 'N': case 'n': e.s[i] = N_CODE; break;
         default:
+            if (g_warn_sink) warn_line(&e, header_size, e.s[i], i - header_size);
             e.s[i] = N_CODE;
             (*warnings)++; /* the reference prints a WARNING line here (encodedSequence.go:39) */
         }
@@ -458,6 +480,20 @@ int to_translate(const uint8_t *in, size_t n, const to_options *opt, uint8_t **o
     *out = sink.out.p ? sink.out.p : (uint8_t *)malloc(1);
     *out_n = sink.out.len;
     return 0;
+}
+
+/* to_translate plus the text of the WARNING lines (the reader goroutine prints them in input
+ * order, encodedSequence.go:39).  Not reentrant: one call at a time. */
+int to_translate_warn(const uint8_t *in, size_t n, const to_options *opt, uint8_t **out, size_t *out_n,
+                      uint8_t **warn_text, size_t *warn_n, char *err, size_t errcap) {
+    bytes sink = {0, 0, 0};
+    uint64_t count = 0;
+    g_warn_sink = &sink;
+    int rc = to_translate(in, n, opt, out, out_n, &count, err, errcap);
+    g_warn_sink = NULL;
+    *warn_text = sink.p ? sink.p : (uint8_t *)malloc(1);
+    *warn_n = sink.len;
+    return rc;
 }
 
 void to_free(void *p) { free(p); }

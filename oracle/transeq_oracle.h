@@ -55,6 +55,13 @@ int to_translate(const uint8_t *in, size_t n, const to_options *opt,
                  uint8_t **out, size_t *out_n, uint64_t *n_warnings,
                  char *err, size_t errcap);
 
+/* As to_translate, and *warn_text (malloc'ed) receives the bytes the reference would have printed
+ * to stdout: one "WARNING: invalid char in sequence %s: '%s' ( pos %d), replacing with 'N'\n"
+ * line per invalid nucleotide, in input order (encodedSequence.go:39; the first %s is the 4 raw
+ * little-endian bytes of header length + 4 followed by the header line). */
+int to_translate_warn(const uint8_t *in, size_t n, const to_options *opt, uint8_t **out, size_t *out_n,
+                      uint8_t **warn_text, size_t *warn_n, char *err, size_t errcap);
+
 void to_free(void *p);
 
 /* Test hook: override the bufio.Scanner max token size (transeq.go:27,186; default 100 MiB). */
