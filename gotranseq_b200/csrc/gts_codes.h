@@ -5,8 +5,8 @@
 // standard map code.go:16-81 overlaid with the per-table diff, U read as T), in T,C,A,G
 // codon order (index = 16*b0 + 4*b1 + b2).  They reproduce the reference as coded, which is
 // the parity target (e.g. its table 11 equals the standard code and its table 23 differs
-// from it only by TTA -> '*').  tests/test_codes.py re-derives them from the reference
-// checkout when it is present and from the oracle's independent diff lists otherwise.
+// from it only by TTA -> '*').  tests/test_abi.py checks all 21 against tests/golden/ncbi_tables.json,
+// derived from the reference's ncbicode/code.go by tests/golden/make_ncbi_tables.py.
 #pragma once
 #include <cstdint>
 #include <cstring>

@@ -114,7 +114,7 @@ int main(int argc, char **argv) {
             if (out < 0) {
                 err = "open " + outseq + ": " + go_errno(errno);
             } else {
-                err = transeq::TranslateFd(in, out, opt);
+                err = transeq::TranslateFd(in, out, opt, outseq.c_str());
                 ::close(out);
             }
             ::close(in);

@@ -85,7 +85,7 @@ std::string Translate(std::istream &in, std::ostream &out, const Options &o) {
     return err;
 }
 
-std::string TranslateFd(int fd_in, int fd_out, const Options &o) {
+std::string TranslateFd(int fd_in, int fd_out, const Options &o, const char *out_path) {
     std::string err;
     gts_ctx *ctx = create(o, &err);
     if (!ctx) return err;
@@ -100,7 +100,10 @@ std::string TranslateFd(int fd_in, int fd_out, const Options &o) {
                 const ssize_t w = ::write(fd_out, p + done, n - done);
                 if (w < 0) {
                     if (errno == EINTR) continue;
-                    gts_report_write_error(ctx, std::strerror(errno));
+                    // (*os.File).Write returns a *PathError: "write <path>: <errno text, lower case>"
+                    std::string m = std::strerror(errno);
+                    if (!m.empty() && m[0] >= 'A' && m[0] <= 'Z') m[0] = (char)(m[0] - 'A' + 'a');
+                    gts_report_write_error(ctx, (std::string("write ") + out_path + ": " + m).c_str());
                     return;
                 }
                 done += (size_t)w;

@@ -31,6 +31,6 @@ struct Options {
 };
 
 std::string Translate(std::istream &inputSequence, std::ostream &out, const Options &options);
-std::string TranslateFd(int fd_in, int fd_out, const Options &options);
+std::string TranslateFd(int fd_in, int fd_out, const Options &options, const char *out_path = "");
 
 }  // namespace transeq

@@ -35,4 +35,14 @@ def translate_shard(buf, rank, world, translate):
     lo, hi = shard_ranges(buf, world)[rank]
     if hi == lo and not (rank == 0 and len(buf) == 0):
         return b""
+    if hi < len(buf) and _blank_only(buf[lo:hi]):
+        return b""  # (only shard 0 can be blank: the others start with a header line)
     return translate(buf[lo:hi])
+
+
+def _blank_only(part):
+    """True if every line of `part` is empty after bufio.ScanLines dropped one trailing CR
+    (transeq.go:195-197 skips such lines): alone it would be an input that is empty altogether."""
+    if part.strip(b"\r\n"):
+        return False
+    return all(line in (b"", b"\r") for line in part.split(b"\n"))

@@ -73,17 +73,30 @@ def test_fused_lut_matches_the_reference_code_array():
                         assert (v >> 8) == ca[comp(c2) | comp(c1) << 8 | comp(c0) << 16]
 
 
-def test_reference_tables_if_checkout_present():
-    """Re-derive the effective codon maps from the reference's own source when it is mounted."""
+def test_all_codon_tables_match_the_reference_source():
+    """All 21 effective codon maps (standard + every diff, U read as T) as derived from the reference's
+    ncbicode/code.go by tests/golden/make_ncbi_tables.py: the library's tables and the oracle's
+    independent transcription must both equal them.  When the checkout is mounted the fixture itself
+    is re-derived and compared, so it cannot go stale."""
+    import json
+    from gotranseq_b200 import _lib
+    from fasta_gen import ALL_TABLES
+    L = _lib.lib()
+    with open(os.path.join(ROOT, "tests", "golden", "ncbi_tables.json")) as f:
+        fixture = json.load(f)
+    assert sorted(int(k) for k in fixture) == sorted(ALL_TABLES) and len(fixture) == 21
+    for t in ALL_TABLES:
+        buf = ctypes.create_string_buffer(64)
+        assert L.gts_codon_table(t, buf) == 0
+        assert buf.raw.decode() == fixture[str(t)], t
+        assert oracle.table_code(t) == fixture[str(t)], t
     path = "/root/reference/ncbicode/code.go"
-    if not os.path.exists(path):
-        pytest.skip("reference checkout not present")
-    src = open(path).read()
-    std = dict(re.findall(r'"([ACGT]{3})":\s*\'(.)\'', src[src.index("standard = map"):src.index("}", src.index("standard = map"))]))
-    assert len(std) == 64
-    order = "TCAG"
-    aa = "".join(std[a + b + c] for a in order for b in order for c in order)
-    assert aa == oracle.table_code(0)
+    if os.path.exists(path):
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("make_ncbi_tables", os.path.join(ROOT, "tests", "golden", "make_ncbi_tables.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        assert mod.parse(open(path).read()) == fixture
 
 
 def test_no_gpu_fails_loudly():
@@ -119,6 +132,19 @@ def test_cli_reports_option_errors_like_the_reference(tmp_path):
                         (["-f", "6", "-t", "1"], "invalid table code: 1")):
         r = subprocess.run([exe, "-s", str(src), "-o", str(tmp_path / "o.faa")] + flags, capture_output=True, text=True)
         assert text in r.stdout + r.stderr, (flags, r.stdout, r.stderr)
+    # main.go:74: flag errors -> "wrong arguments: ..., try gotranseq --help for more informations", exit 1
+    r = subprocess.run([exe, "-s", str(src), "-o", str(tmp_path / "o.faa"), "-t", "abc"], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stdout.startswith("wrong arguments: ") and \
+        r.stdout.endswith(", try gotranseq --help for more informations\n")
+    r = subprocess.run([exe, "--nosuchflag"], capture_output=True, text=True)
+    assert r.returncode == 1 and "unknown flag `nosuchflag'" in r.stdout
+    # main.go:89: run errors -> "fail to translate file:\n%v" (no trailing newline), exit 0
+    r = subprocess.run([exe, "-s", str(src), "-o", str(tmp_path / "o.faa"), "-f", "7"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout == "fail to translate file:\nwrong value for -f | --frame parameter: 7"
+    r = subprocess.run([exe, "-o", str(tmp_path / "o.faa")], capture_output=True, text=True)
+    assert r.stdout == "fail to translate file:\nmissing required parameter -s | -sequence, try gotranseq --help for details"
+    r = subprocess.run([exe, "-s", str(tmp_path / "absent.fna"), "-o", str(tmp_path / "o.faa")], capture_output=True, text=True)
+    assert r.stdout == "fail to translate file:\nopen %s: no such file or directory" % (tmp_path / "absent.fna")
     r = subprocess.run([exe, "--help"], capture_output=True, text=True)
     for flag in ("--sequence", "--outseq", "--frame", "--table", "--clean", "--alternative", "--trim", "--numcpu"):
         assert flag in r.stdout + r.stderr, flag
