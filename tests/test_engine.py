@@ -109,7 +109,7 @@ def test_many_chunks_through_the_stream():
         out = io.BytesIO()
         t.translate_stream(io.BytesIO(data), out)
         assert out.getvalue() == want
-        assert t.stats()["passes"] > 1000
+        assert t.stats()["passes"] > 150
 
 
 def _warning_cases(goldens):
