@@ -33,6 +33,14 @@ __device__ __forceinline__ u32 prmt(u32 a, u32 b, u32 sel) {
     return r;
 }
 
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization
+// attribute may start while its predecessor in the stream is still running; it must not touch the
+// predecessor's results before pdl_wait() (which returns once that grid has completed and its
+// writes are visible).  pdl_launch() lets the successor's CTAs be scheduled early.  Both are
+// no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 #ifdef GTS_PHASE_TIMING
 __device__ __forceinline__ u64 gtime() {
     u64 t;
@@ -67,6 +75,10 @@ __device__ __forceinline__ u32 gather_flags16(u32 f0, u32 f1, u32 f2, u32 f3) { 
 }
 __device__ __forceinline__ u32 newline_mask16(uint4 v) {
     return gather_flags16(newline_flags(v.x), newline_flags(v.y), newline_flags(v.z), newline_flags(v.w));
+}
+// 0x80 in every byte of x that equals c (c replicated into the four bytes of c4)
+__device__ __forceinline__ u32 byte_eq_flags(u32 x, u32 c4) {
+    return __vabsdiffu4(__vabsdiffu4(x, c4), 0x80808080u) & 0x80808080u;
 }
 // 0x80 in every byte of x that is 'N' or 'n'
 __device__ __forceinline__ u32 n_flags(u32 x) {

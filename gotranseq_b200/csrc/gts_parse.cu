@@ -4,12 +4,17 @@
 //   readSequenceFromFasta  transeq/transeq.go:183-216 with bufio.ScanLines semantics (lines end at
 //                          '\n', one trailing '\r' is dropped, empty lines are skipped, a line whose
 //                          first byte is '>' starts a record)
-//   newEncodedSequence     transeq/encodedSequence.go:17-43 (A/a 1, C/c 2, T/t/U/u 3, G/g 4, else 0)
+//   newEncodedSequence     transeq/encodedSequence.go:17-43 (A/a 1, C/c 2, T/t/U/u 3, G/g 4, else 0;
+//                          anything that is not ACGTUN is also reported: the WARNING line of :39)
 // tests/gpu_model.py parse() is the executable specification of the line rules used here.
 //
-// Every tile is independent: its symbols are compacted inside its own slot, the header lines it
-// finds are appended to an unordered event list, and the stream offsets are assigned afterwards by
-// k_tile_scan / k_records.
+// One WARP per tile of 8 KB: it walks the tile's eight rows of 1 KB (32 lanes x 32 bytes) in order
+// and carries the line state (at a line start / inside a header line / inside a sequence line) and
+// the running symbol count from row to row in registers.  Nothing is exchanged between warps: no
+// CTA barrier, no scan across warps, and the backward search for the line a tile starts in runs
+// once per tile.  Every tile is independent of every other tile: its symbols are compacted inside
+// its own slot, the header lines it finds are appended to an unordered event list, and the stream
+// offsets are assigned afterwards by k_tile_scan / k_records.
 #include "gts_common.cuh"
 #include "gts_kernels.h"
 
@@ -21,13 +26,19 @@ namespace gts {
 
 enum { LS = 0, SEQ = 1, HDR = 2 };
 
+constexpr int kParseWarps = 4;                          // tiles per CTA, one warp each
+constexpr int kRowBytes = 32 * kParseBytesPerThread;    // 1 KB per row
+constexpr int kRows = kParseTile / kRowBytes;           // 8 rows per tile
+constexpr int kSymBuf = 16 + kRowBytes + 64 + 48;       // carried symbols + a row's symbols + zero tail
+static_assert(kSymBuf % 16 == 0, "row buffers stay 16-byte aligned");
+
+struct WarpShared {
+    alignas(16) uint8_t raw[kRowBytes];  // the row's raw bytes
+    alignas(16) uint8_t sym[kSymBuf];    // symbols not yet packed, one per byte: [0, carry) from the rows before
+};
 struct ParseShared {
-    alignas(16) uint8_t raw[kParseTile];
-    alignas(16) uint8_t sym[kSlotSyms + 32];  // the tile's symbols, one per byte (+ zero tail)
+    WarpShared w[kParseWarps];
     uint8_t enc[256];
-    u32 warp_sum[kParseThreads / 32];
-    u32 warp_nl[kParseThreads / 32];  // first newline << 16 | last newline + 1 of each warp (tile relative)
-    volatile u32 ev_base;  // first slot of the tile's header events, ~0u until allocated
 };
 
 // Symbols and header lines of one 32-byte chunk (scalar walk over its lines; used for the chunks
@@ -95,384 +106,418 @@ __device__ __forceinline__ void remove_byte(u32 (&C)[9], int p) {
     }
 }
 
-__global__ void __launch_bounds__(kParseThreads, GTS_PARSE_CTAS) k_parse(const __grid_constant__ Job job) {
+// The line the byte at `base` (0 < base < n, a multiple of 16) lies in: is `base` its first byte,
+// and if not, is it a header line?  Backward search for the previous '\n' in windows of 512 bytes,
+// all 32 lanes; the results are uniform over the warp.
+__device__ __forceinline__ void line_state_at(const Job &job, u64 base, int lane, bool &at_start, bool &in_hdr) {
+    at_start = false;
+    in_hdr = false;
+    u64 hi = base;
+    while (true) {
+        const i64 st = (i64)hi - 16 * (lane + 1);
+        u32 m16 = 0;
+        if (st >= 0) m16 = newline_mask16(__ldg(reinterpret_cast<const uint4 *>(job.in + st)));
+        const unsigned b = __ballot_sync(0xFFFFFFFFu, m16 != 0);
+        if (b) {
+            const int l = __ffs(b) - 1;  // the lane holding the closest newline
+            const u32 mm = __shfl_sync(0xFFFFFFFFu, m16, l);
+            const int o = 31 - __clz(mm);  // its offset in that lane's 16 bytes
+            const u64 ls = hi - 16ull * (l + 1) + o + 1;  // first byte of the line
+            if (ls == base) at_start = true;
+            else in_hdr = job.in[ls] == '>';  // (uniform address: one load, broadcast)
+            return;
+        }
+        if (hi <= 512) {  // the line starts at the beginning of the input
+            in_hdr = job.in[0] == '>';
+            return;
+        }
+        hi -= 512;
+    }
+}
+
+__global__ void __launch_bounds__(kParseWarps * 32, GTS_PARSE_CTAS) k_parse(const __grid_constant__ Job job) {
     __shared__ ParseShared sh;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-#ifdef GTS_PHASE_TIMING
-    u64 tprev = gtime();
-#endif
-    {
+#pragma unroll
+    for (int k = 0; k < 256 / (kParseWarps * 32); k++) {
+        const int b = tid + k * kParseWarps * 32;
         uint8_t c = 0;
-        switch (tid) {
+        switch (b) {
             case 'A': case 'a': c = 1; break;
             case 'C': case 'c': c = 2; break;
             case 'T': case 't': case 'U': case 'u': c = 3; break;
             case 'G': case 'g': c = 4; break;
         }
-        sh.enc[tid] = c;
-        if (tid == 0) sh.ev_base = ~0u;
+        sh.enc[b] = c;
     }
-    const u32 t = blockIdx.x;
+    __syncthreads();  // the only CTA-wide barrier: the table of the slow path
+    pdl_launch();     // k_tile_scan's CTAs may be scheduled while the parse drains
+    const u32 t = blockIdx.x * kParseWarps + warp;
+    if (t >= job.ntiles) return;
+    WarpShared &ws = sh.w[warp];
+    const u64 n = job.n;
     const u64 tile_base = (u64)t * kParseTile;
-    const u64 warp_base = tile_base + (u64)warp * 1024u;
-    const u64 pos0 = warp_base + (u64)lane * kParseBytesPerThread;
-    const int len = pos0 >= job.n ? 0 : (job.n - pos0 < 32 ? (int)(job.n - pos0) : 32);
+    const unsigned lt = (1u << lane) - 1u;
 
-    // ---- load the chunk, keep a copy of the tile in shared memory ----
-    uint4 v0 = make_uint4(0, 0, 0, 0), v1 = make_uint4(0, 0, 0, 0);
-    if (len == 32) {
-        const uint4 *p = reinterpret_cast<const uint4 *>(job.in + pos0);
-        v0 = __ldg(p);
-        v1 = __ldg(p + 1);
-    } else if (len > 0) {
-        u32 w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int i = 0; i < len; i++) w[i >> 2] |= (u32)job.in[pos0 + i] << (8 * (i & 3));
-        v0 = make_uint4(w[0], w[1], w[2], w[3]);
-        v1 = make_uint4(w[4], w[5], w[6], w[7]);
-    }
-    // the 512 bytes before the warp's first byte, for the line the warp starts in
-    uint4 vb = make_uint4(0, 0, 0, 0);
-    const i64 back_start = (i64)warp_base - 16 * (lane + 1);
-    const bool back_ok = warp_base < job.n && back_start >= 0;
-    if (back_ok) vb = __ldg(reinterpret_cast<const uint4 *>(job.in + back_start));
+    // ---- the line the tile starts in ----
+    bool row_ls = true, row_in_hdr = false;  // uniform: the row's first byte starts a line / continues a header line
+    if (tile_base > 0 && tile_base < n) line_state_at(job, tile_base, lane, row_ls, row_in_hdr);
 
-    uint8_t *raw = sh.raw + tid * kParseBytesPerThread;
-    reinterpret_cast<uint4 *>(raw)[0] = v0;
-    reinterpret_cast<uint4 *>(raw)[1] = v1;
-    u32 nlmask = newline_mask16(v0) | newline_mask16(v1) << 16;
-    if (len < 32) nlmask &= len ? ((1u << len) - 1u) : 0u;
-
-    // ---- start of the line each chunk begins in, and the class of that line ----
-    // before the warp's first byte: backward search for the previous '\n' (first in the 512 bytes
-    // already loaded, then further back); `warp_first` is the first byte of that line
-    u64 warp_ls = 0;
-    uint8_t warp_first = 0;
-    if (warp_base < job.n && warp_base > 0) {
-        u32 m16 = back_ok ? newline_mask16(vb) : 0u;
-        u64 hi = warp_base;
-        uint4 vv = vb;
-        while (true) {
-            const unsigned b = __ballot_sync(0xFFFFFFFFu, m16 != 0);
-            if (b) {
-                const int l = __ffs(b) - 1;
-                const u32 mm = __shfl_sync(0xFFFFFFFFu, m16, l);
-                const int o = 31 - __clz(mm);  // offset of the newline in lane l's 16 bytes
-                warp_ls = hi - 16ull * (l + 1) + o + 1;
-                // the byte after it: in lane l's vector, or the first byte of lane l-1's
-                const int ol = o + 1;
-                const int src = ol < 16 ? l : l - 1;
-                const int oo = ol & 15;
-                const u32 wsel = (oo >> 2) == 0 ? vv.x : (oo >> 2) == 1 ? vv.y : (oo >> 2) == 2 ? vv.z : vv.w;
-                const u32 byte = (wsel >> (8 * (oo & 3))) & 0xFFu;
-                if (src >= 0) warp_first = (uint8_t)__shfl_sync(0xFFFFFFFFu, byte, src);
-                break;  // src < 0: the line starts at hi (== warp_base in the first round): not used
-            }
-            if (hi <= 512) {  // the line starts at the beginning of the input
-                warp_ls = 0;
-                warp_first = job.in[0];
-                break;
-            }
-            hi -= 512;
-            const i64 st2 = (i64)hi - 16 * (lane + 1);
-            vv = make_uint4(0, 0, 0, 0);
-            m16 = 0;
-            if (st2 >= 0) {
-                vv = __ldg(reinterpret_cast<const uint4 *>(job.in + st2));
-                m16 = newline_mask16(vv);
-            }
-        }
-        // a newline found in a later round sits below hi: its successor may be the first byte of the
-        // previous round's window, which the shuffle above cannot see; reload it in that rare case
-        if (warp_ls != 0 && warp_ls != warp_base && (warp_ls & 511u) == 0) warp_first = job.in[warp_ls];
-    }
-    const u32 my_last = nlmask ? (u32)(lane * 32 + (31 - __clz(nlmask)) + 1) : 0u;
-    u32 inc_max = my_last;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const u32 y = __shfl_up_sync(0xFFFFFFFFu, inc_max, o);
-        if (lane >= o) inc_max = max(inc_max, y);
-    }
-    u32 excl_max = __shfl_up_sync(0xFFFFFFFFu, inc_max, 1);
-    if (lane == 0) excl_max = 0;
-    __syncwarp();  // the warp's raw bytes are in shared memory
-    const u64 line_start = excl_max ? warp_base + excl_max : warp_ls;
-    int state = LS;
-    if (len > 0 && line_start != pos0) {
-        // the line's first byte: inside the warp's own kilobyte, or found by the backward search
-        const uint8_t first = line_start >= warp_base ? sh.raw[warp * 1024 + (u32)(line_start - warp_base)] : warp_first;
-        state = first == '>' ? HDR : SEQ;
-    }
-    const bool last_cr = len > 0 && raw[len - 1] == '\r';
-    const bool cr_end = last_cr && ((pos0 + len >= job.n) || job.in[pos0 + len] == '\n');
-    const bool eof_chunk = len > 0 && pos0 + len == job.n;
-    const bool first_thread = (t == 0 && tid == 0);
-
-    // ---- classify the chunk ----
-    //   fast:  32 bytes of sequence lines only, at most two bytes to drop (newline, CR)
-    //   slow:  anything with a header line start / end in it, or short (end of input), ...
-    //   none:  no symbols (inside a header line, or past the end of the input)
-    u32 removed = 0;
-    bool slow = false, fast = false;
-    if (len > 0) {
-        if (state == HDR) {
-            slow = nlmask != 0;  // the header line ends here
-        } else {
-            slow = (state == LS && raw[0] == '>') || len < 32 || first_thread;
-            u32 m = nlmask;
-            u32 crd = cr_end ? (1u << (len - 1)) : 0u;
-            while (m) {
-                const int e = __ffs(m) - 1;
-                m &= m - 1;
-                if (e + 1 < len && raw[e + 1] == '>') slow = true;
-                if (e > 0 && raw[e - 1] == '\r') crd |= 1u << (e - 1);
-            }
-            removed = nlmask | crd;
-            if (__popc(removed) > 2) slow = true;
-            fast = !slow;
-        }
-    }
-    u32 nsym = 0, nhdr = 0;
-    if (fast) {
-        nsym = 32u - (u32)__popc(removed);
-    } else if (slow) {
-        count_chunk(raw, len, nlmask, state, cr_end, nsym, nhdr);
-        if (first_thread) nsym += 2;  // pads of slot 0
-    } else if (first_thread) {
-        nsym = 2;  // empty input
-        slow = true;
-    }
-    PHASE_MARK(job, 1, tprev);  // load, masks, line start, classify, count
-
-    // ---- scan over the tile ----
-    const u32 packed = nsym | nhdr << 16;
-    u32 inc = packed;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const u32 y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
-        if (lane >= o) inc += y;
-    }
-    if (lane == 31) sh.warp_sum[warp] = inc;
-    const bool track_nl = job.n >= job.max_line;  // only then can a line reach the reference's limit
-    if (track_nl) {
-        u32 fn = nlmask ? (u32)(tid * 32 + __ffs(nlmask) - 1) : 0xFFFFu;
-        u32 ln = nlmask ? (u32)(tid * 32 + (31 - __clz(nlmask)) + 1) : 0u;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            fn = min(fn, __shfl_xor_sync(0xFFFFFFFFu, fn, o));
-            ln = max(ln, __shfl_xor_sync(0xFFFFFFFFu, ln, o));
-        }
-        if (lane == 0) sh.warp_nl[warp] = fn << 16 | ln;
-    }
-    __syncthreads();
-    u32 excl = inc - packed;
-    u32 tile_total = 0;
-#pragma unroll
-    for (int w = 0; w < kParseThreads / 32; w++) {
-        const u32 s = sh.warp_sum[w];
-        if (w < warp) excl += s;
-        tile_total += s;
-    }
-    const bool last_tile = (t + 1 == job.ntiles);
-    const u32 S_own = tile_total & 0xFFFFu, R_tile = tile_total >> 16;
-    const u32 S_tile = S_own + (last_tile && !job.no_end_pads ? 2u : 0u);  // the last tile owns the two end pads
-    const u32 d = excl & 0xFFFFu;                      // slot index of the chunk's first symbol
-    if (tid == 0 && R_tile) {
-        // one slot range of the event list for the tile's header lines
-        const u32 base = atomicAdd(&job.counters[2], R_tile);
-        sh.ev_base = base;
-    }
-    PHASE_MARK(job, 2, tprev);  // barrier + tile scan
-
-    // ---- fast chunks: encode, drop the newline / CR bytes, store whole words ----
-    {
-        // fast chunks (>= 30 symbols) link up: a chunk's last, partial word is completed with the
-        // first symbols of the next lane's chunk and stored whole
-        const unsigned bigm = __ballot_sync(0xFFFFFFFFu, fast);
-        u32 C[9];
-        C[8] = 0;
-        if (fast) {
-            C[0] = encode4(v0.x); C[1] = encode4(v0.y); C[2] = encode4(v0.z); C[3] = encode4(v0.w);
-            C[4] = encode4(v1.x); C[5] = encode4(v1.y); C[6] = encode4(v1.z); C[7] = encode4(v1.w);
-            if (job.warn) {
-                // invalid nucleotides (encodedSequence.go:36-40): code 0, not N/n, not a dropped byte
-                const u32 zc = gather_flags16(zero_code_flags(C[0]), zero_code_flags(C[1]), zero_code_flags(C[2]), zero_code_flags(C[3])) |
-                               gather_flags16(zero_code_flags(C[4]), zero_code_flags(C[5]), zero_code_flags(C[6]), zero_code_flags(C[7])) << 16;
-                const u32 nm = gather_flags16(n_flags(v0.x), n_flags(v0.y), n_flags(v0.z), n_flags(v0.w)) |
-                               gather_flags16(n_flags(v1.x), n_flags(v1.y), n_flags(v1.z), n_flags(v1.w)) << 16;
-                u32 inv = zc & ~nm & ~removed;
-                while (inv) {
-                    const int i = __ffs(inv) - 1;
-                    inv &= inv - 1;
-                    const u32 spos = d + (u32)i - (u32)__popc(removed & ((1u << i) - 1u));
-                    const u32 slot = atomicAdd(&job.counters[4], 1u);
-                    if (slot < job.warn_cap) job.warn[slot] = (u64)t << 32 | (u64)spos << 8 | raw[i];
-                }
-            }
-            u32 rm = removed;
-            while (rm) {
-                const int p = 31 - __clz(rm);
-                rm &= ~(1u << p);
-                remove_byte(C, p);
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 8; i++) C[i] = 0;
-        }
-        const u32 next3 = __shfl_down_sync(0xFFFFFFFFu, C[0], 1);
-        if (fast) {
-            const bool link_next = lane < 31 && ((bigm >> (lane + 1)) & 1u);
-            const bool link_prev = lane > 0 && ((bigm >> (lane - 1)) & 1u);
-            const u32 k = nsym;  // 30..32
-            if (link_next) {      // append the next chunk's first symbols after symbol k-1
-                const u32 shb = 8u * (k & 3u);
-                if (k == 32u) {
-                    C[8] = next3;
-                } else {
-                    C[7] |= next3 << shb;
-                    C[8] = next3 >> (32u - shb);  // shb is 16 or 24 here
-                }
-            }
-            const u32 a = d & 3u;
-            const u32 selA = 0x3210u + 0x1111u * (4u - a);
-            u32 D[9];
-            D[0] = prmt(0u, C[0], selA);
-#pragma unroll
-            for (int j = 1; j < 9; j++) D[j] = prmt(C[j - 1], C[j], selA);
-            u32 *dstw = reinterpret_cast<u32 *>(sh.sym + (d - a));
-            uint8_t *dstb = sh.sym + (d - a);
-            // word 0: whole if aligned; otherwise its bytes a..3 are ours unless the previous lane stores them
-            if (a == 0) {
-                dstw[0] = D[0];
-            } else if (!link_prev) {
-                if (a <= 1) dstb[1] = (uint8_t)(D[0] >> 8);
-                if (a <= 2) dstb[2] = (uint8_t)(D[0] >> 16);
-                dstb[3] = (uint8_t)(D[0] >> 24);
-            }
-#pragma unroll
-            for (int j = 1; j < 7; j++) dstw[j] = D[j];  // always whole (k >= 28)
-            const u32 jt = (a + k) >> 2, nb = (a + k) & 3u;  // last, partial word and its bytes
-            if (jt > 7) dstw[7] = D[7];
-            if (nb) {
-                const u32 Dt = jt == 7 ? D[7] : D[8];
-                if (link_next) {
-                    dstw[jt] = Dt;
-                } else {
-                    dstb[4 * jt] = (uint8_t)Dt;
-                    if (nb >= 2) dstb[4 * jt + 1] = (uint8_t)(Dt >> 8);
-                    if (nb >= 3) dstb[4 * jt + 2] = (uint8_t)(Dt >> 16);
-                }
-            }
-        }
-    }
-    PHASE_MARK(job, 3, tprev);  // fast chunks
-
-    // ---- slow chunks: the 32 lanes of the warp take one byte each ----
-    {
-        unsigned slowm = __ballot_sync(0xFFFFFFFFu, slow);
-        while (slowm) {
-            const int c = __ffs(slowm) - 1;
-            slowm &= slowm - 1;
-            const int c_len = __shfl_sync(0xFFFFFFFFu, len, c);
-            const int c_state = __shfl_sync(0xFFFFFFFFu, state, c);
-            const u32 c_d = __shfl_sync(0xFFFFFFFFu, d, c);
-            const u32 c_rec = __shfl_sync(0xFFFFFFFFu, excl >> 16, c);
-            const bool c_cr_end = __shfl_sync(0xFFFFFFFFu, (int)cr_end, c) != 0;
-            const bool c_first = (t == 0 && warp == 0 && c == 0);
-            const u64 c_pos0 = warp_base + (u64)c * 32u;
-            const bool valid = lane < c_len;
-            const uint8_t b = valid ? sh.raw[(warp * 32 + c) * 32 + lane] : 0;
-            const unsigned lt = (1u << lane) - 1u;
-            const unsigned nl = __ballot_sync(0xFFFFFFFFu, valid && b == '\n');
-            const unsigned before = nl & lt;
-            const int ls = before ? 32 - __clz(before) : -1;  // start of this byte's line, -1: before the chunk
-            const int first_idx = ls >= 0 ? ls : 0;
-            const uint8_t first = (uint8_t)__shfl_sync(0xFFFFFFFFu, (int)b, first_idx);
-            const bool fresh = ls >= 0 || c_state == LS;  // the line starts inside the chunk
-            const bool is_hdr = fresh ? first == '>' : c_state == HDR;
-            const bool is_nl = valid && b == '\n';
-            const bool hstart = valid && !is_nl && fresh && lane == first_idx && b == '>';
-            const unsigned hs = __ballot_sync(0xFFFFFFFFu, hstart);
-            const uint8_t nextb = (uint8_t)__shfl_down_sync(0xFFFFFFFFu, (int)b, 1);
-            const bool next_nl = lane + 1 < c_len ? nextb == '\n' : c_cr_end;
-            const bool keep = valid && !is_nl && !is_hdr && !(b == '\r' && next_nl);
-            const unsigned keepm = __ballot_sync(0xFFFFFFFFu, keep);
-            const u32 lead = c_first ? 2u : 0u;
-            const u32 off = lead + (u32)__popc(keepm & lt) + 2u * (u32)__popc(hs & lt);
-            if (c_first && lane == 0) {  // pads of slot 0 (the bytes before the first header line)
-                sh.sym[0] = job.has_carry ? (uint8_t)((job.carry >> 4) & 0xFu) : 0;
-                sh.sym[1] = job.has_carry ? (uint8_t)(job.carry & 0xFu) : 0;
-            }
-            if (keep) {
-                const uint8_t code = sh.enc[b];
-                sh.sym[c_d + off] = code;
-                if (job.warn && code == 0 && (b & 0xDF) != 'N') {
-                    const u32 slot = atomicAdd(&job.counters[4], 1u);
-                    if (slot < job.warn_cap) job.warn[slot] = (u64)t << 32 | (u64)(c_d + off) << 8 | b;
-                }
-            }
-            if (hstart) {
-                sh.sym[c_d + off] = 0;
-                sh.sym[c_d + off + 1] = 0;
-                const u32 k = c_rec + (u32)__popc(hs & lt);  // index among the tile's header lines
-                u32 base;
-                do {
-                    base = sh.ev_base;
-                } while (base == ~0u);
-                if ((u64)base + k < job.rec_cap) {
-                    HeaderEvent ev;
-                    ev.hdr_off = c_pos0 + lane;
-                    ev.tile = t;
-                    ev.k = (uint16_t)k;
-                    ev.pos = (uint16_t)(c_d + off + 2);
-                    job.events[base + k] = ev;
-                }
-            }
-        }
-    }
-    if (tid < 32) sh.sym[S_own + tid] = 0;  // end pads (last tile) and zero fill of the last word
-    PHASE_MARK(job, 4, tprev);  // slow chunks, hints
-    __syncthreads();  // all symbols staged
-    PHASE_MARK(job, 5, tprev);  // barrier
-
-    // ---- pack two symbols per byte and write the slot ----
-    const u32 nw = (S_tile + 7u) >> 3;
+    // ---- running state of the tile ----
+    u32 S = 0, R = 0;        // symbols / header lines of the rows done
+    u32 carry = 0;           // symbols at the front of ws.sym that are not packed yet
+    u32 done_w = 0;          // slot words written
+    u32 tail_last = 0, tail_prev = 0;  // (lane 0) the slot's last two symbols so far
+    u32 fn = 0xFFFFu, ln = 0;          // first newline / last newline + 1 of the tile (over-long line rule)
+    const bool track_nl = n >= job.max_line;  // only then can a line reach the reference's limit
     u32 *gw = job.sym + (u64)t * kSlotWords;
-#pragma unroll
-    for (int i = 0; i < (kSlotWords + kParseThreads - 1) / kParseThreads; i++) {
-        const u32 w = tid + i * kParseThreads;
-        if (w < nw) {
-            const uint2 s2 = *reinterpret_cast<const uint2 *>(sh.sym + 8 * w);
-            gw[w] = s2.x | (s2.y << 4);
+    if (lane < 4) reinterpret_cast<u32 *>(ws.sym)[lane] = 0;
+    __syncwarp();
+    if (t == 0) {  // pads of slot 0 (the bytes before the first header line), or the two symbols in front of a piece
+        if (lane == 0) {
+            tail_prev = job.has_carry ? ((job.carry >> 4) & 0xFu) : 0u;
+            tail_last = job.has_carry ? (job.carry & 0xFu) : 0u;
+            ws.sym[0] = (uint8_t)tail_prev;
+            ws.sym[1] = (uint8_t)tail_last;
         }
+        carry = 2;
+        S = 2;
     }
-    if (tid == 0) {
+    __syncwarp();
+
+    // ---- rows: the next row's bytes are requested while the current one is worked on ----
+    uint4 nx0 = make_uint4(0, 0, 0, 0), nx1 = make_uint4(0, 0, 0, 0);
+    auto load_row = [&](u64 row_base) {
+        const u64 p0 = row_base + (u64)lane * kParseBytesPerThread;
+        nx0 = make_uint4(0, 0, 0, 0);
+        nx1 = make_uint4(0, 0, 0, 0);
+        if (p0 + 32 <= n) {
+            const uint4 *p = reinterpret_cast<const uint4 *>(job.in + p0);
+            nx0 = __ldg(p);
+            nx1 = __ldg(p + 1);
+        } else if (p0 < n) {
+            u32 w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            const int l = (int)(n - p0);
+            for (int i = 0; i < l; i++) w[i >> 2] |= (u32)job.in[p0 + i] << (8 * (i & 3));
+            nx0 = make_uint4(w[0], w[1], w[2], w[3]);
+            nx1 = make_uint4(w[4], w[5], w[6], w[7]);
+        }
+    };
+    load_row(tile_base);
+
+    for (int r = 0; r < kRows; r++) {
+        const u64 row_base = tile_base + (u64)r * kRowBytes;
+        if (row_base >= n) break;  // (an empty input has no row at all)
+        const uint4 v0 = nx0, v1 = nx1;
+        const bool has_next_row = r + 1 < kRows && row_base + kRowBytes < n;
+        if (has_next_row) load_row(row_base + kRowBytes);
+        // first byte behind the row: the next row's first byte (already requested), or the next tile's
+        u32 after_row = 0;
+        if (lane == 0) {
+            if (has_next_row) after_row = nx0.x & 0xFFu;
+            else if (row_base + kRowBytes < n) after_row = job.in[row_base + kRowBytes];
+        }
+        const u64 pos0 = row_base + (u64)lane * kParseBytesPerThread;
+        const int len = pos0 >= n ? 0 : (n - pos0 < 32 ? (int)(n - pos0) : 32);
+        uint8_t *raw = ws.raw + lane * kParseBytesPerThread;
+        reinterpret_cast<uint4 *>(raw)[0] = v0;
+        reinterpret_cast<uint4 *>(raw)[1] = v1;
+        u32 nlmask = newline_mask16(v0) | newline_mask16(v1) << 16;
+        if (len < 32) nlmask &= len ? ((1u << len) - 1u) : 0u;
+        const u32 b0 = v0.x & 0xFFu;
+
+        // ---- the state each chunk starts in ----
+        const unsigned NL = __ballot_sync(0xFFFFFFFFu, nlmask != 0);
+        const unsigned LNL = __ballot_sync(0xFFFFFFFFu, (nlmask >> 31) != 0);  // the chunk's last byte is '\n'
+        const unsigned G = __ballot_sync(0xFFFFFFFFu, len > 0 && b0 == '>');
+        u32 next_first = __shfl_down_sync(0xFFFFFFFFu, b0, 1);
+        const u32 ar = __shfl_sync(0xFFFFFFFFu, after_row, 0);
+        if (lane == 31) next_first = ar;
+        // is the line that starts behind the chunk's last newline a header line?
+        bool tail_hdr = false;
+        if (nlmask) {
+            const int e = 31 - __clz(nlmask);
+            if (e < 31) tail_hdr = e + 1 < len && raw[e + 1] == '>';
+            else tail_hdr = pos0 + 32 < n && next_first == '>';
+        }
+        const unsigned TH = __ballot_sync(0xFFFFFFFFu, tail_hdr);
+        const bool row_line_hdr = row_ls ? (G & 1u) != 0 : row_in_hdr;  // the line the row's first byte lies in
+        const unsigned prev_nl = NL & lt;
+        const bool chunk_ls = lane > 0 ? ((LNL >> (lane - 1)) & 1u) != 0 : row_ls;
+        const bool hdr_line = prev_nl ? ((TH >> (31 - __clz(prev_nl))) & 1u) != 0 : row_line_hdr;
+        const int state = chunk_ls ? LS : (hdr_line ? HDR : SEQ);
+        // ... and the next row's
+        const bool next_ls = (LNL >> 31) != 0;
+        const bool next_in_hdr = NL ? ((TH >> (31 - __clz(NL))) & 1u) != 0 : row_line_hdr;
+
+        const bool last_cr = len == 32 ? (v1.w >> 24) == '\r' : (len > 0 && raw[len - 1] == '\r');
+        const bool cr_end = last_cr && ((pos0 + len >= n) || next_first == '\n');
+
+        // ---- classify the chunk ----
+        //   fast:  32 bytes of sequence lines only, at most two bytes to drop (newline, CR)
+        //   slow:  anything with a header line start / end in it, or short (end of input), ...
+        //   none:  no symbols (inside a header line, or past the end of the input)
+        u32 removed = 0;
+        bool slow = false, fast = false;
+        if (len > 0) {
+            if (state == HDR) {
+                slow = nlmask != 0;  // the header line ends here
+            } else {
+                slow = (state == LS && b0 == '>') || len < 32;
+                u32 m = nlmask;
+                u32 crd = cr_end ? (1u << (len - 1)) : 0u;
+                while (m) {
+                    const int e = __ffs(m) - 1;
+                    m &= m - 1;
+                    if (e + 1 < len && raw[e + 1] == '>') slow = true;
+                    if (e > 0 && raw[e - 1] == '\r') crd |= 1u << (e - 1);
+                }
+                removed = nlmask | crd;
+                if (__popc(removed) > 2) slow = true;
+                fast = !slow;
+            }
+        }
+        u32 nsym = 0, nhdr = 0;
+        if (fast) nsym = 32u - (u32)__popc(removed);
+        else if (slow) count_chunk(raw, len, nlmask, state, cr_end, nsym, nhdr);
+
+        // ---- positions: scan over the row ----
+        const u32 packed = nsym | nhdr << 16;
+        u32 inc = packed;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 y = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+            if (lane >= o) inc += y;
+        }
+        const u32 row_total = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        const u32 row_syms = row_total & 0xFFFFu, row_hdrs = row_total >> 16;
+        const u32 excl = inc - packed;
+        const u32 d = carry + (excl & 0xFFFFu);  // buffer index of the chunk's first symbol
+        const u32 slot0 = S - carry;             // slot index of buffer index 0
+        u32 ev_base = 0;
+        if (row_hdrs) {  // one range of the event list for the row's header lines
+            if (lane == 0) ev_base = atomicAdd(&job.counters[2], row_hdrs);
+            ev_base = __shfl_sync(0xFFFFFFFFu, ev_base, 0);
+        }
+        if (track_nl && NL) {
+            const int l1 = 31 - __clz(NL);
+            const u32 m1 = __shfl_sync(0xFFFFFFFFu, nlmask, l1);
+            ln = (u32)(r * kRowBytes + l1 * 32 + (31 - __clz(m1)) + 1);  // rows are walked upwards
+            if (fn == 0xFFFFu) {
+                const int l0 = __ffs(NL) - 1;
+                const u32 m0 = __shfl_sync(0xFFFFFFFFu, nlmask, l0);
+                fn = (u32)(r * kRowBytes + l0 * 32 + __ffs(m0) - 1);
+            }
+        }
+
+        // ---- fast chunks: encode, drop the newline / CR bytes, store whole words ----
+        {
+            // fast chunks (>= 30 symbols) link up: a chunk's last, partial word is completed with the
+            // first symbols of the next lane's chunk and stored whole
+            const unsigned bigm = __ballot_sync(0xFFFFFFFFu, fast);
+            u32 C[9];
+            C[8] = 0;
+            if (fast) {
+                C[0] = encode4(v0.x); C[1] = encode4(v0.y); C[2] = encode4(v0.z); C[3] = encode4(v0.w);
+                C[4] = encode4(v1.x); C[5] = encode4(v1.y); C[6] = encode4(v1.z); C[7] = encode4(v1.w);
+                if (job.warn) {
+                    // invalid nucleotides (encodedSequence.go:36-40): code 0, not N/n, not a dropped byte
+                    const u32 zc = gather_flags16(zero_code_flags(C[0]), zero_code_flags(C[1]), zero_code_flags(C[2]), zero_code_flags(C[3])) |
+                                   gather_flags16(zero_code_flags(C[4]), zero_code_flags(C[5]), zero_code_flags(C[6]), zero_code_flags(C[7])) << 16;
+                    const u32 nm = gather_flags16(n_flags(v0.x), n_flags(v0.y), n_flags(v0.z), n_flags(v0.w)) |
+                                   gather_flags16(n_flags(v1.x), n_flags(v1.y), n_flags(v1.z), n_flags(v1.w)) << 16;
+                    u32 inv = zc & ~nm & ~removed;
+                    while (inv) {
+                        const int i = __ffs(inv) - 1;
+                        inv &= inv - 1;
+                        const u32 spos = slot0 + d + (u32)i - (u32)__popc(removed & ((1u << i) - 1u));
+                        const u32 slot = atomicAdd(&job.counters[4], 1u);
+                        if (slot < job.warn_cap) job.warn[slot] = (u64)t << 32 | (u64)spos << 8 | raw[i];
+                    }
+                }
+                u32 rm = removed;
+                while (rm) {
+                    const int p = 31 - __clz(rm);
+                    rm &= ~(1u << p);
+                    remove_byte(C, p);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; i++) C[i] = 0;
+            }
+            const u32 next3 = __shfl_down_sync(0xFFFFFFFFu, C[0], 1);
+            if (fast) {
+                const bool link_next = lane < 31 && ((bigm >> (lane + 1)) & 1u);
+                const bool link_prev = lane > 0 && ((bigm >> (lane - 1)) & 1u);
+                const u32 k = nsym;  // 30..32
+                if (link_next) {      // append the next chunk's first symbols after symbol k-1
+                    const u32 shb = 8u * (k & 3u);
+                    if (k == 32u) {
+                        C[8] = next3;
+                    } else {
+                        C[7] |= next3 << shb;
+                        C[8] = next3 >> (32u - shb);  // shb is 16 or 24 here
+                    }
+                }
+                const u32 a = d & 3u;
+                const u32 selA = 0x3210u + 0x1111u * (4u - a);
+                u32 D[9];
+                D[0] = prmt(0u, C[0], selA);
+#pragma unroll
+                for (int j = 1; j < 9; j++) D[j] = prmt(C[j - 1], C[j], selA);
+                u32 *dstw = reinterpret_cast<u32 *>(ws.sym + (d - a));
+                uint8_t *dstb = ws.sym + (d - a);
+                // word 0: whole if aligned; otherwise its bytes a..3 are ours unless the previous lane stores them
+                if (a == 0) {
+                    dstw[0] = D[0];
+                } else if (!link_prev) {
+                    if (a <= 1) dstb[1] = (uint8_t)(D[0] >> 8);
+                    if (a <= 2) dstb[2] = (uint8_t)(D[0] >> 16);
+                    dstb[3] = (uint8_t)(D[0] >> 24);
+                }
+#pragma unroll
+                for (int j = 1; j < 7; j++) dstw[j] = D[j];  // always whole (k >= 28)
+                const u32 jt = (a + k) >> 2, nb = (a + k) & 3u;  // last, partial word and its bytes
+                if (jt > 7) dstw[7] = D[7];
+                if (nb) {
+                    const u32 Dt = jt == 7 ? D[7] : D[8];
+                    if (link_next) {
+                        dstw[jt] = Dt;
+                    } else {
+                        dstb[4 * jt] = (uint8_t)Dt;
+                        if (nb >= 2) dstb[4 * jt + 1] = (uint8_t)(Dt >> 8);
+                        if (nb >= 3) dstb[4 * jt + 2] = (uint8_t)(Dt >> 16);
+                    }
+                }
+            }
+        }
+
+        // ---- slow chunks: the 32 lanes of the warp take one byte each ----
+        {
+            unsigned slowm = __ballot_sync(0xFFFFFFFFu, slow);
+            if (slowm) __syncwarp();  // the row's raw bytes are read across lanes
+            while (slowm) {
+                const int c = __ffs(slowm) - 1;
+                slowm &= slowm - 1;
+                const int c_len = __shfl_sync(0xFFFFFFFFu, len, c);
+                const int c_state = __shfl_sync(0xFFFFFFFFu, state, c);
+                const u32 c_d = __shfl_sync(0xFFFFFFFFu, d, c);
+                const u32 c_rec = R + __shfl_sync(0xFFFFFFFFu, excl >> 16, c);
+                const bool c_cr_end = __shfl_sync(0xFFFFFFFFu, (int)cr_end, c) != 0;
+                const u64 c_pos0 = row_base + (u64)c * 32u;
+                const bool valid = lane < c_len;
+                const uint8_t b = valid ? ws.raw[c * 32 + lane] : 0;
+                const unsigned nl = __ballot_sync(0xFFFFFFFFu, valid && b == '\n');
+                const unsigned before = nl & lt;
+                const int ls = before ? 32 - __clz(before) : -1;  // start of this byte's line, -1: before the chunk
+                const int first_idx = ls >= 0 ? ls : 0;
+                const uint8_t first = (uint8_t)__shfl_sync(0xFFFFFFFFu, (int)b, first_idx);
+                const bool fresh = ls >= 0 || c_state == LS;  // the line starts inside the chunk
+                const bool is_hdr = fresh ? first == '>' : c_state == HDR;
+                const bool is_nl = valid && b == '\n';
+                const bool hstart = valid && !is_nl && fresh && lane == first_idx && b == '>';
+                const unsigned hs = __ballot_sync(0xFFFFFFFFu, hstart);
+                const uint8_t nextb = (uint8_t)__shfl_down_sync(0xFFFFFFFFu, (int)b, 1);
+                const bool next_nl = lane + 1 < c_len ? nextb == '\n' : c_cr_end;
+                const bool keep = valid && !is_nl && !is_hdr && !(b == '\r' && next_nl);
+                const unsigned keepm = __ballot_sync(0xFFFFFFFFu, keep);
+                const u32 off = (u32)__popc(keepm & lt) + 2u * (u32)__popc(hs & lt);
+                if (keep) {
+                    const uint8_t code = sh.enc[b];
+                    ws.sym[c_d + off] = code;
+                    if (job.warn && code == 0 && (b & 0xDF) != 'N') {
+                        const u32 slot = atomicAdd(&job.counters[4], 1u);
+                        if (slot < job.warn_cap) job.warn[slot] = (u64)t << 32 | (u64)(slot0 + c_d + off) << 8 | b;
+                    }
+                }
+                if (hstart) {
+                    ws.sym[c_d + off] = 0;
+                    ws.sym[c_d + off + 1] = 0;
+                    const u32 k = c_rec + (u32)__popc(hs & lt);  // index among the tile's header lines
+                    const u32 e = ev_base + (k - R);
+                    if ((u64)e < job.rec_cap) {
+                        HeaderEvent ev;
+                        ev.hdr_off = c_pos0 + lane;
+                        ev.tile = t;
+                        ev.k = (uint16_t)k;
+                        ev.pos = (uint16_t)(slot0 + c_d + off + 2);
+                        job.events[e] = ev;
+                    }
+                }
+            }
+        }
+        const u32 end = carry + row_syms;                    // buffer index behind the row's last symbol
+        ws.sym[end + lane] = 0;                              // zero tail: the last word's fill, the end pads
+        if (lane < 16) ws.sym[end + 32 + lane] = 0;
+        __syncwarp();  // the row's symbols are staged
+
+        // ---- pack two symbols per byte and write the slot words that are complete ----
+        const u32 nw = end >> 3;  // <= (7 + 32 * 32 + 2) / 8 = 129
+        {
+            u32 *gp = gw + done_w + lane;
+            const uint2 *sp = reinterpret_cast<const uint2 *>(ws.sym) + lane;
+#pragma unroll
+            for (int i = 0; i < 5; i++) {
+                if ((u32)lane + 32u * i < nw) {
+                    const uint2 s2 = sp[32 * i];
+                    gp[32 * i] = s2.x | (s2.y << 4);
+                }
+            }
+        }
+        if (lane == 0) {
+            if (row_syms >= 2) {
+                tail_last = ws.sym[end - 1];
+                tail_prev = ws.sym[end - 2];
+            } else if (row_syms == 1) {
+                tail_prev = tail_last;
+                tail_last = ws.sym[end - 1];
+            }
+        }
+        // the symbols behind the last complete word move to the front (with zeros behind them)
+        u32 keepw = 0;
+        if (lane < 4) keepw = reinterpret_cast<const u32 *>(ws.sym + 8 * nw)[lane];
+        __syncwarp();
+        if (lane < 4) reinterpret_cast<u32 *>(ws.sym)[lane] = keepw;
+        __syncwarp();
+        carry = end & 7u;
+        done_w += nw;
+        S += row_syms;
+        R += row_hdrs;
+        row_ls = next_ls;
+        row_in_hdr = next_in_hdr;
+    }
+
+    // ---- the tile's last word(s), its counts ----
+    const bool last_tile = (t + 1 == job.ntiles);
+    const u32 S_tile = S + (last_tile && !job.no_end_pads ? 2u : 0u);  // the last tile owns the two end pads
+    const u32 nw_total = (S_tile + 7u) >> 3;
+    if (done_w + (u32)lane < nw_total) {  // at most two words: up to 7 carried symbols + 2 pads, zero filled
+        const uint2 s2 = *reinterpret_cast<const uint2 *>(ws.sym + 8 * lane);
+        gw[done_w + lane] = s2.x | (s2.y << 4);
+    }
+    if (lane == 0) {
         TileInfo ti;
         ti.nsym = (uint16_t)S_tile;
-        ti.nhdr = (uint16_t)R_tile;
-        const u32 l1 = S_tile >= 1 ? sh.sym[S_tile - 1] : 0u, l2 = S_tile >= 2 ? sh.sym[S_tile - 2] : 0u;
+        ti.nhdr = (uint16_t)R;
+        u32 l1 = tail_last, l2 = tail_prev;
+        if (S_tile != S) { l1 = 0; l2 = 0; }  // the end pads are the slot's last two symbols
+        if (S_tile < 2) l2 = 0;
+        if (S_tile < 1) l1 = 0;
         ti.tail = (uint8_t)(l1 | l2 << 4);
         ti.pad[0] = ti.pad[1] = ti.pad[2] = 0;
         ti.has_nl = 0; ti.first_nl = 0; ti.last_nl = 0;
-        if (track_nl) {
-            u32 fn = 0xFFFFu, ln = 0;
-            for (int w = 0; w < kParseThreads / 32; w++) {
-                fn = min(fn, sh.warp_nl[w] >> 16);
-                ln = max(ln, sh.warp_nl[w] & 0xFFFFu);
-            }
-            if (ln) {
-                ti.has_nl = 1;
-                ti.first_nl = (uint16_t)fn;
-                ti.last_nl = (uint16_t)(ln - 1);
-            }
+        if (track_nl && ln) {
+            ti.has_nl = 1;
+            ti.first_nl = (uint16_t)fn;
+            ti.last_nl = (uint16_t)(ln - 1);
         }
         job.tile_info[t] = ti;
     }
-    PHASE_MARK(job, 6, tprev);  // pack
 }
 
 cudaError_t launch_parse(const Job &job, cudaStream_t stream) {
-    k_parse<<<job.ntiles, kParseThreads, 0, stream>>>(job);
+    k_parse<<<(job.ntiles + kParseWarps - 1) / kParseWarps, kParseWarps * 32, 0, stream>>>(job);
     return cudaGetLastError();
 }
 

@@ -34,6 +34,8 @@ __global__ void __launch_bounds__(kScanThreads) k_tile_scan(const __grid_constan
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 ntiles = job.ntiles;
     const u32 nscan = (ntiles + kScanTile - 1) / kScanTile;
+    pdl_launch();
+    pdl_wait();  // k_parse's tile records
     while (true) {
         __syncthreads();
         if (tid == 0) s_tile = atomicAdd(&job.counters[0], 1u);
@@ -192,6 +194,8 @@ __global__ void __launch_bounds__(kScanThreads) k_tile_scan(const __grid_constan
 // k_records: header events -> record table
 // =====================================================================================
 __global__ void __launch_bounds__(256) k_records(const __grid_constant__ Job job) {
+    pdl_launch();
+    pdl_wait();  // k_tile_scan's tile offsets and totals
     if (job.n >= job.max_line && blockIdx.x == 0 && threadIdx.x == 0) {
         // over-long line rule: fold the scan tiles' newline summaries, then the unterminated last line
         const u32 nscan = (job.ntiles + kScanTile - 1) / kScanTile;
@@ -214,28 +218,52 @@ __global__ void __launch_bounds__(256) k_records(const __grid_constant__ Job job
     }
     const u64 R = job.totals->n_headers;
     if (R + 2 > job.rec_cap) return;  // overflow: the host retries with a larger table
-    const u64 stride = (u64)gridDim.x * blockDim.x;
-    for (u64 e = (u64)blockIdx.x * blockDim.x + threadIdx.x; e < R; e += stride) {
+    // Half a warp per header line: the record's table entry, and the header line measured 64 bytes
+    // per step (aligned words, one per lane): its length up to the '\n' or the end of the input, one
+    // trailing CR dropped (bufio.ScanLines), and the index of its first space (writer.go:121).
+    const int lane = threadIdx.x & 31, sub = lane & 15, hshift = lane & 16;
+    const unsigned hmask = 0xFFFFu << hshift;
+    const u64 nhalf = ((u64)gridDim.x * blockDim.x) >> 4;
+    for (u64 e = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 4; e < R; e += nhalf) {
         const HeaderEvent ev = job.events[e];
         const TilePrefix tp = job.tile_pre[ev.tile];
         const u64 slot = (u64)tp.R0 + ev.k + 1;
-        job.hdr_off[slot] = ev.hdr_off;
-        job.dbase[slot] = tp.T0 + ev.pos;
-        job.loc[slot] = (u64)ev.tile << 16 | ev.pos;
-        // header line: up to its '\n' (or the end of the input), one trailing CR dropped
-        // (bufio.ScanLines); sp = index of its first space (writer.go:121), H if there is none
         const u64 off = ev.hdr_off;
-        u64 p = off, sp = ~0ull;
-        while (p < job.n) {
-            const uint8_t c = job.in[p];
-            if (c == '\n') break;
-            if (c == ' ' && sp == ~0ull) sp = p - off;
-            p++;
+        u64 p = job.n, sp = ~0ull;  // newline (or end of input), first space
+        for (u64 base = off & ~3ull; base < job.n; base += 64) {
+            const u64 wa = base + 4u * (u32)sub;
+            u32 w = 0, vm = 0;  // the word, 0x80 in its bytes that belong to [off, n)
+            if (wa < job.n) {
+                w = *reinterpret_cast<const u32 *>(job.in + wa);
+                vm = 0x80808080u;
+                if (wa < off) vm <<= 8 * (u32)(off - wa);
+                if (job.n - wa < 4) vm &= 0x80808080u >> (8 * (4 - (u32)(job.n - wa)));
+            }
+            const u32 fnl = byte_eq_flags(w, 0x0A0A0A0Au) & vm, fsp = byte_eq_flags(w, 0x20202020u) & vm;
+            const unsigned bnl = (__ballot_sync(hmask, fnl != 0) >> hshift) & 0xFFFFu;
+            const unsigned bsp = (__ballot_sync(hmask, fsp != 0) >> hshift) & 0xFFFFu;
+            if (bsp && sp == ~0ull) {
+                const int l = __ffs(bsp) - 1;
+                const u32 f = __shfl_sync(hmask, fsp, hshift + l);
+                sp = base + 4u * l + ((__ffs(f) - 1) >> 3);
+            }
+            if (bnl) {
+                const int l = __ffs(bnl) - 1;
+                const u32 f = __shfl_sync(hmask, fnl, hshift + l);
+                p = base + 4u * l + ((__ffs(f) - 1) >> 3);
+                break;
+            }
         }
-        u64 H = p - off;
-        if (job.in[p - 1] == '\r') H--;  // p > off: the line holds at least the '>'
-        if (sp > H) sp = H;
-        job.hinfo[slot] = H | sp << 32;
+        if (sub == 0) {
+            u64 H = p - off;
+            if (job.in[p - 1] == '\r') H--;  // p > off: the line holds at least the '>'
+            u64 s0 = sp == ~0ull || sp >= p ? H : sp - off;
+            if (s0 > H) s0 = H;
+            job.hdr_off[slot] = off;
+            job.dbase[slot] = tp.T0 + ev.pos;
+            job.loc[slot] = (u64)ev.tile << 16 | ev.pos;
+            job.hinfo[slot] = H | s0 << 32;
+        }
     }
 }
 
@@ -322,6 +350,8 @@ __global__ void __launch_bounds__(kSizeThreads) k_size(const __grid_constant__ J
     __shared__ u32 s_tile;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 128) lut[tid] = job.lut.v[tid];
+    pdl_launch();
+    pdl_wait();  // k_records' record table
     const u64 R = job.totals->n_headers;
     if (R + 2 > job.rec_cap) return;  // record table overflow: the host retries with a larger one
     const u64 nslots = R + 1;
@@ -450,6 +480,7 @@ __global__ void __launch_bounds__(kSizeThreads) k_size(const __grid_constant__ J
 // k_warn: invalid nucleotides -> (record, position) for the WARNING lines of encodedSequence.go:39
 // =====================================================================================
 __global__ void __launch_bounds__(256) k_warn(const __grid_constant__ Job job) {
+    pdl_wait();  // k_size (the record table is complete after k_records already)
     const u32 n = job.counters[4];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         job.totals->n_warn = n;
@@ -478,21 +509,38 @@ __global__ void __launch_bounds__(256) k_warn(const __grid_constant__ Job job) {
     }
 }
 
+// Launch with programmatic stream serialization: the kernel's CTAs may be scheduled while the
+// kernel before it in the stream drains; it waits in pdl_wait() before touching that kernel's results.
+template <typename K>
+static cudaError_t launch_pdl(K kernel, dim3 grid, dim3 block, cudaStream_t stream, const Job &job) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, job);
+}
+
 cudaError_t launch_warn(const Job &job, int sm_count, cudaStream_t stream) {
-    k_warn<<<sm_count, 256, 0, stream>>>(job);
-    return cudaGetLastError();
+    return launch_pdl(k_warn, dim3(sm_count), dim3(256), stream, job);
 }
 
 cudaError_t launch_sizes(const Job &job, int sm_count, cudaStream_t stream) {
     const u32 nscan = (job.ntiles + kScanTile - 1) / kScanTile;
-    k_tile_scan<<<nscan < (u32)sm_count ? nscan : (u32)sm_count, kScanThreads, 0, stream>>>(job);
-    const u64 rec_blocks = (job.rec_cap + 255) / 256;
-    k_records<<<(u32)(rec_blocks < (u64)sm_count * 8 ? rec_blocks : (u64)sm_count * 8), 256, 0, stream>>>(job);
+    cudaError_t e = launch_pdl(k_tile_scan, dim3(nscan < (u32)sm_count ? nscan : (u32)sm_count), dim3(kScanThreads), stream, job);
+    if (e != cudaSuccess) return e;
+    const u64 rec_blocks = (job.rec_cap + 15) / 16;  // half a warp per header line
+    e = launch_pdl(k_records, dim3((u32)(rec_blocks < (u64)sm_count * 8 ? rec_blocks : (u64)sm_count * 8)), dim3(256), stream, job);
+    if (e != cudaSuccess) return e;
     const u64 size_tiles = (job.rec_cap + kSizeTile - 1) / kSizeTile;
     u32 size_grid = (u32)(size_tiles < (u64)sm_count * 4 ? size_tiles : (u64)sm_count * 4);
     if (size_grid == 0) size_grid = 1;
-    k_size<<<size_grid, kSizeThreads, 0, stream>>>(job);
-    return cudaGetLastError();
+    return launch_pdl(k_size, dim3(size_grid), dim3(kSizeThreads), stream, job);
 }
 
 }  // namespace gts

@@ -245,7 +245,7 @@ def test_c_driver_of_the_shim_call_sequence(goldens, tmp_path):
         src, dst = tmp_path / ("in%d.fna" % k), tmp_path / ("out%d.faa" % k)
         src.write_bytes(data)
         want_out, want_warn = oracle.translate_with_warnings(data, **kw)
-        for ngpu, chunk, read_size, fail in ((0, 1 << 16, 0, None), (3, 1 << 14, 5000, None), (2, 1 << 15, 0, 1)):
+        for ngpu, chunk, read_size, fail in ((0, 1 << 16, 0, None), (3, 1 << 14, 5000, None), (2, 1 << 15, 0, 0)):
             args = [exe, str(src), str(dst), kw["frame"], str(kw.get("table", 0)), str(int(kw.get("clean", False))),
                     str(int(kw.get("alternative", False))), str(int(kw.get("trim", False))), str(chunk), str(ngpu),
                     str(read_size)] + ([str(fail)] if fail is not None else [])
