@@ -54,7 +54,8 @@ class gts_piece_info(ctypes.Structure):
 class gts_piece(ctypes.Structure):
     _fields_ = [("nt_before", ctypes.c_uint64), ("nt_total", ctypes.c_uint64), ("header_len", ctypes.c_uint32),
                 ("carry", ctypes.c_uint8 * 2), ("first", ctypes.c_uint8), ("last", ctypes.c_uint8),
-                ("next_head", ctypes.c_uint8 * 192)]
+                ("next_head", ctypes.c_uint8 * 192), ("has_trim_len", ctypes.c_uint8), ("reserved", ctypes.c_uint8 * 7),
+                ("trim_len", ctypes.c_uint64 * 6)]
 
 
 class gts_segment(ctypes.Structure):
@@ -101,6 +102,11 @@ EXPORTS = {
                                                   ctypes.POINTER(gts_piece), ctypes.c_void_p, ctypes.c_size_t,
                                                   ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(gts_segment),
                                                   ctypes.POINTER(ctypes.c_int), ctypes.c_void_p]),
+    "gts_frame_lengths": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64)]),
+    "gts_piece_trim_device": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.POINTER(gts_piece),
+                                             ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint8), ctypes.c_void_p]),
+    "gts_piece_trim": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(gts_piece), ctypes.POINTER(ctypes.c_uint64),
+                                      ctypes.POINTER(ctypes.c_uint8)]),
     "gts_piece_scan": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
                                       ctypes.POINTER(gts_piece_info)]),
     "gts_piece_translate": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(gts_piece), ctypes.POINTER(ctypes.c_size_t),

@@ -120,6 +120,11 @@ struct DevCtx {  // one GPU: streams, scratch of a device pass, chunk slots, wor
     bool pending = false;
     gts::Job job;
     cudaStream_t job_stream = nullptr;
+    bool job_scan_only = false;
+    // the slots in d_sym hold the parse of this buffer (a piece scanned, not yet translated)
+    const void *slots_of = nullptr;
+    size_t slots_n = 0;
+    u64 *d_pt = nullptr;  // k_piece_trim's results
 
     // ---- per-kernel timing ----
     std::vector<cudaEvent_t> prof_events;  // 5 per recorded pass
@@ -312,6 +317,8 @@ struct PassArgs {
     u64 cap = 0;
     cudaStream_t stream = nullptr;
     bool sizes_only = false;
+    bool scan_only = false;        // k_parse + k_tile_scan only (piece scan)
+    bool reuse_slots = false;      // the slots of the pass before are still valid: no k_parse (piece translate)
     gts::Totals *h_dst = nullptr;  // pinned destination of the totals (default: dev->h_totals)
     bool more_follows = false;
     u64 *d_warn = nullptr;         // warning list (nullptr = off)
@@ -357,6 +364,9 @@ int enqueue_pass(gts_ctx *ctx, DevCtx *dev, const PassArgs &a, std::string *err)
     job.t0_base = 0; job.win_lo = 0; job.ov_slot = 0; job.ov_n = 0; job.ov_dbase = 0;
     job.head_out = nullptr;
     std::memset(job.head, 0, sizeof(job.head));
+    job.ov_trim = 0; job.ov_last = 0; job.pt_before = 0; job.pt_out = nullptr;
+    std::memset(job.ov_len, 0, sizeof(job.ov_len));
+    std::memset(job.pt_len, 0, sizeof(job.pt_len));
     if (ctx->piece_on) {
         const gts::Job &p = ctx->piece_job;
         job.piece = p.piece; job.no_end_pads = p.no_end_pads; job.has_carry = p.has_carry; job.carry = p.carry;
@@ -364,10 +374,14 @@ int enqueue_pass(gts_ctx *ctx, DevCtx *dev, const PassArgs &a, std::string *err)
         job.ov_slot = p.ov_slot; job.ov_n = p.ov_n; job.ov_dbase = p.ov_dbase;
         job.head_out = p.head_out;
         std::memcpy(job.head, p.head, sizeof(job.head));
+        job.ov_trim = p.ov_trim; job.ov_last = p.ov_last;
+        std::memcpy(job.ov_len, p.ov_len, sizeof(job.ov_len));
     }
     job.lut = ctx->lut;
     job.lutb = ctx->lutb;
     dev->job_stream = a.stream;
+    dev->job_scan_only = a.scan_only;
+    dev->slots_of = nullptr;  // (set again by the piece scan once its pass has finished)
     cudaEvent_t *ev = nullptr;
     if (ctx->profiling && !a.sizes_only) {
         while (dev->prof_events.size() < dev->prof_used + 5) {
@@ -380,10 +394,24 @@ int enqueue_pass(gts_ctx *ctx, DevCtx *dev, const PassArgs &a, std::string *err)
         CUE(cudaEventRecord(ev[0], a.stream));
     }
     CUE(cudaMemsetAsync(dev->d_zero, 0, z.bytes, a.stream));
-    CUE(gts::launch_parse(job, a.stream));
+    u64 launches = 0;
+    if (a.reuse_slots) {
+        CUE(gts::launch_piece_fix(job, a.stream));
+    } else {
+        CUE(gts::launch_parse(job, a.stream));
+    }
+    launches++;
     if (ev) CUE(cudaEventRecord(ev[1], a.stream));
+    if (a.scan_only) {
+        CUE(gts::launch_tile_scan(job, dev->sm_count, a.stream));
+        CUE(cudaMemcpyAsync(a.h_dst ? a.h_dst : dev->h_totals, job.totals, sizeof(gts::Totals), cudaMemcpyDeviceToHost, a.stream));
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->stats.kernel_launches += launches + 1;
+        ctx->stats.passes++;
+        return GTS_OK;
+    }
     CUE(gts::launch_sizes(job, dev->sm_count, a.stream));
-    u64 launches = 4;
+    launches += 3;
     if (job.warn) {
         CUE(gts::launch_warn(job, dev->sm_count, a.stream));
         launches++;
@@ -414,6 +442,7 @@ int finish_pass(gts_ctx *ctx, DevCtx *dev, bool sizes_only) {
         PassArgs a;
         a.d_in = dev->job.in; a.n = dev->job.n; a.d_out = dev->job.out; a.cap = dev->job.out_cap;
         a.stream = dev->job_stream; a.sizes_only = sizes_only;
+        a.scan_only = dev->job_scan_only;  // (a retry parses again: the slots are not reused)
         if (t.flags & gts::kFlagLongLine) {
             // the reference stops reading at a line of >= 100 MiB (transeq.go:186): redo the pass on
             // the bytes in front of that line
@@ -479,7 +508,7 @@ void dev_destroy(DevCtx *dev) {
     cudaFree(dev->d_sym); cudaFree(dev->d_tile_info); cudaFree(dev->d_tile_pre);
     cudaFree(dev->d_zero); cudaFree(dev->d_scan_nl);
     free_rec(dev);
-    cudaFree(dev->d_in); cudaFree(dev->d_out); cudaFree(dev->d_head);
+    cudaFree(dev->d_in); cudaFree(dev->d_out); cudaFree(dev->d_head); cudaFree(dev->d_pt);
     for (PassSlot &s : dev->slots) {
         cudaFree(s.d_in); cudaFree(s.d_out); cudaFree(s.d_warn); cudaFree(s.d_wres);
         if (s.h_totals) cudaFreeHost(s.h_totals);
@@ -966,6 +995,8 @@ int piece_segments(uint32_t mask, bool alternative, const gts_piece &p, u64 n_pi
     const u64 n = p.nt_total, H = p.header_len;
     u64 L[6];
     host_frame_lengths(n, alternative, L);
+    if (p.has_trim_len)
+        for (int f = 0; f < 6; f++) L[f] = p.trim_len[f];
     // Output line b of a strand's frames is one block of 180 nucleotides; the block belongs to the
     // piece that holds its anchor, the last symbol of its lowest codon (k_lines, gts_lines.cu).
     // Anchors as indices into the record's nucleotides (n, n + 1 = the two pads behind it):
@@ -1496,10 +1527,18 @@ int gts_kernel_times(gts_ctx *ctx, double ms[4], uint64_t *passes) {
 
 // ---- one record split over several GPUs ---------------------------------------------------
 
+// untrimmed residues of each frame of a record with n nucleotides (writer.go:97-112)
+int gts_frame_lengths(const gts_ctx *ctx, uint64_t n, uint64_t len[6]) {
+    if (!ctx || !len) return GTS_ERR_ARG;
+    u64 L[6];
+    host_frame_lengths(n, ctx->opt.alternative != 0, L);
+    for (int f = 0; f < 6; f++) len[f] = ((ctx->mask >> f) & 1u) ? L[f] : 0;
+    return GTS_OK;
+}
+
 int gts_piece_scan_device(gts_ctx *ctx, const void *d_in, size_t n, int first, gts_piece_info *info, void *stream) {
     if (!ctx || !info) return GTS_ERR_ARG;
     if (n && !d_in) return fail(ctx, GTS_ERR_ARG, "d_in is NULL");
-    if (ctx->opt.trim) return fail(ctx, GTS_ERR_ARG, "a split record cannot be trimmed");
     DevCtx *dev = dev0(ctx);
     CU(cudaSetDevice(dev->device));
     std::lock_guard<std::mutex> dl(dev->mu);
@@ -1511,10 +1550,15 @@ int gts_piece_scan_device(gts_ctx *ctx, const void *d_in, size_t n, int first, g
     ctx->last_truncated = false;
     PassArgs a;
     a.d_in = static_cast<const uint8_t *>(d_in); a.n = n; a.stream = static_cast<cudaStream_t>(stream);
-    a.sizes_only = true;
+    a.scan_only = true;  // k_parse + k_tile_scan: the counts, the head codes, the header line's length
     std::string emsg;
     int rc = enqueue_pass(ctx, dev, a, &emsg);
     if (rc) fail(ctx, rc, emsg);
+    if (!rc) {
+        // (the head codes travel with the totals: one synchronisation for the whole scan)
+        cudaError_t ce = cudaMemcpyAsync(info->head, dev->d_head, sizeof(info->head), cudaMemcpyDeviceToHost, a.stream);
+        if (ce != cudaSuccess) rc = cuda_fail(ctx, ce, "copy of the head codes");
+    }
     if (!rc) {
         dev->pending = true;
         rc = finish_pass(ctx, dev, true);
@@ -1529,33 +1573,24 @@ int gts_piece_scan_device(gts_ctx *ctx, const void *d_in, size_t n, int first, g
     info->tail[1] = (uint8_t)((t.tail >> 4) & 0xF);
     info->reserved[0] = info->reserved[1] = 0;
     info->header_len = 0;
-    CU(cudaMemcpy(info->head, dev->d_head, sizeof(info->head), cudaMemcpyDeviceToHost));
     if (first) {
         if (t.n_headers != 1) return fail(ctx, GTS_ERR_ARG, "the first piece must hold exactly one header line");
-        u64 hoff = 0, hinfo = 0;
-        CU(cudaMemcpy(&hoff, dev->d_hdr_off + 1, sizeof(u64), cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(&hinfo, dev->d_hinfo + 1, sizeof(u64), cudaMemcpyDeviceToHost));
-        if (hoff != 0) return fail(ctx, GTS_ERR_ARG, "the first piece must start with the header line");
-        info->header_len = (uint32_t)(hinfo & 0xFFFFFFFFull);
+        if (t.aux == ~0ull) return fail(ctx, GTS_ERR_ARG, "the first piece must start with the header line");
+        info->header_len = (uint32_t)t.aux;
     } else if (t.n_headers != 0) {
         return fail(ctx, GTS_ERR_ARG, "only the first piece of a split record may hold a header line");
     }
+    dev->slots_of = d_in;  // the translate pass of the same buffer reuses the parse
+    dev->slots_n = n;
     return GTS_OK;
 }
 
-int gts_piece_translate_device(gts_ctx *ctx, const void *d_in, size_t n, const gts_piece *piece, void *d_out,
-                               size_t cap, size_t *out_total, gts_segment segs[GTS_MAX_SEGMENTS], int *nseg,
-                               void *stream) {
-    if (!ctx || !piece || !segs || !nseg) return GTS_ERR_ARG;
-    if (n && !d_in) return fail(ctx, GTS_ERR_ARG, "d_in is NULL");
-    if (ctx->opt.trim) return fail(ctx, GTS_ERR_ARG, "a split record cannot be trimmed");
-    DevCtx *dev = dev0(ctx);
-    CU(cudaSetDevice(dev->device));
-    std::lock_guard<std::mutex> dl(dev->mu);
-    gts::Job &p = ctx->piece_job;
+// The piece fields of a pass from the caller's description of the piece.
+static void fill_piece_job(gts::Job &p, const gts_piece *piece) {
     p = gts::Job();
     p.piece = 1;
     p.no_end_pads = piece->last ? 0 : 1;
+    p.ov_last = piece->last ? 1 : 0;
     p.no_headers = piece->first ? 0 : 1;
     p.ov_H = piece->header_len;
     p.ov_n = piece->nt_total;
@@ -1572,10 +1607,58 @@ int gts_piece_translate_device(gts_ctx *ctx, const void *d_in, size_t n, const g
         p.t0_base = piece->nt_before + 2;
         p.win_lo = p.t0_base + 2;
     }
+    if (piece->has_trim_len) {
+        p.ov_trim = 1;
+        for (int f = 0; f < 6; f++) p.ov_len[f] = (u32)piece->trim_len[f];
+    }
+}
+
+int gts_piece_trim_device(gts_ctx *ctx, const void *d_in, size_t n, const gts_piece *piece, uint64_t len[6],
+                          uint8_t resolved[6], void *stream) {
+    if (!ctx || !piece || !len || !resolved) return GTS_ERR_ARG;
+    DevCtx *dev = dev0(ctx);
+    CU(cudaSetDevice(dev->device));
+    std::lock_guard<std::mutex> dl(dev->mu);
+    if (dev->slots_of != d_in || dev->slots_n != n)
+        return fail(ctx, GTS_ERR_ARG, "gts_piece_trim: the piece must have been scanned by the call before (gts_piece_scan)");
+    if (!dev->d_pt) CU(cudaMalloc(&dev->d_pt, 12 * sizeof(u64)));
+    gts::Job job = dev->job;  // the scan pass's tables: slots, tile records, tile offsets, totals
+    gts::Job p;
+    fill_piece_job(p, piece);
+    job.has_carry = p.has_carry; job.carry = p.carry; job.ov_last = p.ov_last; job.ov_n = p.ov_n;
+    std::memcpy(job.head, p.head, sizeof(job.head));
+    job.pt_before = piece->nt_before;
+    job.pt_out = dev->d_pt;
+    for (int f = 0; f < 6; f++) job.pt_len[f] = len[f];
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CU(gts::launch_piece_trim(job, st));
+    u64 out[12];
+    CU(cudaMemcpyAsync(out, dev->d_pt, sizeof(out), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int f = 0; f < 6; f++) {
+        len[f] = out[f];
+        resolved[f] = (uint8_t)out[6 + f];
+    }
+    ctx->stats.kernel_launches++;
+    return GTS_OK;
+}
+
+int gts_piece_translate_device(gts_ctx *ctx, const void *d_in, size_t n, const gts_piece *piece, void *d_out,
+                               size_t cap, size_t *out_total, gts_segment segs[GTS_MAX_SEGMENTS], int *nseg,
+                               void *stream) {
+    if (!ctx || !piece || !segs || !nseg) return GTS_ERR_ARG;
+    if (n && !d_in) return fail(ctx, GTS_ERR_ARG, "d_in is NULL");
+    if (ctx->opt.trim && !piece->has_trim_len)
+        return fail(ctx, GTS_ERR_ARG, "--trim on a split record needs the trimmed frame lengths (gts_piece_trim)");
+    DevCtx *dev = dev0(ctx);
+    CU(cudaSetDevice(dev->device));
+    std::lock_guard<std::mutex> dl(dev->mu);
+    fill_piece_job(ctx->piece_job, piece);
     ctx->piece_on = true;
     PassArgs a;
     a.d_in = static_cast<const uint8_t *>(d_in); a.n = n; a.d_out = static_cast<uint8_t *>(d_out); a.cap = cap;
     a.stream = static_cast<cudaStream_t>(stream);
+    a.reuse_slots = dev->slots_of == d_in && dev->slots_n == n;  // parsed by gts_piece_scan: no second k_parse
     std::string emsg;
     int rc = enqueue_pass(ctx, dev, a, &emsg);
     if (rc) fail(ctx, rc, emsg);
@@ -1620,6 +1703,8 @@ int gts_piece_translate(gts_ctx *ctx, const gts_piece *piece, size_t *out_total,
     // the whole record's output size is known from the counts alone
     u64 L[6], total = 0;
     host_frame_lengths(piece->nt_total, ctx->opt.alternative != 0, L);
+    if (piece->has_trim_len)
+        for (int f = 0; f < 6; f++) L[f] = piece->trim_len[f];
     for (int f = 0; f < 6; f++)
         if ((ctx->mask >> f) & 1u) total += host_run_size(piece->header_len, L[f]);
     std::string emsg;
@@ -1644,6 +1729,13 @@ int gts_piece_translate(gts_ctx *ctx, const gts_piece *piece, size_t *out_total,
     CU(cudaStreamSynchronize(dev->stream));
     if (out_total) *out_total = tot;
     return GTS_OK;
+}
+
+int gts_piece_trim(gts_ctx *ctx, const gts_piece *piece, uint64_t len[6], uint8_t resolved[6]) {
+    if (!ctx || !piece) return GTS_ERR_ARG;
+    if ((piece->first != 0) != ctx->piece_first) return fail(ctx, GTS_ERR_ARG, "gts_piece_trim: not the piece last scanned");
+    DevCtx *dev = dev0(ctx);
+    return gts_piece_trim_device(ctx, dev->d_in, ctx->piece_n, piece, len, resolved, dev->stream);
 }
 
 void *gts_host_alloc(size_t bytes) {

@@ -69,7 +69,7 @@ struct Totals {  // device-resident result block, copied to pinned host memory a
     u64 cut;          // with kFlagLongLine: the reference stops reading at this offset
     u64 tail;         // the stream's last two symbols (end pads excluded): last | second-to-last << 4
     u64 n_warn;       // invalid nucleotides seen (WARNING lines of encodedSequence.go:39), exact even on overflow
-    u64 pad;
+    u64 aux;          // piece scan: bytes of the header line the buffer starts with (CR dropped), ~0 if it starts with none
 };
 constexpr u64 kFlagRecOverflow = 1;  // record table too small (n_headers is still exact)
 constexpr u64 kFlagOutOverflow = 2;  // output buffer too small (out_total is still exact)
@@ -195,6 +195,13 @@ struct Job {  // kernel argument block (by value)
     u64 ov_dbase;      // stream index of its first nucleotide
     uint8_t *head_out; // scan pass: receives the codes of the buffer's first 192 nucleotides
     uint8_t head[192]; // the 192 symbols behind the buffer (the record goes on in the next piece)
+    u32 ov_trim;       // --trim on a split record: the record's trimmed frame lengths are given (ov_len)
+    u32 ov_last;       // this piece ends the record (k_piece_fix adds the end pads to the reused slots)
+    u32 ov_len[6];
+    // k_piece_trim: one step of the trim walk over the pieces (writer.go:141-163 on a split record)
+    u64 pt_len[6];     // residues of each frame not yet known to be trimmed away
+    u64 pt_before;     // nucleotides of the record in front of the piece
+    u64 *pt_out;       // [12] the lengths after this piece's part of the walk, then "resolved" flags
     Lut lut;
     LutBytes lutb;
 };

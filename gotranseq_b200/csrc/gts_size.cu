@@ -128,6 +128,15 @@ __global__ void __launch_bounds__(kScanThreads) k_tile_scan(const __grid_constan
                         job.totals->tail = tail;
                     }
                     if (job.head_out) {
+                        // the header line the buffer starts with (first piece of a split record): its
+                        // length up to the '\n', one trailing CR dropped (bufio.ScanLines)
+                        u64 hl = ~0ull;
+                        if (job.n > 0 && job.in[0] == '>') {
+                            u64 p = 0;
+                            while (p < job.n && job.in[p] != '\n') p++;
+                            hl = p - (job.in[p - 1] == '\r' ? 1 : 0);
+                        }
+                        job.totals->aux = hl;
                         // codes of the buffer's first 192 nucleotides (a piece of a split record: the
                         // piece before it needs them); slot 0's pads and a header's pads are skipped
                         const u32 skip = 2u + 2u * (u32)R;
@@ -380,7 +389,10 @@ __global__ void __launch_bounds__(kSizeThreads) k_size(const __grid_constant__ J
                 }
                 u64 L[6];
                 frame_lengths(n, job.alternative != 0, L);
-                if (job.trim) {
+                if (job.piece && job.ov_trim) {
+                    if (s == job.ov_slot)
+                        for (int f = 0; f < 6; f++) L[f] = job.ov_len[f];  // reduced over the pieces (k_piece_trim)
+                } else if (job.trim) {
                     trimmed_lengths(job, lut, s, n, L);
 #pragma unroll
                     for (int f = 0; f < 6; f++) job.trim_len[s * 6 + f] = (u32)L[f];
@@ -474,6 +486,110 @@ __global__ void __launch_bounds__(kSizeThreads) k_size(const __grid_constant__ J
             off += size[i];
         }
     }
+}
+
+// =====================================================================================
+// Split record (gts_piece_*): the translate pass reuses the slots of the scan pass
+// =====================================================================================
+// The scan pass parsed the piece without knowing its neighbours.  What changes for the translate
+// pass: the two symbols in front of the piece (slot 0's pads become the carried nucleotides), and,
+// for the record's last piece, the two end pads behind its last symbol.
+__global__ void k_piece_fix(const __grid_constant__ Job job) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (job.has_carry) {
+        const u32 c_prev = (job.carry >> 4) & 0xFu, c_last = job.carry & 0xFu;
+        u32 w = job.sym[0];  // symbol 0 = low nibble of byte 0, symbol 1 = low nibble of byte 1
+        w = (w & ~0x00000F0Fu) | c_prev | c_last << 8;
+        job.sym[0] = w;
+        TileInfo ti = job.tile_info[0];
+        if (ti.nsym == 2) ti.tail = (uint8_t)job.carry;
+        else if (ti.nsym == 3) ti.tail = (uint8_t)((ti.tail & 0xFu) | c_last << 4);
+        job.tile_info[0] = ti;
+    }
+    if (job.ov_last) {
+        const u32 t = job.ntiles - 1;
+        TileInfo ti = job.tile_info[t];
+        u32 *slot = job.sym + (u64)t * kSlotWords;
+        for (u32 i = ti.nsym; i < (u32)ti.nsym + 2u; i++) {  // two zero symbols behind the last one
+            const u32 b = i & 7u, sh = 8 * (b & 3) + 4 * (b >> 2);
+            slot[i >> 3] &= ~(0xFu << sh);
+        }
+        ti.nsym = (uint16_t)(ti.nsym + 2);
+        ti.tail = 0;
+        job.tile_info[t] = ti;
+    }
+}
+
+// One piece's part of the trim walk (writer.go:141-163): lanes 0..5 = frames.  The residues of a frame
+// are checked from its last one backwards while they are 'X' or '*'; a piece can check the windows
+// whose first symbol it holds (the first piece also the two windows that start on the record's front
+// pads), with the two carried symbols in front and the head of the next piece behind.
+__global__ void __launch_bounds__(32) k_piece_trim(const __grid_constant__ Job job) {
+    const int f = threadIdx.x;
+    if (f >= 6) return;
+    u64 len = job.pt_len[f];
+    u32 resolved = 0;
+    if (!((job.frame_mask >> f) & 1u) || len == 0) {
+        resolved = 1;
+    } else {
+        const u64 n = job.ov_n;
+        const bool first = job.has_carry == 0, last = job.ov_last != 0;
+        const u64 base = first ? 4 : 2;                       // local stream index of the piece's first nucleotide
+        const i64 m = (i64)(job.totals->total_sym - base);     // nucleotides of the piece (scan pass: no end pads)
+        const i64 own_lo = first ? -2 : 0;
+        const i64 step = f < 3 ? -3 : 3;
+        i64 q;
+        if (f < 3) q = (i64)f + 3 * (i64)(len - 1);
+        else q = (i64)n - 3 - reverse_start(n, f - 3, job.alternative != 0) - 3 * (i64)(len - 1);
+        i64 i = q - (i64)job.pt_before;
+        Cursor c;
+        c.tile = 0;
+        c.pos = 0;
+        i64 c_at = -(i64)base;  // the cursor stands on local stream index 0 = nucleotide index -base
+        auto psym = [&](i64 x) -> u32 {
+            if (x < 0) return first ? 0u : (x == -1 ? (job.carry & 0xFu) : ((job.carry >> 4) & 0xFu));
+            if (x >= m) return last ? 0u : (u32)job.head[x - m];
+            if (x != c_at) {
+                if (c_at == -(i64)base && x > 4096) {  // first positioning far into the piece: binary search over the tiles
+                    u32 lo = 0, hi = job.ntiles - 1;
+                    const u64 idx = base + (u64)x;
+                    while (lo < hi) {
+                        const u32 mid = (lo + hi + 1) >> 1;
+                        if (job.tile_pre[mid].T0 <= idx) lo = mid; else hi = mid - 1;
+                    }
+                    c.tile = lo;
+                    c.pos = (int)(idx - job.tile_pre[lo].T0);
+                } else {
+                    cursor_move(job, c, (int)(x - c_at));
+                }
+                c_at = x;
+            }
+            return slot_symbol(job.sym, c.tile, (u32)c.pos);
+        };
+        while (i >= own_lo && i < m) {
+            const u32 idx = psym(i) + 5 * psym(i + 1) + 25 * psym(i + 2);
+            const u32 aa = f < 3 ? (job.lut.v[idx] & 0xFFu) : (job.lut.v[idx] >> 8);
+            if (aa != 'X' && aa != '*') { resolved = 1; break; }
+            if (--len == 0) { resolved = 1; break; }
+            i += step;
+        }
+    }
+    job.pt_out[f] = len;
+    job.pt_out[6 + f] = resolved;
+}
+
+cudaError_t launch_piece_fix(const Job &job, cudaStream_t stream) {
+    k_piece_fix<<<1, 32, 0, stream>>>(job);
+    return cudaGetLastError();
+}
+cudaError_t launch_piece_trim(const Job &job, cudaStream_t stream) {
+    k_piece_trim<<<1, 32, 0, stream>>>(job);
+    return cudaGetLastError();
+}
+cudaError_t launch_tile_scan(const Job &job, int sm_count, cudaStream_t stream) {
+    const u32 nscan = (job.ntiles + kScanTile - 1) / kScanTile;
+    k_tile_scan<<<nscan < (u32)sm_count ? nscan : (u32)sm_count, kScanThreads, 0, stream>>>(job);
+    return cudaGetLastError();
 }
 
 // =====================================================================================

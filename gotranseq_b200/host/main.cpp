@@ -97,6 +97,7 @@ int main(int argc, char **argv) {
     if (help) { usage(); return 0; }  // main.go:77-81
     if (version) { std::printf("%s (B200) version %s\n", kTool, GTS_VERSION); return 0; }
     if (const char *g = std::getenv("GOTRANSEQ_B200_GPUS")) opt.NumGpus = std::atoi(g);
+    if (const char *t = std::getenv("GOTRANSEQ_B200_IO_THREADS")) opt.IoThreads = std::atoi(t);
     if (const char *c = std::getenv("GOTRANSEQ_B200_CHUNK_MB")) opt.ChunkBytes = (unsigned long long)(std::atof(c) * (1 << 20));
 
     // run(), main.go:39-65

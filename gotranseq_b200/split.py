@@ -51,6 +51,31 @@ def plan_pieces(infos):
     return pieces
 
 
+def merge_trim(lens, results):
+    """One round of the --trim walk: every piece reports (lens, resolved) for its part; exactly one
+    piece holds the residue a frame's walk stands on, the others return the lengths unchanged."""
+    out, done = list(lens), [False] * 6
+    for f in range(6):
+        settled = [r[0][f] for r in results if r[1][f]]
+        if settled:
+            out[f], done[f] = min(settled), True
+        else:
+            out[f] = min(r[0][f] for r in results)
+    return out, done
+
+
+def settle_trim(start_lens, walk_round, max_rounds):
+    """Trimmed frame lengths of a split record (writer.go:141-163): walk_round(lens) -> [(lens, resolved)
+    of every piece]; repeated until every frame's walk has stopped (one round unless a piece is
+    nothing but 'X' / '*' at one of the record's ends)."""
+    lens = list(start_lens)
+    for _ in range(max_rounds):
+        lens, done = merge_trim(lens, walk_round(lens))
+        if all(done):
+            return lens
+    raise RuntimeError("the trim walk over the pieces did not settle")
+
+
 def assemble(total, segment_lists):
     """The record's protein FASTA from the pieces' (offset, bytes) segments; checks that they
     tile [0, total) exactly."""
@@ -67,7 +92,7 @@ def assemble(total, segment_lists):
     return bytes(out)
 
 
-def translate_split(buf, npieces, make_translator):
+def translate_split(buf, npieces, make_translator, trim=False):
     """Single-process driver (tests, and the model of what N ranks do): one Translator per piece.
     make_translator() -> a gotranseq_b200.Translator."""
     ranges = piece_ranges(buf, npieces)
@@ -75,6 +100,11 @@ def translate_split(buf, npieces, make_translator):
     try:
         infos = [tr.piece_scan(buf[lo:hi], k == 0) for k, (tr, (lo, hi)) in enumerate(zip(trs, ranges))]
         pieces = plan_pieces(infos)
+        if trim:
+            lens = settle_trim(trs[0].frame_lengths(pieces[0]["nt_total"]),
+                               lambda ln: [tr.piece_trim(p, ln) for tr, p in zip(trs, pieces)], len(pieces) + 2)
+            for p in pieces:
+                p["trim_len"] = lens
         results = [tr.piece_translate(p) for tr, p in zip(trs, pieces)]
     finally:
         for tr in trs:
@@ -83,11 +113,14 @@ def translate_split(buf, npieces, make_translator):
     return assemble(total, [segs for _, segs in results])
 
 
-def translate_split_rank(buf, rank, world, translator, all_gather):
+def translate_split_rank(buf, rank, world, translator, all_gather, trim=False):
     """What rank `rank` of `world` does.  all_gather(obj) -> list of every rank's obj, in rank order
     (torch.distributed.all_gather_object).  Returns (total output size, this rank's segments)."""
     lo, hi = piece_ranges(buf, world)[rank]
     info = translator.piece_scan(buf[lo:hi], rank == 0)
     infos = all_gather(info)
     piece = plan_pieces(infos)[rank]
+    if trim:
+        piece["trim_len"] = settle_trim(translator.frame_lengths(piece["nt_total"]),
+                                        lambda ln: all_gather(translator.piece_trim(piece, ln)), world + 2)
     return translator.piece_translate(piece)

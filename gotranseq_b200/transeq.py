@@ -193,7 +193,33 @@ class Translator:
         p.first, p.last = (1 if piece["first"] else 0), (1 if piece["last"] else 0)
         nh = bytes(piece.get("next_head", b""))[:192]
         ctypes.memmove(p.next_head, nh + bytes(192 - len(nh)), 192)
+        if piece.get("trim_len") is not None:
+            p.has_trim_len = 1
+            for f in range(6):
+                p.trim_len[f] = int(piece["trim_len"][f])
         return p
+
+    def frame_lengths(self, n):
+        """Untrimmed residues of the six frames of a record with n nucleotides (0 for frames not requested)."""
+        out = (ctypes.c_uint64 * 6)()
+        self._check(self._L.gts_frame_lengths(self._h, n, out))
+        return list(out)
+
+    def piece_trim(self, piece, lens):
+        """This piece's part of the --trim walk (the piece last scanned by piece_scan): (lens, resolved)."""
+        p = self._piece_struct(piece)
+        ln = (ctypes.c_uint64 * 6)(*[int(x) for x in lens])
+        res = (ctypes.c_uint8 * 6)()
+        self._check(self._L.gts_piece_trim(self._h, ctypes.byref(p), ln, res))
+        return list(ln), [bool(x) for x in res]
+
+    def piece_trim_device(self, d_in, n, piece, lens, stream=0):
+        p = self._piece_struct(piece)
+        ln = (ctypes.c_uint64 * 6)(*[int(x) for x in lens])
+        res = (ctypes.c_uint8 * 6)()
+        self._check(self._L.gts_piece_trim_device(self._h, ctypes.c_void_p(d_in), n, ctypes.byref(p), ln, res,
+                                                  ctypes.c_void_p(stream)))
+        return list(ln), [bool(x) for x in res]
 
     def piece_translate(self, piece):
         """Translate the piece last scanned.  Returns (size of the whole record's output,

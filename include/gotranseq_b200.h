@@ -250,8 +250,17 @@ int gts_set_max_line_length(gts_ctx *ctx, size_t n);
  * The pieces' segments are disjoint and cover the record's output exactly.  Output lines are
  * never shared: a 60-residue line (180 nucleotides) is computed by the piece that holds the last
  * nucleotide of the line's lowest codon; carry and next_head supply what the line needs from the
- * neighbouring pieces, so no sequence bytes travel besides those ~200.  --trim is not supported
- * here (GTS_ERR_ARG).
+ * neighbouring pieces, so no sequence bytes travel besides those ~200.
+ *
+ * With --trim (writer.go:141-163) the frame lengths depend on the residues at the record's ends:
+ * between steps 2 and 3 the pieces walk them.  Start with len = gts_frame_lengths(nt_total) and
+ * call gts_piece_trim* on the pieces until every requested frame is resolved: a piece checks the
+ * residues whose codon starts in it, from len[f] - 1 backwards while they are 'X' or '*', and
+ * reports where it stopped (resolved[f] = 1) or that the walk leaves the piece (resolved[f] = 0,
+ * len[f] = what is left for the neighbouring piece).  Forward frames end in the last piece, reverse
+ * frames in the first, so one call on each usually settles everything; the result goes into
+ * gts_piece.trim_len (has_trim_len = 1) of every piece.  gts_piece_translate* of a buffer that was
+ * scanned by the call before reuses that parse (no second k_parse).
  */
 typedef struct gts_piece_info {
     uint64_t nucleotides; /* nucleotides in the piece                                          */
@@ -270,6 +279,9 @@ typedef struct gts_piece {
     uint8_t first;        /* this piece starts with the record's header line                    */
     uint8_t last;         /* this piece ends the record                                         */
     uint8_t next_head[192]; /* codes of the 192 nucleotides behind the piece (0 beyond the record) */
+    uint8_t has_trim_len; /* --trim: trim_len holds the record's trimmed frame lengths           */
+    uint8_t reserved[7];
+    uint64_t trim_len[6]; /* residues of frames 1,2,3,-1,-2,-3 after --trim (gts_piece_trim)      */
 } gts_piece;
 
 typedef struct gts_segment {
@@ -280,8 +292,11 @@ typedef struct gts_segment {
 
 /* Device-resident: d_in as for gts_translate_device.  d_out holds the WHOLE record's output
  * (*out_total bytes, reported also on GTS_ERR_CAPACITY); the piece writes its segments only. */
+int gts_frame_lengths(const gts_ctx *ctx, uint64_t n, uint64_t len[6]);
 int gts_piece_scan_device(gts_ctx *ctx, const void *d_in, size_t n, int first, gts_piece_info *info,
                           void *stream);
+int gts_piece_trim_device(gts_ctx *ctx, const void *d_in, size_t n, const gts_piece *piece, uint64_t len[6],
+                          uint8_t resolved[6], void *stream);
 int gts_piece_translate_device(gts_ctx *ctx, const void *d_in, size_t n, const gts_piece *piece,
                                void *d_out, size_t cap, size_t *out_total,
                                gts_segment segs[GTS_MAX_SEGMENTS], int *nseg, void *stream);
@@ -289,6 +304,7 @@ int gts_piece_translate_device(gts_ctx *ctx, const void *d_in, size_t n, const g
  * gts_piece_translate, which hands segment i back as data[i] (pinned, owned by ctx, valid until
  * the next call on ctx). */
 int gts_piece_scan(gts_ctx *ctx, const uint8_t *in, size_t n, int first, gts_piece_info *info);
+int gts_piece_trim(gts_ctx *ctx, const gts_piece *piece, uint64_t len[6], uint8_t resolved[6]);
 int gts_piece_translate(gts_ctx *ctx, const gts_piece *piece, size_t *out_total,
                         gts_segment segs[GTS_MAX_SEGMENTS], const uint8_t *data[GTS_MAX_SEGMENTS],
                         int *nseg);

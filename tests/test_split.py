@@ -48,12 +48,12 @@ def frame_lengths(n, alt):
     return L
 
 
-def segments(frames, alt, H, n, before, m, first, last):
+def segments(frames, alt, H, n, before, m, first, last, trim_len=None):
     """Byte ranges of the record's output owned by the piece holding nucleotides [before, before+m).
     Output line b of a strand = one block of 180 nucleotides, owned by the piece that holds the
     block's anchor (the last symbol of its lowest codon): forward 2 + 180 b; reverse n - 189 - 180 b,
     or 0 for the blocks at the record's start (gts_lines.cu)."""
-    L = frame_lengths(n, alt)
+    L = list(trim_len) if trim_len is not None else frame_lengths(n, alt)
     a, e = before, before + m + (2 if last else 0)
     f_lo = -((2 - a) // 180) if a > 2 else 0
     f_hi = -((2 - e) // 180) if e > 2 else 0
@@ -80,10 +80,14 @@ def segments(frames, alt, H, n, before, m, first, last):
 
 
 class FakeTranslator:
-    """Answers piece_scan / piece_translate from the oracle's output of the WHOLE record."""
+    """Answers piece_scan / piece_trim / piece_translate from the oracle: the output of the WHOLE
+    record for the bytes, the reference's codon array for the trim walk (restated here on the
+    piece's own nucleotides plus the carried / following codes, like the device does it)."""
 
-    def __init__(self, whole, frame, alt):
-        self.whole, self.frame, self.alt = whole, frame, alt
+    def __init__(self, whole, frame, alt, trim=False, table=0, clean=False):
+        self.whole, self.frame, self.alt, self.trim = whole, frame, alt, trim
+        self.kw = dict(frame=frame, alternative=alt, trim=trim, table=table, clean=clean)
+        self.codes = oracle.code_array(table, clean)
 
     def piece_scan(self, data, first):
         self.nts = nucleotides(data, first)
@@ -97,10 +101,51 @@ class FakeTranslator:
         return dict(nucleotides=len(self.nts), headers=1 if first else 0, header_len=hl, tail=tail,
                     head=head + bytes(192 - len(head)))
 
+    def frame_lengths(self, n):
+        L = frame_lengths(n, self.alt)
+        return [L[f] if f in FRAME_MASKS[self.frame] else 0 for f in range(6)]
+
+    def piece_trim(self, p, lens):
+        """writer.go:141-163 on the residues whose codon starts in this piece."""
+        comp = lambda c: 0 if c == 0 else ((c - 1) ^ 2) + 1
+        own = [CODES[c] for c in self.nts]
+        m, n, before = len(own), p["nt_total"], p["nt_before"]
+        nh = bytes(p.get("next_head", b""))
+
+        def sym(i):
+            if i < 0:
+                return 0 if p["first"] else (p["carry"][0] if i == -1 else p["carry"][1])
+            if i >= m:
+                return 0 if p["last"] else (nh[i - m] if i - m < len(nh) else 0)
+            return own[i]
+
+        out, res = list(lens), [False] * 6
+        for f in range(6):
+            if f not in FRAME_MASKS[self.frame] or out[f] == 0:
+                res[f] = True
+                continue
+            lo = -2 if p["first"] else 0
+            while True:
+                j = out[f] - 1
+                q = f + 3 * j if f < 3 else n - 3 - reverse_start(n, f - 3, self.alt) - 3 * j
+                i = q - before
+                if i < lo or i >= m:
+                    break
+                c0, c1, c2 = sym(i), sym(i + 1), sym(i + 2)
+                aa = self.codes[c0 | c1 << 8 | c2 << 16] if f < 3 else self.codes[comp(c2) | comp(c1) << 8 | comp(c0) << 16]
+                if aa not in b"X*":
+                    res[f] = True
+                    break
+                out[f] -= 1
+                if out[f] == 0:
+                    res[f] = True
+                    break
+        return out, res
+
     def piece_translate(self, p):
-        want = oracle.translate(self.whole, frame=self.frame, alternative=self.alt)
+        want = oracle.translate(self.whole, **self.kw)
         total, segs = segments(FRAME_MASKS[self.frame], self.alt, p["header_len"], p["nt_total"], p["nt_before"],
-                               len(self.nts), p["first"], p["last"])
+                               len(self.nts), p["first"], p["last"], p.get("trim_len"))
         assert total == len(want)
         return total, [(o, want[o:o + n]) for o, n in segs]
 
@@ -154,6 +199,39 @@ def test_split_host_logic_against_oracle(frame):
                 assert got == want, (seed, frame, alt, k)
 
 
+def trim_record(seed, n, width=60):
+    """A record whose ends translate to long runs of 'X' / '*': N runs, stop codons, lower case."""
+    rng = random.Random(seed)
+    def run(k):
+        kind = rng.random()
+        if kind < 0.4:
+            return b"N" * k
+        if kind < 0.7:
+            return (b"TAA" * (k // 3 + 1))[:k]
+        return bytes(rng.choice(b"NNNTAGX") for _ in range(k))
+    mid = bytes(rng.choice(b"ACGTacgtN") for _ in range(n))
+    seq = run(rng.choice((0, 1, 5, 200, 2000))) + mid + run(rng.choice((0, 2, 7, 300, 2500)))
+    return b">t%d some words\n" % seed + b"\n".join(seq[i:i + width] for i in range(0, len(seq), width)) + b"\n"
+
+
+@pytest.mark.parametrize("frame", ["1", "F", "-2", "R", "6"])
+def test_split_trim_host_logic_against_oracle(frame):
+    """--trim on a split record: the walk over the pieces (split.settle_trim) with the fake pieces."""
+    for seed in range(10):
+        n = [0, 1, 4, 60, 181, 700, 3000, 10, 999, 2][seed]
+        buf = trim_record(seed, n, width=(60, 7, 13)[seed % 3])
+        for alt in (False, True):
+            for table, clean in ((0, False), (11, True)):
+                want = oracle.translate(buf, frame=frame, alternative=alt, trim=True, table=table, clean=clean)
+                for k in (1, 2, 3, 5, 9):
+                    got = split.translate_split(buf, k, lambda: FakeTranslator(buf, frame, alt, True, table, clean), trim=True)
+                    assert got == want, (seed, frame, alt, table, k)
+    # a record that is nothing but N: every piece hands the walk on to the next one
+    buf = b">n\n" + b"\n".join([b"N" * 60] * 40) + b"\n"
+    want = oracle.translate(buf, frame="6", trim=True)
+    assert split.translate_split(buf, 7, lambda: FakeTranslator(buf, "6", False, True), trim=True) == want
+
+
 def test_assemble_rejects_gaps():
     with pytest.raises(ValueError):
         split.assemble(10, [[(0, b"abc")], [(4, b"defghi")]])
@@ -175,7 +253,8 @@ def _split_worker(rank, world, port, buf, frame, alt, q):
         dist.all_gather_object(objs, obj)
         return objs
 
-    total, segs = split.translate_split_rank(buf, rank, world, FakeTranslator(buf, frame, alt), all_gather)
+    total, segs = split.translate_split_rank(buf, rank, world, FakeTranslator(buf, frame, alt, trim=True), all_gather,
+                                             trim=True)
     q.put((rank, total, segs))
     dist.barrier()
     dist.destroy_process_group()
@@ -185,7 +264,7 @@ def test_split_two_ranks_gloo():
     """The exchange between the ranks of a split record (three integers per piece), world_size 2."""
     import socket
     import torch.multiprocessing as mp
-    buf = one_record(3, 5000, width=60)
+    buf = trim_record(3, 5000, width=60)
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
@@ -200,7 +279,7 @@ def test_split_two_ranks_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res[0][1] == res[1][1]
-    assert split.assemble(res[0][1], [r[2] for r in res]) == oracle.translate(buf, frame="6")
+    assert split.assemble(res[0][1], [r[2] for r in res]) == oracle.translate(buf, frame="6", trim=True)
 
 
 # ---- GPU: the real pieces ----
@@ -256,6 +335,27 @@ def test_gpu_split_ragged_lines_and_tiny_pieces():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("frame", ["1", "F", "-3", "R", "6"])
+def test_gpu_split_trim(frame):
+    """--trim on a split record through the C ABI (gts_piece_trim): ends that are long runs of X / *."""
+    for seed in range(10):
+        n = [0, 1, 4, 60, 181, 700, 30000, 10, 999, 2][seed]
+        buf = trim_record(seed, n, width=(60, 7, 13)[seed % 3])
+        for alt in (False, True):
+            for table, clean in ((0, False), (11, True)):
+                want = oracle.translate(buf, frame=frame, alternative=alt, trim=True, table=table, clean=clean)
+                for k in (1, 2, 3, 5, 9):
+                    got = split.translate_split(buf, k, make_gpu(frame, alt, table=table, clean=clean, trim=True), trim=True)
+                    assert got == want, (seed, frame, alt, table, k)
+    buf = b">n\n" + b"\n".join([b"N" * 60] * 4000) + b"\n"  # nothing but N: the walk crosses every piece
+    want = oracle.translate(buf, frame="6", trim=True)
+    assert split.translate_split(buf, 5, make_gpu("6", False, trim=True), trim=True) == want
+    buf = one_record(78, 2_000_000, width=60)
+    want = oracle.translate(buf, frame="6", table=11, clean=True, trim=True)
+    assert split.translate_split(buf, 4, make_gpu("6", False, table=11, clean=True, trim=True), trim=True) == want
+
+
+@pytest.mark.gpu
 def test_gpu_split_argument_errors():
     import gotranseq_b200
     tr = make_gpu("6", False)()
@@ -267,6 +367,8 @@ def test_gpu_split_argument_errors():
         tr.piece_scan(b"ACG\n>b\nAC\n", False)
     tr.close()
     tr = make_gpu("6", False, trim=True)()
-    with pytest.raises(gotranseq_b200.TranseqError, match="cannot be trimmed"):
-        tr.piece_scan(b">a\nACG\n", True)
+    info = tr.piece_scan(b">a\nACG\n", True)
+    piece = split.plan_pieces([info])[0]
+    with pytest.raises(gotranseq_b200.TranseqError, match="needs the trimmed frame lengths"):
+        tr.piece_translate(piece)
     tr.close()

@@ -10,19 +10,7 @@ run --steps 20 --warmup 3 > gpurun_out/${tag}_readme_n$n.json 2> gpurun_out/${ta
 run --workload short_reads --steps 10 --warmup 3 --stream-gb 20.4 --no-cpu-baseline > gpurun_out/${tag}_short_n$n.json 2> gpurun_out/${tag}_short_n$n.err; echo "short rc=$?"
 run --workload contigs --per-gpu 40 --steps 10 --warmup 3 --stream-gb 25.4 --no-cpu-baseline > gpurun_out/${tag}_contigs_n$n.json 2> gpurun_out/${tag}_contigs_n$n.err; echo "contigs rc=$?"
 for f in readme short contigs; do tail -c 300 gpurun_out/${tag}_${f}_n$n.err; done
-if [ $n -eq 1 ]; then
-  python - <<PY
-import workloads, time
-d = workloads.readme189()
-open('/dev/shm/in.fna','wb').write(d)
-PY
-  ls -la /dev/shm/in.fna
-  for i in 1 2 3; do /usr/bin/time -f "cli %e s wall" gotranseq_b200/bin/gotranseq -s /dev/shm/in.fna -o /dev/shm/out.faa -f 6 > /dev/shm/warn.txt; done 2>&1 | tee gpurun_out/${tag}_cli.txt
-  ls -la /dev/shm/out.faa | tee -a gpurun_out/${tag}_cli.txt; sha256sum /dev/shm/out.faa | tee -a gpurun_out/${tag}_cli.txt
-  /usr/bin/time -f "oracle_cli %e s wall" oracle/transeq_oracle_cli -s /dev/shm/in.fna -o /dev/shm/out_ref.faa -f 6 -n 1 --timing 2>&1 | tee -a gpurun_out/${tag}_cli.txt
-  sha256sum /dev/shm/out_ref.faa | tee -a gpurun_out/${tag}_cli.txt
-  /usr/bin/time -f "oracle_cli_allcores %e s wall" oracle/transeq_oracle_cli -s /dev/shm/in.fna -o /dev/shm/out_ref2.faa -f 6 --timing 2>&1 | tee -a gpurun_out/${tag}_cli.txt
-fi
+if [ $n -eq 1 ]; then python tools/cli_time.py > gpurun_out/${tag}_cli.json 2> gpurun_out/${tag}_cli.err; cat gpurun_out/${tag}_cli.json; tail -3 gpurun_out/${tag}_cli.err; fi
 python - <<PY
 import json
 for f in ('readme','short','contigs'):
