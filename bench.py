@@ -314,8 +314,8 @@ def raw_copy(torch, nbytes_in, nbytes_out, steps, chunk=16 << 20, devices=None):
         with torch.cuda.device(d):
             h_a = torch.empty(nbytes_in, dtype=torch.uint8).pin_memory()
             h_b = torch.empty(nbytes_out, dtype=torch.uint8).pin_memory()
-            d_a = torch.empty(nbytes_in, dtype=torch.uint8, device="cuda")
-            d_b = torch.empty(nbytes_out, dtype=torch.uint8, device="cuda")
+            d_a = torch.empty(nbytes_in, dtype=torch.uint8, device=torch.device("cuda", d))
+            d_b = torch.empty(nbytes_out, dtype=torch.uint8, device=torch.device("cuda", d))
             st.append((d, h_a, h_b, d_a, d_b, torch.cuda.Stream(), torch.cuda.Stream()))
 
     def once():
@@ -365,10 +365,10 @@ def run_split(args, rank, local_rank, world):
     stream = torch.cuda.current_stream().cuda_stream
     d_in = torch.from_numpy(np.frombuffer(piece_bytes, dtype=np.uint8).copy()).cuda()
     cap = len(data) * 2 + 4096  # three frames of n/3 residues + newlines + headers
-    d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    d_out = torch.empty(cap, dtype=torch.uint8, device=torch.device("cuda", local_rank))
     W = 4 + 192  # nucleotide count, header length, last two codes, first 192 codes
-    mine = torch.zeros(W, dtype=torch.int64, device="cuda")
-    every = torch.zeros(W * world, dtype=torch.int64, device="cuda")
+    mine = torch.zeros(W, dtype=torch.int64, device=torch.device("cuda", local_rank))
+    every = torch.zeros(W * world, dtype=torch.int64, device=torch.device("cuda", local_rank))
 
     def step():
         info = tr.piece_scan_device(d_in.data_ptr(), n, rank == 0, stream)
@@ -415,8 +415,8 @@ def run_split(args, rank, local_rank, world):
         for off, length in segs:
             ok = ok and host[off:off + length] == want[off:off + length]
     seg_bytes = sum(length for _, length in segs)
-    t = torch.tensor([dev_s, 0.0 if ok else 1.0], dtype=torch.float64, device="cuda")
-    sb = torch.tensor([seg_bytes], dtype=torch.int64, device="cuda")
+    t = torch.tensor([dev_s, 0.0 if ok else 1.0], dtype=torch.float64, device=torch.device("cuda", local_rank))
+    sb = torch.tensor([seg_bytes], dtype=torch.int64, device=torch.device("cuda", local_rank))
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(sb, op=dist.ReduceOp.SUM)
@@ -512,7 +512,7 @@ def main():
     # ---- device-resident: input already in HBM, output stays in HBM ----
     d_in = torch.from_numpy(batch.array()).cuda()
     cap = nbytes * 4 + 4096
-    d_out = torch.empty(cap, dtype=torch.uint8, device="cuda")
+    d_out = torch.empty(cap, dtype=torch.uint8, device=torch.device("cuda", local_rank))
     out_n = tr.translate_device(d_in.data_ptr(), nbytes, d_out.data_ptr(), cap, stream)
     sampler = ClockSampler(local_rank)
     sampler.start()  # (sampled across the warm-up as well: the timed region is only ~10 ms long)
@@ -594,15 +594,15 @@ def main():
 
     # ---- max over ranks, sum of the work ----
     if world > 1:
-        tt = torch.tensor([dev_s, e2e_s, stream_s, raw_s, 0.0 if verified in (True, None) else 1.0], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([dev_s, e2e_s, stream_s, raw_s, 0.0 if verified in (True, None) else 1.0], dtype=torch.float64, device=torch.device("cuda", local_rank))
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dev_s, e2e_s, stream_s, raw_s = (float(x) for x in tt[:4])
         verified = (float(tt[4]) == 0.0) if verified is not None else None
-        ws = torch.tensor([nt, nbytes, out_n], dtype=torch.float64, device="cuda")
+        ws = torch.tensor([nt, nbytes, out_n], dtype=torch.float64, device=torch.device("cuda", local_rank))
         dist.all_reduce(ws, op=dist.ReduceOp.SUM)
         nt_all, in_all, out_all = float(ws[0]), float(ws[1]), float(ws[2])
-        sizes = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(world)]
-        dist.all_gather(sizes, torch.tensor([out_n], dtype=torch.int64, device="cuda"))
+        sizes = [torch.zeros(1, dtype=torch.int64, device=torch.device("cuda", local_rank)) for _ in range(world)]
+        dist.all_gather(sizes, torch.tensor([out_n], dtype=torch.int64, device=torch.device("cuda", local_rank)))
         shard_out_offsets = np.concatenate(([0], np.cumsum([int(s) for s in sizes]))).tolist()
     else:
         nt_all, in_all, out_all = float(nt), float(nbytes), float(out_n)
@@ -639,7 +639,7 @@ def main():
         t0 = time.perf_counter()
         rr = stream_once(tr, batch.h_in, nbytes, repeats=repeats)
         dt = time.perf_counter() - t0
-        tt = torch.tensor([dt, 0.0 if (periods_ok and rr["out"] == repeats * out_n) else 1.0], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([dt, 0.0 if (periods_ok and rr["out"] == repeats * out_n) else 1.0], dtype=torch.float64, device=torch.device("cuda", local_rank))
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         long_stream = {"api": "gts_acquire_input / gts_submit / gts_wait_output, reader = memcpy into the pinned buffer",

@@ -197,6 +197,13 @@ struct gts_ctx {
 
 namespace {
 
+// The calling thread's current device is put back when an entry point that visits several GPUs returns.
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 int fail(gts_ctx *ctx, int code, const std::string &msg) {
     if (ctx) ctx->err = msg; else g_create_error = msg;
     return code;
@@ -1114,8 +1121,8 @@ int gts_create(const gts_options *opt, gts_ctx **out) {
                                                    (e != cudaSuccess ? cudaGetErrorString(e) : "no device"));
         for (int i = 0; i < count && i < 8; i++) ids.push_back(i);
     }
-    int prev = -1;
-    cudaGetDevice(&prev);
+    DeviceGuard guard;
+    const bool keep_current = ids.size() > 1;  // several GPUs: the caller's current device stays what it was
     for (int id : ids) {
         std::unique_ptr<DevCtx> dev;
         std::string emsg;
@@ -1127,7 +1134,7 @@ int gts_create(const gts_options *opt, gts_ctx **out) {
         }
         ctx->devs.push_back(std::move(dev));
     }
-    if (ids.size() > 1 || ids[0] >= 0) cudaSetDevice(ctx->devs[0]->device);
+    if (!keep_current) guard.prev = ctx->devs[0]->device;  // one GPU: it becomes current (as cudaSetDevice(device) would)
     ctx->in_max = kSlots * ctx->devs.size() + 2;
     ctx->out_max = ctx->in_max + 1;
     ctx->poison = std::getenv("GTS_POISON_OUTPUT") != nullptr;
@@ -1137,6 +1144,7 @@ int gts_create(const gts_options *opt, gts_ctx **out) {
 
 void gts_destroy(gts_ctx *ctx) {
     if (!ctx) return;
+    DeviceGuard guard;
     if (ctx->workers_started) {
         {
             std::unique_lock<std::mutex> lk(ctx->mu);
@@ -1505,6 +1513,7 @@ int gts_kernel_times(gts_ctx *ctx, double ms[4], uint64_t *passes) {
     if (!ctx || !ms) return GTS_ERR_ARG;
     for (int k = 0; k < 4; k++) ms[k] = 0.0;
     size_t np_all = 0;
+    DeviceGuard guard;
     for (auto &d : ctx->devs) {
         CU(cudaSetDevice(d->device));
         const size_t np = d->prof_used / 5;
@@ -1520,7 +1529,6 @@ int gts_kernel_times(gts_ctx *ctx, double ms[4], uint64_t *passes) {
         d->prof_used = 0;
         np_all += np;
     }
-    CU(cudaSetDevice(dev0(ctx)->device));
     if (passes) *passes = np_all;
     return GTS_OK;
 }
