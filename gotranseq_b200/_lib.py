@@ -63,6 +63,7 @@ class gts_segment(ctypes.Structure):
 
 
 GTS_MAX_SEGMENTS = 12
+GTS_PIECE_INFO_BYTES = 256
 
 EXPORTS = {
     # name: (restype, argtypes)
@@ -107,6 +108,11 @@ EXPORTS = {
                                              ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint8), ctypes.c_void_p]),
     "gts_piece_trim": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(gts_piece), ctypes.POINTER(ctypes.c_uint64),
                                       ctypes.POINTER(ctypes.c_uint8)]),
+    "gts_piece_scan_async": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]),
+    "gts_piece_translate_async": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "gts_piece_result": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(gts_segment),
+                                        ctypes.POINTER(ctypes.c_int), ctypes.POINTER(gts_piece)]),
     "gts_piece_scan": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
                                       ctypes.POINTER(gts_piece_info)]),
     "gts_piece_translate": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(gts_piece), ctypes.POINTER(ctypes.c_size_t),

@@ -125,6 +125,9 @@ struct DevCtx {  // one GPU: streams, scratch of a device pass, chunk slots, wor
     const void *slots_of = nullptr;
     size_t slots_n = 0;
     u64 *d_pt = nullptr;  // k_piece_trim's results
+    gts::PieceParams *d_pp = nullptr;     // k_piece_plan's result
+    gts::PieceInfoDev *h_infos = nullptr; // pinned copy of the all-gathered piece summaries
+    int piece_rank = 0, piece_world = 1;
 
     // ---- per-kernel timing ----
     std::vector<cudaEvent_t> prof_events;  // 5 per recorded pass
@@ -367,21 +370,18 @@ int enqueue_pass(gts_ctx *ctx, DevCtx *dev, const PassArgs &a, std::string *err)
     job.alternative = ctx->opt.alternative ? 1 : 0;
     job.trim = ctx->opt.trim ? 1 : 0;
     job.more_follows = a.more_follows ? 1 : 0;
-    job.piece = 0; job.no_end_pads = 0; job.has_carry = 0; job.carry = 0; job.no_headers = 0; job.ov_H = 0;
-    job.t0_base = 0; job.win_lo = 0; job.ov_slot = 0; job.ov_n = 0; job.ov_dbase = 0;
-    job.head_out = nullptr;
-    std::memset(job.head, 0, sizeof(job.head));
-    job.ov_trim = 0; job.ov_last = 0; job.pt_before = 0; job.pt_out = nullptr;
+    std::memset(&job.pv, 0, sizeof(job.pv));
+    job.pp = nullptr;
+    job.info_out = nullptr;
+    job.ov_trim = 0; job.pad1 = 0; job.pt_before = 0; job.pt_out = nullptr;
     std::memset(job.ov_len, 0, sizeof(job.ov_len));
     std::memset(job.pt_len, 0, sizeof(job.pt_len));
     if (ctx->piece_on) {
         const gts::Job &p = ctx->piece_job;
-        job.piece = p.piece; job.no_end_pads = p.no_end_pads; job.has_carry = p.has_carry; job.carry = p.carry;
-        job.no_headers = p.no_headers; job.ov_H = p.ov_H; job.t0_base = p.t0_base; job.win_lo = p.win_lo;
-        job.ov_slot = p.ov_slot; job.ov_n = p.ov_n; job.ov_dbase = p.ov_dbase;
-        job.head_out = p.head_out;
-        std::memcpy(job.head, p.head, sizeof(job.head));
-        job.ov_trim = p.ov_trim; job.ov_last = p.ov_last;
+        job.pv = p.pv;
+        job.pp = p.pp;
+        job.info_out = p.info_out;
+        job.ov_trim = p.ov_trim;
         std::memcpy(job.ov_len, p.ov_len, sizeof(job.ov_len));
     }
     job.lut = ctx->lut;
@@ -515,7 +515,8 @@ void dev_destroy(DevCtx *dev) {
     cudaFree(dev->d_sym); cudaFree(dev->d_tile_info); cudaFree(dev->d_tile_pre);
     cudaFree(dev->d_zero); cudaFree(dev->d_scan_nl);
     free_rec(dev);
-    cudaFree(dev->d_in); cudaFree(dev->d_out); cudaFree(dev->d_head); cudaFree(dev->d_pt);
+    cudaFree(dev->d_in); cudaFree(dev->d_out); cudaFree(dev->d_head); cudaFree(dev->d_pt); cudaFree(dev->d_pp);
+    if (dev->h_infos) cudaFreeHost(dev->h_infos);
     for (PassSlot &s : dev->slots) {
         cudaFree(s.d_in); cudaFree(s.d_out); cudaFree(s.d_warn); cudaFree(s.d_wres);
         if (s.h_totals) cudaFreeHost(s.h_totals);
@@ -1552,9 +1553,9 @@ int gts_piece_scan_device(gts_ctx *ctx, const void *d_in, size_t n, int first, g
     std::lock_guard<std::mutex> dl(dev->mu);
     ctx->piece_on = true;
     ctx->piece_job = gts::Job();
-    ctx->piece_job.no_end_pads = 1;  // count only: no pass of its own end
-    if (!dev->d_head) CU(cudaMalloc(&dev->d_head, 256));
-    ctx->piece_job.head_out = dev->d_head;
+    ctx->piece_job.pv.no_end_pads = 1;  // count only: no pass of its own end
+    if (!dev->d_head) CU(cudaMalloc(&dev->d_head, sizeof(gts::PieceInfoDev)));
+    ctx->piece_job.info_out = reinterpret_cast<gts::PieceInfoDev *>(dev->d_head);
     ctx->last_truncated = false;
     PassArgs a;
     a.d_in = static_cast<const uint8_t *>(d_in); a.n = n; a.stream = static_cast<cudaStream_t>(stream);
@@ -1562,10 +1563,11 @@ int gts_piece_scan_device(gts_ctx *ctx, const void *d_in, size_t n, int first, g
     std::string emsg;
     int rc = enqueue_pass(ctx, dev, a, &emsg);
     if (rc) fail(ctx, rc, emsg);
+    gts::PieceInfoDev inf;
     if (!rc) {
-        // (the head codes travel with the totals: one synchronisation for the whole scan)
-        cudaError_t ce = cudaMemcpyAsync(info->head, dev->d_head, sizeof(info->head), cudaMemcpyDeviceToHost, a.stream);
-        if (ce != cudaSuccess) rc = cuda_fail(ctx, ce, "copy of the head codes");
+        // (the piece's summary travels with the totals: one synchronisation for the whole scan)
+        cudaError_t ce = cudaMemcpyAsync(&inf, dev->d_head, sizeof(inf), cudaMemcpyDeviceToHost, a.stream);
+        if (ce != cudaSuccess) rc = cuda_fail(ctx, ce, "copy of the piece summary");
     }
     if (!rc) {
         dev->pending = true;
@@ -1575,16 +1577,17 @@ int gts_piece_scan_device(gts_ctx *ctx, const void *d_in, size_t n, int first, g
     if (rc) return rc;
     const gts::Totals &t = *dev->h_totals;
     if (ctx->last_truncated) return fail(ctx, GTS_ERR_ARG, "a split record cannot hold an over-long line");
-    info->headers = t.n_headers;
-    info->nucleotides = t.total_sym - 2 - 2 * t.n_headers;
-    info->tail[0] = (uint8_t)(t.tail & 0xF);
-    info->tail[1] = (uint8_t)((t.tail >> 4) & 0xF);
+    info->headers = inf.headers;
+    info->nucleotides = inf.nucleotides;
+    info->tail[0] = (uint8_t)(inf.tail & 0xF);
+    info->tail[1] = (uint8_t)((inf.tail >> 4) & 0xF);
     info->reserved[0] = info->reserved[1] = 0;
     info->header_len = 0;
+    std::memcpy(info->head, inf.head, sizeof(info->head));
     if (first) {
         if (t.n_headers != 1) return fail(ctx, GTS_ERR_ARG, "the first piece must hold exactly one header line");
-        if (t.aux == ~0ull) return fail(ctx, GTS_ERR_ARG, "the first piece must start with the header line");
-        info->header_len = (uint32_t)t.aux;
+        if (inf.header_len == ~0ull) return fail(ctx, GTS_ERR_ARG, "the first piece must start with the header line");
+        info->header_len = (uint32_t)inf.header_len;
     } else if (t.n_headers != 0) {
         return fail(ctx, GTS_ERR_ARG, "only the first piece of a split record may hold a header line");
     }
@@ -1594,8 +1597,9 @@ int gts_piece_scan_device(gts_ctx *ctx, const void *d_in, size_t n, int first, g
 }
 
 // The piece fields of a pass from the caller's description of the piece.
-static void fill_piece_job(gts::Job &p, const gts_piece *piece) {
-    p = gts::Job();
+static void fill_piece_job(gts::Job &j, const gts_piece *piece) {
+    j = gts::Job();
+    gts::PieceParams &p = j.pv;
     p.piece = 1;
     p.no_end_pads = piece->last ? 0 : 1;
     p.ov_last = piece->last ? 1 : 0;
@@ -1616,8 +1620,8 @@ static void fill_piece_job(gts::Job &p, const gts_piece *piece) {
         p.win_lo = p.t0_base + 2;
     }
     if (piece->has_trim_len) {
-        p.ov_trim = 1;
-        for (int f = 0; f < 6; f++) p.ov_len[f] = (u32)piece->trim_len[f];
+        j.ov_trim = 1;
+        for (int f = 0; f < 6; f++) j.ov_len[f] = (u32)piece->trim_len[f];
     }
 }
 
@@ -1633,8 +1637,8 @@ int gts_piece_trim_device(gts_ctx *ctx, const void *d_in, size_t n, const gts_pi
     gts::Job job = dev->job;  // the scan pass's tables: slots, tile records, tile offsets, totals
     gts::Job p;
     fill_piece_job(p, piece);
-    job.has_carry = p.has_carry; job.carry = p.carry; job.ov_last = p.ov_last; job.ov_n = p.ov_n;
-    std::memcpy(job.head, p.head, sizeof(job.head));
+    job.pv = p.pv;
+    job.pp = nullptr;
     job.pt_before = piece->nt_before;
     job.pt_out = dev->d_pt;
     for (int f = 0; f < 6; f++) job.pt_len[f] = len[f];
@@ -1683,6 +1687,105 @@ int gts_piece_translate_device(gts_ctx *ctx, const void *d_in, size_t n, const g
     const u64 n_piece = t.total_sym - 2 - (piece->first ? 2 : 0);
     u64 total = 0;
     *nseg = piece_segments(ctx->mask, ctx->opt.alternative != 0, *piece, n_piece, segs, &total);
+    if (total != t.out_total) return fail(ctx, GTS_ERR_ARG, "split record: host and device output sizes differ");
+    return GTS_OK;
+}
+
+// ---- the same step without a host round trip between scan and translate ---------------------
+// scan (k_parse + k_tile_scan) -> the caller all-gathers the 256-byte summaries on the same stream
+// (NCCL) -> plan on the device (k_piece_plan) + the translate kernels on the reused slots -> one
+// synchronisation at the end (gts_piece_result).
+
+int gts_piece_scan_async(gts_ctx *ctx, const void *d_in, size_t n, void *d_info, void *stream) {
+    if (!ctx || !d_info) return GTS_ERR_ARG;
+    if (n && !d_in) return fail(ctx, GTS_ERR_ARG, "d_in is NULL");
+    DevCtx *dev = dev0(ctx);
+    CU(cudaSetDevice(dev->device));
+    std::lock_guard<std::mutex> dl(dev->mu);
+    ctx->piece_on = true;
+    ctx->piece_job = gts::Job();
+    ctx->piece_job.pv.no_end_pads = 1;
+    ctx->piece_job.info_out = static_cast<gts::PieceInfoDev *>(d_info);
+    PassArgs a;
+    a.d_in = static_cast<const uint8_t *>(d_in); a.n = n; a.stream = static_cast<cudaStream_t>(stream);
+    a.scan_only = true;
+    std::string emsg;
+    int rc = enqueue_pass(ctx, dev, a, &emsg);
+    ctx->piece_on = false;
+    if (rc) return fail(ctx, rc, emsg);
+    dev->slots_of = d_in;  // (valid once the stream has run the pass; the translate call is enqueued behind it)
+    dev->slots_n = n;
+    return GTS_OK;
+}
+
+int gts_piece_translate_async(gts_ctx *ctx, const void *d_in, size_t n, int rank, int world, const void *d_infos,
+                              void *d_out, size_t cap, void *stream) {
+    if (!ctx || !d_infos || rank < 0 || world < 1 || rank >= world || world > 64) return GTS_ERR_ARG;
+    if (ctx->opt.trim) return fail(ctx, GTS_ERR_ARG, "--trim on a split record goes through gts_piece_scan / gts_piece_trim / gts_piece_translate");
+    DevCtx *dev = dev0(ctx);
+    CU(cudaSetDevice(dev->device));
+    std::lock_guard<std::mutex> dl(dev->mu);
+    if (dev->slots_of != d_in || dev->slots_n != n)
+        return fail(ctx, GTS_ERR_ARG, "gts_piece_translate_async: the piece must have been scanned by the call before");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (!dev->d_pp) CU(cudaMalloc(&dev->d_pp, sizeof(gts::PieceParams)));
+    if (!dev->h_infos) CU(cudaHostAlloc(&dev->h_infos, 64 * sizeof(gts::PieceInfoDev), cudaHostAllocPortable));
+    CU(gts::launch_piece_plan(static_cast<const gts::PieceInfoDev *>(d_infos), rank, world, dev->d_pp, st));
+    CU(cudaMemcpyAsync(dev->h_infos, d_infos, (size_t)world * sizeof(gts::PieceInfoDev), cudaMemcpyDeviceToHost, st));
+    dev->piece_rank = rank;
+    dev->piece_world = world;
+    ctx->piece_on = true;
+    ctx->piece_job = gts::Job();
+    ctx->piece_job.pp = dev->d_pp;
+    PassArgs a;
+    a.d_in = static_cast<const uint8_t *>(d_in); a.n = n; a.d_out = static_cast<uint8_t *>(d_out); a.cap = cap;
+    a.stream = st;
+    a.reuse_slots = true;
+    std::string emsg;
+    int rc = enqueue_pass(ctx, dev, a, &emsg);
+    ctx->piece_on = false;
+    if (rc) return fail(ctx, rc, emsg);
+    dev->pending = true;
+    ctx->stats.kernel_launches++;
+    return GTS_OK;
+}
+
+int gts_piece_result(gts_ctx *ctx, size_t *out_total, gts_segment segs[GTS_MAX_SEGMENTS], int *nseg, gts_piece *piece_out) {
+    if (!ctx || !segs || !nseg) return GTS_ERR_ARG;
+    DevCtx *dev = dev0(ctx);
+    CU(cudaSetDevice(dev->device));
+    std::lock_guard<std::mutex> dl(dev->mu);
+    if (!dev->pending || !dev->h_infos) return fail(ctx, GTS_ERR_ARG, "gts_piece_result: no piece enqueued");
+    CU(cudaStreamSynchronize(dev->job_stream));
+    dev->pending = false;
+    const gts::Totals &t = *dev->h_totals;
+    if (t.flags & (gts::kFlagRecOverflow | gts::kFlagLongLine))
+        return fail(ctx, GTS_ERR_ARG, "split record: the piece needs the host-driven calls (record table / line length)");
+    // the same plan on the host, for the segments
+    const gts::PieceInfoDev *all = dev->h_infos;
+    const int rank = dev->piece_rank, world = dev->piece_world;
+    for (int k = 0; k < world; k++) {
+        if (all[k].headers != (k == 0 ? 1u : 0u) || (k == 0 && all[0].header_len == ~0ull))
+            return fail(ctx, GTS_ERR_ARG, "a split record is ONE record: the first piece starts with its header line, the others hold none");
+    }
+    gts_piece p;
+    std::memset(&p, 0, sizeof(p));
+    uint64_t total_nt = 0, before = 0;
+    for (int k = 0; k < world; k++) {
+        if (k < rank) before += all[k].nucleotides;
+        total_nt += all[k].nucleotides;
+    }
+    p.nt_before = before;
+    p.nt_total = total_nt;
+    p.header_len = (uint32_t)all[0].header_len;
+    p.first = rank == 0;
+    p.last = rank == world - 1;
+    if (piece_out) *piece_out = p;
+    if (out_total) *out_total = t.out_total;
+    if (t.flags & gts::kFlagOutOverflow)
+        return fail(ctx, GTS_ERR_CAPACITY, "output buffer too small: need " + std::to_string(t.out_total) + " bytes");
+    u64 total = 0;
+    *nseg = piece_segments(ctx->mask, ctx->opt.alternative != 0, p, all[rank].nucleotides, segs, &total);
     if (total != t.out_total) return fail(ctx, GTS_ERR_ARG, "split record: host and device output sizes differ");
     return GTS_OK;
 }

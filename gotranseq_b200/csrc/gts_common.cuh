@@ -87,6 +87,9 @@ __device__ __forceinline__ u32 n_flags(u32 x) {
 // 0x80 in every byte of c (nucleotide codes 0..4) that is 0
 __device__ __forceinline__ u32 zero_code_flags(u32 c) { return (0x80808080u - c) & 0x80808080u; }
 
+// the piece description of a pass: in device memory when the pass was planned on the device
+__device__ __forceinline__ const PieceParams &piece_of(const Job &job) { return job.pp ? *job.pp : job.pv; }
+
 struct Pair {
     u64 a, b;
 };

@@ -139,6 +139,38 @@ struct LutBytes {  // k_lines' tables, one residue per byte (125 used entries ea
     u32 r[32];     // reverse-strand residue of the codon read downwards: index s2 + 5 s1 + 25 s0
 };
 
+// A piece of one record split over several GPUs (gts_piece_*).  The piece's symbols keep their index
+// in the whole record's stream: t0_base is the stream index of the buffer's first symbol, and one
+// record slot is given the whole record's geometry.
+struct PieceParams {
+    u32 piece;         // 0 = an ordinary pass
+    u32 no_end_pads;   // the stream goes on after this buffer: no end pads
+    u32 has_carry;     // the two symbols in front of the buffer are `carry` (they replace slot 0's pads)
+    u32 carry;         // last | second-to-last << 4
+    u32 no_headers;    // the record's header lines are written by the first piece only
+    u32 ov_H;          // the record's header line bytes
+    u32 ov_last;       // this piece ends the record (k_piece_fix adds the end pads to the reused slots)
+    u32 pad;
+    u64 t0_base;
+    u64 win_lo;        // windows ending below this stream index belong to the piece before
+    u64 ov_slot;       // the record's slot in this pass; every other slot is silent
+    u64 ov_n;          // the whole record's nucleotides
+    u64 ov_dbase;      // stream index of its first nucleotide
+    uint8_t head[192]; // the 192 symbols behind the buffer (the record goes on in the next piece)
+};
+
+// What the scan of a piece reports (256 bytes: the unit of the all-gather between the ranks).
+struct PieceInfoDev {
+    u64 nucleotides;
+    u64 headers;       // header lines seen: 1 for the first piece, 0 for the others
+    u64 header_len;    // bytes of the header line the buffer starts with (CR dropped), ~0 = it starts with none
+    u32 tail;          // codes of its last | second-to-last << 4 nucleotide
+    u32 pad;
+    uint8_t head[192]; // codes of its first 192 nucleotides (0 beyond its end)
+    uint8_t fill[32];
+};
+static_assert(sizeof(PieceInfoDev) == 256, "all-gather unit");
+
 struct Job {  // kernel argument block (by value)
     const uint8_t *in;  // raw FASTA, 16-byte aligned
     u64 n;
@@ -180,23 +212,13 @@ struct Job {  // kernel argument block (by value)
     u32 more_follows;  // this buffer is not the end of the stream: an empty slot 0 is never emitted
 
     // ---- a piece of ONE record split over several passes / GPUs (gts_piece_*) ----
-    // The piece's symbols keep their index in the whole record's stream: t0_base is the stream index
-    // of the buffer's first symbol, and one record slot is given the whole record's geometry.
-    u32 piece;         // 0 = an ordinary pass
-    u32 no_end_pads;   // the stream goes on after this buffer: no end pads
-    u32 has_carry;     // the two symbols in front of the buffer are `carry` (they replace slot 0's pads)
-    u32 carry;         // last | second-to-last << 4
-    u32 no_headers;    // the record's header lines are written by the first piece only
-    u32 ov_H;          // the record's header line bytes
-    u64 t0_base;
-    u64 win_lo;        // windows ending below this stream index belong to the piece before
-    u64 ov_slot;       // the record's slot in this pass; every other slot is silent
-    u64 ov_n;          // the whole record's nucleotides
-    u64 ov_dbase;      // stream index of its first nucleotide
-    uint8_t *head_out; // scan pass: receives the codes of the buffer's first 192 nucleotides
-    uint8_t head[192]; // the 192 symbols behind the buffer (the record goes on in the next piece)
+    // The piece's description: by value (pv, host-driven calls) or in device memory (pp, written by
+    // k_piece_plan from the all-gathered scan results: no host round trip between scan and translate).
+    PieceParams pv;
+    const PieceParams *pp;
+    PieceInfoDev *info_out;  // scan pass: receives the piece's counts and boundary codes
     u32 ov_trim;       // --trim on a split record: the record's trimmed frame lengths are given (ov_len)
-    u32 ov_last;       // this piece ends the record (k_piece_fix adds the end pads to the reused slots)
+    u32 pad1;
     u32 ov_len[6];
     // k_piece_trim: one step of the trim walk over the pieces (writer.go:141-163 on a split record)
     u64 pt_len[6];     // residues of each frame not yet known to be trimmed away

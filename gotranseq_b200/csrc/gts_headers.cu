@@ -21,7 +21,7 @@ namespace gts {
 __global__ void __launch_bounds__(128) k_headers(const __grid_constant__ Job job) {
     const int lane = threadIdx.x & 31, sub = lane & 15, half = lane >> 4;
     const u64 R = job.totals->n_headers;
-    if (job.totals->flags != 0 || job.no_headers) return;
+    if (job.totals->flags != 0 || piece_of(job).no_headers) return;
     const u64 nhalf = (u64)gridDim.x * (blockDim.x >> 4);
     for (u64 s = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 4; s <= R; s += nhalf) {
         // everything that is indexed by the record goes first, in one round of loads

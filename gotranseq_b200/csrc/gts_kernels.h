@@ -13,6 +13,7 @@ cudaError_t init_kernels();
 cudaError_t launch_parse(const Job &job, cudaStream_t stream);                // k_parse
 cudaError_t launch_sizes(const Job &job, int sm_count, cudaStream_t stream);  // k_tile_scan, k_records, k_size
 cudaError_t launch_tile_scan(const Job &job, int sm_count, cudaStream_t stream);  // k_tile_scan alone (piece scan)
+cudaError_t launch_piece_plan(const PieceInfoDev *all, int rank, int world, PieceParams *out, cudaStream_t stream);  // k_piece_plan
 cudaError_t launch_piece_fix(const Job &job, cudaStream_t stream);    // k_piece_fix: carry / end pads into reused slots
 cudaError_t launch_piece_trim(const Job &job, cudaStream_t stream);   // k_piece_trim: one piece's part of the trim walk
 cudaError_t launch_warn(const Job &job, int sm_count, cudaStream_t stream);   // k_warn (only when job.warn is set)

@@ -127,6 +127,7 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
     for (int i = tid; i < (kLeft - 2) / 2; i += kLinesThreads) reinterpret_cast<uint16_t *>(sh.symf)[i] = 0;
     const u64 flags = job.totals->flags;
     const u64 R = job.totals->n_headers;
+    const PieceParams &PP = piece_of(job);
     if (flags != 0) return;
 
     // persistent CTAs: the grid is one wave; a CTA starts with tile blockIdx.x and claims its next
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
         continue;
     }
     const u64 T0 = tp.T0, Tend = tp.T0 + nsym;
-    const u32 tlo = job.win_lo > T0 ? (u32)(job.win_lo - T0) : 0u;  // 2 in the first tile of a later piece of a split record
+    const u32 tlo = PP.win_lo > T0 ? (u32)(PP.win_lo - T0) : 0u;  // 2 in the first tile of a later piece of a split record
     const uintptr_t out_mis = (uintptr_t)job.out & 15u;
 
     // Record pieces of the tile: the record open at its first byte, then one per header line.  A
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
         }
     }
     // the 192 symbols after the tile: the stream goes on in the next slot ...
-    const bool from_head = job.piece && job.no_end_pads;  // a split record goes on in the next piece
+    const bool from_head = PP.piece && PP.no_end_pads;  // a split record goes on in the next piece
     if (has_next ? next_nsym >= (u32)kHalo : !from_head) {
         if (tid < kHalo / 8) {
             const u32 lo4 = hw & 0x0F0F0F0Fu, hi4 = (hw >> 4) & 0x0F0F0F0Fu;
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
                 off -= nu;
                 u++;
             }
-            if (!found && from_head) v = job.head[off];  // off < kHalo symbols past the end of the piece
+            if (!found && from_head) v = PP.head[off];  // off < kHalo symbols past the end of the piece
             sh.symf[kLeft + nsym + i] = (uint8_t)v;
         }
     }

@@ -176,8 +176,8 @@ __global__ void __launch_bounds__(kParseWarps * 32, GTS_PARSE_CTAS) k_parse(cons
     __syncwarp();
     if (t == 0) {  // pads of slot 0 (the bytes before the first header line), or the two symbols in front of a piece
         if (lane == 0) {
-            tail_prev = job.has_carry ? ((job.carry >> 4) & 0xFu) : 0u;
-            tail_last = job.has_carry ? (job.carry & 0xFu) : 0u;
+            tail_prev = job.pv.has_carry ? ((job.pv.carry >> 4) & 0xFu) : 0u;
+            tail_last = job.pv.has_carry ? (job.pv.carry & 0xFu) : 0u;
             ws.sym[0] = (uint8_t)tail_prev;
             ws.sym[1] = (uint8_t)tail_last;
         }
@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(kParseWarps * 32, GTS_PARSE_CTAS) k_parse(cons
 
     // ---- the tile's last word(s), its counts ----
     const bool last_tile = (t + 1 == job.ntiles);
-    const u32 S_tile = S + (last_tile && !job.no_end_pads ? 2u : 0u);  // the last tile owns the two end pads
+    const u32 S_tile = S + (last_tile && !job.pv.no_end_pads ? 2u : 0u);  // the last tile owns the two end pads
     const u32 nw_total = (S_tile + 7u) >> 3;
     if (done_w + (u32)lane < nw_total) {  // at most two words: up to 7 carried symbols + 2 pads, zero filled
         const uint2 s2 = *reinterpret_cast<const uint2 *>(ws.sym + 8 * lane);

@@ -36,6 +36,7 @@ __global__ void __launch_bounds__(kScanThreads) k_tile_scan(const __grid_constan
     const u32 nscan = (ntiles + kScanTile - 1) / kScanTile;
     pdl_launch();
     pdl_wait();  // k_parse's tile records
+    const PieceParams &PP = piece_of(job);
     while (true) {
         __syncthreads();
         if (tid == 0) s_tile = atomicAdd(&job.counters[0], 1u);
@@ -112,14 +113,15 @@ __global__ void __launch_bounds__(kScanThreads) k_tile_scan(const __grid_constan
                 if (st + 1 == nscan) {
                     // totals; the last tile's two end pads are not counted as stream symbols
                     const u64 S2 = ex.a + tot_s, R = ex.b + tot_r;
-                    const u64 S = S2 - (job.no_end_pads ? 0 : 2);
+                    const u64 S = S2 - (PP.no_end_pads ? 0 : 2);
                     job.totals->total_sym = S;
+                    u32 tail = 0;
                     {   // the stream's last two symbols (a later piece of the same record needs them)
-                        u32 got = 0, tail = 0;
+                        u32 got = 0;
                         for (i64 u = (i64)ntiles - 1; got < 2 && u >= 0; u--) {
                             const TileInfo ti = job.tile_info[u];
                             // the last tile's end pads are not part of the record
-                            const u32 ns_u = ti.nsym - ((u32)u == ntiles - 1 && !job.no_end_pads ? 2u : 0u);
+                            const u32 ns_u = ti.nsym - ((u32)u == ntiles - 1 && !PP.no_end_pads ? 2u : 0u);
                             for (u32 k = 0; k < ns_u && got < 2; k++) {
                                 tail |= slot_symbol(job.sym, (u32)u, ns_u - 1 - k) << (4 * got);
                                 got++;
@@ -127,34 +129,41 @@ __global__ void __launch_bounds__(kScanThreads) k_tile_scan(const __grid_constan
                         }
                         job.totals->tail = tail;
                     }
-                    if (job.head_out) {
+                    if (job.info_out) {
+                        // piece scan: the counts and boundary codes the other pieces need
+                        PieceInfoDev inf;
+                        inf.headers = R;
+                        inf.nucleotides = S - 2 - 2 * R;
+                        inf.tail = tail;
+                        inf.pad = 0;
                         // the header line the buffer starts with (first piece of a split record): its
                         // length up to the '\n', one trailing CR dropped (bufio.ScanLines)
-                        u64 hl = ~0ull;
+                        inf.header_len = ~0ull;
                         if (job.n > 0 && job.in[0] == '>') {
                             u64 p = 0;
                             while (p < job.n && job.in[p] != '\n') p++;
-                            hl = p - (job.in[p - 1] == '\r' ? 1 : 0);
+                            inf.header_len = p - (job.in[p - 1] == '\r' ? 1 : 0);
                         }
-                        job.totals->aux = hl;
-                        // codes of the buffer's first 192 nucleotides (a piece of a split record: the
-                        // piece before it needs them); slot 0's pads and a header's pads are skipped
+                        // codes of the buffer's first 192 nucleotides (the piece before it needs them);
+                        // slot 0's pads and a header's pads are skipped
                         const u32 skip = 2u + 2u * (u32)R;
                         u32 seen = 0, got = 0;
                         for (u32 u = 0; u < ntiles && got < 192u; u++) {
-                            const u32 ns_u = job.tile_info[u].nsym - (u == ntiles - 1 && !job.no_end_pads ? 2u : 0u);
+                            const u32 ns_u = job.tile_info[u].nsym - (u == ntiles - 1 && !PP.no_end_pads ? 2u : 0u);
                             for (u32 k = 0; k < ns_u && got < 192u; k++, seen++)
-                                if (seen >= skip) job.head_out[got++] = (uint8_t)slot_symbol(job.sym, u, k);
+                                if (seen >= skip) inf.head[got++] = (uint8_t)slot_symbol(job.sym, u, k);
                         }
-                        for (; got < 192u; got++) job.head_out[got] = 0;
+                        for (; got < 192u; got++) inf.head[got] = 0;
+                        for (int i = 0; i < 32; i++) inf.fill[i] = 0;
+                        *job.info_out = inf;
                     }
                     job.totals->n_headers = R;
                     if (R + 2 <= job.rec_cap) {
                         // slot 0 (bytes before the first header line) and the sentinel after the last record
                         job.hdr_off[0] = 0;
-                        job.dbase[0] = job.t0_base + 2;
+                        job.dbase[0] = PP.t0_base + 2;
                         job.loc[0] = 2;
-                        job.dbase[R + 1] = job.t0_base + S + 2;
+                        job.dbase[R + 1] = PP.t0_base + S + 2;
                         job.loc[R + 1] = (u64)(ntiles - 1) << 16 | job.tile_info[ntiles - 1].nsym;
                     } else {
                         atomicOr(&job.totals->flags, kFlagRecOverflow);
@@ -163,7 +172,7 @@ __global__ void __launch_bounds__(kScanThreads) k_tile_scan(const __grid_constan
             }
         }
         __syncthreads();
-        u64 T = job.t0_base + s_excl_s + ex_s, Rr = s_excl_r + ex_r;
+        u64 T = PP.t0_base + s_excl_s + ex_s, Rr = s_excl_r + ex_r;
         // the two symbols before the thread's first tile (windows reach back two symbols): from the
         // tiles before it; for its other tiles they follow from its own tiles' tails
         u32 carry = 0;
@@ -363,6 +372,7 @@ __global__ void __launch_bounds__(kSizeThreads) k_size(const __grid_constant__ J
     pdl_wait();  // k_records' record table
     const u64 R = job.totals->n_headers;
     if (R + 2 > job.rec_cap) return;  // record table overflow: the host retries with a larger one
+    const PieceParams &PP = piece_of(job);
     const u64 nslots = R + 1;
     const u64 ntiles = (nslots + kSizeTile - 1) / kSizeTile;
     while (true) {
@@ -383,14 +393,14 @@ __global__ void __launch_bounds__(kSizeThreads) k_size(const __grid_constant__ J
             if (s < nslots) {
                 u64 D = job.dbase[s];
                 u64 n = job.dbase[s + 1] - 2 - D;
-                if (job.piece && s == job.ov_slot) {  // the whole record's geometry
-                    D = job.ov_dbase;
-                    n = job.ov_n;
+                if (PP.piece && s == PP.ov_slot) {  // the whole record's geometry
+                    D = PP.ov_dbase;
+                    n = PP.ov_n;
                 }
                 u64 L[6];
                 frame_lengths(n, job.alternative != 0, L);
-                if (job.piece && job.ov_trim) {
-                    if (s == job.ov_slot)
+                if (PP.piece && job.ov_trim) {
+                    if (s == PP.ov_slot)
                         for (int f = 0; f < 6; f++) L[f] = job.ov_len[f];  // reduced over the pieces (k_piece_trim)
                 } else if (job.trim) {
                     trimmed_lengths(job, lut, s, n, L);
@@ -399,9 +409,9 @@ __global__ void __launch_bounds__(kSizeThreads) k_size(const __grid_constant__ J
                 }
                 u64 H = s >= 1 ? (job.hinfo[s] & 0xFFFFFFFFull) : 0;
                 bool em = record_emitted(s, n, R, job.more_follows != 0);
-                if (job.piece) {
-                    em = s == job.ov_slot;
-                    if (em) H = job.ov_H;
+                if (PP.piece) {
+                    em = s == PP.ov_slot;
+                    if (em) H = PP.ov_H;
                 }
                 if (em) {
 #pragma unroll
@@ -496,17 +506,18 @@ __global__ void __launch_bounds__(kSizeThreads) k_size(const __grid_constant__ J
 // for the record's last piece, the two end pads behind its last symbol.
 __global__ void k_piece_fix(const __grid_constant__ Job job) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (job.has_carry) {
-        const u32 c_prev = (job.carry >> 4) & 0xFu, c_last = job.carry & 0xFu;
+    const PieceParams &PP = piece_of(job);
+    if (PP.has_carry) {
+        const u32 c_prev = (PP.carry >> 4) & 0xFu, c_last = PP.carry & 0xFu;
         u32 w = job.sym[0];  // symbol 0 = low nibble of byte 0, symbol 1 = low nibble of byte 1
         w = (w & ~0x00000F0Fu) | c_prev | c_last << 8;
         job.sym[0] = w;
         TileInfo ti = job.tile_info[0];
-        if (ti.nsym == 2) ti.tail = (uint8_t)job.carry;
+        if (ti.nsym == 2) ti.tail = (uint8_t)PP.carry;
         else if (ti.nsym == 3) ti.tail = (uint8_t)((ti.tail & 0xFu) | c_last << 4);
         job.tile_info[0] = ti;
     }
-    if (job.ov_last) {
+    if (PP.ov_last) {
         const u32 t = job.ntiles - 1;
         TileInfo ti = job.tile_info[t];
         u32 *slot = job.sym + (u64)t * kSlotWords;
@@ -532,8 +543,9 @@ __global__ void __launch_bounds__(32) k_piece_trim(const __grid_constant__ Job j
     if (!((job.frame_mask >> f) & 1u) || len == 0) {
         resolved = 1;
     } else {
-        const u64 n = job.ov_n;
-        const bool first = job.has_carry == 0, last = job.ov_last != 0;
+        const PieceParams &PP = job.pv;
+        const u64 n = PP.ov_n;
+        const bool first = PP.has_carry == 0, last = PP.ov_last != 0;
         const u64 base = first ? 4 : 2;                       // local stream index of the piece's first nucleotide
         const i64 m = (i64)(job.totals->total_sym - base);     // nucleotides of the piece (scan pass: no end pads)
         const i64 own_lo = first ? -2 : 0;
@@ -547,8 +559,8 @@ __global__ void __launch_bounds__(32) k_piece_trim(const __grid_constant__ Job j
         c.pos = 0;
         i64 c_at = -(i64)base;  // the cursor stands on local stream index 0 = nucleotide index -base
         auto psym = [&](i64 x) -> u32 {
-            if (x < 0) return first ? 0u : (x == -1 ? (job.carry & 0xFu) : ((job.carry >> 4) & 0xFu));
-            if (x >= m) return last ? 0u : (u32)job.head[x - m];
+            if (x < 0) return first ? 0u : (x == -1 ? (PP.carry & 0xFu) : ((PP.carry >> 4) & 0xFu));
+            if (x >= m) return last ? 0u : (u32)PP.head[x - m];
             if (x != c_at) {
                 if (c_at == -(i64)base && x > 4096) {  // first positioning far into the piece: binary search over the tiles
                     u32 lo = 0, hi = job.ntiles - 1;
@@ -576,6 +588,54 @@ __global__ void __launch_bounds__(32) k_piece_trim(const __grid_constant__ Job j
     }
     job.pt_out[f] = len;
     job.pt_out[6 + f] = resolved;
+}
+
+// The piece description of rank `rank` from the all-gathered scan results (what split.plan_pieces
+// does on the host): nucleotides before it and in total, the two nucleotides in front of it, the
+// 192 behind it, the header length.  Runs between the all-gather and the translate kernels, so the
+// step needs no host round trip.
+__global__ void k_piece_plan(const PieceInfoDev *all, int rank, int world, PieceParams *out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    PieceParams p;
+    u64 total = 0, before = 0;
+    u32 last = 0, second = 0;  // codes of the two nucleotides before the current piece (0 = the pads)
+    for (int k = 0; k < world; k++) {
+        const u64 m = all[k].nucleotides;
+        if (k < rank) {
+            before += m;
+            if (m >= 2) { last = all[k].tail & 0xFu; second = (all[k].tail >> 4) & 0xFu; }
+            else if (m == 1) { second = last; last = all[k].tail & 0xFu; }
+        }
+        total += m;
+    }
+    u32 got = 0;
+    for (int k = rank + 1; k < world && got < 192u; k++) {
+        const u64 m = all[k].nucleotides;
+        for (u32 i = 0; i < 192u && i < m && got < 192u; i++) p.head[got++] = all[k].head[i] > 4 ? 0 : all[k].head[i];
+    }
+    for (; got < 192u; got++) p.head[got] = 0;
+    const bool first = rank == 0, lastp = rank == world - 1;
+    p.piece = 1;
+    p.no_end_pads = lastp ? 0 : 1;
+    p.ov_last = lastp ? 1 : 0;
+    p.no_headers = first ? 0 : 1;
+    p.ov_H = (u32)all[0].header_len;
+    p.ov_n = total;
+    p.ov_dbase = 4;
+    p.pad = 0;
+    if (first) {
+        p.ov_slot = 1; p.has_carry = 0; p.carry = 0; p.t0_base = 0; p.win_lo = 0;
+    } else {
+        p.ov_slot = 0; p.has_carry = 1; p.carry = last | second << 4;
+        p.t0_base = before + 2;
+        p.win_lo = p.t0_base + 2;
+    }
+    *out = p;
+}
+
+cudaError_t launch_piece_plan(const PieceInfoDev *all, int rank, int world, PieceParams *out, cudaStream_t stream) {
+    k_piece_plan<<<1, 32, 0, stream>>>(all, rank, world, out);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_piece_fix(const Job &job, cudaStream_t stream) {

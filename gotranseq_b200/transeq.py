@@ -255,6 +255,31 @@ class Translator:
         self._check(rc)
         return total.value, [(segs[i].offset, segs[i].length) for i in range(nseg.value)]
 
+    # ---- the split step planned on the device: scan -> all-gather (caller, NCCL) -> translate ----
+    def piece_scan_async(self, d_in, n, d_info, stream=0):
+        """Enqueue the scan of a piece; its 256-byte summary lands at device address d_info."""
+        self._check(self._L.gts_piece_scan_async(self._h, ctypes.c_void_p(d_in), n, ctypes.c_void_p(d_info),
+                                                 ctypes.c_void_p(stream)))
+
+    def piece_translate_async(self, d_in, n, rank, world, d_infos, d_out, cap, stream=0):
+        """Enqueue the translate pass of the piece just scanned, planned on the device from the
+        all-gathered summaries at d_infos (world x 256 bytes, rank order)."""
+        self._check(self._L.gts_piece_translate_async(self._h, ctypes.c_void_p(d_in), n, rank, world, ctypes.c_void_p(d_infos),
+                                                      ctypes.c_void_p(d_out), cap, ctypes.c_void_p(stream)))
+
+    def piece_result(self):
+        """Wait for the enqueued piece: (size of the whole record's output, [(offset, length), ...], piece dict)."""
+        segs = (_lib.gts_segment * _lib.GTS_MAX_SEGMENTS)()
+        nseg = ctypes.c_int()
+        total = ctypes.c_size_t()
+        p = _lib.gts_piece()
+        rc = self._L.gts_piece_result(self._h, ctypes.byref(total), segs, ctypes.byref(nseg), ctypes.byref(p))
+        if rc == _lib.GTS_ERR_CAPACITY:
+            raise TranseqError(rc, f"output buffer too small: need {total.value} bytes")
+        self._check(rc)
+        return (total.value, [(segs[i].offset, segs[i].length) for i in range(nseg.value)],
+                dict(nt_before=p.nt_before, nt_total=p.nt_total, header_len=p.header_len, first=bool(p.first), last=bool(p.last)))
+
     # ---- streaming (what the Go shim's Translate loop does, INTEGRATION.md) ----
     def translate_stream(self, reader, writer):
         L, h = self._L, self._h

@@ -300,6 +300,21 @@ int gts_piece_trim_device(gts_ctx *ctx, const void *d_in, size_t n, const gts_pi
 int gts_piece_translate_device(gts_ctx *ctx, const void *d_in, size_t n, const gts_piece *piece,
                                void *d_out, size_t cap, size_t *out_total,
                                gts_segment segs[GTS_MAX_SEGMENTS], int *nseg, void *stream);
+/*
+ * The same step without a host round trip between scan and translate (what bench.py's
+ * chromosome_split runs): gts_piece_scan_async enqueues the scan and leaves the piece's 256-byte
+ * summary in device memory (d_info); the caller all-gathers the summaries of all ranks on the same
+ * stream (NCCL) into d_infos (world x 256 bytes, rank order); gts_piece_translate_async plans the
+ * piece on the device from them and enqueues the translate kernels on the scan's slots;
+ * gts_piece_result waits, checks, and returns the piece's segments (and, optionally, its gts_piece).
+ * No --trim here (GTS_ERR_ARG): the walk over the pieces needs the host-driven calls.
+ */
+#define GTS_PIECE_INFO_BYTES 256
+int gts_piece_scan_async(gts_ctx *ctx, const void *d_in, size_t n, void *d_info, void *stream);
+int gts_piece_translate_async(gts_ctx *ctx, const void *d_in, size_t n, int rank, int world, const void *d_infos,
+                              void *d_out, size_t cap, void *stream);
+int gts_piece_result(gts_ctx *ctx, size_t *out_total, gts_segment segs[GTS_MAX_SEGMENTS], int *nseg,
+                     gts_piece *piece_out);
 /* Host buffers: gts_piece_scan copies the piece to the device and keeps it there for
  * gts_piece_translate, which hands segment i back as data[i] (pinned, owned by ctx, valid until
  * the next call on ctx). */

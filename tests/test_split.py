@@ -356,6 +356,43 @@ def test_gpu_split_trim(frame):
 
 
 @pytest.mark.gpu
+def test_gpu_split_planned_on_the_device():
+    """gts_piece_scan_async -> (all-gather) -> gts_piece_translate_async -> gts_piece_result: the piece
+    description is computed by k_piece_plan from the gathered 256-byte summaries.  One process plays all
+    ranks: one Translator per piece, the gather is a copy into one device tensor."""
+    import torch
+    from gotranseq_b200 import _lib
+    IB = _lib.GTS_PIECE_INFO_BYTES
+    rng = random.Random(9)
+    cases = [one_record(90 + i, n, width=w, crlf=(i % 3 == 1)) for i, (n, w) in enumerate(
+        [(0, 60), (1, 60), (2, 7), (5, 60), (181, 60), (1000, 13), (40_000, 60), (700_001, 60)])]
+    for buf in cases:
+        for frame, alt in (("6", False), ("R", True), ("F", False), ("-2", False)):
+            want = oracle.translate(buf, frame=frame, alternative=alt)
+            for world in (1, 2, 3, 8):
+                ranges = split.piece_ranges(buf, world)
+                trs = [make_gpu(frame, alt)() for _ in ranges]
+                d_ins = [torch.frombuffer(bytearray(buf[lo:hi] or b"\0"), dtype=torch.uint8).cuda() for lo, hi in ranges]
+                d_all = torch.zeros(IB * world, dtype=torch.uint8, device="cuda")
+                d_out = torch.full((len(want) + 64,), 0xEE, dtype=torch.uint8, device="cuda")
+                for k, (tr, (lo, hi)) in enumerate(zip(trs, ranges)):
+                    tr.piece_scan_async(d_ins[k].data_ptr(), hi - lo, d_all[IB * k:].data_ptr(), 0)
+                torch.cuda.synchronize()
+                seg_lists = []
+                for k, (tr, (lo, hi)) in enumerate(zip(trs, ranges)):
+                    tr.piece_translate_async(d_ins[k].data_ptr(), hi - lo, k, world, d_all.data_ptr(), d_out.data_ptr(),
+                                             d_out.numel(), 0)
+                    total, segs, piece = tr.piece_result()
+                    assert total == len(want)
+                    host = bytes(d_out[:total].cpu().numpy())
+                    seg_lists.append([(o, host[o:o + n]) for o, n in segs])
+                for tr in trs:
+                    tr.close()
+                assert split.assemble(len(want), seg_lists) == want, (len(buf), frame, alt, world)
+    _ = rng
+
+
+@pytest.mark.gpu
 def test_gpu_split_argument_errors():
     import gotranseq_b200
     tr = make_gpu("6", False)()
