@@ -80,8 +80,19 @@ __host__ __device__ constexpr u32 codon_weights(int k, int j, int word) {
 
 // Line i of one frame of a block run: 63 codons of phase K from the block's symbols c[] -> 64 image
 // bytes (60 residues, '\n', 3 residues of the next line).
+// (shared-window addresses throughout: `lut` is the table's, so that a lookup is one LDS.U8 [R]
+// without an add of the window's base -- 189 of them per block -- and `dst` the line's in the image)
+__device__ __forceinline__ u32 lds_u8(u32 saddr) {
+    u32 v;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(u32 saddr, u32 v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
+}
+
 template <int K>
-__device__ __forceinline__ void emit_frame(uint8_t *smem, const u32 (&c)[49], u32 lut, u32 dst, bool first) {
+__device__ __forceinline__ void emit_frame(const u32 (&c)[49], u32 lut, u32 dst, bool first) {
     const u32 a = dst & 3u;
     const u32 sela = 0x3210u + 0x1111u * ((4u - a) & 7u);
     u32 z[16];
@@ -98,7 +109,7 @@ __device__ __forceinline__ void emit_frame(uint8_t *smem, const u32 (&c)[49], u3
                 const u32 m = codon_weights(K, j, w);
                 if (m != 0 && 3 * g + w < 49) addr = __dp4a(c[3 * g + w], m, addr);
             }
-            r[j] = smem[addr];
+            r[j] = lds_u8(addr);
         }
         if (g < 15) {
             z[g] = prmt(prmt(r[0], r[1], 0x0040u), prmt(r[2], r[3], 0x0040u), 0x5410u);
@@ -108,10 +119,10 @@ __device__ __forceinline__ void emit_frame(uint8_t *smem, const u32 (&c)[49], u3
     }
     // image word g holds line bytes 4g - a .. 4g - a + 3; a lane owns the words that start in its
     // line (word 0 only when the line starts on a word, or when no line precedes it)
-    u32 *dw = reinterpret_cast<u32 *>(smem + (dst & ~3u));
-    if (a == 0 || first) dw[0] = prmt(0u, z[0], sela);
+    const u32 dw = dst & ~3u;
+    if (a == 0 || first) sts_u32(dw, prmt(0u, z[0], sela));
 #pragma unroll
-    for (int g = 1; g < 16; g++) dw[g] = prmt(z[g - 1], z[g], sela);
+    for (int g = 1; g < 16; g++) sts_u32(dw + 4u * g, prmt(z[g - 1], z[g], sela));
 }
 
 __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const __grid_constant__ Job job) {
@@ -254,10 +265,11 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
     }
 
     // offsets in the CTA's shared memory
-    const u32 symf_addr = (u32)offsetof(LinesShared, symf);
-    const u32 lutf_addr = (u32)offsetof(LinesShared, lutf);
-    const u32 lutr_addr = (u32)offsetof(LinesShared, lutr);
-    const u32 image_addr = (u32)offsetof(LinesShared, image);
+    const u32 smem_base = (u32)__cvta_generic_to_shared(smem_raw);  // addresses in the shared window
+    const u32 symf_addr = (u32)offsetof(LinesShared, symf);         // (relative: the symbol loads go through pointers)
+    const u32 lutf_addr = smem_base + (u32)offsetof(LinesShared, lutf);
+    const u32 lutr_addr = smem_base + (u32)offsetof(LinesShared, lutr);
+    const u32 image_addr = smem_base + (u32)offsetof(LinesShared, image);
 
     while (done < npieces) {
         // ---- build (warp 0): one lane per (record piece, strand) ----
@@ -422,23 +434,31 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
                 x0 = (a & ~3u) + 4u;
                 sels = (0x0123u + 0x1111u * (a & 3u)) ^ 0x4444u;  // bytes reversed; word m is the HIGH word of pair m
             }
-            const int step = 4 * dir;
             u32 c[49];
             {
-                const uint8_t *sp = smem_raw + x0;
-                u32 wprev = *reinterpret_cast<const u32 *>(sp);
+                // (constant word offsets in both directions: no address arithmetic between the loads)
+                const u32 *sp = reinterpret_cast<const u32 *>(smem_raw + x0);
+                u32 wprev = sp[0];
+                if (dir > 0) {
 #pragma unroll
-                for (int m = 0; m < 49; m++) {
-                    sp += step;
-                    const u32 w = *reinterpret_cast<const u32 *>(sp);
-                    c[m] = prmt(wprev, w, sels);
-                    wprev = w;
+                    for (int m = 0; m < 49; m++) {
+                        const u32 w = sp[m + 1];
+                        c[m] = prmt(wprev, w, sels);
+                        wprev = w;
+                    }
+                } else {
+#pragma unroll
+                    for (int m = 0; m < 49; m++) {
+                        const u32 w = sp[-(m + 1)];
+                        c[m] = prmt(wprev, w, sels);
+                        wprev = w;
+                    }
                 }
             }
             const u32 lut = r.lut;
-            if (i < r.fr[0].nl) emit_frame<0>(smem_raw, c, lut, image_addr + r.fr[0].img + 61u * i, i == 0);
-            if (i < r.fr[1].nl) emit_frame<1>(smem_raw, c, lut, image_addr + r.fr[1].img + 61u * i, i == 0);
-            if (i < r.fr[2].nl) emit_frame<2>(smem_raw, c, lut, image_addr + r.fr[2].img + 61u * i, i == 0);
+            if (i < r.fr[0].nl) emit_frame<0>(c, lut, image_addr + r.fr[0].img + 61u * i, i == 0);
+            if (i < r.fr[1].nl) emit_frame<1>(c, lut, image_addr + r.fr[1].img + 61u * i, i == 0);
+            if (i < r.fr[2].nl) emit_frame<2>(c, lut, image_addr + r.fr[2].img + 61u * i, i == 0);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // image writes -> visible to the bulk copy engine
         __syncthreads();                                               // image complete

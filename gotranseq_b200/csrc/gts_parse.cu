@@ -19,14 +19,14 @@
 #include "gts_kernels.h"
 
 #ifndef GTS_PARSE_CTAS
-#define GTS_PARSE_CTAS 8
+#define GTS_PARSE_CTAS 32
 #endif
 
 namespace gts {
 
 enum { LS = 0, SEQ = 1, HDR = 2 };
 
-constexpr int kParseWarps = 4;                          // tiles per CTA, one warp each
+constexpr int kParseWarps = 1;                          // one warp per CTA: the tile index is uniform for the compiler
 constexpr int kRowBytes = 32 * kParseBytesPerThread;    // 1 KB per row
 constexpr int kRows = kParseTile / kRowBytes;           // 8 rows per tile
 constexpr int kSymBuf = 16 + kRowBytes + 64 + 48;       // carried symbols + a row's symbols + zero tail
@@ -123,12 +123,13 @@ __device__ __forceinline__ void line_state_at(const Job &job, u64 base, int lane
             const u32 mm = __shfl_sync(0xFFFFFFFFu, m16, l);
             const int o = 31 - __clz(mm);  // its offset in that lane's 16 bytes
             const u64 ls = hi - 16ull * (l + 1) + o + 1;  // first byte of the line
-            if (ls == base) at_start = true;
-            else in_hdr = job.in[ls] == '>';  // (uniform address: one load, broadcast)
+            // (uniform address: one load, broadcast; the votes make the results uniform for the compiler too)
+            at_start = __any_sync(0xFFFFFFFFu, ls == base);
+            in_hdr = __any_sync(0xFFFFFFFFu, ls != base && job.in[ls] == '>');
             return;
         }
         if (hi <= 512) {  // the line starts at the beginning of the input
-            in_hdr = job.in[0] == '>';
+            in_hdr = __any_sync(0xFFFFFFFFu, job.in[0] == '>');
             return;
         }
         hi -= 512;
@@ -206,29 +207,62 @@ __global__ void __launch_bounds__(kParseWarps * 32, GTS_PARSE_CTAS) k_parse(cons
     };
     load_row(tile_base);
 
+    const u32 tile_bytes = n - tile_base < (u64)kParseTile ? (u32)(n - tile_base) : (u32)kParseTile;  // (0 for an empty input)
+#pragma unroll 1
     for (int r = 0; r < kRows; r++) {
+        if ((u32)r * kRowBytes >= tile_bytes) break;  // (an empty input has no row at all)
         const u64 row_base = tile_base + (u64)r * kRowBytes;
-        if (row_base >= n) break;  // (an empty input has no row at all)
         const uint4 v0 = nx0, v1 = nx1;
-        const bool has_next_row = r + 1 < kRows && row_base + kRowBytes < n;
+        const bool full_row = (u32)(r + 1) * kRowBytes <= tile_bytes;
+        const bool has_next_row = r + 1 < kRows && (u32)(r + 1) * kRowBytes < tile_bytes;
         if (has_next_row) load_row(row_base + kRowBytes);
+
+        // ---- newlines ----
+        const u32 f0 = newline_flags(v0.x), f1 = newline_flags(v0.y), f2 = newline_flags(v0.z), f3 = newline_flags(v0.w);
+        const u32 f4 = newline_flags(v1.x), f5 = newline_flags(v1.y), f6 = newline_flags(v1.z), f7 = newline_flags(v1.w);
+        u32 nlmask = gather_flags16(f0, f1, f2, f3) | gather_flags16(f4, f5, f6, f7) << 16;
+
+        // ---- plain rows: 1 KB of sequence lines and nothing else ----
+        // Every byte is a letter (bit 6 set: no '>', no CR, no blank, no digit) or a '\n', no chunk
+        // holds more than two newlines, and the row does not start inside a header line: then every
+        // chunk is a "fast" chunk, there is no header line in the row and no state to work out.
+        const u32 letters = (v0.x | (f0 >> 1)) & (v0.y | (f1 >> 1)) & (v0.z | (f2 >> 1)) & (v0.w | (f3 >> 1)) &
+                            (v1.x | (f4 >> 1)) & (v1.y | (f5 >> 1)) & (v1.z | (f6 >> 1)) & (v1.w | (f7 >> 1));
+        const bool plain_chunk = (letters & 0x40404040u) == 0x40404040u && __popc(nlmask) <= 2;
+        const bool plain_row = full_row && (row_ls || !row_in_hdr) && __all_sync(0xFFFFFFFFu, plain_chunk);
+
+        u32 removed = 0, nsym = 0, nhdr = 0, excl_syms = 0, excl_hdrs = 0, row_syms = 0, row_hdrs = 0;
+        bool slow = false, fast = false, cr_end = false, next_ls, next_in_hdr;
+        int state = SEQ, len = 32;
+        unsigned NL;
+        uint8_t *raw = ws.raw + lane * kParseBytesPerThread;
+        const u64 pos0 = row_base + (u64)lane * kParseBytesPerThread;
+        if (plain_row) {
+            removed = nlmask;
+            fast = true;
+            const u32 k = (u32)__popc(nlmask);  // 0, 1 or 2 newlines: the prefix sums come from two ballots
+            nsym = 32u - k;
+            const unsigned c1 = __ballot_sync(0xFFFFFFFFu, k >= 1u), c2 = __ballot_sync(0xFFFFFFFFu, k == 2u);
+            NL = c1;
+            excl_syms = 32u * (u32)lane - (u32)__popc(c1 & lt) - (u32)__popc(c2 & lt);
+            row_syms = 32u * 32u - (u32)__popc(c1) - (u32)__popc(c2);
+            next_ls = __any_sync(0xFFFFFFFFu, lane == 31 && (nlmask >> 31) != 0);
+            next_in_hdr = false;
+        } else {
         // first byte behind the row: the next row's first byte (already requested), or the next tile's
         u32 after_row = 0;
         if (lane == 0) {
             if (has_next_row) after_row = nx0.x & 0xFFu;
             else if (row_base + kRowBytes < n) after_row = job.in[row_base + kRowBytes];
         }
-        const u64 pos0 = row_base + (u64)lane * kParseBytesPerThread;
-        const int len = pos0 >= n ? 0 : (n - pos0 < 32 ? (int)(n - pos0) : 32);
-        uint8_t *raw = ws.raw + lane * kParseBytesPerThread;
+        len = pos0 >= n ? 0 : (n - pos0 < 32 ? (int)(n - pos0) : 32);
         reinterpret_cast<uint4 *>(raw)[0] = v0;
         reinterpret_cast<uint4 *>(raw)[1] = v1;
-        u32 nlmask = newline_mask16(v0) | newline_mask16(v1) << 16;
         if (len < 32) nlmask &= len ? ((1u << len) - 1u) : 0u;
         const u32 b0 = v0.x & 0xFFu;
 
         // ---- the state each chunk starts in ----
-        const unsigned NL = __ballot_sync(0xFFFFFFFFu, nlmask != 0);
+        NL = __ballot_sync(0xFFFFFFFFu, nlmask != 0);
         const unsigned LNL = __ballot_sync(0xFFFFFFFFu, (nlmask >> 31) != 0);  // the chunk's last byte is '\n'
         const unsigned G = __ballot_sync(0xFFFFFFFFu, len > 0 && b0 == '>');
         u32 next_first = __shfl_down_sync(0xFFFFFFFFu, b0, 1);
@@ -246,20 +280,18 @@ __global__ void __launch_bounds__(kParseWarps * 32, GTS_PARSE_CTAS) k_parse(cons
         const unsigned prev_nl = NL & lt;
         const bool chunk_ls = lane > 0 ? ((LNL >> (lane - 1)) & 1u) != 0 : row_ls;
         const bool hdr_line = prev_nl ? ((TH >> (31 - __clz(prev_nl))) & 1u) != 0 : row_line_hdr;
-        const int state = chunk_ls ? LS : (hdr_line ? HDR : SEQ);
+        state = chunk_ls ? LS : (hdr_line ? HDR : SEQ);
         // ... and the next row's
-        const bool next_ls = (LNL >> 31) != 0;
-        const bool next_in_hdr = NL ? ((TH >> (31 - __clz(NL))) & 1u) != 0 : row_line_hdr;
+        next_ls = (LNL >> 31) != 0;
+        next_in_hdr = NL ? ((TH >> (31 - __clz(NL))) & 1u) != 0 : row_line_hdr;
 
         const bool last_cr = len == 32 ? (v1.w >> 24) == '\r' : (len > 0 && raw[len - 1] == '\r');
-        const bool cr_end = last_cr && ((pos0 + len >= n) || next_first == '\n');
+        cr_end = last_cr && ((pos0 + len >= n) || next_first == '\n');
 
         // ---- classify the chunk ----
         //   fast:  32 bytes of sequence lines only, at most two bytes to drop (newline, CR)
         //   slow:  anything with a header line start / end in it, or short (end of input), ...
         //   none:  no symbols (inside a header line, or past the end of the input)
-        u32 removed = 0;
-        bool slow = false, fast = false;
         if (len > 0) {
             if (state == HDR) {
                 slow = nlmask != 0;  // the header line ends here
@@ -278,7 +310,6 @@ __global__ void __launch_bounds__(kParseWarps * 32, GTS_PARSE_CTAS) k_parse(cons
                 fast = !slow;
             }
         }
-        u32 nsym = 0, nhdr = 0;
         if (fast) nsym = 32u - (u32)__popc(removed);
         else if (slow) count_chunk(raw, len, nlmask, state, cr_end, nsym, nhdr);
 
@@ -291,10 +322,13 @@ __global__ void __launch_bounds__(kParseWarps * 32, GTS_PARSE_CTAS) k_parse(cons
             if (lane >= o) inc += y;
         }
         const u32 row_total = __shfl_sync(0xFFFFFFFFu, inc, 31);
-        const u32 row_syms = row_total & 0xFFFFu, row_hdrs = row_total >> 16;
-        const u32 excl = inc - packed;
-        const u32 d = carry + (excl & 0xFFFFu);  // buffer index of the chunk's first symbol
-        const u32 slot0 = S - carry;             // slot index of buffer index 0
+        row_syms = row_total & 0xFFFFu;
+        row_hdrs = row_total >> 16;
+        excl_syms = (inc - packed) & 0xFFFFu;
+        excl_hdrs = (inc - packed) >> 16;
+        }  // generic row
+        const u32 d = carry + excl_syms;  // buffer index of the chunk's first symbol
+        const u32 slot0 = S - carry;      // slot index of buffer index 0
         u32 ev_base = 0;
         if (row_hdrs) {  // one range of the event list for the row's header lines
             if (lane == 0) ev_base = atomicAdd(&job.counters[2], row_hdrs);
@@ -333,7 +367,9 @@ __global__ void __launch_bounds__(kParseWarps * 32, GTS_PARSE_CTAS) k_parse(cons
                         inv &= inv - 1;
                         const u32 spos = slot0 + d + (u32)i - (u32)__popc(removed & ((1u << i) - 1u));
                         const u32 slot = atomicAdd(&job.counters[4], 1u);
-                        if (slot < job.warn_cap) job.warn[slot] = (u64)t << 32 | (u64)spos << 8 | raw[i];
+                        const u32 wsel = i < 16 ? (i < 8 ? (i < 4 ? v0.x : v0.y) : (i < 12 ? v0.z : v0.w))
+                                                : (i < 24 ? (i < 20 ? v1.x : v1.y) : (i < 28 ? v1.z : v1.w));
+                        if (slot < job.warn_cap) job.warn[slot] = (u64)t << 32 | (u64)spos << 8 | ((wsel >> (8 * (i & 3))) & 0xFFu);
                     }
                 }
                 u32 rm = removed;
@@ -403,7 +439,7 @@ __global__ void __launch_bounds__(kParseWarps * 32, GTS_PARSE_CTAS) k_parse(cons
                 const int c_len = __shfl_sync(0xFFFFFFFFu, len, c);
                 const int c_state = __shfl_sync(0xFFFFFFFFu, state, c);
                 const u32 c_d = __shfl_sync(0xFFFFFFFFu, d, c);
-                const u32 c_rec = R + __shfl_sync(0xFFFFFFFFu, excl >> 16, c);
+                const u32 c_rec = R + __shfl_sync(0xFFFFFFFFu, excl_hdrs, c);
                 const bool c_cr_end = __shfl_sync(0xFFFFFFFFu, (int)cr_end, c) != 0;
                 const u64 c_pos0 = row_base + (u64)c * 32u;
                 const bool valid = lane < c_len;
