@@ -153,6 +153,7 @@ struct gts_ctx {
     size_t chunk = (size_t)16 << 20;
     u64 max_line = 100ull << 20;  // bufio.Scanner token limit of the reference (transeq.go:27)
     bool poison = false;          // GTS_POISON_OUTPUT=1: fill the output with 0xEE first (tests)
+    bool short_on = true;         // GTS_NO_SHORT=1: short records go through k_lines / k_headers as well (A/B runs)
     bool profiling = false;
 
     // ---- piece of a split record (gts_piece_*) ----
@@ -370,6 +371,8 @@ int enqueue_pass(gts_ctx *ctx, DevCtx *dev, const PassArgs &a, std::string *err)
     job.alternative = ctx->opt.alternative ? 1 : 0;
     job.trim = ctx->opt.trim ? 1 : 0;
     job.more_follows = a.more_follows ? 1 : 0;
+    job.short_on = ctx->short_on ? 1 : 0;
+    job.pad2 = 0;
     std::memset(&job.pv, 0, sizeof(job.pv));
     job.pp = nullptr;
     job.info_out = nullptr;
@@ -427,7 +430,7 @@ int enqueue_pass(gts_ctx *ctx, DevCtx *dev, const PassArgs &a, std::string *err)
     if (!a.sizes_only) {
         CUE(gts::launch_emit(job, dev->sm_count, a.stream, ev ? ev[3] : nullptr, dev->s_side, dev->ev_fork, dev->ev_join));
         if (ev) CUE(cudaEventRecord(ev[4], a.stream));
-        launches += 2;
+        launches += job.short_on ? 3 : 2;
     }
     CUE(cudaMemcpyAsync(a.h_dst ? a.h_dst : dev->h_totals, job.totals, sizeof(gts::Totals), cudaMemcpyDeviceToHost, a.stream));
     {
@@ -1139,6 +1142,7 @@ int gts_create(const gts_options *opt, gts_ctx **out) {
     ctx->in_max = kSlots * ctx->devs.size() + 2;
     ctx->out_max = ctx->in_max + 1;
     ctx->poison = std::getenv("GTS_POISON_OUTPUT") != nullptr;
+    ctx->short_on = std::getenv("GTS_NO_SHORT") == nullptr;
     *out = ctx.release();
     return GTS_OK;
 }

@@ -47,6 +47,11 @@ constexpr int kScanThreads = 256;
 #endif
 constexpr int kScanPerThread = GTS_SCAN_PER_THREAD;
 constexpr int kScanTile = kScanThreads * kScanPerThread;  // parse tiles per scan tile
+// ---- k_short: records small enough for the warp-per-16-records emit (gts_short.cu) ----
+constexpr int kShortMaxN = 180;    // nucleotides: every frame is a single output line
+constexpr int kShortMaxH = 64;     // header line bytes
+constexpr int kShortMaxOut = 672;  // output bytes of the record (all requested frames)
+
 constexpr int kSizeThreads = 256;
 #ifndef GTS_SIZE_PER_THREAD
 #define GTS_SIZE_PER_THREAD 1
@@ -69,6 +74,7 @@ struct Totals {  // device-resident result block, copied to pinned host memory a
     u64 cut;          // with kFlagLongLine: the reference stops reading at this offset
     u64 tail;         // the stream's last two symbols (end pads excluded): last | second-to-last << 4
     u64 n_warn;       // invalid nucleotides seen (WARNING lines of encodedSequence.go:39), exact even on overflow
+    u64 n_short;      // records handed to k_short (RecInfo.emitted == 2)
     u64 aux;          // piece scan: bytes of the header line the buffer starts with (CR dropped), ~0 if it starts with none
 };
 constexpr u64 kFlagRecOverflow = 1;  // record table too small (n_headers is still exact)
@@ -121,7 +127,7 @@ struct RecInfo {  // 32 bytes per record slot, written by k_size, read by k_line
     u64 dbase;    // stream index of the record's first nucleotide
     u64 n;        // nucleotides
     u32 H;        // header line bytes (CR dropped)
-    u32 emitted;  // 0: the record produces no output (empty slot 0)
+    u32 emitted;  // 0: the record produces no output (empty slot 0); 1: written by k_lines + k_headers; 2: by k_short
 };
 
 struct FrameTab {  // 80 bytes per record slot, written by k_size, read by k_lines
@@ -210,6 +216,8 @@ struct Job {  // kernel argument block (by value)
     u32 alternative;
     u32 trim;
     u32 more_follows;  // this buffer is not the end of the stream: an empty slot 0 is never emitted
+    u32 short_on;      // short records go to k_short (emitted == 2)
+    u32 pad2;
 
     // ---- a piece of ONE record split over several passes / GPUs (gts_piece_*) ----
     // The piece's description: by value (pv, host-driven calls) or in device memory (pp, written by

@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(128) k_headers(const __grid_constant__ Job job
         u64 base[6];
 #pragma unroll
         for (int f = 0; f < 6; f++) base[f] = ft->body[f];
-        if (!ri.emitted) continue;
+        if (ri.emitted != 1) continue;  // (2: the whole record is written by k_short)
         const u32 H = ri.H;
         const u32 sp = (u32)(hinf >> 32);
         const uint8_t *hdr = job.in + hoff;
@@ -59,7 +59,13 @@ __global__ void __launch_bounds__(128) k_headers(const __grid_constant__ Job job
 cudaError_t init_lines();
 cudaError_t launch_lines(const Job &job, int sm_count, cudaStream_t stream);
 
-cudaError_t init_kernels() { return init_lines(); }
+cudaError_t init_short();
+cudaError_t launch_short(const Job &job, int sm_count, cudaStream_t stream);
+
+cudaError_t init_kernels() {
+    cudaError_t e = init_lines();
+    return e != cudaSuccess ? e : init_short();
+}
 
 // k_headers only needs the record table, so it runs on `side` (when given) next to k_lines: the
 // persistent k_lines grid leaves room for its small CTAs on every SM.
@@ -72,6 +78,7 @@ cudaError_t launch_emit(const Job &job, int sm_count, cudaStream_t stream, cudaE
         GTS_TRY(cudaStreamWaitEvent(side, ev_fork, 0));
         k_headers<<<sm_count * GTS_HDR_BLOCKS, 128, 0, side>>>(job);
         GTS_TRY(cudaGetLastError());
+        if (job.short_on) GTS_TRY(launch_short(job, sm_count, side));
         GTS_TRY(cudaEventRecord(ev_join, side));
         GTS_TRY(launch_lines(job, sm_count, stream));
         if (ev_mid) GTS_TRY(cudaEventRecord(ev_mid, stream));
@@ -81,6 +88,7 @@ cudaError_t launch_emit(const Job &job, int sm_count, cudaStream_t stream, cudaE
         if (ev_mid) GTS_TRY(cudaEventRecord(ev_mid, stream));
         k_headers<<<sm_count * GTS_HDR_BLOCKS, 128, 0, stream>>>(job);
         GTS_TRY(cudaGetLastError());
+        if (job.short_on) GTS_TRY(launch_short(job, sm_count, stream));
     }
 #undef GTS_TRY
     return cudaSuccess;

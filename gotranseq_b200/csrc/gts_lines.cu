@@ -18,6 +18,7 @@
 #include <cstddef>
 
 #include "gts_common.cuh"
+#include "gts_emit.cuh"
 #include "gts_kernels.h"
 
 namespace gts {
@@ -67,64 +68,6 @@ struct LinesShared {
     u32 total_jobs, nlisted, npieces_done, next_tile;
 };
 
-// dp4a weights (1, 5, 25 for a codon's three symbols) of codon j of phase k inside word `word` of
-// a 12-symbol group (word 3 = the first word of the next group); 0 = the codon has no symbol there
-__host__ __device__ constexpr u32 codon_weights(int k, int j, int word) {
-    u32 m = 0;
-    for (int t = 0; t < 3; t++) {
-        const int b = k + 3 * j + t;
-        if ((b >> 2) == word) m |= (t == 0 ? 1u : t == 1 ? 5u : 25u) << (8 * (b & 3));
-    }
-    return m;
-}
-
-// Line i of one frame of a block run: 63 codons of phase K from the block's symbols c[] -> 64 image
-// bytes (60 residues, '\n', 3 residues of the next line).
-// (shared-window addresses throughout: `lut` is the table's, so that a lookup is one LDS.U8 [R]
-// without an add of the window's base -- 189 of them per block -- and `dst` the line's in the image)
-__device__ __forceinline__ u32 lds_u8(u32 saddr) {
-    u32 v;
-    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(saddr));
-    return v;
-}
-__device__ __forceinline__ void sts_u32(u32 saddr, u32 v) {
-    asm volatile("st.shared.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
-}
-
-template <int K>
-__device__ __forceinline__ void emit_frame(const u32 (&c)[49], u32 lut, u32 dst, bool first) {
-    const u32 a = dst & 3u;
-    const u32 sela = 0x3210u + 0x1111u * ((4u - a) & 7u);
-    u32 z[16];
-#pragma unroll
-    for (int g = 0; g < 16; g++) {
-        u32 r[4];
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            u32 addr = lut;  // table offset of the codon: lut + s0 + 5 s1 + 25 s2
-#pragma unroll
-            for (int w = 0; w < 4; w++) {
-                constexpr int dummy = 0;
-                (void)dummy;
-                const u32 m = codon_weights(K, j, w);
-                if (m != 0 && 3 * g + w < 49) addr = __dp4a(c[3 * g + w], m, addr);
-            }
-            r[j] = lds_u8(addr);
-        }
-        if (g < 15) {
-            z[g] = prmt(prmt(r[0], r[1], 0x0040u), prmt(r[2], r[3], 0x0040u), 0x5410u);
-        } else {  // residues 60..62 belong to the next line: they follow this line's newline
-            z[g] = prmt(prmt(0x0Au, r[0], 0x0040u), prmt(r[1], r[2], 0x0040u), 0x5410u);
-        }
-    }
-    // image word g holds line bytes 4g - a .. 4g - a + 3; a lane owns the words that start in its
-    // line (word 0 only when the line starts on a word, or when no line precedes it)
-    const u32 dw = dst & ~3u;
-    if (a == 0 || first) sts_u32(dw, prmt(0u, z[0], sela));
-#pragma unroll
-    for (int g = 1; g < 16; g++) sts_u32(dw + 4u * g, prmt(z[g - 1], z[g], sela));
-}
-
 __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const __grid_constant__ Job job) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     LinesShared &sh = *reinterpret_cast<LinesShared *>(smem_raw);
@@ -140,6 +83,7 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
     const u64 R = job.totals->n_headers;
     const PieceParams &PP = piece_of(job);
     if (flags != 0) return;
+    if (job.totals->records != 0 && job.totals->n_short == job.totals->records) return;  // reads only: all k_short's
 
     // persistent CTAs: the grid is one wave; a CTA starts with tile blockIdx.x and claims its next
     // tile from a counter one iteration ahead (tiles differ in cost: the wave stays balanced)
@@ -281,7 +225,7 @@ __global__ void __launch_bounds__(kLinesThreads, GTS_LINES_CTAS) k_lines(const _
                 run.fr[k].g0 = 0; run.fr[k].img = 0; run.fr[k].nbytes = 0; run.fr[k].nl = 0; run.fr[k].flags = 0;
             }
             u32 need = 0;
-            if (ri.emitted) {
+            if (ri.emitted == 1) {  // (2: the whole record is written by k_short)
                 const i64 d = (i64)ri.dbase - (i64)T0;  // the record's first nucleotide, relative to the tile
                 const u64 n = ri.n;
                 // the strand's frames by codon phase k: forward frame k; the reverse frame whose first

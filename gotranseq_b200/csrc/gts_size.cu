@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(kSizeThreads) k_size(const __grid_constant__ J
         RecInfo ri[kSizePerThread];
         u32 flen[kSizePerThread][6];
         u64 sum = 0, nt = 0;
-        u32 nrec = 0;
+        u32 nrec = 0, nshort = 0;
 #pragma unroll
         for (int i = 0; i < kSizePerThread; i++) {
             const u64 s = t * kSizeTile + (u64)tid * kSizePerThread + i;
@@ -426,6 +426,17 @@ __global__ void __launch_bounds__(kSizeThreads) k_size(const __grid_constant__ J
                 ri[i].n = n;
                 ri[i].H = (u32)H;
                 ri[i].emitted = em ? 1u : 0u;
+                if (em && job.short_on && !PP.piece && n <= (u64)kShortMaxN && H <= (u64)kShortMaxH && size[i] <= (u64)kShortMaxOut) {
+                    // short enough for k_short -- if its symbols and the two pads behind them lie in one slot,
+                    // or go on in the next one and end there
+                    const u64 l = job.loc[s];
+                    const u32 tl = (u32)(l >> 16);
+                    const u64 endp = (l & 0xFFFFu) + n + 2, nsa = job.tile_info[tl].nsym;
+                    if (endp <= nsa || (tl + 1 < job.ntiles && endp - nsa <= (u64)job.tile_info[tl + 1].nsym)) {
+                        ri[i].emitted = 2u;
+                        nshort++;
+                    }
+                }
             }
             sum += size[i];
         }
@@ -440,11 +451,13 @@ __global__ void __launch_bounds__(kSizeThreads) k_size(const __grid_constant__ J
         for (int o = 16; o > 0; o >>= 1) {
             nt += __shfl_xor_sync(0xFFFFFFFFu, nt, o);
             nrec += __shfl_xor_sync(0xFFFFFFFFu, nrec, o);
+            nshort += __shfl_xor_sync(0xFFFFFFFFu, nshort, o);
         }
         if (lane == 31) warp_sum[warp] = inc;
         if (lane == 0) {
             warp_nt[warp] = nt;
             warp_rec[warp] = nrec;
+            if (nshort) atomicAdd(&job.totals->n_short, (u64)nshort);
         }
         __syncthreads();
         u64 excl = inc - sum, tile_total = 0, tile_nt = 0;

@@ -7,6 +7,8 @@
 
 #include <algorithm>
 #include <cerrno>
+#include <chrono>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <thread>
@@ -116,8 +118,11 @@ bool is_regular(int fd) {
 
 std::string TranslateFd(int fd_in, int fd_out, const Options &o, const char *out_path) {
     std::string err;
+    const bool timing = std::getenv("GOTRANSEQ_B200_TIMING") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
     gts_ctx *ctx = create(o, &err);
     if (!ctx) return err;
+    const auto t1 = std::chrono::steady_clock::now();
     const int io_threads = o.IoThreads > 0 ? o.IoThreads : 4;
     const bool in_reg = is_regular(fd_in), out_reg = is_regular(fd_out);
     // the writer: every finished chunk, in input order (flush, writer.go:171-181)
@@ -197,7 +202,16 @@ std::string TranslateFd(int fd_in, int fd_out, const Options &o, const char *out
         size_t n = 0;
         if (gts_next_output(ctx, &p, &n) != GTS_OK) err = gts_last_error(ctx);
     }
+    const auto t2 = std::chrono::steady_clock::now();
     gts_destroy(ctx);
+    if (timing) {
+        const auto t3 = std::chrono::steady_clock::now();
+        auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+            return std::chrono::duration<double, std::milli>(b - a).count();
+        };
+        std::fprintf(stderr, "{\"create_ms\": %.1f, \"stream_ms\": %.1f, \"destroy_ms\": %.1f, \"gpus\": %d}\n", ms(t0, t1), ms(t1, t2),
+                     ms(t2, t3), 0);
+    }
     return err;
 }
 

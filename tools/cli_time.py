@@ -20,14 +20,22 @@ nt = s.nucleotides()
 exe = os.path.join(ROOT, "gotranseq_b200", "bin", "gotranseq")
 res = {"in_bytes": os.path.getsize(src), "nucleotides": nt, "runs": []}
 for threads in ("1", "4", "8"):
-    env = dict(os.environ, GOTRANSEQ_B200_IO_THREADS=threads)
-    best = None
+    env = dict(os.environ, GOTRANSEQ_B200_IO_THREADS=threads, GOTRANSEQ_B200_TIMING="1")
+    best, phases = None, None
     for _ in range(3):
         t0 = time.perf_counter()
-        subprocess.run([exe, "-s", src, "-o", dst, "-f", "6"], check=True, stdout=subprocess.DEVNULL, env=env)
+        r = subprocess.run([exe, "-s", src, "-o", dst, "-f", "6"], check=True, stdout=subprocess.DEVNULL,
+                           stderr=subprocess.PIPE, env=env)
         dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    res["runs"].append({"io_threads": int(threads), "wall_s": best, "Gbp_per_s": nt / best / 1e9})
+        if best is None or dt < best:
+            best = dt
+            try:
+                phases = json.loads(r.stderr.decode().strip().splitlines()[-1])
+            except Exception:
+                phases = None
+    stream_s = phases["stream_ms"] / 1e3 if phases else None
+    res["runs"].append({"io_threads": int(threads), "wall_s": best, "Gbp_per_s_wall": nt / best / 1e9, "phases_ms": phases,
+                        "Gbp_per_s_read_translate_write": nt / stream_s / 1e9 if stream_s else None})
 res["out_bytes"] = os.path.getsize(dst)
 res["out_sha256"] = hashlib.sha256(open(dst, "rb").read()).hexdigest()
 oc = os.path.join(ROOT, "oracle", "transeq_oracle_cli")
