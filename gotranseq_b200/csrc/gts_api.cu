@@ -90,6 +90,8 @@ struct DevCtx {  // one GPU: streams, scratch of a device pass, chunk slots, wor
     int sm_count = 148;
     cudaStream_t stream = nullptr;  // kernels of the host entry points
     cudaStream_t s_side = nullptr;  // k_headers runs here, next to k_lines
+    cudaStream_t s_side2 = nullptr; // ... and k_short here
+    cudaEvent_t ev_join2 = nullptr;
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
@@ -428,7 +430,9 @@ int enqueue_pass(gts_ctx *ctx, DevCtx *dev, const PassArgs &a, std::string *err)
     }
     if (ev) CUE(cudaEventRecord(ev[2], a.stream));
     if (!a.sizes_only) {
-        CUE(gts::launch_emit(job, dev->sm_count, a.stream, ev ? ev[3] : nullptr, dev->s_side, dev->ev_fork, dev->ev_join));
+        gts::EmitStreams es;
+        es.side = dev->s_side; es.side2 = dev->s_side2; es.fork = dev->ev_fork; es.join = dev->ev_join; es.join2 = dev->ev_join2;
+        CUE(gts::launch_emit(job, dev->sm_count, a.stream, ev ? ev[3] : nullptr, es));
         if (ev) CUE(cudaEventRecord(ev[4], a.stream));
         launches += job.short_on ? 3 : 2;
     }
@@ -530,6 +534,8 @@ void dev_destroy(DevCtx *dev) {
     for (cudaEvent_t e : dev->prof_events) cudaEventDestroy(e);
     if (dev->stream) cudaStreamDestroy(dev->stream);
     if (dev->s_side) cudaStreamDestroy(dev->s_side);
+    if (dev->s_side2) cudaStreamDestroy(dev->s_side2);
+    if (dev->ev_join2) cudaEventDestroy(dev->ev_join2);
     if (dev->s_h2d) cudaStreamDestroy(dev->s_h2d);
     if (dev->s_d2h) cudaStreamDestroy(dev->s_d2h);
     if (dev->ev_fork) cudaEventDestroy(dev->ev_fork);
@@ -556,6 +562,8 @@ int dev_create(int ordinal, std::unique_ptr<DevCtx> *out, std::string *err) {
     CUE(gts::init_kernels());
     CUE(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     CUE(cudaStreamCreateWithFlags(&p->s_side, cudaStreamNonBlocking));
+    CUE(cudaStreamCreateWithFlags(&p->s_side2, cudaStreamNonBlocking));
+    CUE(cudaEventCreateWithFlags(&p->ev_join2, cudaEventDisableTiming));
     CUE(cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking));
     CUE(cudaStreamCreateWithFlags(&p->s_d2h, cudaStreamNonBlocking));
     CUE(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));

@@ -67,29 +67,25 @@ cudaError_t init_kernels() {
     return e != cudaSuccess ? e : init_short();
 }
 
-// k_headers only needs the record table, so it runs on `side` (when given) next to k_lines: the
-// persistent k_lines grid leaves room for its small CTAs on every SM.
-cudaError_t launch_emit(const Job &job, int sm_count, cudaStream_t stream, cudaEvent_t ev_mid, cudaStream_t side,
-                        cudaEvent_t ev_fork, cudaEvent_t ev_join) {
+// k_headers and k_short only need the record table, so they run on side streams next to k_lines:
+// the persistent k_lines grid leaves room for their CTAs on every SM, and their launches overlap.
+cudaError_t launch_emit(const Job &job, int sm_count, cudaStream_t stream, cudaEvent_t ev_mid, const EmitStreams &es) {
     cudaError_t e;
 #define GTS_TRY(call) do { e = (call); if (e != cudaSuccess) return e; } while (0)
-    if (side) {
-        GTS_TRY(cudaEventRecord(ev_fork, stream));
-        GTS_TRY(cudaStreamWaitEvent(side, ev_fork, 0));
-        k_headers<<<sm_count * GTS_HDR_BLOCKS, 128, 0, side>>>(job);
-        GTS_TRY(cudaGetLastError());
-        if (job.short_on) GTS_TRY(launch_short(job, sm_count, side));
-        GTS_TRY(cudaEventRecord(ev_join, side));
-        GTS_TRY(launch_lines(job, sm_count, stream));
-        if (ev_mid) GTS_TRY(cudaEventRecord(ev_mid, stream));
-        GTS_TRY(cudaStreamWaitEvent(stream, ev_join, 0));
-    } else {
-        GTS_TRY(launch_lines(job, sm_count, stream));
-        if (ev_mid) GTS_TRY(cudaEventRecord(ev_mid, stream));
-        k_headers<<<sm_count * GTS_HDR_BLOCKS, 128, 0, stream>>>(job);
-        GTS_TRY(cudaGetLastError());
-        if (job.short_on) GTS_TRY(launch_short(job, sm_count, stream));
+    GTS_TRY(cudaEventRecord(es.fork, stream));
+    GTS_TRY(cudaStreamWaitEvent(es.side, es.fork, 0));
+    k_headers<<<sm_count * GTS_HDR_BLOCKS, 128, 0, es.side>>>(job);
+    GTS_TRY(cudaGetLastError());
+    GTS_TRY(cudaEventRecord(es.join, es.side));
+    if (job.short_on) {
+        GTS_TRY(cudaStreamWaitEvent(es.side2, es.fork, 0));
+        GTS_TRY(launch_short(job, sm_count, es.side2));
+        GTS_TRY(cudaEventRecord(es.join2, es.side2));
     }
+    GTS_TRY(launch_lines(job, sm_count, stream));
+    if (ev_mid) GTS_TRY(cudaEventRecord(ev_mid, stream));
+    GTS_TRY(cudaStreamWaitEvent(stream, es.join, 0));
+    if (job.short_on) GTS_TRY(cudaStreamWaitEvent(stream, es.join2, 0));
 #undef GTS_TRY
     return cudaSuccess;
 }

@@ -19,7 +19,10 @@ cudaError_t launch_piece_trim(const Job &job, cudaStream_t stream);   // k_piece
 cudaError_t launch_warn(const Job &job, int sm_count, cudaStream_t stream);   // k_warn (only when job.warn is set)
 // k_lines and k_headers; with a side stream (and two events to fork / join) the two run
 // concurrently; ev_mid (optional) is recorded on `stream` after k_lines
-cudaError_t launch_emit(const Job &job, int sm_count, cudaStream_t stream, cudaEvent_t ev_mid,
-                        cudaStream_t side = nullptr, cudaEvent_t ev_fork = nullptr, cudaEvent_t ev_join = nullptr);
+struct EmitStreams {  // side streams of the emit stage (k_headers and k_short run next to k_lines) and their events
+    cudaStream_t side = nullptr, side2 = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr, join2 = nullptr;
+};
+cudaError_t launch_emit(const Job &job, int sm_count, cudaStream_t stream, cudaEvent_t ev_mid, const EmitStreams &es);
 
 }  // namespace gts
