@@ -218,8 +218,10 @@ int gts_get_stats(const gts_ctx *ctx, gts_stats *st);
 /*
  * Per-kernel timing (bench.py's roofline numbers).  While enabled, CUDA events are recorded on
  * the pass's stream around each kernel.  gts_kernel_times waits for the recorded passes, adds
- * their durations up in ms -- [0] scratch reset + k_parse, [1] k_size, [2] k_lines,
- * [3] k_headers -- reports how many passes that covers and starts a new accumulation.
+ * their durations up in ms -- [0] scratch reset + k_parse, [1] k_tile_scan + k_records + k_size
+ * (+ k_warn), [2] k_lines, [3] what is left of k_headers and k_short (they run on side streams next
+ * to k_lines) once k_lines has finished -- reports how many passes that covers and starts a new
+ * accumulation.
  */
 int gts_set_profiling(gts_ctx *ctx, int enable);
 int gts_kernel_times(gts_ctx *ctx, double ms[4], uint64_t *passes);

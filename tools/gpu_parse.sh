@@ -8,6 +8,6 @@ for v in default p5 p8; do
   for wl in readme189 contigs short_reads; do
     timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-e2e --workload $wl 2>>gpurun_out/${tag}_bench.err | python -c "
 import sys,json
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$v','$wl',round(d['value'],1),round(d['ms_per_step'],4),{k:round(x,4) for k,x in d['kernels_ms_per_step'].items()})"
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('$v','$wl',round(d['value'],1),round(d['ms_per_step'],4),{k[:14]:round(x,4) for k,x in d['kernels_ms_per_step'].items()})"
   done
 done
