@@ -145,6 +145,8 @@ class Batch:
     memory (gts_host_alloc)."""
 
     def __init__(self, workload, rank, world, L, per_gpu=None):
+        """L: the C ABI library (pinned memory through gts_host_alloc), or None: a plain numpy buffer
+        (the reference arm loads nothing of the product)."""
         import workloads
         self.workload, self.L = workload, L
         _, self.opts = workloads.WORKLOADS[workload]
@@ -167,9 +169,14 @@ class Batch:
         self.nbytes = int(self.stream.offsets[self.hi] - self.stream.offsets[self.lo])
         self.nt = self.stream.nucleotides(self.lo, self.hi)
         self.records = self.hi - self.lo
-        self.h_in = L.gts_host_alloc(self.nbytes + 64)
-        if not self.h_in:
-            raise MemoryError("gts_host_alloc")
+        if L is None:
+            import numpy as np
+            self._np = np.empty(self.nbytes + 64, dtype=np.uint8)
+            self.h_in = self._np.ctypes.data
+        else:
+            self.h_in = L.gts_host_alloc(self.nbytes + 64)
+            if not self.h_in:
+                raise MemoryError("gts_host_alloc")
         self.stream.generate(self.lo, self.hi, out_addr=self.h_in)
 
     def array(self):
@@ -177,9 +184,9 @@ class Batch:
         return np.ctypeslib.as_array((ctypes.c_uint8 * self.nbytes).from_address(self.h_in))
 
     def free(self):
-        if self.h_in:
+        if self.h_in and self.L is not None:
             self.L.gts_host_free(self.h_in)
-            self.h_in = None
+        self.h_in = None
 
 
 def record_cut(arr, limit):
@@ -205,9 +212,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     import oracle
-    from gotranseq_b200 import _lib
-    L = _lib.lib()
-    batch = Batch(args.workload, 0, 1, L)
+    batch = Batch(args.workload, 0, 1, None)
     arr = batch.array()
     cores = os.cpu_count() or 1
     cut = record_cut(arr, args.ref_sample_bytes)
