@@ -561,8 +561,16 @@ int dev_create(int ordinal, std::unique_ptr<DevCtx> *out, std::string *err) {
     DevCtx *p = out->get();
     CUE(gts::init_kernels());
     CUE(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
-    CUE(cudaStreamCreateWithFlags(&p->s_side, cudaStreamNonBlocking));
-    CUE(cudaStreamCreateWithFlags(&p->s_side2, cudaStreamNonBlocking));
+    {
+        // k_headers / k_short run next to the persistent k_lines grid; with a higher stream priority
+        // their CTAs are placed first when both become ready (GTS_SIDE_PRIO=0: plain streams, A/B runs)
+        int lo = 0, hi = 0;
+        CUE(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        const char *sp = std::getenv("GTS_SIDE_PRIO");
+        const int prio = (sp && std::atoi(sp) != 0) ? hi : lo;
+        CUE(cudaStreamCreateWithPriority(&p->s_side, cudaStreamNonBlocking, prio));
+        CUE(cudaStreamCreateWithPriority(&p->s_side2, cudaStreamNonBlocking, prio));
+    }
     CUE(cudaEventCreateWithFlags(&p->ev_join2, cudaEventDisableTiming));
     CUE(cudaStreamCreateWithFlags(&p->s_h2d, cudaStreamNonBlocking));
     CUE(cudaStreamCreateWithFlags(&p->s_d2h, cudaStreamNonBlocking));

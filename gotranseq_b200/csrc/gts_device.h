@@ -52,6 +52,12 @@ constexpr int kShortMaxN = 180;    // nucleotides: every frame is a single outpu
 constexpr int kShortMaxH = 64;     // header line bytes
 constexpr int kShortMaxOut = 672;  // output bytes of the record (all requested frames)
 
+// ---- k_records: lanes per header line (a power of two; each lane reads 16 bytes per step) ----
+#ifndef GTS_REC_LANES
+#define GTS_REC_LANES 4
+#endif
+constexpr int kRecLanes = GTS_REC_LANES;
+
 constexpr int kSizeThreads = 256;
 #ifndef GTS_SIZE_PER_THREAD
 #define GTS_SIZE_PER_THREAD 1
@@ -122,7 +128,7 @@ struct HeaderEvent {  // 16 bytes per header line, appended by k_parse in no par
     uint16_t pos;  // slot index of the record's first nucleotide (its pads sit at pos-2, pos-1)
 };
 
-struct RecInfo {  // 32 bytes per record slot, written by k_size, read by k_lines / k_headers
+struct alignas(16) RecInfo {  // 32 bytes per record slot, written by k_size, read by k_lines / k_headers
     u64 out_off;  // offset of the record's first output byte
     u64 dbase;    // stream index of the record's first nucleotide
     u64 n;        // nucleotides
@@ -130,7 +136,7 @@ struct RecInfo {  // 32 bytes per record slot, written by k_size, read by k_line
     u32 emitted;  // 0: the record produces no output (empty slot 0); 1: written by k_lines + k_headers; 2: by k_short
 };
 
-struct FrameTab {  // 80 bytes per record slot, written by k_size, read by k_lines
+struct alignas(16) FrameTab {  // 80 bytes per record slot, written by k_size, read by k_lines
     u64 body[6];   // output offset of the first residue of each requested frame
     u32 len[6];    // residues of the frame (after --trim); 0 for frames not requested / records not emitted
     u32 pad[2];

@@ -2,6 +2,8 @@
 //
 // Reference behaviour reproduced (feliixx/gotranseq):
 //   k_headers    writeHeader            transeq/writer.go:120-131
+#include <cstdlib>
+
 #include "gts_common.cuh"
 #include "gts_kernels.h"
 
@@ -15,15 +17,22 @@ namespace gts {
 // k_headers
 // =====================================================================================
 // Header line of one frame (writer.go:120-131): the header's bytes with '_' and the frame digit
-// inserted before its first space (or appended), then '\n'.  Half a warp per record, lane i holding
-// output bytes i, i+16, ...: the line is assembled once (only the digit differs between frames)
-// and stored once per requested frame, in front of the frame's residues (frame table of k_size).
+// inserted before its first space (or appended), then '\n'.  A group of kHdrLanes lanes per record,
+// each lane holding four consecutive bytes of the line per step: the line is assembled once (only the
+// digit differs between frames) and stored once per requested frame, in front of the frame's residues
+// (frame table of k_size).  The kernel is a chain of two rounds of loads (record table, header bytes)
+// followed by stores: small groups keep many records in flight.
+#ifndef GTS_HDR_LANES
+#define GTS_HDR_LANES 16
+#endif
 __global__ void __launch_bounds__(128) k_headers(const __grid_constant__ Job job) {
-    const int lane = threadIdx.x & 31, sub = lane & 15, half = lane >> 4;
+    constexpr int G = GTS_HDR_LANES;
+    const int sub = threadIdx.x & (G - 1);
     const u64 R = job.totals->n_headers;
     if (job.totals->flags != 0 || piece_of(job).no_headers) return;
-    const u64 nhalf = (u64)gridDim.x * (blockDim.x >> 4);
-    for (u64 s = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 4; s <= R; s += nhalf) {
+    if (job.totals->records != 0 && job.totals->n_short == job.totals->records) return;  // reads only: all k_short's
+    const u64 ngroups = ((u64)gridDim.x * blockDim.x) / G;
+    for (u64 s = ((u64)blockIdx.x * blockDim.x + threadIdx.x) / G; s <= R; s += ngroups) {
         // everything that is indexed by the record goes first, in one round of loads
         const RecInfo ri = job.rec[s];
         const u64 hinf = s >= 1 ? job.hinfo[s] : 0;
@@ -38,19 +47,27 @@ __global__ void __launch_bounds__(128) k_headers(const __grid_constant__ Job job
         const uint8_t *hdr = job.in + hoff;
 #pragma unroll
         for (int f = 0; f < 6; f++) base[f] -= H + 3;
-        for (u32 i = sub; i < H + 3; i += 16) {
-            // byte i of the line; the digit at sp+1 is patched per frame
-            uint8_t c = '\n';
-            if (i < sp) c = hdr[i];
-            else if (i == sp) c = '_';
-            else if (i > sp + 1 && i < H + 2) c = hdr[i - 2];
-            const bool digit = i == sp + 1;
+        for (u32 i0 = 4u * (u32)sub; i0 < H + 3; i0 += 4u * G) {
+            // bytes i0 .. i0+3 of the line (all loads first); the digit at sp+1 is patched per frame
+            uint8_t c[4];
 #pragma unroll
-            for (int f = 0; f < 6; f++)
-                if ((job.frame_mask >> f) & 1u) job.out[base[f] + i] = digit ? (uint8_t)('1' + f) : c;
+            for (int k = 0; k < 4; k++) {
+                const u32 i = i0 + k;
+                c[k] = '\n';
+                if (i < sp) c[k] = hdr[i];
+                else if (i == sp) c[k] = '_';
+                else if (i > sp + 1 && i < H + 2) c[k] = hdr[i - 2];
+            }
+#pragma unroll
+            for (int f = 0; f < 6; f++) {
+                if (!((job.frame_mask >> f) & 1u)) continue;
+                uint8_t *o = job.out + base[f] + i0;
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (i0 + k < H + 3) o[k] = (i0 + k == sp + 1) ? (uint8_t)('1' + f) : c[k];
+            }
         }
     }
-    (void)half;
 }
 
 // =====================================================================================
@@ -72,11 +89,17 @@ cudaError_t init_kernels() {
 cudaError_t launch_emit(const Job &job, int sm_count, cudaStream_t stream, cudaEvent_t ev_mid, const EmitStreams &es) {
     cudaError_t e;
 #define GTS_TRY(call) do { e = (call); if (e != cudaSuccess) return e; } while (0)
+    static const int hdr_order = std::getenv("GTS_HDR_ORDER") ? std::atoi(std::getenv("GTS_HDR_ORDER")) : 0;
     GTS_TRY(cudaEventRecord(es.fork, stream));
-    GTS_TRY(cudaStreamWaitEvent(es.side, es.fork, 0));
-    k_headers<<<sm_count * GTS_HDR_BLOCKS, 128, 0, es.side>>>(job);
-    GTS_TRY(cudaGetLastError());
-    GTS_TRY(cudaEventRecord(es.join, es.side));
+    if (hdr_order == 0) {
+        GTS_TRY(cudaStreamWaitEvent(es.side, es.fork, 0));
+        k_headers<<<sm_count * GTS_HDR_BLOCKS, 128, 0, es.side>>>(job);
+        GTS_TRY(cudaGetLastError());
+        GTS_TRY(cudaEventRecord(es.join, es.side));
+    } else if (hdr_order == 2) {
+        k_headers<<<sm_count * GTS_HDR_BLOCKS, 128, 0, stream>>>(job);
+        GTS_TRY(cudaGetLastError());
+    }
     if (job.short_on) {
         GTS_TRY(cudaStreamWaitEvent(es.side2, es.fork, 0));
         GTS_TRY(launch_short(job, sm_count, es.side2));
@@ -84,7 +107,12 @@ cudaError_t launch_emit(const Job &job, int sm_count, cudaStream_t stream, cudaE
     }
     GTS_TRY(launch_lines(job, sm_count, stream));
     if (ev_mid) GTS_TRY(cudaEventRecord(ev_mid, stream));
-    GTS_TRY(cudaStreamWaitEvent(stream, es.join, 0));
+    if (hdr_order == 0) {
+        GTS_TRY(cudaStreamWaitEvent(stream, es.join, 0));
+    } else if (hdr_order == 1) {
+        k_headers<<<sm_count * GTS_HDR_BLOCKS, 128, 0, stream>>>(job);
+        GTS_TRY(cudaGetLastError());
+    }
     if (job.short_on) GTS_TRY(cudaStreamWaitEvent(stream, es.join2, 0));
 #undef GTS_TRY
     return cudaSuccess;

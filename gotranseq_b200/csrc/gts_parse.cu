@@ -38,7 +38,7 @@ struct WarpShared {
 };
 struct ParseShared {
     WarpShared w[kParseWarps];
-    uint8_t enc[256];
+    alignas(4) uint8_t enc[256];
 };
 
 // Symbols and header lines of one 32-byte chunk (scalar walk over its lines; used for the chunks
@@ -140,17 +140,15 @@ __global__ void __launch_bounds__(kParseWarps * 32, GTS_PARSE_CTAS) k_parse(cons
     __shared__ ParseShared sh;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-#pragma unroll
-    for (int k = 0; k < 256 / (kParseWarps * 32); k++) {
-        const int b = tid + k * kParseWarps * 32;
-        uint8_t c = 0;
-        switch (b) {
-            case 'A': case 'a': c = 1; break;
-            case 'C': case 'c': c = 2; break;
-            case 'T': case 't': case 'U': case 'u': c = 3; break;
-            case 'G': case 'g': c = 4; break;
-        }
-        sh.enc[b] = c;
+    {
+        // code table of the slow path (encodedSequence.go:25-41), 64 words: only the words holding
+        // "@ABC" / "DEFG" / "TUVW" and their lower-case twins are not zero
+        static_assert(kParseWarps == 1, "one warp writes the table");
+        const int w = lane & 7;  // words 16..31 hold the letters: 16 + w upper case, 24 + w lower case
+        const u32 v = w == 0 ? 0x02000100u : w == 1 ? 0x04000000u : w == 5 ? 0x00000303u : 0u;
+        u32 *e = reinterpret_cast<u32 *>(sh.enc);
+        e[lane] = lane >= 16 ? v : 0u;
+        e[32 + lane] = 0u;
     }
     __syncthreads();  // the only CTA-wide barrier: the table of the slow path
     pdl_launch();     // k_tile_scan's CTAs may be scheduled while the parse drains

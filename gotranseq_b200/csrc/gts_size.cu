@@ -236,45 +236,65 @@ __global__ void __launch_bounds__(256) k_records(const __grid_constant__ Job job
     }
     const u64 R = job.totals->n_headers;
     if (R + 2 > job.rec_cap) return;  // overflow: the host retries with a larger table
-    // Half a warp per header line: the record's table entry, and the header line measured 64 bytes
-    // per step (aligned words, one per lane): its length up to the '\n' or the end of the input, one
-    // trailing CR dropped (bufio.ScanLines), and the index of its first space (writer.go:121).
-    const int lane = threadIdx.x & 31, sub = lane & 15, hshift = lane & 16;
-    const unsigned hmask = 0xFFFFu << hshift;
-    const u64 nhalf = ((u64)gridDim.x * blockDim.x) >> 4;
-    for (u64 e = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 4; e < R; e += nhalf) {
+    // A group of kRecLanes lanes per header line: the record's table entry, and the header line measured
+    // 16 * kRecLanes bytes per step (one aligned 16-byte load per lane, ballots inside the group for the
+    // newline and the first space): its length up to the '\n' or the end of the input, one trailing CR
+    // dropped (bufio.ScanLines), and the index of its first space (writer.go:121).  Small groups keep
+    // many header lines in flight: the kernel is a chain of dependent loads (event -> tile offset ->
+    // header bytes) and nothing else.
+    constexpr int G = kRecLanes;
+    const int lane = threadIdx.x & 31, sub = lane & (G - 1), gshift = lane & ~(G - 1);
+    const unsigned gbits = G == 32 ? 0xFFFFFFFFu : ((1u << G) - 1u);
+    const unsigned gmask = gbits << gshift;
+    const u64 ngroups = ((u64)gridDim.x * blockDim.x) / G;
+    for (u64 e = ((u64)blockIdx.x * blockDim.x + threadIdx.x) / G; e < R; e += ngroups) {
         const HeaderEvent ev = job.events[e];
         const TilePrefix tp = job.tile_pre[ev.tile];
         const u64 slot = (u64)tp.R0 + ev.k + 1;
         const u64 off = ev.hdr_off;
         u64 p = job.n, sp = ~0ull;  // newline (or end of input), first space
-        for (u64 base = off & ~3ull; base < job.n; base += 64) {
-            const u64 wa = base + 4u * (u32)sub;
-            u32 w = 0, vm = 0;  // the word, 0x80 in its bytes that belong to [off, n)
-            if (wa < job.n) {
-                w = *reinterpret_cast<const u32 *>(job.in + wa);
-                vm = 0x80808080u;
-                if (wa < off) vm <<= 8 * (u32)(off - wa);
-                if (job.n - wa < 4) vm &= 0x80808080u >> (8 * (4 - (u32)(job.n - wa)));
+        u32 cr = 0;                  // the byte in front of p is a CR
+        u32 last_cr = 0;             // ... the last byte of the step before
+        for (u64 base = off & ~15ull; base < job.n; base += 16u * G) {
+            const u64 wa = base + 16u * (u32)sub;
+            u32 mnl = 0, msp = 0, mcr = 0;  // bit i: byte wa + i is a '\n' / a space / a CR, bytes outside [off, n) masked away
+            if (wa < job.n && wa + 16 > off) {
+                // (the aligned 16 bytes hold at least one byte of the input: the load stays inside its allocation)
+                const uint4 v = *reinterpret_cast<const uint4 *>(job.in + wa);
+                u32 vm = job.n - wa < 16 ? (1u << (u32)(job.n - wa)) - 1u : 0xFFFFu;
+                if (wa < off) vm &= ~((1u << (u32)(off - wa)) - 1u);
+                mnl = newline_mask16(v) & vm;
+                msp = gather_flags16(byte_eq_flags(v.x, 0x20202020u), byte_eq_flags(v.y, 0x20202020u),
+                                     byte_eq_flags(v.z, 0x20202020u), byte_eq_flags(v.w, 0x20202020u)) & vm;
+                mcr = gather_flags16(byte_eq_flags(v.x, 0x0D0D0D0Du), byte_eq_flags(v.y, 0x0D0D0D0Du),
+                                     byte_eq_flags(v.z, 0x0D0D0D0Du), byte_eq_flags(v.w, 0x0D0D0D0Du)) & vm;
             }
-            const u32 fnl = byte_eq_flags(w, 0x0A0A0A0Au) & vm, fsp = byte_eq_flags(w, 0x20202020u) & vm;
-            const unsigned bnl = (__ballot_sync(hmask, fnl != 0) >> hshift) & 0xFFFFu;
-            const unsigned bsp = (__ballot_sync(hmask, fsp != 0) >> hshift) & 0xFFFFu;
+            const unsigned bnl = (__ballot_sync(gmask, mnl != 0) >> gshift) & gbits;
+            const unsigned bsp = (__ballot_sync(gmask, msp != 0) >> gshift) & gbits;
+            // bit i: the byte in front of byte wa + i is a CR (the lane before, or the step before, supplies bit 0)
+            u32 before = __shfl_up_sync(gmask, mcr, 1, G) >> 15;
+            if (sub == 0) before = last_cr;
+            const u32 crb = (mcr << 1) | (before & 1u);
             if (bsp && sp == ~0ull) {
                 const int l = __ffs(bsp) - 1;
-                const u32 f = __shfl_sync(hmask, fsp, hshift + l);
-                sp = base + 4u * l + ((__ffs(f) - 1) >> 3);
+                const u32 f = __shfl_sync(gmask, msp, gshift + l);
+                sp = base + 16u * l + (u32)(__ffs(f) - 1);
             }
             if (bnl) {
                 const int l = __ffs(bnl) - 1;
-                const u32 f = __shfl_sync(hmask, fnl, hshift + l);
-                p = base + 4u * l + ((__ffs(f) - 1) >> 3);
+                const u32 f = __shfl_sync(gmask, mnl, gshift + l);
+                const u32 c = __shfl_sync(gmask, crb, gshift + l);
+                const int j = __ffs(f) - 1;
+                p = base + 16u * l + (u32)j;
+                cr = (c >> j) & 1u;
                 break;
             }
+            last_cr = __shfl_sync(gmask, mcr, gshift + G - 1) >> 15;
         }
+        // (no newline: the line ends with the input, and a CR as its last byte is dropped as well)
+        if (p == job.n) cr = job.in[p - 1] == '\r' ? 1u : 0u;  // (p > off: the line holds at least the '>')
         if (sub == 0) {
-            u64 H = p - off;
-            if (job.in[p - 1] == '\r') H--;  // p > off: the line holds at least the '>'
+            u64 H = p - off - cr;
             u64 s0 = sp == ~0ull || sp >= p ? H : sp - off;
             if (s0 > H) s0 = H;
             job.hdr_off[slot] = off;
@@ -359,7 +379,10 @@ __device__ void trimmed_lengths(const Job &job, const uint16_t *lut, u64 s, u64 
     }
 }
 
-__global__ void __launch_bounds__(kSizeThreads) k_size(const __grid_constant__ Job job) {
+#ifndef GTS_SIZE_CTAS
+#define GTS_SIZE_CTAS 4
+#endif
+__global__ void __launch_bounds__(kSizeThreads, GTS_SIZE_CTAS) k_size(const __grid_constant__ Job job) {
     __shared__ uint16_t lut[128];
     __shared__ u64 warp_sum[kSizeThreads / 32];
     __shared__ u64 warp_nt[kSizeThreads / 32];
@@ -723,11 +746,11 @@ cudaError_t launch_sizes(const Job &job, int sm_count, cudaStream_t stream) {
     const u32 nscan = (job.ntiles + kScanTile - 1) / kScanTile;
     cudaError_t e = launch_pdl(k_tile_scan, dim3(nscan < (u32)sm_count ? nscan : (u32)sm_count), dim3(kScanThreads), stream, job);
     if (e != cudaSuccess) return e;
-    const u64 rec_blocks = (job.rec_cap + 15) / 16;  // half a warp per header line
+    const u64 rec_blocks = (job.rec_cap * kRecLanes + 255) / 256;  // kRecLanes lanes per header line
     e = launch_pdl(k_records, dim3((u32)(rec_blocks < (u64)sm_count * 8 ? rec_blocks : (u64)sm_count * 8)), dim3(256), stream, job);
     if (e != cudaSuccess) return e;
     const u64 size_tiles = (job.rec_cap + kSizeTile - 1) / kSizeTile;
-    u32 size_grid = (u32)(size_tiles < (u64)sm_count * 4 ? size_tiles : (u64)sm_count * 4);
+    u32 size_grid = (u32)(size_tiles < (u64)sm_count * GTS_SIZE_CTAS ? size_tiles : (u64)sm_count * GTS_SIZE_CTAS);
     if (size_grid == 0) size_grid = 1;
     return launch_pdl(k_size, dim3(size_grid), dim3(kSizeThreads), stream, job);
 }
