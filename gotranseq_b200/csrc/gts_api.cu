@@ -15,7 +15,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
+#include <functional>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -38,7 +40,9 @@ static thread_local std::string g_create_error;
 
 namespace {
 
-constexpr int kSlots = 3;  // chunks in flight per GPU: one in H2D, one in the kernels, one in D2H
+constexpr int kSlots = 8;  // chunk slots per GPU (device input / output buffers allocated on first use)
+// slots in use: one chunk in H2D, one in the kernels, up to two in (or queued for) D2H (GTS_SLOTS: A/B runs)
+static const int g_slots = [] { const char *e = std::getenv("GTS_SLOTS"); const int v = e ? std::atoi(e) : 4; return v < 2 ? 2 : (v > kSlots ? kSlots : v); }();
 
 size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -72,7 +76,18 @@ struct XJob {  // one chunk on its way through the engine
     int rc = 0;
     std::string err;
     bool done = false;
+    // ---- retirer: the device-to-host copy is in flight (issued, not yet waited for) ----
+    bool d2h_issued = false;
+    uint8_t *d2h_dst = nullptr;
+    size_t d2h_total = 0;
+    std::vector<gts::WarnRec> wr_raw;
+    double t_disp = 0, t_issue0 = 0, t_issue1 = 0, t_comp = 0, t_d2h0 = 0, t_d2h1 = 0;  // GTS_TRACE=1: host clock, ms
 };
+
+static const bool g_trace = std::getenv("GTS_TRACE") != nullptr;
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 struct PassSlot {  // device side of one chunk in flight
     uint8_t *d_in = nullptr, *d_out = nullptr;
@@ -81,7 +96,7 @@ struct PassSlot {  // device side of one chunk in flight
     u64 *d_warn = nullptr;
     gts::WarnRec *d_wres = nullptr;
     size_t warn_cap = 0;
-    cudaEvent_t ev_h2d = nullptr, ev_comp = nullptr;
+    cudaEvent_t ev_h2d = nullptr, ev_comp = nullptr, ev_d2h = nullptr;
     bool busy = false;
 };
 
@@ -333,6 +348,7 @@ struct PassArgs {
     bool scan_only = false;        // k_parse + k_tile_scan only (piece scan)
     bool reuse_slots = false;      // the slots of the pass before are still valid: no k_parse (piece translate)
     gts::Totals *h_dst = nullptr;  // pinned destination of the totals (default: dev->h_totals)
+    bool publish = false;          // the totals reach h_dst by a store from the device, not by a copy (chunk engine)
     bool more_follows = false;
     u64 *d_warn = nullptr;         // warning list (nullptr = off)
     gts::WarnRec *d_wres = nullptr;
@@ -436,7 +452,14 @@ int enqueue_pass(gts_ctx *ctx, DevCtx *dev, const PassArgs &a, std::string *err)
         if (ev) CUE(cudaEventRecord(ev[4], a.stream));
         launches += job.short_on ? 3 : 2;
     }
-    CUE(cudaMemcpyAsync(a.h_dst ? a.h_dst : dev->h_totals, job.totals, sizeof(gts::Totals), cudaMemcpyDeviceToHost, a.stream));
+    if (a.publish && a.h_dst) {
+        // A copy would queue up behind the device-to-host copy of the chunk before (one copy engine per
+        // direction) and delay this chunk's completion event by the whole of it.
+        CUE(gts::launch_publish(job.totals, a.h_dst, a.stream));
+        launches++;
+    } else {
+        CUE(cudaMemcpyAsync(a.h_dst ? a.h_dst : dev->h_totals, job.totals, sizeof(gts::Totals), cudaMemcpyDeviceToHost, a.stream));
+    }
     {
         std::lock_guard<std::mutex> lk(ctx->mu);
         ctx->stats.kernel_launches += launches;
@@ -529,6 +552,7 @@ void dev_destroy(DevCtx *dev) {
         if (s.h_totals) cudaFreeHost(s.h_totals);
         if (s.ev_h2d) cudaEventDestroy(s.ev_h2d);
         if (s.ev_comp) cudaEventDestroy(s.ev_comp);
+        if (s.ev_d2h) cudaEventDestroy(s.ev_d2h);
     }
     if (dev->h_totals) cudaFreeHost(dev->h_totals);
     for (cudaEvent_t e : dev->prof_events) cudaEventDestroy(e);
@@ -581,6 +605,7 @@ int dev_create(int ordinal, std::unique_ptr<DevCtx> *out, std::string *err) {
         CUE(cudaHostAlloc(&s.h_totals, sizeof(gts::Totals), cudaHostAllocPortable));
         CUE(cudaEventCreateWithFlags(&s.ev_h2d, cudaEventDisableTiming));
         CUE(cudaEventCreateWithFlags(&s.ev_comp, cudaEventDisableTiming));
+        CUE(cudaEventCreateWithFlags(&s.ev_d2h, cudaEventDisableTiming));
     }
 #ifdef GTS_PHASE_TIMING
     if (std::getenv("GTS_PHASE_TIMING")) {
@@ -667,7 +692,7 @@ HostBuf *pool_take(gts_ctx *ctx, std::unique_lock<std::mutex> &lk, std::vector<H
 }
 
 int free_slot(const DevCtx *dev) {
-    for (int i = 0; i < kSlots; i++)
+    for (int i = 0; i < g_slots; i++)
         if (!dev->slots[i].busy) return i;
     return -1;
 }
@@ -701,7 +726,7 @@ int issue_job(gts_ctx *ctx, DevCtx *dev, XJob *job) {
     if (ctx->poison) CUE(cudaMemsetAsync(s.d_out, 0xEE, s.d_out_cap, dev->stream));
     PassArgs a;
     a.d_in = s.d_in; a.n = job->n; a.d_out = s.d_out; a.cap = s.d_out_cap; a.stream = dev->stream;
-    a.h_dst = s.h_totals; a.more_follows = !job->last;
+    a.h_dst = s.h_totals; a.more_follows = !job->last; a.publish = true;
     if (ctx->warn_fn) { a.d_warn = s.d_warn; a.d_wres = s.d_wres; a.warn_cap = s.warn_cap; }
     rc = enqueue_pass(ctx, dev, a, err);
     if (rc) return rc;
@@ -709,11 +734,21 @@ int issue_job(gts_ctx *ctx, DevCtx *dev, XJob *job) {
     return GTS_OK;
 }
 
-// Wait for a chunk's kernels, repair the rare overflows, copy the result to the host.
-int retire_job(gts_ctx *ctx, DevCtx *dev, XJob *job) {
+// Wait for a chunk's kernels, repair the rare overflows, start the copy of the result to the host.
+// The copy is NOT waited for (retire_finish does that): the retirer goes on to the next chunk, whose
+// copy queues up behind this one, so the device-to-host stream never idles between chunks.
+// `drain` finishes the copies this retirer still has in flight; it is called before any wait that
+// only the consumer of those chunks can end (an output buffer, the one-shot output growing).
+struct PendingCopies {  // the retirer's copies in flight, seen from retire_issue
+    std::function<void()> drain;
+    std::function<bool()> any;
+};
+int retire_issue(gts_ctx *ctx, DevCtx *dev, XJob *job, const PendingCopies &pc) {
+    const std::function<void()> &drain = pc.drain;
     std::string *err = &job->err;
     PassSlot &s = dev->slots[job->slot];
     CUE(cudaEventSynchronize(s.ev_comp));
+    if (g_trace) job->t_comp = now_ms();
     size_t n_eff = job->n;
     bool more_follows = !job->last;
     for (int attempt = 0; s.h_totals->flags != 0; attempt++) {
@@ -749,7 +784,7 @@ int retire_job(gts_ctx *ctx, DevCtx *dev, XJob *job) {
         }
         PassArgs a;
         a.d_in = s.d_in; a.n = n_eff; a.d_out = s.d_out; a.cap = s.d_out_cap; a.stream = dev->stream;
-        a.h_dst = s.h_totals; a.more_follows = more_follows;
+        a.h_dst = s.h_totals; a.more_follows = more_follows; a.publish = true;
         if (ctx->warn_fn) { a.d_warn = s.d_warn; a.d_wres = s.d_wres; a.warn_cap = s.warn_cap; }
         if (ctx->poison) CUE(cudaMemsetAsync(s.d_out, 0xEE, s.d_out_cap, dev->stream));
         int rc = enqueue_pass(ctx, dev, a, err);
@@ -766,12 +801,25 @@ int retire_job(gts_ctx *ctx, DevCtx *dev, XJob *job) {
     if (ctx->direct) {
         // one-shot call: straight to its final place behind the chunks before it
         std::unique_lock<std::mutex> lk(ctx->mu);
-        ctx->cv.wait(lk, [&] { return stream_dead(ctx) || ctx->direct_turn == job->seq || job->seq > ctx->trunc_seq; });
+        while (true) {
+            ctx->cv.wait(lk, [&] {
+                return stream_dead(ctx) || ctx->direct_turn == job->seq || job->seq > ctx->trunc_seq || (ctx->direct_growing && pc.any());
+            });
+            if (stream_dead(ctx) || ctx->direct_turn == job->seq || job->seq > ctx->trunc_seq) break;
+            // the one-shot output is being moved to a larger block: that waits for every copy in flight, ours too
+            lk.unlock();
+            drain();
+            lk.lock();
+        }
         if (stream_dead(ctx) || job->seq > ctx->trunc_seq) return GTS_OK;  // (the reference never read this far)
         if (job->truncated) ctx->trunc_seq = job->seq;
         const size_t off = ctx->direct_off;
         if (off + total > ctx->h_out_cap) {
+            lk.unlock();
+            drain();  // (our own copies count in direct_active)
+            lk.lock();
             ctx->direct_growing = true;
+            ctx->cv.notify_all();  // (retirers waiting for their turn finish their copies in flight)
             ctx->cv.wait(lk, [&] { return ctx->direct_active == 0; });
             lk.unlock();
             int rc = ensure_pinned(&ctx->h_out, &ctx->h_out_cap, (off + total) + (off + total) / 2, off, err);
@@ -791,6 +839,15 @@ int retire_job(gts_ctx *ctx, DevCtx *dev, XJob *job) {
         std::unique_lock<std::mutex> lk(ctx->mu);
         // (window rule: only the out_max oldest chunks may hold an output buffer, so the chunk the
         // caller waits for can always get one)
+        auto ready = [&] {
+            return stream_dead(ctx) || (job->seq < ctx->consume_seq + ctx->out_max && (!ctx->out_free.empty() || ctx->out_count < ctx->out_max));
+        };
+        if (!ready()) {
+            // the caller may be waiting for a chunk whose copy this thread has not finished yet
+            lk.unlock();
+            drain();
+            lk.lock();
+        }
         ctx->cv.wait(lk, [&] { return stream_dead(ctx) || job->seq < ctx->consume_seq + ctx->out_max; });
         if (stream_dead(ctx)) return GTS_OK;
         int rc = GTS_OK;
@@ -799,27 +856,49 @@ int retire_job(gts_ctx *ctx, DevCtx *dev, XJob *job) {
         job->outbuf = b;
         dst = b->p;
     }
-    int rc = GTS_OK;
     cudaError_t ce = cudaSuccess;
     if (total) ce = cudaMemcpyAsync(dst, s.d_out, total, cudaMemcpyDeviceToHost, dev->s_d2h);
-    std::vector<gts::WarnRec> wr;
     if (ce == cudaSuccess && ctx->warn_fn && t.n_warn) {
-        wr.resize(t.n_warn);
-        ce = cudaMemcpyAsync(wr.data(), s.d_wres, t.n_warn * sizeof(gts::WarnRec), cudaMemcpyDeviceToHost, dev->s_d2h);
+        job->wr_raw.resize(t.n_warn);
+        ce = cudaMemcpyAsync(job->wr_raw.data(), s.d_wres, t.n_warn * sizeof(gts::WarnRec), cudaMemcpyDeviceToHost, dev->s_d2h);
     }
-    if (ce == cudaSuccess) ce = cudaStreamSynchronize(dev->s_d2h);
+    if (ce == cudaSuccess) ce = cudaEventRecord(s.ev_d2h, dev->s_d2h);
+    if (g_trace) job->t_d2h0 = now_ms();
+    job->d2h_issued = true;  // (also after a failed enqueue: retire_finish settles direct_active)
+    job->d2h_dst = dst;
+    job->d2h_total = total;
     if (ce != cudaSuccess) {
         *err = std::string("device to host copy: ") + cudaGetErrorString(ce);
-        rc = cuda_code(ce);
+        return cuda_code(ce);
     }
+    return GTS_OK;
+}
+
+// Wait for the chunk's device-to-host copy; its result and warnings become visible to the caller.
+int retire_finish(gts_ctx *ctx, DevCtx *dev, XJob *job) {
+    std::string *err = &job->err;
+    PassSlot &s = dev->slots[job->slot];
+    int rc = job->rc;
+    if (rc == GTS_OK) {
+        const cudaError_t ce = cudaEventSynchronize(s.ev_d2h);
+        if (g_trace) job->t_d2h1 = now_ms();
+        if (ce != cudaSuccess) {
+            *err = std::string("device to host copy: ") + cudaGetErrorString(ce);
+            rc = cuda_code(ce);
+        }
+    } else {
+        cudaStreamSynchronize(dev->s_d2h);  // whatever was enqueued of it
+    }
+    job->d2h_issued = false;
     if (ctx->direct) {
         std::lock_guard<std::mutex> lk(ctx->mu);
         ctx->direct_active--;
         ctx->cv.notify_all();
     }
     if (rc) return rc;
-    job->out = dst;
-    job->out_n = total;
+    job->out = job->d2h_dst;
+    job->out_n = job->d2h_total;
+    std::vector<gts::WarnRec> &wr = job->wr_raw;
     if (!wr.empty()) {
         // the reader goroutine prints the warnings in input order (encodedSequence.go:39)
         std::sort(wr.begin(), wr.end(), [](const gts::WarnRec &x, const gts::WarnRec &y) { return x.key < y.key; });
@@ -831,6 +910,8 @@ int retire_job(gts_ctx *ctx, DevCtx *dev, XJob *job) {
             o.byte = (uint8_t)w.byte;
             job->warns.push_back(std::move(o));
         }
+        wr.clear();
+        wr.shrink_to_fit();
     }
     return GTS_OK;
 }
@@ -847,7 +928,9 @@ void issuer_main(gts_ctx *ctx, DevCtx *dev) {
         dev->slots[job->slot].busy = true;
         job->skipped = ctx->cancelled || ctx->e_rc != 0 || job->seq > ctx->trunc_seq;
         lk.unlock();
+        if (g_trace) job->t_issue0 = now_ms();
         if (!job->skipped) job->rc = issue_job(ctx, dev, job);
+        if (g_trace) job->t_issue1 = now_ms();
         lk.lock();
         dev->inflight.push_back(job);
         ctx->cv.notify_all();
@@ -856,20 +939,10 @@ void issuer_main(gts_ctx *ctx, DevCtx *dev) {
 
 void retirer_main(gts_ctx *ctx, DevCtx *dev) {
     cudaSetDevice(dev->device);
+    std::deque<XJob *> pend;  // chunks whose device-to-host copy is in flight, oldest first (this thread only)
     std::unique_lock<std::mutex> lk(ctx->mu);
-    while (true) {
-        ctx->cv.wait(lk, [&] { return ctx->exiting || !dev->inflight.empty(); });
-        if (ctx->exiting) return;
-        XJob *job = dev->inflight.front();
-        dev->inflight.pop_front();
-        const bool run = !job->skipped && job->rc == 0;
-        lk.unlock();
-        if (run) {
-            job->rc = retire_job(ctx, dev, job);
-        } else if (!job->skipped) {
-            cudaStreamSynchronize(dev->stream);  // a failed enqueue: let what was enqueued finish
-        }
-        lk.lock();
+    // (called with the lock held) the chunk leaves the engine: slot and input buffer free, counters, `done`
+    auto complete = [&](XJob *job, bool run) {
         dev->slots[job->slot].busy = false;
         if (job->inbuf) {
             ctx->in_free.push_back(job->inbuf);
@@ -887,6 +960,46 @@ void retirer_main(gts_ctx *ctx, DevCtx *dev) {
         }
         job->done = true;
         ctx->cv.notify_all();
+    };
+    // (called WITHOUT the lock) finish the oldest copy in flight
+    auto finish_one = [&] {
+        XJob *job = pend.front();
+        pend.pop_front();
+        job->rc = retire_finish(ctx, dev, job);
+        std::lock_guard<std::mutex> g(ctx->mu);
+        complete(job, true);
+    };
+    PendingCopies pc;
+    pc.drain = [&] { while (!pend.empty()) finish_one(); };
+    pc.any = [&] { return !pend.empty(); };
+    const std::function<void()> &drain = pc.drain;
+    while (true) {
+        ctx->cv.wait(lk, [&] { return ctx->exiting || !dev->inflight.empty() || !pend.empty(); });
+        if (ctx->exiting) return;
+        if (!dev->inflight.empty() && pend.size() < 2) {
+            // the next chunk: wait for its kernels and queue its copy behind the ones in flight
+            XJob *job = dev->inflight.front();
+            dev->inflight.pop_front();
+            const bool run = !job->skipped && job->rc == 0;
+            lk.unlock();
+            if (run) {
+                job->rc = retire_issue(ctx, dev, job, pc);
+                if (job->d2h_issued) {
+                    pend.push_back(job);
+                    lk.lock();
+                    continue;
+                }
+            } else if (!job->skipped) {
+                cudaStreamSynchronize(dev->stream);  // a failed enqueue: let what was enqueued finish
+            }
+            drain();  // chunks leave in order
+            lk.lock();
+            complete(job, run);
+        } else {
+            lk.unlock();
+            finish_one();
+            lk.lock();
+        }
     }
 }
 
@@ -904,6 +1017,7 @@ int start_workers(gts_ctx *ctx) {
 // Hand a chunk to its GPU (round robin over the chunks keeps every GPU's queue equally long).
 void dispatch_locked(gts_ctx *ctx, XJob *job) {
     job->seq = ctx->next_seq++;
+    if (g_trace) job->t_disp = now_ms();
     job->dev = (int)(job->seq % ctx->devs.size());
     ctx->window.push_back(job);
     ctx->devs[job->dev]->inq.push_back(job);
@@ -1155,7 +1269,7 @@ int gts_create(const gts_options *opt, gts_ctx **out) {
         ctx->devs.push_back(std::move(dev));
     }
     if (!keep_current) guard.prev = ctx->devs[0]->device;  // one GPU: it becomes current (as cudaSetDevice(device) would)
-    ctx->in_max = kSlots * ctx->devs.size() + 2;
+    ctx->in_max = g_slots * ctx->devs.size() + 2;
     ctx->out_max = ctx->in_max + 1;
     ctx->poison = std::getenv("GTS_POISON_OUTPUT") != nullptr;
     ctx->short_on = std::getenv("GTS_NO_SHORT") == nullptr;
@@ -1305,6 +1419,14 @@ int gts_translate_buffer(gts_ctx *ctx, const uint8_t *in, size_t n, const uint8_
     ctx->consume_seq = ctx->next_seq;
     ctx->direct = false;
     lk.unlock();
+    if (g_trace) {
+        const double t0 = jobs.empty() ? 0 : jobs[0]->t_disp, t_end = now_ms();
+        for (XJob *j : jobs)
+            std::fprintf(stderr, "[gts trace] chunk %llu dev %d n %zu out %zu: dispatched %.3f issue %.3f..%.3f kernels done %.3f d2h issued %.3f done %.3f\n",
+                         (unsigned long long)j->seq, j->dev, j->n, j->out_n, j->t_disp - t0, j->t_issue0 - t0, j->t_issue1 - t0,
+                         j->t_comp - t0, j->t_d2h0 - t0, j->t_d2h1 - t0);
+        std::fprintf(stderr, "[gts trace] call returns at %.3f\n", t_end - t0);
+    }
     for (XJob *j : jobs) {
         if (rc == GTS_OK && j->seq <= ctx->trunc_seq) {
             fire_warnings(ctx, j);

@@ -58,7 +58,10 @@ constexpr int kShortMaxOut = 672;  // output bytes of the record (all requested 
 #endif
 constexpr int kRecLanes = GTS_REC_LANES;
 
-constexpr int kSizeThreads = 256;
+#ifndef GTS_SIZE_THREADS
+#define GTS_SIZE_THREADS 512
+#endif
+constexpr int kSizeThreads = GTS_SIZE_THREADS;
 #ifndef GTS_SIZE_PER_THREAD
 #define GTS_SIZE_PER_THREAD 1
 #endif

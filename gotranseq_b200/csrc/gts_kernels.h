@@ -16,6 +16,8 @@ cudaError_t launch_tile_scan(const Job &job, int sm_count, cudaStream_t stream);
 cudaError_t launch_piece_plan(const PieceInfoDev *all, int rank, int world, PieceParams *out, cudaStream_t stream);  // k_piece_plan
 cudaError_t launch_piece_fix(const Job &job, cudaStream_t stream);    // k_piece_fix: carry / end pads into reused slots
 cudaError_t launch_piece_trim(const Job &job, cudaStream_t stream);   // k_piece_trim: one piece's part of the trim walk
+// k_publish: the pass's totals into pinned host memory by stores from the device (no copy engine involved)
+cudaError_t launch_publish(const Totals *d_totals, Totals *h_totals, cudaStream_t stream);
 cudaError_t launch_warn(const Job &job, int sm_count, cudaStream_t stream);   // k_warn (only when job.warn is set)
 // k_lines and k_headers; with a side stream (and two events to fork / join) the two run
 // concurrently; ev_mid (optional) is recorded on `stream` after k_lines

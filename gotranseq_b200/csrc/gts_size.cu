@@ -380,7 +380,7 @@ __device__ void trimmed_lengths(const Job &job, const uint16_t *lut, u64 s, u64 
 }
 
 #ifndef GTS_SIZE_CTAS
-#define GTS_SIZE_CTAS 4
+#define GTS_SIZE_CTAS (1024 / GTS_SIZE_THREADS)
 #endif
 __global__ void __launch_bounds__(kSizeThreads, GTS_SIZE_CTAS) k_size(const __grid_constant__ Job job) {
     __shared__ uint16_t lut[128];
@@ -671,6 +671,21 @@ __global__ void k_piece_plan(const PieceInfoDev *all, int rank, int world, Piece
 
 cudaError_t launch_piece_plan(const PieceInfoDev *all, int rank, int world, PieceParams *out, cudaStream_t stream) {
     k_piece_plan<<<1, 32, 0, stream>>>(all, rank, world, out);
+    return cudaGetLastError();
+}
+
+// The totals of a pass, stored straight into (mapped) pinned host memory.  The chunk engine waits for
+// an event behind this kernel; a cudaMemcpyAsync in its place would wait in the device-to-host copy
+// engine behind the previous chunk's result.
+__global__ void k_publish(const Totals *d_totals, Totals *h_totals) {
+    static_assert(sizeof(Totals) % 8 == 0 && sizeof(Totals) / 8 <= 32, "one word per lane");
+    const u64 *src = reinterpret_cast<const u64 *>(d_totals);
+    volatile u64 *dst = reinterpret_cast<volatile u64 *>(h_totals);
+    if (threadIdx.x < sizeof(Totals) / 8) dst[threadIdx.x] = src[threadIdx.x];
+    __threadfence_system();
+}
+cudaError_t launch_publish(const Totals *d_totals, Totals *h_totals, cudaStream_t stream) {
+    k_publish<<<1, 32, 0, stream>>>(d_totals, h_totals);
     return cudaGetLastError();
 }
 
