@@ -579,7 +579,8 @@ def main():
         host_out = (ctypes.c_char * on).from_address(optr)
         barrier()
         # the streaming interface (reader memcpy into the library's pinned buffers, writer thread)
-        stream_once(tr, batch.h_in, nbytes)
+        for _ in range(2):  # (the pinned buffer pools settle on their sizes)
+            stream_once(tr, batch.h_in, nbytes)
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
@@ -587,7 +588,8 @@ def main():
         stream1_s = time.perf_counter() - t0
         assert stream_res["out"] == out_n, (stream_res, out_n)
         barrier()
-        stream_once(tr, batch.h_in, nbytes, reader_threads=args.reader_threads)
+        for _ in range(2):
+            stream_once(tr, batch.h_in, nbytes, reader_threads=args.reader_threads)
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):

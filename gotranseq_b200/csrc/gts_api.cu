@@ -186,6 +186,7 @@ struct gts_ctx {
     bool workers_started = false, exiting = false;
     std::vector<HostBuf *> in_free, out_free;
     size_t in_count = 0, out_count = 0, in_max = 0, out_max = 0;
+    size_t out_want = 0;  // largest chunk result so far: output buffers are (re)allocated at this size, so the pool settles after one pass over it
     std::deque<XJob *> window;  // submitted and not yet consumed, in input order
     uint64_t next_seq = 0, consume_seq = 0;
     uint64_t trunc_seq = ~0ull;  // chunk in which the reference stops reading
@@ -521,7 +522,9 @@ int ensure_pinned(uint8_t **p, size_t *cap, size_t need, size_t keep, std::strin
     if (need <= *cap && *p) return GTS_OK;
     const size_t want = round_up(need + need / 8 + 4096, 4096);
     uint8_t *q = nullptr;
+    const double t0 = g_trace ? now_ms() : 0;
     CUE(cudaHostAlloc(&q, want, cudaHostAllocPortable));
+    if (g_trace) std::fprintf(stderr, "[gts trace] pinned allocation of %zu bytes (was %zu): %.3f ms\n", want, *cap, now_ms() - t0);
     if (keep && *p) std::memcpy(q, *p, keep);
     if (*p) cudaFreeHost(*p);
     *p = q;
@@ -631,7 +634,7 @@ size_t boundary_below(const uint8_t *p, size_t lo, size_t pos) {
     return 0;
 }
 // First record boundary at or above `pos` (pos >= 1), n = none.
-size_t boundary_above(const uint8_t *p, size_t pos, size_t n) {
+size_t boundary_above_serial(const uint8_t *p, size_t pos, size_t n) {
     size_t i = pos;
     while (i < n) {
         const void *q = memchr(p + i, '>', n - i);
@@ -640,6 +643,29 @@ size_t boundary_above(const uint8_t *p, size_t pos, size_t n) {
         if (p[i - 1] == '\n') return i;
         i++;
     }
+    return n;
+}
+// A record larger than a chunk (a chromosome) makes this the only work of the calling thread while
+// the GPUs wait for the chunk: long ranges are searched by a few threads, one segment each.
+size_t boundary_above(const uint8_t *p, size_t pos, size_t n) {
+    const size_t len = n - pos;
+    const unsigned hw = std::thread::hardware_concurrency();
+    const size_t nthreads = std::min<size_t>(std::min<size_t>(8, hw ? hw : 1), len >> 24);  // >= 16 MB per thread
+    if (nthreads < 2) return boundary_above_serial(p, pos, n);
+    std::vector<size_t> found(nthreads, n);
+    std::vector<std::thread> th;
+    const size_t seg = (len + nthreads - 1) / nthreads;
+    for (size_t t = 0; t < nthreads; t++) {
+        th.emplace_back([&, t] {
+            const size_t lo = pos + t * seg, hi = std::min(n, lo + seg);
+            // (a boundary is looked at by the segment that holds its '>'; the byte in front of it may lie in the one before)
+            const size_t r = lo < hi ? boundary_above_serial(p, lo, hi) : hi;
+            found[t] = r < hi ? r : n;
+        });
+    }
+    for (auto &x : th) x.join();
+    for (size_t t = 0; t < nthreads; t++)
+        if (found[t] < n) return found[t];
     return n;
 }
 
@@ -851,7 +877,8 @@ int retire_issue(gts_ctx *ctx, DevCtx *dev, XJob *job, const PendingCopies &pc) 
         ctx->cv.wait(lk, [&] { return stream_dead(ctx) || job->seq < ctx->consume_seq + ctx->out_max; });
         if (stream_dead(ctx)) return GTS_OK;
         int rc = GTS_OK;
-        HostBuf *b = pool_take(ctx, lk, ctx->out_free, ctx->out_count, ctx->out_max, total + 64, err, &rc);
+        ctx->out_want = std::max(ctx->out_want, total + 64);
+        HostBuf *b = pool_take(ctx, lk, ctx->out_free, ctx->out_count, ctx->out_max, ctx->out_want, err, &rc);
         if (!b) return rc;
         job->outbuf = b;
         dst = b->p;

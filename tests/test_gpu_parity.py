@@ -265,6 +265,33 @@ def test_tiles_without_symbols_and_short_tiles():
         assert gpu(data, **kw) == oracle.translate(data, **kw), kw
 
 
+def test_header_geometry_sweep():
+    """Header lines of every length around the 16-byte lanes / 64-byte steps of k_records and the
+    4-byte lanes / 64-byte steps of k_headers, at every alignment of the '>' in the input, with the
+    first space (writer.go:121) at the start, in the middle, at the end or absent, LF and CRLF line
+    ends, and a last header line that ends with the input (with and without a CR)."""
+    import random
+    rng = random.Random(21)
+    parts = []
+    for H in list(range(1, 40)) + list(range(58, 72)) + [127, 128, 129, 190, 200, 257]:
+        for variant in range(4):
+            body = bytearray(rng.choice(b"abcdefghijklmnopqrstuvwxyz0123456789_|.") for _ in range(H - 1))
+            if variant == 1 and H > 2:
+                body[rng.randrange(len(body))] = 0x20
+            elif variant == 2 and H > 1:
+                body[-1] = 0x20
+            elif variant == 3 and H > 1:
+                body[0] = 0x20
+            eol = b"\r\n" if (H + variant) % 3 == 0 else b"\n"
+            # (the sequence length moves the next '>' to another alignment)
+            parts.append(b">" + bytes(body) + eol + _seq(rng, rng.randrange(0, 70)) + eol)
+    data = b"".join(parts)
+    for tail in (b">last header without a newline", b">last header with a CR\r", b">x", b">"):
+        d = data + tail
+        for kw in (dict(frame="6"), dict(frame="1", trim=True), dict(frame="R", alternative=True)):
+            assert gpu(d, **kw) == oracle.translate(d, **kw), (tail, kw)
+
+
 def test_thousands_of_tiny_records_per_tile():
     """More record pieces in a tile than one batch of the run table holds (16), up to 4096 empty ones."""
     import random

@@ -1,10 +1,11 @@
 #!/bin/bash
-# e2e A/B: gpu_e2e.sh TAG ENVSPEC...   ENVSPEC = name[:ENV=val,ENV=val]
+# e2e A/B: gpu_e2e.sh TAG SPEC...   SPEC = name[:lib.so|default[:ENV=val,ENV=val]]
 tag=$1; shift
 mkdir -p gpurun_out
 for spec in "$@"; do
-  IFS=: read -r name envs <<< "$spec"
+  IFS=: read -r name lib envs <<< "$spec"
   (
+    if [ -n "$lib" ] && [ "$lib" != default ]; then export GOTRANSEQ_B200_LIB=$PWD/$lib; fi
     if [ -n "$envs" ]; then for kv in ${envs//,/ }; do export "$kv"; done; fi
     python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-verify 2>gpurun_out/${tag}_${name}.err | python -c "
 import sys,json
