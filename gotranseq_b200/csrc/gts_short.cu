@@ -141,8 +141,25 @@ __global__ void __launch_bounds__(kShortWarps * 32) k_short(const __grid_constan
         if (s <= R) ri = job.rec[s];
         const bool ok = ri.emitted == 2;
         if (!__any_sync(0xFFFFFFFFu, ok)) continue;
-        const FrameTab *ft = job.ftab + s;
         const u32 n = (u32)ri.n;
+        // The record's frame table (k_size writes FrameTab only for the records of k_lines / k_headers):
+        // residues of every requested frame (frame_lengths of gts_common.cuh for n <= 180; --trim: the
+        // lengths k_size found) and where its first residue lies, relative to the record's first output byte.
+        u32 flen6[6], body6[6], rec_bytes = 0;
+        {
+            const u32 n3r = n - 3u * ((n * 43691u) >> 17);  // n % 3
+#pragma unroll
+            for (int f = 0; f < 6; f++) {
+                u32 start = (u32)(f % 3);
+                if (f >= 3 && !job.alternative) start = (n3r + 3u - start) % 3u;  // reverse_start (writer.go:64-79)
+                u32 L = n >= start ? ((n - start + 2u) * 43691u) >> 17 : 0u;     // ceil((n - start) / 3)
+                if (job.trim && ok) L = job.trim_len[s * 6 + f];
+                const bool req = ((job.frame_mask >> f) & 1u) != 0;
+                flen6[f] = req ? L : 0u;
+                body6[f] = rec_bytes + ri.H + 3u;
+                if (req) rec_bytes += ri.H + 3u + L + (L ? 1u : 0u);  // run_size for one line at most
+            }
+        }
         // ---- the record's slot in the image, its frames ----
         u64 gaddr = 0;
         u32 lo = 0;
@@ -173,8 +190,9 @@ __global__ void __launch_bounds__(kShortWarps * 32) k_short(const __grid_constan
                 // forward frame k; the reverse frame whose first codon starts k nucleotides from the record's end
                 const u32 i = (strand == 0 || job.alternative) ? (u32)k : (n3 + 3u - (u32)k) % 3u;
                 const u32 f = 3u * strand + i;
-                flen[k] = ft->len[f];
-                fdst[k] = image_addr + slot_img + lo + (u32)(ft->body[f] - ri.out_off);
+                flen[k] = f == 0 ? flen6[0] : f == 1 ? flen6[1] : f == 2 ? flen6[2] : f == 3 ? flen6[3] : f == 4 ? flen6[4] : flen6[5];
+                const u32 brel = f == 0 ? body6[0] : f == 1 ? body6[1] : f == 2 ? body6[2] : f == 3 ? body6[3] : f == 4 ? body6[4] : body6[5];
+                fdst[k] = image_addr + slot_img + lo + brel;
             }
             const u64 l = job.loc[s];
             loc_tile = (u32)(l >> 16);
@@ -184,14 +202,14 @@ __global__ void __launch_bounds__(kShortWarps * 32) k_short(const __grid_constan
             if (strand == 0) {
                 ShortMeta m;
 #pragma unroll
-                for (int f = 0; f < 6; f++) m.img[f] = slot_img + lo + (u32)(ft->body[f] - ri.out_off) - (ri.H + 3u);
+                for (int f = 0; f < 6; f++) m.img[f] = slot_img + lo + body6[f] - (ri.H + 3u);
                 m.H = ri.H;
                 const u64 hinf = s >= 1 ? job.hinfo[s] : 0;
                 m.sp = (u32)(hinf >> 32);
                 m.hoff = s >= 1 ? job.hdr_off[s] : 0;
                 m.g0 = gaddr;
                 m.lo = slot_img + lo;
-                m.hi = slot_img + lo + (u32)(job.rec[s + 1].out_off - ri.out_off);
+                m.hi = slot_img + lo + rec_bytes;
                 m.ok = 1;
                 m.pad = 0;
                 ws.meta[r] = m;

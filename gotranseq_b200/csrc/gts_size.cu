@@ -518,16 +518,18 @@ __global__ void __launch_bounds__(kSizeThreads, GTS_SIZE_CTAS) k_size(const __gr
             if (s < nslots) {
                 ri[i].out_off = off;
                 job.rec[s] = ri[i];
-                FrameTab ft;
-                u64 base = off;
+                if (ri[i].emitted != 2u) {  // (k_short works its records' frame tables out itself: 80 bytes less per read)
+                    FrameTab ft;
+                    u64 base = off;
 #pragma unroll
-                for (int f = 0; f < 6; f++) {
-                    ft.body[f] = base + ri[i].H + 3;
-                    ft.len[f] = flen[i][f];
-                    if (ri[i].emitted && ((job.frame_mask >> f) & 1u)) base += run_size(ri[i].H, flen[i][f]);
+                    for (int f = 0; f < 6; f++) {
+                        ft.body[f] = base + ri[i].H + 3;
+                        ft.len[f] = flen[i][f];
+                        if (ri[i].emitted && ((job.frame_mask >> f) & 1u)) base += run_size(ri[i].H, flen[i][f]);
+                    }
+                    ft.pad[0] = ft.pad[1] = 0;
+                    job.ftab[s] = ft;
                 }
-                ft.pad[0] = ft.pad[1] = 0;
-                job.ftab[s] = ft;
             }
             off += size[i];
         }
