@@ -29,6 +29,7 @@
 #include <vector>
 
 #include "../../include/gotranseq_b200.h"
+#include "gts_boundary.h"
 #include "gts_codes.h"
 #include "gts_device.h"
 #include "gts_kernels.h"
@@ -620,54 +621,6 @@ int dev_create(int ordinal, std::unique_ptr<DevCtx> *out, std::string *err) {
 }
 
 // ---- chunk engine -----------------------------------------------------------------------
-
-// Record boundary (a '>' that starts a line, transeq.go:198) closest below `pos`, searched back to
-// `lo` (exclusive); 0 = none.
-size_t boundary_below(const uint8_t *p, size_t lo, size_t pos) {
-    size_t i = pos;
-    while (i > lo + 1) {
-        const void *q = memrchr(p + lo + 1, '>', i - (lo + 1));
-        if (!q) return 0;
-        i = (size_t)(static_cast<const uint8_t *>(q) - p);
-        if (p[i - 1] == '\n') return i;
-    }
-    return 0;
-}
-// First record boundary at or above `pos` (pos >= 1), n = none.
-size_t boundary_above_serial(const uint8_t *p, size_t pos, size_t n) {
-    size_t i = pos;
-    while (i < n) {
-        const void *q = memchr(p + i, '>', n - i);
-        if (!q) return n;
-        i = (size_t)(static_cast<const uint8_t *>(q) - p);
-        if (p[i - 1] == '\n') return i;
-        i++;
-    }
-    return n;
-}
-// A record larger than a chunk (a chromosome) makes this the only work of the calling thread while
-// the GPUs wait for the chunk: long ranges are searched by a few threads, one segment each.
-size_t boundary_above(const uint8_t *p, size_t pos, size_t n) {
-    const size_t len = n - pos;
-    const unsigned hw = std::thread::hardware_concurrency();
-    const size_t nthreads = std::min<size_t>(std::min<size_t>(8, hw ? hw : 1), len >> 24);  // >= 16 MB per thread
-    if (nthreads < 2) return boundary_above_serial(p, pos, n);
-    std::vector<size_t> found(nthreads, n);
-    std::vector<std::thread> th;
-    const size_t seg = (len + nthreads - 1) / nthreads;
-    for (size_t t = 0; t < nthreads; t++) {
-        th.emplace_back([&, t] {
-            const size_t lo = pos + t * seg, hi = std::min(n, lo + seg);
-            // (a boundary is looked at by the segment that holds its '>'; the byte in front of it may lie in the one before)
-            const size_t r = lo < hi ? boundary_above_serial(p, lo, hi) : hi;
-            found[t] = r < hi ? r : n;
-        });
-    }
-    for (auto &x : th) x.join();
-    for (size_t t = 0; t < nthreads; t++)
-        if (found[t] < n) return found[t];
-    return n;
-}
 
 bool stream_dead(const gts_ctx *ctx) { return ctx->cancelled || ctx->e_rc != 0 || ctx->exiting; }
 
@@ -1419,8 +1372,8 @@ int gts_translate_buffer(gts_ctx *ctx, const uint8_t *in, size_t n, const uint8_
     do {
         size_t end = n;
         if (n - pos > chunk + chunk / 2) {
-            end = boundary_below(in, pos, pos + chunk);
-            if (end == 0) end = boundary_above(in, pos + chunk, n);  // one record larger than a chunk
+            end = gts_host::boundary_below(in, pos, pos + chunk);
+            if (end == 0) end = gts_host::boundary_above(in, pos + chunk, n);  // one record larger than a chunk
         }
         XJob *job = new XJob();
         job->in = in + pos;
@@ -1532,7 +1485,7 @@ int gts_submit(gts_ctx *ctx, size_t nbytes, int eof) {
     {
         const size_t from = std::max<size_t>(std::max<size_t>(ctx->scan_from, old_fill), 1);
         if (ctx->fill_n > from) {
-            const size_t b = boundary_below(cur->p, from - 1, ctx->fill_n);
+            const size_t b = gts_host::boundary_below(cur->p, from - 1, ctx->fill_n);
             if (b) ctx->last_boundary = b;
         }
         ctx->scan_from = ctx->fill_n;

@@ -121,6 +121,17 @@ def test_header_compiles_as_c_and_links(tmp_path):
     assert r.stdout.startswith("abi ok")
 
 
+def test_record_boundary_search_of_the_chunk_engine(tmp_path):
+    """gts_boundary.h (where the engine may cut the stream, transeq.go:198) against a byte loop, on a
+    96 MB buffer: the single-threaded and the multi-threaded paths of both directions."""
+    import subprocess
+    exe = tmp_path / "boundary_test"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-Wall", "-Wextra", os.path.join(ROOT, "tests", "c", "boundary_test.cpp"),
+                    "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.startswith("ok"), (r.returncode, r.stdout, r.stderr)
+
+
 def test_cli_reports_option_errors_like_the_reference(tmp_path):
     """main.go prints the error of transeq.Translate and returns (exit status 0); the option errors
     come before any device is touched, so this runs without a GPU."""
