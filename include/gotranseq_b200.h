@@ -97,7 +97,9 @@ int gts_fused_lut(int32_t table, int clean, uint16_t lut[125]);
  * reverseComplement encodedSequence.go:71-97, writer.translate / translate3Frames / writeHeader
  * / writeAA / trimAndReturn writer.go:57-169), on a FASTA buffer already in device memory.
  *   d_in   device pointer to n bytes of FASTA (treated as one complete input: start of file
- *          to EOF); must be 16-byte aligned (cudaMalloc / torch allocations are)
+ *          to EOF); must be 16-byte aligned (cudaMalloc / torch allocations are).  The kernels
+ *          read whole aligned 16-byte units: the unit that holds byte n-1 is read to its end, so
+ *          the allocation must cover n rounded up to 16 (every CUDA allocation does)
  *   d_out  device pointer, capacity cap bytes; receives the protein FASTA
  *   out_n  receives the exact output size; if it exceeds cap nothing is written past cap and
  *          GTS_ERR_CAPACITY is returned (out_n is still set, so the caller can retry)
