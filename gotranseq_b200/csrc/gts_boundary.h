@@ -25,16 +25,19 @@ inline size_t boundary_below_serial(const uint8_t *p, size_t lo, size_t pos) {
     }
     return 0;
 }
-// (long ranges -- the new bytes of a record much larger than a chunk -- on a few threads, one segment each)
+// (Ordinary FASTA has a boundary a few KB to a few MB below `pos`: the top 16 MB are searched by the
+// calling thread alone, which stops at the first hit.  Only what lies below them -- the new bytes of
+// a record much larger than a chunk -- goes to a few threads, one segment each.)
 inline size_t boundary_below(const uint8_t *p, size_t lo, size_t pos) {
     const size_t len = pos > lo ? pos - lo : 0;
-    const unsigned hw = std::thread::hardware_concurrency();
-    const size_t nthreads = std::min<size_t>(std::min<size_t>(8, hw ? hw : 1), len >> 23);  // >= 8 MB per thread
-    if (nthreads < 2) return boundary_below_serial(p, lo, pos);
-    // the quick look first: ordinary FASTA has a record boundary in the last few KB
-    const size_t near = boundary_below_serial(p, pos - (1u << 16), pos);
+    const size_t top = (size_t)16 << 20;
+    if (len <= 2 * top) return boundary_below_serial(p, lo, pos);
+    const size_t near = boundary_below_serial(p, pos - top, pos);
     if (near) return near;
-    const size_t hi_all = pos - (1u << 16) + 1;  // a '>' at hi_all - 1 or below has not been looked at yet
+    const size_t hi_all = pos - top + 1;  // a '>' at hi_all - 1 or below has not been looked at yet
+    const unsigned hw = std::thread::hardware_concurrency();
+    const size_t nthreads = std::min<size_t>(std::min<size_t>(8, hw ? hw : 1), (hi_all - lo) >> 23);  // >= 8 MB per thread
+    if (nthreads < 2) return boundary_below_serial(p, lo, hi_all);
     std::vector<size_t> found(nthreads, 0);
     std::vector<std::thread> th;
     const size_t seg = (hi_all - lo + nthreads - 1) / nthreads;
