@@ -470,6 +470,10 @@ def run_split(args, rank, local_rank, world):
 
 # ---------------------------------------------------------------------------------------------
 def main():
+    # The streaming legs run a reader (this thread + memcpy helpers) and a writer thread in one Python
+    # process: with the default 5 ms switch interval a thread that needs the GIL back after a ctypes
+    # call can wait 5 ms for it, several times per step -- more than the step itself.
+    sys.setswitchinterval(1e-4)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
