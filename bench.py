@@ -39,7 +39,7 @@ METRIC = "6-frame Gbp/s device-resident"
 UNIT = "Gbp/s"
 # DRAM bytes of one launch of the dominant kernel on the default workload, from the committed ncu
 # capture named in NCU_SOURCE (dram__bytes_read.sum + dram__bytes_write.sum); null for other workloads
-NCU_TRAFFIC = {"readme189": 140850688 + 333663232}
+NCU_TRAFFIC = {"readme189": 140930304 + 333649920}
 NCU_SOURCE = "profiles/r2b_ncu_full_summary.txt"
 
 
