@@ -590,8 +590,9 @@ int dev_create(int ordinal, std::unique_ptr<DevCtx> *out, std::string *err) {
     CUE(gts::init_kernels());
     CUE(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     {
-        // k_headers / k_short run next to the persistent k_lines grid; with a higher stream priority
-        // their CTAs are placed first when both become ready (GTS_SIDE_PRIO=0: plain streams, A/B runs)
+        // k_headers / k_short run next to the persistent k_lines grid.  GTS_SIDE_PRIO=1 (A/B runs) gives
+        // their streams the highest priority: measured, it moves time from the tail into k_lines and
+        // leaves the step where it was (profiles/r2_notes.md), so plain streams are the default
         int lo = 0, hi = 0;
         CUE(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         const char *sp = std::getenv("GTS_SIDE_PRIO");

@@ -20,8 +20,10 @@ namespace gts {
 // inserted before its first space (or appended), then '\n'.  A group of kHdrLanes lanes per record,
 // each lane holding four consecutive bytes of the line per step: the line is assembled once (only the
 // digit differs between frames) and stored once per requested frame, in front of the frame's residues
-// (frame table of k_size).  The kernel is a chain of two rounds of loads (record table, header bytes)
-// followed by stores: small groups keep many records in flight.
+// (frame table of k_size).  Sixteen lanes per record measured best (profiles/r2_notes.md): the lines
+// sit between residues that k_lines writes, so the kernel is bound by its scattered partial-sector
+// accesses -- fewer lanes per record put more records, i.e. more sectors, into every warp instruction
+// (8 / 4 / 2 lanes: 52 / 79 / 106 us against 42 us alone on the GPU).
 #ifndef GTS_HDR_LANES
 #define GTS_HDR_LANES 16
 #endif
@@ -89,6 +91,8 @@ cudaError_t init_kernels() {
 cudaError_t launch_emit(const Job &job, int sm_count, cudaStream_t stream, cudaEvent_t ev_mid, const EmitStreams &es) {
     cudaError_t e;
 #define GTS_TRY(call) do { e = (call); if (e != cudaSuccess) return e; } while (0)
+    // (A/B switch of the measurements in profiles/r2_notes.md: 0 = k_headers on a side stream next to
+    // k_lines (the default), 1 = after k_lines, 2 = in front of k_lines, both on the main stream)
     static const int hdr_order = std::getenv("GTS_HDR_ORDER") ? std::atoi(std::getenv("GTS_HDR_ORDER")) : 0;
     GTS_TRY(cudaEventRecord(es.fork, stream));
     if (hdr_order == 0) {
