@@ -16,6 +16,7 @@
 // its lowest codon, so the tile's two carried symbols and the 192 after it are all a lane ever
 // needs.  The image is written out with TMA bulk stores.
 #include <cstddef>
+#include <cstdlib>
 
 #include "gts_common.cuh"
 #include "gts_emit.cuh"
@@ -443,7 +444,14 @@ cudaError_t init_lines() {
 }
 
 cudaError_t launch_lines(const Job &job, int sm_count, cudaStream_t stream) {
-    const u32 wave = (u32)sm_count * GTS_LINES_CTAS;
+    // (A/B switch: GTS_LINES_WAVE = CTAs per SM of the persistent grid, 1..GTS_LINES_CTAS; a smaller
+    // wave leaves registers for another pass's k_parse on the same SM, profiles/r2_notes.md)
+    // (GTS_TUNE=1: read again at every launch, so that one process can sweep it)
+    static const bool tune = std::getenv("GTS_TUNE") != nullptr;
+    static const int wave_static = std::getenv("GTS_LINES_WAVE") ? std::atoi(std::getenv("GTS_LINES_WAVE")) : 0;
+    const int wave_env = tune && std::getenv("GTS_LINES_WAVE") ? std::atoi(std::getenv("GTS_LINES_WAVE")) : wave_static;
+    const u32 per_sm = wave_env >= 1 && wave_env <= GTS_LINES_CTAS ? (u32)wave_env : (u32)GTS_LINES_CTAS;
+    const u32 wave = (u32)sm_count * per_sm;
     k_lines<<<job.ntiles < wave ? job.ntiles : wave, kLinesThreads, sizeof(LinesShared), stream>>>(job);
     return cudaGetLastError();
 }
