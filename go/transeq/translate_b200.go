@@ -37,8 +37,14 @@ import (
 	"unsafe"
 )
 
+// AnyOrder lets the stream hand results back as they complete instead of in input order: what the
+// reference does with NumWorker > 1, where every worker writes its own buffer when it is full
+// (writer.go:171-173).  Whole records, each exactly once.  Off by default: the output is then the
+// reference's -n 1 output byte for byte.  (A package variable: Options must stay the reference's struct.)
+var AnyOrder = false
+
 // Translate keeps the reference's signature (transeq.go:114).  NumWorker is accepted and ignored:
-// every visible GPU is used and the output is always in input order (the reference's -n 1 order).
+// every visible GPU is used and the output is in input order (the reference's -n 1 order) unless AnyOrder is set.
 func Translate(inputSequence io.Reader, out io.Writer, options Options) error {
 	return TranslateContext(context.Background(), inputSequence, out, options)
 }
@@ -54,6 +60,9 @@ func TranslateContext(cctx context.Context, inputSequence io.Reader, out io.Writ
 		clean: b2u(options.Clean), alternative: b2u(options.Alternative), trim: b2u(options.Trim),
 		num_worker: C.int32_t(options.NumWorker), device: -1,
 		num_gpus: -1, // every visible GPU
+	}
+	if AnyOrder {
+		opt.any_order = 1
 	}
 	var ctx *C.gts_ctx
 	if rc := C.gts_create(&opt, &ctx); rc != C.GTS_OK {

@@ -32,7 +32,7 @@ class gts_options(ctypes.Structure):
         ("chunk_bytes", ctypes.c_uint64),
         ("num_gpus", ctypes.c_int32),
         ("device_ids", ctypes.c_int32 * 8),
-        ("reserved1", ctypes.c_int32),
+        ("any_order", ctypes.c_int32),
     ]
 
 

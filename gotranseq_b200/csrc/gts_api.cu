@@ -192,6 +192,7 @@ struct gts_ctx {
     uint64_t next_seq = 0, consume_seq = 0;
     uint64_t trunc_seq = ~0ull;  // chunk in which the reference stops reading
     bool cancelled = false;
+    bool any_order = false;  // gts_options.any_order: results are handed back as they complete
     int e_rc = 0;  // first error of the stream (sticky until gts_stream_reset)
     std::string e_err;
     XJob *handed = nullptr;  // result currently with the caller
@@ -819,8 +820,10 @@ int retire_issue(gts_ctx *ctx, DevCtx *dev, XJob *job, const PendingCopies &pc) 
         std::unique_lock<std::mutex> lk(ctx->mu);
         // (window rule: only the out_max oldest chunks may hold an output buffer, so the chunk the
         // caller waits for can always get one)
+        // (any_order: the caller takes whatever chunk is complete, so whoever holds a buffer gets consumed)
+        auto in_window = [&] { return ctx->any_order || job->seq < ctx->consume_seq + ctx->out_max; };
         auto ready = [&] {
-            return stream_dead(ctx) || (job->seq < ctx->consume_seq + ctx->out_max && (!ctx->out_free.empty() || ctx->out_count < ctx->out_max));
+            return stream_dead(ctx) || (in_window() && (!ctx->out_free.empty() || ctx->out_count < ctx->out_max));
         };
         if (!ready()) {
             // the caller may be waiting for a chunk whose copy this thread has not finished yet
@@ -828,7 +831,7 @@ int retire_issue(gts_ctx *ctx, DevCtx *dev, XJob *job, const PendingCopies &pc) 
             drain();
             lk.lock();
         }
-        ctx->cv.wait(lk, [&] { return stream_dead(ctx) || job->seq < ctx->consume_seq + ctx->out_max; });
+        ctx->cv.wait(lk, [&] { return stream_dead(ctx) || in_window(); });
         if (stream_dead(ctx)) return GTS_OK;
         int rc = GTS_OK;
         ctx->out_want = std::max(ctx->out_want, total + 64);
@@ -1064,8 +1067,16 @@ int next_output(gts_ctx *ctx, const uint8_t **buf, size_t *n, bool block) {
             *n = ctx->handed->out_n;
             return GTS_OK;
         }
-        if (!ctx->window.empty() && ctx->window.front()->done) {
-            XJob *job = ctx->window.front();
+        // the oldest chunk -- or, with any_order, the oldest COMPLETE chunk that no chunk in front of it can
+        // still silence: a line of >= max_line bytes (transeq.go:186) lies inside one record, hence inside one
+        // chunk, so only a chunk of at least that size can turn out to be where the reference stops reading
+        XJob *ready_job = nullptr;
+        for (XJob *j : ctx->window) {
+            if (j->done) { ready_job = j; break; }
+            if (!ctx->any_order || j->n >= ctx->max_line) break;
+        }
+        if (ready_job) {
+            XJob *job = ready_job;
             if (job->seq > ctx->trunc_seq) {  // the reference stopped reading before this chunk
                 job->out_n = 0;
                 job->warns.clear();
@@ -1077,7 +1088,7 @@ int next_output(gts_ctx *ctx, const uint8_t **buf, size_t *n, bool block) {
                 continue;
             }
             if (job->out_n == 0) {
-                ctx->window.pop_front();
+                ctx->window.erase(std::find(ctx->window.begin(), ctx->window.end(), job));
                 ctx->consume_seq++;
                 recycle_job_locked(ctx, job);
                 ctx->cv.notify_all();
@@ -1252,6 +1263,7 @@ int gts_create(const gts_options *opt, gts_ctx **out) {
     if (!keep_current) guard.prev = ctx->devs[0]->device;  // one GPU: it becomes current (as cudaSetDevice(device) would)
     ctx->in_max = g_slots * ctx->devs.size() + 2;
     ctx->out_max = ctx->in_max + 1;
+    ctx->any_order = opt->any_order != 0;
     ctx->poison = std::getenv("GTS_POISON_OUTPUT") != nullptr;
     ctx->short_on = std::getenv("GTS_NO_SHORT") == nullptr;
     *out = ctx.release();
@@ -1547,8 +1559,9 @@ int gts_release_output(gts_ctx *ctx) {
     XJob *job = ctx->handed;
     if (!job) return GTS_OK;
     ctx->handed = nullptr;
-    if (!ctx->window.empty() && ctx->window.front() == job) {
-        ctx->window.pop_front();
+    auto it = std::find(ctx->window.begin(), ctx->window.end(), job);  // (the front, unless any_order)
+    if (it != ctx->window.end()) {
+        ctx->window.erase(it);
         ctx->consume_seq++;
         recycle_job_locked(ctx, job);
     }

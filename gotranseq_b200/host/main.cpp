@@ -98,6 +98,7 @@ int main(int argc, char **argv) {
     if (version) { std::printf("%s (B200) version %s\n", kTool, GTS_VERSION); return 0; }
     if (const char *g = std::getenv("GOTRANSEQ_B200_GPUS")) opt.NumGpus = std::atoi(g);
     if (const char *t = std::getenv("GOTRANSEQ_B200_IO_THREADS")) opt.IoThreads = std::atoi(t);
+    if (const char *a = std::getenv("GOTRANSEQ_B200_ANY_ORDER")) opt.AnyOrder = std::atoi(a) != 0;
     if (const char *c = std::getenv("GOTRANSEQ_B200_CHUNK_MB")) opt.ChunkBytes = (unsigned long long)(std::atof(c) * (1 << 20));
 
     // run(), main.go:39-65

@@ -44,6 +44,7 @@ gts_ctx *create(const Options &o, std::string *err) {
     opt.device = o.Device;
     opt.chunk_bytes = o.ChunkBytes;
     opt.num_gpus = o.NumGpus < 0 ? -1 : o.NumGpus;
+    opt.any_order = o.AnyOrder ? 1 : 0;
     for (int i = 0; i < 8; i++) opt.device_ids[i] = i;
     gts_ctx *ctx = nullptr;
     if (gts_create(&opt, &ctx) != GTS_OK) {

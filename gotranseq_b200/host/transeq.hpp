@@ -28,6 +28,7 @@ struct Options {
     int NumGpus = -1;          // 0 = one GPU (Device), -1 = every visible GPU, n = GPUs 0..n-1
     unsigned long long ChunkBytes = 0;  // streaming chunk size, 0 = library default
     bool Warnings = true;      // print the reference's WARNING lines to stdout
+    bool AnyOrder = false;     // results are written as they complete (the reference's -n > 1 order), not in input order
     int IoThreads = 0;         // TranslateFd: threads per file read / write (0 = 4)
 };
 

@@ -38,11 +38,13 @@ class Options:
 class Translator:
     """One gts_ctx: a decoded option set plus its device scratch.  Not thread safe."""
 
-    def __init__(self, options=None, device=-1, chunk_bytes=0, devices=None, warnings=None, **kw):
+    def __init__(self, options=None, device=-1, chunk_bytes=0, devices=None, warnings=None, any_order=False, **kw):
         """devices: None = one GPU (`device`); "all" = every visible GPU; a list of ordinals = those GPUs
         (record-aligned chunks are dealt to them in turn, results come back in input order).
         warnings: a callable(bytes) receiving each WARNING line of encodedSequence.go:39 exactly as the
-        reference prints it to stdout (None = invalid nucleotides are not reported)."""
+        reference prints it to stdout (None = invalid nucleotides are not reported).
+        any_order: the streaming calls hand results back as they complete (the reference's `-n > 1` order:
+        whole records, each exactly once, in no particular order)."""
         if options is None:
             options = Options(**kw)
         self.options = options
@@ -63,6 +65,7 @@ class Translator:
         o.num_worker = int(options.NumWorker)
         o.device = int(device)
         o.chunk_bytes = int(chunk_bytes)
+        o.any_order = 1 if any_order else 0
         h = ctypes.c_void_p()
         rc = L.gts_create(ctypes.byref(o), ctypes.byref(h))
         if rc != _lib.GTS_OK:

@@ -39,7 +39,7 @@ enum {
 /*
  * Mirrors `type Options struct` (transeq/options.go:4-11) field for field.
  * num_worker is accepted for source compatibility and ignored (the GPU path has no worker
- * goroutines; output is always in input order, i.e. the reference's `-n 1` order).
+ * goroutines; output is in input order, i.e. the reference's `-n 1` order, unless any_order is set).
  */
 typedef struct gts_options {
     const char *frame;    /* Options.Frame: "1","2","3","F","-1","-2","-3","R","6"           */
@@ -60,7 +60,14 @@ typedef struct gts_options {
      * The device-resident and gts_piece_* entry points use the first device only. */
     int32_t num_gpus;
     int32_t device_ids[8];
-    int32_t reserved1;
+    /* any_order != 0: the streaming calls hand a chunk's result back as soon as it is complete, whatever
+     * chunks before it are still on their way -- the reference's `-n > 1` behaviour, where every worker
+     * writes its buffer when it is full (writer.go:171-173) and the order of the records in the output
+     * is up to the scheduler.  Each result is still a whole number of records, every record appears
+     * exactly once, and with one GPU the order stays the input order in practice.  A chunk never
+     * overtakes one that could hold a line of >= 100 MiB (transeq.go:27,186: nothing behind such a line
+     * may be written).  gts_translate_buffer is not affected (its result is one buffer in input order). */
+    int32_t any_order;
 } gts_options;
 
 typedef struct gts_ctx gts_ctx;

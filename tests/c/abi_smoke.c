@@ -1,5 +1,6 @@
 /* The header must be usable from plain C (this is what a cgo shim compiles against), and the
  * option-decoding entry points must work without a device.  Built and run by tests/test_abi.py. */
+#include <stddef.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -31,6 +32,8 @@ int main(void) {
     opt.device = -1;
     if (gts_create(&opt, &ctx) != GTS_ERR_FRAME || ctx != NULL) return 6;
     if (strstr(gts_last_error(NULL), "wrong value for -f | --frame parameter: 9") == NULL) return 7;
-    printf("abi ok %s %u bytes/piece_info %u bytes/piece\n", GTS_VERSION, (unsigned)sizeof(info), (unsigned)sizeof(piece));
+    opt.any_order = 1; /* (the reference's -n > 1 order; a plain int32 at the end of the options) */
+    printf("abi ok %s %u bytes/piece_info %u bytes/piece options %u any_order %u\n", GTS_VERSION, (unsigned)sizeof(info),
+           (unsigned)sizeof(piece), (unsigned)sizeof(opt), (unsigned)offsetof(gts_options, any_order));
     return 0;
 }

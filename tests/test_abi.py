@@ -119,6 +119,11 @@ def test_header_compiles_as_c_and_links(tmp_path):
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
     assert r.stdout.startswith("abi ok")
+    # the ctypes mirror of gts_options has the C layout (any_order: the last field)
+    from gotranseq_b200 import _lib
+    words = r.stdout.split()
+    assert int(words[words.index("options") + 1]) == ctypes.sizeof(_lib.gts_options)
+    assert int(words[words.index("any_order") + 1]) == _lib.gts_options.any_order.offset
 
 
 def test_record_boundary_search_of_the_chunk_engine(tmp_path):

@@ -271,3 +271,69 @@ def test_cli_write_failure_and_warnings(goldens, tmp_path):
         r = subprocess.run([exe, "-s", str(src), "-o", "/dev/full", "-f", "6"], capture_output=True)
         assert r.returncode == 0
         assert r.stdout.endswith(b"fail to translate file:\nfail to write to output file: write /dev/full: no space left on device")
+
+
+# ---- any_order: the reference's -n > 1 behaviour (writer.go:171-173: whoever is full writes) ----
+
+def _entries(out):
+    """The output as a sorted list of its per-frame entries (an entry starts with '>' at a line start)."""
+    assert out[:1] in (b"", b">") and out[-1:] in (b"", b"\n")
+    return sorted(p.rstrip(b"\n") for p in (b"\n" + out).split(b"\n>")[1:])
+
+
+class _Blocks:
+    def __init__(self):
+        self.blocks = []
+
+    def write(self, b):
+        self.blocks.append(bytes(b))
+
+
+def test_any_order_hands_back_every_record_exactly_once():
+    import gotranseq_b200
+    data = bulk(6_000_000, 51) + regular_fasta(52, 400, 10, 300) + regular_fasta(53, 3, 150_000, 200_000) + bulk(500_000, 54)
+    for kw, okw in ((dict(Frame="6"), dict(frame="6")), (dict(Frame="R", Trim=True), dict(frame="R", trim=True))):
+        want = oracle.translate(data, **okw)
+        want_entries = _entries(want)
+        for devs in _devsets():
+            for chunk in (1 << 14, 1 << 18):
+                with gotranseq_b200.Translator(gotranseq_b200.Options(**kw), devices=devs, chunk_bytes=chunk, any_order=True) as t:
+                    w = _Blocks()
+                    t.translate_stream(io.BytesIO(data), w)
+                    got = b"".join(w.blocks)
+                    assert len(got) == len(want), (kw, devs, chunk)
+                    # every result is a whole number of records
+                    assert all(b[:1] == b">" and b[-1:] == b"\n" for b in w.blocks), (kw, devs, chunk)
+                    assert _entries(got) == want_entries, (kw, devs, chunk)
+                    st = t.stats()
+                    assert st["out_bytes"] == len(want) and st["in_bytes"] == len(data)
+                    # the one-shot call is not affected: one buffer, input order
+                    assert t.translate_bytes(data) == want
+                    # and the context streams again
+                    w2 = _Blocks()
+                    t.translate_stream(io.BytesIO(data), w2)
+                    assert _entries(b"".join(w2.blocks)) == want_entries
+
+
+def test_any_order_never_writes_behind_an_over_long_line():
+    """transeq.go:27,186: nothing behind a line of >= 100 MiB is ever written, in whatever order the
+    chunks complete (a chunk may overtake only chunks too small to hold such a line)."""
+    import gotranseq_b200
+    cap = 20000
+    rng = random.Random(9)
+    seq = lambda n: "".join(rng.choice("ACGT") for _ in range(n))
+    rec = lambda i, n, w=60: ">r%d\n" % i + "\n".join(seq(n)[j:j + w] for j in range(0, n, w)) + "\n"
+    text = "".join(rec(i, 2000) for i in range(80)) + ">q\n" + seq(3 * cap) + "\n" + "".join(rec(100 + i, 1500) for i in range(80))
+    data = text.encode()
+    oracle.set_max_line_length(cap)
+    try:
+        want = oracle.translate(data, frame="6")
+    finally:
+        oracle.set_max_line_length(100 << 20)
+    assert b">r99" not in want and b">r100" not in want and b">r79" in want
+    for devs in ([0], [0, 0, 0]):
+        with gotranseq_b200.Translator(gotranseq_b200.Options(Frame="6"), devices=devs, chunk_bytes=4096, any_order=True) as t:
+            t.set_max_line_length(cap)
+            w = _Blocks()
+            t.translate_stream(io.BytesIO(data), w)
+            assert _entries(b"".join(w.blocks)) == _entries(want), devs
