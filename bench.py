@@ -28,6 +28,7 @@ import ctypes
 import hashlib
 import json
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -278,11 +279,61 @@ def _copy(dst, src, n, threads):
         f.result()
 
 
-def stream_once(tr, h_in, nbytes, repeats=1, hasher=None, read_size=0, reader_threads=1):
+class _StreamApi(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("acquire_input", "submit", "wait_output", "release_output", "cancel")]
+
+
+class _StreamResult(ctypes.Structure):
+    _fields_ = [("out_bytes", ctypes.c_uint64), ("chunks", ctypes.c_uint64), ("rc", ctypes.c_int)]
+
+
+_HARNESS = {}
+HARNESS_SRC = os.path.join(ROOT, "tools", "stream_harness.cpp")
+HARNESS_LIB = os.path.join(ROOT, "tools", "libstream_harness.so")
+
+
+def stream_harness(force=False):
+    """tools/stream_harness.cpp: the shim's loop in C++ (reader thread + memcpy helpers, writer thread), so
+    that the streaming legs measure the library and the copies, not the interpreter's thread hand-overs.
+    Compiled with g++ on first use; returns the loaded library, or None when it cannot be built."""
+    if "lib" in _HARNESS and not force:
+        return _HARNESS["lib"]
+    lib = None
+    try:
+        stale = not os.path.exists(HARNESS_LIB) or os.path.getmtime(HARNESS_LIB) < os.path.getmtime(HARNESS_SRC)
+        if stale or force:
+            tmp = "%s.%d.tmp" % (HARNESS_LIB, os.getpid())  # (several ranks may build at once)
+            subprocess.run(["g++", "-O2", "-std=c++17", "-pthread", "-shared", "-fPIC", "-Wall", "-Wextra", "-o", tmp,
+                            HARNESS_SRC], check=True, capture_output=True)
+            os.replace(tmp, HARNESS_LIB)
+        lib = ctypes.CDLL(HARNESS_LIB)
+        lib.stream_harness_run.restype = ctypes.c_int
+        lib.stream_harness_run.argtypes = [ctypes.POINTER(_StreamApi), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                           ctypes.c_int, ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(_StreamResult)]
+    except Exception as e:  # no compiler on this box: the Python loop below does the same, with more jitter
+        print("bench: stream harness not available (%s), using the Python loop" % e, file=sys.stderr)
+        lib = None
+    _HARNESS["lib"] = lib
+    return lib
+
+
+def stream_once(tr, h_in, nbytes, repeats=1, hasher=None, read_size=0, reader_threads=1, python_loop=False):
     """The shim's loop: reader = this thread (memcpy from h_in into the acquired pinned buffer, with
-    reader_threads helpers), writer thread = gts_wait_output / gts_release_output.  Returns the counters."""
+    reader_threads helpers), writer thread = gts_wait_output / gts_release_output.  Returns the counters.
+    Driven from C++ (tools/stream_harness.cpp) unless the output is to be hashed or python_loop is set."""
     L, h = tr._L, tr._h
-    res = {"out": 0, "chunks": 0, "err": None}
+    res = {"out": 0, "chunks": 0, "err": None, "driver": "python"}
+    H = None if (hasher is not None or python_loop) else stream_harness()
+    if H is not None:
+        api = _StreamApi(*[ctypes.cast(getattr(L, "gts_" + n), ctypes.c_void_p).value for n, _ in _StreamApi._fields_])
+        out = _StreamResult()
+        rc = H.stream_harness_run(ctypes.byref(api), h, ctypes.c_void_p(h_in), nbytes, repeats, reader_threads, read_size,
+                                  ctypes.byref(out))
+        if rc != 0:
+            msg = L.gts_last_error(h).decode()
+            L.gts_stream_reset(h)
+            raise RuntimeError("stream harness: rc %d: %s" % (rc, msg))
+        return {"out": out.out_bytes, "chunks": out.chunks, "err": None, "driver": "c++"}
 
     def writer():
         p, m = ctypes.c_void_p(), ctypes.c_size_t()
@@ -492,6 +543,7 @@ def main():
     ap.add_argument("--reader-threads", type=int, default=4, help="threads of the streaming legs' reader (memcpy into the pinned buffer)")
     ap.add_argument("--no-verify", action="store_true", help="skip the comparison with the oracle")
     ap.add_argument("--warnings", action="store_true", help="install a warning callback (the CLI / shim configuration)")
+    ap.add_argument("--python-stream-loop", action="store_true", help="drive the streaming legs from Python threads instead of tools/stream_harness.cpp")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank, local_rank, world = env_rank()
@@ -583,21 +635,22 @@ def main():
         host_out = (ctypes.c_char * on).from_address(optr)
         barrier()
         # the streaming interface (reader memcpy into the library's pinned buffers, writer thread)
+        pl = args.python_stream_loop
         for _ in range(2):  # (the pinned buffer pools settle on their sizes)
-            stream_once(tr, batch.h_in, nbytes)
+            stream_once(tr, batch.h_in, nbytes, python_loop=pl)
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            stream_res = stream_once(tr, batch.h_in, nbytes)
+            stream_res = stream_once(tr, batch.h_in, nbytes, python_loop=pl)
         stream1_s = time.perf_counter() - t0
         assert stream_res["out"] == out_n, (stream_res, out_n)
         barrier()
         for _ in range(2):
-            stream_once(tr, batch.h_in, nbytes, reader_threads=args.reader_threads)
+            stream_once(tr, batch.h_in, nbytes, reader_threads=args.reader_threads, python_loop=pl)
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            stream_res = stream_once(tr, batch.h_in, nbytes, reader_threads=args.reader_threads)
+            stream_res = stream_once(tr, batch.h_in, nbytes, reader_threads=args.reader_threads, python_loop=pl)
         stream_s = time.perf_counter() - t0
         assert stream_res["out"] == out_n, (stream_res, out_n)
         barrier()
@@ -679,7 +732,7 @@ def main():
         periods_ok = r2["out"] == 2 * r1["out"] and (host_out is None or h1.hexdigest() == hh.hexdigest())
         barrier()
         t0 = time.perf_counter()
-        rr = stream_once(tr, batch.h_in, nbytes, repeats=repeats, reader_threads=args.reader_threads)
+        rr = stream_once(tr, batch.h_in, nbytes, repeats=repeats, reader_threads=args.reader_threads, python_loop=args.python_stream_loop)
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt, 0.0 if (periods_ok and rr["out"] == repeats * out_n) else 1.0], dtype=torch.float64, device=torch.device("cuda", local_rank))
         if world > 1:
@@ -726,6 +779,8 @@ def main():
                            "ms_per_step": stream_s / e2e_steps * 1e3 if stream_s > 0 else None,
                            "api": "gts_acquire_input / gts_submit / gts_wait_output / gts_release_output (the Go shim's calls); "
                                   "the reader memcpy's the FASTA into the acquired pinned buffer with %d threads" % args.reader_threads,
+                           "driver": ("tools/stream_harness.cpp (reader thread + memcpy helpers, writer thread, no interpreter in the loop)"
+                                      if stream_res and stream_res.get("driver") == "c++" else "Python threads (ctypes)"),
                            "single_thread_reader": {"value": nt_all * e2e_steps / stream1_s / 1e9 if stream1_s > 0 else None,
                                                     "ms_per_step": stream1_s / e2e_steps * 1e3 if stream1_s > 0 else None},
                            "chunks_per_step": stream_res["chunks"] if stream_res else None},
