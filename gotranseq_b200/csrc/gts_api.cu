@@ -820,8 +820,18 @@ int retire_issue(gts_ctx *ctx, DevCtx *dev, XJob *job, const PendingCopies &pc) 
         std::unique_lock<std::mutex> lk(ctx->mu);
         // (window rule: only the out_max oldest chunks may hold an output buffer, so the chunk the
         // caller waits for can always get one)
-        // (any_order: the caller takes whatever chunk is complete, so whoever holds a buffer gets consumed)
-        auto in_window = [&] { return ctx->any_order || job->seq < ctx->consume_seq + ctx->out_max; };
+        // (any_order: the caller takes whatever chunk is complete, so whoever holds a buffer gets consumed --
+        // except behind a chunk that is large enough to hold an over-long line and not done yet: nothing
+        // behind it is handed over before it is (next_output), so nothing behind it may take a buffer
+        // that it could be left waiting for)
+        auto in_window = [&] {
+            if (!ctx->any_order) return job->seq < ctx->consume_seq + ctx->out_max;
+            for (const XJob *j : ctx->window) {
+                if (j == job) break;
+                if (!j->done && j->n >= ctx->max_line) return false;
+            }
+            return true;
+        };
         auto ready = [&] {
             return stream_dead(ctx) || (in_window() && (!ctx->out_free.empty() || ctx->out_count < ctx->out_max));
         };
