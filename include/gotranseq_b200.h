@@ -154,7 +154,8 @@ int gts_translate_buffer(gts_ctx *ctx, const uint8_t *in, size_t n, const uint8_
  *   }
  *
  * The library cuts the byte stream at record boundaries ("\n>"), carries the unfinished last
- * record over to the next pass and hands results back strictly in input order.  gts_submit only
+ * record over to the next pass and hands results back strictly in input order (unless
+ * gts_options.any_order is set: then the oldest COMPLETE chunk comes back).  gts_submit only
  * queues the pass: a worker thread owned by ctx runs it (H2D, kernels, D2H) while the caller reads
  * the next chunk into the other pinned input buffer and writes the previous result, so reading,
  * translating and writing overlap.  Before eof gts_next_output does not block: n == 0 means
@@ -196,7 +197,8 @@ int gts_num_devices(const gts_ctx *ctx);
 /*
  * WARNING side channel (encodedSequence.go:36-40): the reference prints one line per nucleotide
  * that is none of ACGTUN (either case) and translates it as N.  With a callback installed the
- * kernels record those bytes and the library reports them in input order, on the caller's thread,
+ * kernels record those bytes and the library reports them in input order (with any_order: chunk by chunk,
+ * in the order the chunks are handed back), on the caller's thread,
  * from gts_next_output / gts_wait_output / gts_translate_buffer before the chunk's output is handed
  * over.  header = the record's header line (without the line break; header_len == 0 for sequence
  * bytes in front of the first header line), pos = index of the nucleotide in its record.
