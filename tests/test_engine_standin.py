@@ -1,0 +1,59 @@
+"""The HOST logic of the library without a GPU: gotranseq_b200/csrc/gts_api.cu (chunk engine: record-boundary
+cuts and carry-over, buffer pools, several device contexts, in-order and any-order hand-back, the WARNING side
+channel, write errors, cancellation, the over-long line rule, the retries of chunks whose tables were too small,
+the device-resident calls) compiled as plain C++ against a stand-in for the device -- tests/c/standin/: the
+CUDA runtime calls carried out on the host and the device pass restated behind the kernels' launchers.  The
+scenarios are the GPU engine tests themselves (tests/test_engine.py, imported by tests/standin_driver.py) plus a
+few that need control over timing; each runs in a process of its own with GOTRANSEQ_B200_LIB pointing at the
+stand-in build, against the oracle.
+
+TEST INFRASTRUCTURE: the stand-in is built and loaded only here; the product has no CPU path
+(tests/test_abi.py::test_no_gpu_fails_loudly), and what the kernels compute is checked on the GPU (-m gpu)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STANDIN = os.path.join(ROOT, "tests", "c", "standin")
+LIB = os.path.join(STANDIN, "libgotranseq_standin.so")
+CSRC = os.path.join(ROOT, "gotranseq_b200", "csrc")
+CUDA_INC = os.environ.get("CUDA_HOME", "/usr/local/cuda") + "/include"
+
+
+@pytest.fixture(scope="module")
+def standin_lib():
+    srcs = [os.path.join(CSRC, "gts_api.cu"), os.path.join(STANDIN, "standin_cuda.cpp"), os.path.join(STANDIN, "standin_pass.cpp")]
+    deps = srcs + [os.path.join(CSRC, f) for f in ("gts_device.h", "gts_kernels.h", "gts_codes.h", "gts_boundary.h")] + \
+        [os.path.join(ROOT, "include", "gotranseq_b200.h")]
+    if not os.path.exists(os.path.join(CUDA_INC, "cuda_runtime_api.h")):
+        pytest.skip("no CUDA headers")
+    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
+        # -Bsymbolic: the library's CUDA calls bind to its own stand-ins even when a real libcudart is loaded
+        # into the process (torch)
+        subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-pthread", "-Wl,-Bsymbolic", "-I", CUDA_INC,
+                        "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", LIB, "-x", "c++"] + srcs, check=True)
+    return LIB
+
+
+def _run(lib, name, env=None, timeout=600):
+    e = dict(os.environ, GOTRANSEQ_B200_LIB=lib)
+    e.update(env or {})
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "standin_driver.py"), name], env=e, capture_output=True,
+                       text=True, timeout=timeout)
+    assert r.returncode == 0 and ("ok " + name) in r.stdout, (name, r.returncode, r.stdout[-2000:], r.stderr[-4000:])
+
+
+@pytest.mark.parametrize("name", ["multi_device_contexts", "random_nasty_streams", "blank_lines_first", "many_chunks",
+                                  "warnings", "write_error", "cancel", "any_order", "any_order_long_line",
+                                  "over_long_lines", "overflow_retries", "device_resident"])
+def test_engine_on_the_stand_in_device(standin_lib, name):
+    _run(standin_lib, name)
+
+
+def test_any_order_behind_a_slow_large_chunk(standin_lib):
+    """The deadlock an earlier build had: with any_order, chunks behind an unfinished chunk that can hold an over-long
+    line took all the output buffers, could not be handed back, and the large chunk waited for a buffer for ever."""
+    _run(standin_lib, "any_order_slow_large_chunk", env={"GTS_STANDIN_SLOW_BYTES": "20000", "GTS_STANDIN_SLOW_MS": "200"},
+         timeout=120)
