@@ -57,3 +57,27 @@ def test_any_order_behind_a_slow_large_chunk(standin_lib):
     line took all the output buffers, could not be handed back, and the large chunk waited for a buffer for ever."""
     _run(standin_lib, "any_order_slow_large_chunk", env={"GTS_STANDIN_SLOW_BYTES": "20000", "GTS_STANDIN_SLOW_MS": "200"},
          timeout=120)
+
+
+def test_engine_under_thread_sanitizer(tmp_path):
+    """tests/c/engine_tsan.cpp: reader, writer and canceller threads of the caller against the engine's issuer /
+    retirer threads, with -fsanitize=thread: no data race reported, results equal to the oracle's."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle
+    import workloads
+    from fasta_gen import nasty_fasta
+    exe = tmp_path / "engine_tsan"
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-g", "-fsanitize=thread", "-pthread", "-I", CUDA_INC,
+                        "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-o", str(exe),
+                        os.path.join(ROOT, "tests", "c", "engine_tsan.cpp"), "-x", "c++", os.path.join(CSRC, "gts_api.cu"),
+                        os.path.join(STANDIN, "standin_cuda.cpp"), os.path.join(STANDIN, "standin_pass.cpp")],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("no ThreadSanitizer build here: " + r.stderr[-300:])
+    data = workloads.readme189(total_bytes=1_500_000, seed=5) + b"".join(nasty_fasta(k, max_records=30, max_len=900) for k in range(12))
+    (tmp_path / "in.fna").write_bytes(data)
+    (tmp_path / "want.faa").write_bytes(oracle.translate(data, frame="6", trim=True))
+    r = subprocess.run([str(exe), str(tmp_path / "in.fna"), str(tmp_path / "want.faa")], capture_output=True, text=True,
+                       timeout=600, env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0"))
+    assert r.returncode == 0 and "tsan driver ok" in r.stdout, (r.returncode, r.stdout[-500:], r.stderr[-3000:])
+    assert "ThreadSanitizer" not in r.stderr, r.stderr[:6000]
