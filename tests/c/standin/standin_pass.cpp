@@ -180,7 +180,7 @@ cudaError_t launch_sizes(const Job &job, int, cudaStream_t) {
 cudaError_t launch_warn(const Job &job, int, cudaStream_t) {
     std::lock_guard<std::mutex> lk(g_mu);
     const Result &r = g_results[job.totals];
-    if (job.totals->flags == 0 && job.wres && r.warns.size() <= job.warn_cap)
+    if (job.totals->flags == 0 && job.wres && !r.warns.empty() && r.warns.size() <= job.warn_cap)
         std::memcpy(job.wres, r.warns.data(), r.warns.size() * sizeof(WarnRec));
     return cudaSuccess;
 }
@@ -188,7 +188,7 @@ cudaError_t launch_emit(const Job &job, int, cudaStream_t, cudaEvent_t, const Em
     maybe_slow(job);
     std::lock_guard<std::mutex> lk(g_mu);
     const Result &r = g_results[job.totals];
-    if (job.totals->flags == 0 && job.out && r.out.size() <= job.out_cap) std::memcpy(job.out, r.out.data(), r.out.size());
+    if (job.totals->flags == 0 && job.out && !r.out.empty() && r.out.size() <= job.out_cap) std::memcpy(job.out, r.out.data(), r.out.size());
     return cudaSuccess;
 }
 cudaError_t launch_publish(const Totals *d_totals, Totals *h_totals, cudaStream_t) {
