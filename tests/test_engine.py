@@ -225,11 +225,11 @@ def test_cancel_mid_stream():
         t2.close()
 
 
-def _build_c(tmp_path, name):
+def _build_c(tmp_path, name, lib_dir=None, lib="gotranseq_b200"):
     exe = tmp_path / name
-    lib_dir = os.path.join(ROOT, "gotranseq_b200")
+    lib_dir = lib_dir or os.path.join(ROOT, "gotranseq_b200")
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
-                    os.path.join(ROOT, "tests", "c", name + ".c"), "-o", str(exe), "-L", lib_dir, "-lgotranseq_b200",
+                    os.path.join(ROOT, "tests", "c", name + ".c"), "-o", str(exe), "-L", lib_dir, "-l" + lib,
                     "-Wl,-rpath," + lib_dir], check=True)
     return str(exe)
 
@@ -237,7 +237,10 @@ def _build_c(tmp_path, name):
 def test_c_driver_of_the_shim_call_sequence(goldens, tmp_path):
     """tests/c/stream_drive.c: gts_acquire_input -> gts_submit -> gts_next_output -> gts_release_output
     from plain C on the device, the calls go/transeq/translate_b200.go makes."""
-    exe = _build_c(tmp_path, "stream_drive")
+    _c_driver_cases(_build_c(tmp_path, "stream_drive"), goldens, tmp_path)
+
+
+def _c_driver_cases(exe, goldens, tmp_path):
     cases = [(goldens["input"].encode(), dict(frame="6")),
              (bulk(4_000_000, 60), dict(frame="6", table=11, clean=True, trim=True)),
              (_warning_cases(goldens)[1], dict(frame="R", alternative=True))]
@@ -259,7 +262,10 @@ def test_c_driver_of_the_shim_call_sequence(goldens, tmp_path):
 def test_cli_write_failure_and_warnings(goldens, tmp_path):
     """main.go:87-90: the error of the run is printed as "fail to translate file:\\n%v"; the WARNING
     lines of encodedSequence.go:39 go to stdout."""
-    exe = os.path.join(ROOT, "gotranseq_b200", "bin", "gotranseq")
+    _cli_cases(os.path.join(ROOT, "gotranseq_b200", "bin", "gotranseq"), goldens, tmp_path)
+
+
+def _cli_cases(exe, goldens, tmp_path):
     data = goldens["input"].encode()
     src = tmp_path / "t.fna"
     src.write_bytes(data)

@@ -81,3 +81,62 @@ def test_engine_under_thread_sanitizer(tmp_path):
                        timeout=600, env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0"))
     assert r.returncode == 0 and "tsan driver ok" in r.stdout, (r.returncode, r.stdout[-500:], r.stderr[-3000:])
     assert "ThreadSanitizer" not in r.stderr, r.stderr[:6000]
+
+
+@pytest.fixture(scope="module")
+def goldens_json():
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "emboss_goldens.json")) as f:
+        return json.load(f)
+
+
+def test_c_driver_of_the_shim_call_sequence_on_the_stand_in(standin_lib, goldens_json, tmp_path):
+    """tests/c/stream_drive.c (the Go shim's call sequence from plain C) linked against the stand-in build: goldens,
+    4 MB of records, the WARNING text, several device contexts, a failing write followed by gts_stream_reset."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import test_engine as E
+    exe = E._build_c(tmp_path, "stream_drive", lib_dir=STANDIN, lib="gotranseq_standin")
+    E._c_driver_cases(exe, goldens_json, tmp_path)
+
+
+def test_cli_on_the_stand_in(standin_lib, goldens_json, tmp_path):
+    """The `gotranseq` CLI (gotranseq_b200/host/main.cpp, transeq.cpp: flags of main.go:21-37, file -> file through
+    TranslateFd with its reader / writer threads, messages of main.go:74,89) linked against the stand-in build: the
+    reference's goldens through the flags, WARNING lines on stdout, a write failure on /dev/full."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle
+    import test_engine as E
+    host = os.path.join(ROOT, "gotranseq_b200", "host")
+    exe = str(tmp_path / "gotranseq")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "include"), "-o", exe,
+                    os.path.join(host, "main.cpp"), os.path.join(host, "transeq.cpp"), "-L", STANDIN, "-lgotranseq_standin",
+                    "-Wl,-rpath," + STANDIN], check=True)
+    E._cli_cases(exe, goldens_json, tmp_path)
+    src = tmp_path / "test.fna"
+    src.write_bytes(goldens_json["input"].encode())
+    want_warn = oracle.translate_with_warnings(goldens_json["input"].encode(), frame="1")[1]
+    for case in goldens_json["cases"]:
+        flags = ["-" + t if t.startswith("-") else t for t in case["options"].split()]  # -frame=6 -> --frame=6
+        dst = tmp_path / "out.faa"
+        for env in ({}, {"GOTRANSEQ_B200_GPUS": "2", "GOTRANSEQ_B200_CHUNK_MB": "0.004"}):
+            r = subprocess.run([exe, "-s", str(src), "-o", str(dst)] + flags, capture_output=True, timeout=120,
+                               env=dict(os.environ, **env))
+            assert r.returncode == 0 and r.stdout == want_warn, (case["options"], r.stdout, r.stderr)
+            assert dst.read_bytes().decode() == case["expected"], (case["options"], env)
+    # a larger file through the reader / writer threads of TranslateFd, several device contexts, any order
+    import workloads
+    data = workloads.readme189(total_bytes=12_000_000, seed=8)
+    big = tmp_path / "big.fna"
+    big.write_bytes(data)
+    want = oracle.translate(data, frame="6", table=11, clean=True, trim=True)
+    for env in ({"GOTRANSEQ_B200_GPUS": "2", "GOTRANSEQ_B200_CHUNK_MB": "1"},
+                {"GOTRANSEQ_B200_GPUS": "2", "GOTRANSEQ_B200_CHUNK_MB": "0.25", "GOTRANSEQ_B200_ANY_ORDER": "1"}):
+        dst = tmp_path / "big.faa"
+        r = subprocess.run([exe, "-s", str(big), "-o", str(dst), "-f", "6", "-t", "11", "-c", "-T"], capture_output=True,
+                           timeout=300, env=dict(os.environ, **env))
+        assert r.returncode == 0 and r.stdout == b"", (r.stdout[-300:], r.stderr[-300:])
+        got = dst.read_bytes()
+        if "GOTRANSEQ_B200_ANY_ORDER" in env:
+            assert E._entries(got) == E._entries(want)
+        else:
+            assert got == want
