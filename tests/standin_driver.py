@@ -127,6 +127,68 @@ def device_resident_calls():
             pass
 
 
+class RaggedReader:
+    """Reads of random sizes (1 .. kmax bytes)."""
+
+    def __init__(self, data, rng, kmax):
+        self.d, self.p, self.rng, self.kmax = data, 0, rng, kmax
+
+    def readinto(self, view):
+        n = min(self.rng.randint(1, self.kmax), len(view), len(self.d) - self.p)
+        view[:n] = self.d[self.p:self.p + n]
+        self.p += n
+        return n
+
+
+def fuzz_streams(seed0=1000, iters=80):
+    """Random FASTA (adversarial records, blank runs, CRLF, no final newline, a record larger than the chunks) x random
+    options x device contexts x chunk sizes x read sizes x in-order / any-order x with / without the warning callback,
+    streamed and one-shot, against the oracle."""
+    from fasta_gen import nasty_fasta, regular_fasta
+    for seed in range(seed0, seed0 + iters):
+        rng = random.Random(seed)
+        parts = []
+        for k in range(rng.randint(1, 6)):
+            c = rng.random()
+            if c < 0.6:
+                parts.append(nasty_fasta(seed * 13 + k, max_records=rng.randint(1, 40), max_len=rng.choice([5, 60, 900, 5000])))
+            elif c < 0.8:
+                parts.append(regular_fasta(seed * 13 + k, rng.randint(1, 200), 0, rng.choice([10, 300, 3000])))
+            elif c < 0.9:
+                parts.append(b"\n" * rng.randint(0, 5000))
+            else:
+                parts.append(b">big\n" + bytes(rng.choice(b"ACGTN") for _ in range(rng.randint(1000, 30000))) + b"\n")
+        data = b"".join(parts)
+        if rng.random() < 0.15:
+            data = data.replace(b"\n", b"\r\n")
+        if rng.random() < 0.1:
+            data = data.rstrip(b"\n")
+        kw = dict(frame=rng.choice(["1", "2", "3", "F", "-1", "-2", "-3", "R", "6", "6"]), table=rng.choice([0, 2, 11, 23, 30]),
+                  clean=rng.random() < 0.5, alternative=rng.random() < 0.5, trim=rng.random() < 0.5)
+        want, want_warn = oracle.translate_with_warnings(data, **kw)
+        O = gotranseq_b200.Options(Frame=kw["frame"], Table=kw["table"], Clean=kw["clean"], Alternative=kw["alternative"], Trim=kw["trim"])
+        devs = rng.choice([[0], [0, 0], [0, 1, 0], [1, 0, 1, 0, 1]])
+        chunk = rng.choice([4096, 5000, 9000, 1 << 14, 1 << 16, 1 << 20])
+        any_order = rng.random() < 0.3
+        warn = rng.random() < 0.5
+        got_w = []
+        what = (seed, kw, devs, chunk, any_order, warn)
+        with gotranseq_b200.Translator(O, devices=devs, chunk_bytes=chunk, any_order=any_order, warnings=(got_w.append if warn else None)) as t:
+            w = E._Blocks()
+            rd = RaggedReader(data, rng, rng.choice([1, 7, 100, 5000, 100000])) if rng.random() < 0.7 else io.BytesIO(data)
+            t.translate_stream(rd, w)
+            got = b"".join(w.blocks)
+            if any_order:  # whole records in any order: the same lines, the same size (headers may be empty or repeated)
+                assert len(got) == len(want) and sorted(got.split(b"\n")) == sorted(want.split(b"\n")), what
+                assert not warn or sorted(b"".join(got_w).split(b"\n")) == sorted(want_warn.split(b"\n")), what
+            else:
+                assert got == want, what
+                assert not warn or b"".join(got_w) == want_warn, what
+            del got_w[:]
+            assert t.translate_bytes(data) == want, what
+            assert not warn or b"".join(got_w) == want_warn, what
+
+
 SCENARIOS = {
     "multi_device_contexts": E.test_multi_device_contexts_match_the_oracle,
     "random_nasty_streams": lambda: [E.test_random_nasty_streams_on_three_contexts(s) for s in range(30)],
@@ -141,6 +203,7 @@ SCENARIOS = {
     "over_long_lines": P.test_over_long_lines,
     "overflow_retries": overflow_retries,
     "device_resident": device_resident_calls,
+    "fuzz_streams": fuzz_streams,
 }
 
 if __name__ == "__main__":
