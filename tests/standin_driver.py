@@ -189,6 +189,26 @@ def fuzz_streams(seed0=1000, iters=80):
             assert not warn or b"".join(got_w) == want_warn, what
 
 
+def bench_stream_legs():
+    """bench.py's streaming legs (tools/stream_harness.cpp and the Python loop) through the real engine."""
+    import hashlib
+    import numpy as np
+    import bench
+    import workloads
+    data = workloads.readme189(total_bytes=12_000_000, seed=3)
+    arr = np.frombuffer(data, dtype=np.uint8).copy()
+    want = oracle.translate(data, frame="6")
+    with gotranseq_b200.Translator(gotranseq_b200.Options(Frame="6"), devices=[0, 1], chunk_bytes=1 << 20) as tr:
+        for threads in (1, 4):
+            r = bench.stream_once(tr, arr.ctypes.data, len(data), reader_threads=threads)
+            assert r["out"] == len(want) and r["chunks"] >= 8, r
+        r = bench.stream_once(tr, arr.ctypes.data, len(data), repeats=3, reader_threads=4)
+        assert r["out"] == 3 * len(want), r
+        h = hashlib.sha256()
+        r = bench.stream_once(tr, arr.ctypes.data, len(data), hasher=h, read_size=300_000)
+        assert r["driver"] == "python" and h.hexdigest() == hashlib.sha256(want).hexdigest()
+
+
 SCENARIOS = {
     "multi_device_contexts": E.test_multi_device_contexts_match_the_oracle,
     "random_nasty_streams": lambda: [E.test_random_nasty_streams_on_three_contexts(s) for s in range(30)],
@@ -204,6 +224,7 @@ SCENARIOS = {
     "overflow_retries": overflow_retries,
     "device_resident": device_resident_calls,
     "fuzz_streams": fuzz_streams,
+    "bench_stream_legs": bench_stream_legs,
 }
 
 if __name__ == "__main__":

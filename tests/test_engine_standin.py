@@ -47,7 +47,7 @@ def _run(lib, name, env=None, timeout=600):
 
 @pytest.mark.parametrize("name", ["multi_device_contexts", "random_nasty_streams", "blank_lines_first", "many_chunks",
                                   "warnings", "write_error", "cancel", "any_order", "any_order_long_line",
-                                  "over_long_lines", "overflow_retries", "device_resident", "fuzz_streams"])
+                                  "over_long_lines", "overflow_retries", "device_resident", "fuzz_streams", "bench_stream_legs"])
 def test_engine_on_the_stand_in_device(standin_lib, name):
     _run(standin_lib, name)
 
