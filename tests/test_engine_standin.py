@@ -79,6 +79,8 @@ def test_engine_under_thread_sanitizer(tmp_path):
     (tmp_path / "want.faa").write_bytes(oracle.translate(data, frame="6", trim=True))
     r = subprocess.run([str(exe), str(tmp_path / "in.fna"), str(tmp_path / "want.faa")], capture_output=True, text=True,
                        timeout=600, env=dict(os.environ, TSAN_OPTIONS="halt_on_error=0"))
+    if "FATAL: ThreadSanitizer" in r.stderr:  # (the sanitizer's runtime cannot map its shadow memory on this kernel)
+        pytest.skip(r.stderr.strip().splitlines()[0])
     assert r.returncode == 0 and "tsan driver ok" in r.stdout, (r.returncode, r.stdout[-500:], r.stderr[-3000:])
     assert "ThreadSanitizer" not in r.stderr, r.stderr[:6000]
 
